@@ -200,3 +200,195 @@ def cells(degree, cell_nodes, cell_origin, cell_h, x, coef, face_ptr=None, face_
     lib().vho_cells(degree, nc, _I(cell_nodes), _P(cell_origin), _P(cell_h), _P(x), _P(coef), _I(face_ptr), _I(face_no),
                     _I(face_bid), _P(K), _P(r), _P(e))
     return K, r, e
+
+
+# ------------------------------------------------------------------------------------------
+# global level: constrained scatter, GMRES + block-Jacobi, Newton with line search
+# ------------------------------------------------------------------------------------------
+def _constraint_maps(T):
+    """C (n_local_dofs x n_local_dofs, scipy CSR) with C[i,i]=1 for unconstrained i, C[i,m]=w for constrained i;
+    and the boolean mask of constrained DoFs.  Closed, homogeneous constraints."""
+    import scipy.sparse as sp
+    NL = 18 * T.n_local_nodes
+    con = np.zeros(NL, dtype=bool)
+    con[T.c_dof] = True
+    rows = [np.nonzero(~con)[0]]
+    cols = [np.nonzero(~con)[0]]
+    vals = [np.ones(rows[0].size)]
+    if T.c_master.size:
+        cnt = np.diff(T.c_ptr)
+        rows.append(np.repeat(T.c_dof, cnt))
+        cols.append(T.c_master.astype(np.int64))
+        vals.append(T.c_weight)
+    C = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(NL, NL))
+    return C, con
+
+
+def assemble_global(T, x_local, coef, want_matrix=True, chunk=256):
+    """What assemble_system() / compute_residual() leave in system_matrix / system_rhs on this rank's owned rows.
+
+    Restates AffineConstraints::distribute_local_to_global (call sites assemble.cc:356-361, residual.cc:287-289,
+    rules in SURVEY.md A.4): unconstrained rows/columns receive C^T K C, constrained rows/columns receive nothing
+    but sum_cells |a_ii| (mean |diag| of the cell if a_ii == 0) on the diagonal; rhs = C^T r, 0 on constrained DoFs.
+    Returns (A: scipy CSR [n_owned_dofs x n_local_dofs] or None, rhs[n_owned_dofs])."""
+    import scipy.sparse as sp
+    n = nodes_per_cell(T.degree)
+    dpc = 18 * n
+    NL = 18 * T.n_local_nodes
+    NO = 18 * T.n_owned_nodes
+    fptr, fno, fbid = T.face_csr()
+    C, con = _constraint_maps(T)
+    dofs = (18 * T.cell_nodes.astype(np.int64)[:, :, None] + np.arange(18)[None, None, :]).reshape(T.n_cells, dpc)
+    rvec = np.zeros(NL)
+    diag = np.zeros(NL)
+    Ku = sp.csr_matrix((NL, NL)) if want_matrix else None
+    dummy = np.zeros(1, np.int32)
+    for c0 in range(0, T.n_cells, chunk):
+        c1 = min(T.n_cells, c0 + chunk)
+        sl = slice(c0, c1)
+        fp = fptr[c0:c1 + 1] - fptr[c0]
+        has = fptr[c1] > fptr[c0]
+        K, r, _ = cells(T.degree, T.cell_nodes[sl], T.cell_origin[sl], T.cell_h[sl], x_local, coef, fp,
+                        fno[fptr[c0]:fptr[c1]] if has else dummy, fbid[fptr[c0]:fptr[c1]] if has else dummy,
+                        want_matrix=want_matrix)
+        np.add.at(rvec, dofs[sl].ravel(), r.ravel())
+        if want_matrix:
+            rr = np.repeat(dofs[sl], dpc, axis=1).ravel()
+            cc = np.tile(dofs[sl], (1, dpc)).ravel()
+            Ku = Ku + sp.csr_matrix((K.ravel(), (rr, cc)), shape=(NL, NL))
+            d = np.abs(np.einsum("eii->ei", K))
+            avg = d.mean(axis=1, keepdims=True)
+            d = np.where(d != 0.0, d, avg)
+            cm = con[dofs[sl]]
+            np.add.at(diag, dofs[sl][cm], d[cm])
+    rhs = (C.T @ rvec)
+    rhs[con] = 0.0
+    A = None
+    if want_matrix:
+        A = C.T @ Ku @ C + sp.diags(diag)
+        A = sp.csr_matrix(A)[:NO, :]
+    return A, rhs[:NO]
+
+
+def block_jacobi_inverse(A, n_owned_nodes):
+    """Inverse of the nodal 18x18 diagonal blocks of A (owned rows); returns [n_owned_nodes,18,18]."""
+    import scipy.sparse as sp
+    B = sp.bsr_matrix(A[:, :18 * n_owned_nodes], blocksize=(18, 18))
+    B.sort_indices()
+    D = np.zeros((n_owned_nodes, 18, 18))
+    for I in range(n_owned_nodes):
+        s, e = B.indptr[I], B.indptr[I + 1]
+        k = np.searchsorted(B.indices[s:e], I)
+        D[I] = B.data[s + k]
+    return np.linalg.inv(D)
+
+
+def gmres_block_jacobi(A, b, Minv, tol_abs, max_it=10000, restart=30, matvec_halo=None, dot=None):
+    """Right-preconditioned restarted GMRES with deal.II SolverFGMRES iteration semantics:
+    modified Gram-Schmidt in deal.II's add_and_dot order; from the second inner step on the (j+1) x j
+    Hessenberg block is solved by least squares and its residual checked with ++accumulated_iterations.
+    A: [n_owned x n_local]; matvec_halo(z_owned) -> z_local fills ghosts (identity for one rank);
+    dot(a,b) all-reduced inner product.  Returns (x_owned, iterations, residual, converged)."""
+    NO = b.size
+    nb = Minv.shape[0]
+    if matvec_halo is None:
+        matvec_halo = lambda z: z  # noqa: E731
+    if dot is None:
+        dot = lambda a, c: float(a @ c)  # noqa: E731
+
+    def prec(v):
+        return np.einsum("ijk,ik->ij", Minv, v.reshape(nb, 18)).ravel()
+
+    def check(step, val):
+        if val <= tol_abs:
+            return "success"
+        if step >= max_it or np.isnan(val):
+            return "failure"
+        return "iterate"
+
+    x = np.zeros(NO)
+    acc = 0
+    res = 0.0
+    state = "iterate"
+    m = restart
+    while state == "iterate":
+        aux = b - A @ matvec_halo(x) if np.any(x) else b.copy()
+        beta = np.sqrt(dot(aux, aux))
+        res = beta
+        state = check(acc, res)
+        if state == "success":
+            break
+        H = np.zeros((m + 1, m))
+        V = np.zeros((m, NO))
+        y = np.zeros(0)
+        a = beta
+        for j in range(m):
+            V[j] = aux / a if a != 0 else 0.0
+            z = prec(V[j])
+            aux = A @ matvec_halo(z)
+            H[0, j] = dot(aux, V[0])
+            for i in range(1, j + 1):
+                aux = aux - H[i - 1, j] * V[i - 1]
+                H[i, j] = dot(aux, V[i])
+            aux = aux - H[j, j] * V[j]
+            a = np.sqrt(dot(aux, aux))
+            H[j + 1, j] = a
+            if j > 0:
+                H1 = H[:j + 1, :j]
+                prhs = np.zeros(j + 1)
+                prhs[0] = beta
+                y, _, _, _ = np.linalg.lstsq(H1, prhs, rcond=None)
+                res = float(np.linalg.norm(prhs - H1 @ y))
+                acc += 1
+                state = check(acc, res)
+                if state != "iterate":
+                    break
+        if y.size:
+            x = x + prec(y @ V[:y.size])
+    return x, acc, res, state == "success"
+
+
+def distribute(T, x_local):
+    """AffineConstraints::distribute: constrained entries overwritten from their masters (solve.cc:181, iteration.cc:180)."""
+    x = x_local.copy()
+    if T.c_dof.size:
+        cnt = np.diff(T.c_ptr)
+        vals = np.zeros(T.c_dof.size)
+        if T.c_master.size:
+            np.add.at(vals, np.repeat(np.arange(T.c_dof.size), cnt), T.c_weight * x_local[T.c_master])
+        x[T.c_dof] = vals
+    return x
+
+
+def energy_global(T, x_local, coef):
+    fptr, fno, fbid = T.face_csr()
+    dummy = np.zeros(1, np.int32)
+    _, _, e = cells(T.degree, T.cell_nodes, T.cell_origin, T.cell_h, x_local, coef, fptr,
+                    fno if fno.size else dummy, fbid if fbid.size else dummy, want_matrix=False, want_energy=True)
+    return float(e[T.cell_owned.astype(bool)].sum())
+
+
+def newton_step(T, x, coef, lin_tol, max_lin_it=10000, restart=30, damped=True, step=0.83):
+    """One pass of run.cc:214-218 on a single rank: assemble_system, solve(tol), newton_iteration.
+    x: owned == local DoF vector.  Returns dict(x, rhs_norm, lin_its, lin_res, res_norm, alpha, n_trials, ...)."""
+    assert T.n_ghost_nodes == 0
+    A, rhs = assemble_global(T, x, coef, True)
+    Minv = block_jacobi_inverse(A, T.n_owned_nodes)
+    bn = float(np.linalg.norm(rhs))
+    d, its, lres, ok = gmres_block_jacobi(A, rhs, Minv, lin_tol * bn, max_lin_it, restart)
+    if not ok:
+        raise RuntimeError("oracle GMRES did not converge")
+    d = distribute(T, d)
+    prev = bn
+    alpha = 1.0
+    n_trials = 0
+    for i in range(100 if damped else 1):
+        alpha = step ** i if damped else 1.0
+        xt = distribute(T, x + alpha * d)
+        _, r = assemble_global(T, xt, coef, False)
+        cur = float(np.linalg.norm(r))
+        n_trials += 1
+        if damped and cur < prev:
+            break
+    return dict(x=xt, delta=d, rhs=rhs, rhs_norm=bn, lin_its=its, lin_res=lres, res_norm=cur, alpha=alpha,
+                n_trials=n_trials, A=A, residual=r)

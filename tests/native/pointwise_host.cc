@@ -1,0 +1,23 @@
+// Test-only host build of the product's __host__ __device__ pointwise math (csrc/vh_pointwise.cuh),
+// so the closed forms the CUDA kernels use are checked against the oracle on the CPU-only container.
+// Never part of the product: the product evaluates these functions on the device only.
+#include "../../verkko-hem-repo_b200/csrc/vh_pointwise.cuh"
+
+extern "C" void vht_pointwise(const double *A, const double *coef, double *g18, double *H324, double *f)
+{
+  double prod[72];
+  for (int e = 0; e < 36; ++e)
+    vh_product_entry(A, e, prod + 2 * e);
+  const double alpha = coef[3], *beta = coef + 4;
+  for (int c = 0; c < 18; ++c)
+    g18[c] = vh_g_component(A, prod, c, alpha, beta);
+  for (int d = 0; d < 18; ++d)
+    {
+      double col[18];
+      vh_hessian_column(A, prod, d, alpha, beta, col);
+      for (int c = 0; c < 18; ++c)
+        H324[18 * c + d] = col[c];
+    }
+  *f = vh_bulk_energy(prod, alpha, beta);
+}
+extern "C" int vht_sym_index(int c, int d) { return vh_sym_index(c, d); }

@@ -1,0 +1,199 @@
+"""verkko-hem-repo_b200 — B200-native femgl Newton hot path (VerHem drop-in) behind a C ABI.
+
+Python is only the test / benchmark harness here: ``ctypes`` bindings over
+
+* ``lib/libvhfemgl.so``  — hand-written sm_100a CUDA (csrc/), C ABI ``include/vh_femgl.h``;
+* ``lib/libvhhost.so``   — host-side tables and the ``FemGL`` driver mirror (host/), the stand-in for deal.II.
+
+There is no CPU fallback: every compute entry point lives in ``libvhfemgl.so`` and raises if it is missing.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__)) if "__file__" in globals() else None
+if _PKG is None or not os.path.isdir(os.path.join(_PKG, "csrc")):
+    _PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "verkko-hem-repo_b200")
+ROOT = os.path.dirname(_PKG)
+LIBDIR = os.path.join(_PKG, "lib")
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+class VhError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("vh error %d: %s" % (code, msg))
+        self.code = code
+
+
+def build(cuda=True, host=True, verbose=False):
+    """Compile the in-tree libraries (nvcc cross-compiles sm_100a without a GPU)."""
+    targets = (["host"] if host else []) + (["cuda"] if cuda else [])
+    cmd = ["make", "-C", _PKG, "-j8"] + targets
+    if not verbose:
+        cmd.insert(1, "-s")
+    subprocess.check_call(cmd)
+
+
+# ------------------------------------------------------------------------------------------
+# host tables (stand-in for deal.II): libvhhost.so
+# ------------------------------------------------------------------------------------------
+_host = None
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        p = os.path.join(LIBDIR, "libvhhost.so")
+        if not os.path.exists(p):
+            build(cuda=False, host=True)
+        L = ctypes.CDLL(p)
+        L.vhh_last_error.restype = ctypes.c_char_p
+        L.vhh_mesh_create.restype = ctypes.c_void_p
+        L.vhh_mesh_create.argtypes = [ctypes.c_int, _dp, _dp, _i32p, _i32p, ctypes.c_int]
+        L.vhh_mesh_free.argtypes = [ctypes.c_void_p]
+        L.vhh_mesh_n_cells.restype = ctypes.c_int64
+        L.vhh_mesh_n_cells.argtypes = [ctypes.c_void_p]
+        L.vhh_mesh_cell_centers.argtypes = [ctypes.c_void_p, _dp]
+        L.vhh_mesh_refine.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int64]
+        L.vhh_mesh_finalize.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.vhh_mesh_global_sizes.argtypes = [ctypes.c_void_p, _i64p]
+        L.vhh_mesh_rank_node_begin.argtypes = [ctypes.c_void_p, _i64p]
+        L.vhh_tables_create.restype = ctypes.c_void_p
+        L.vhh_tables_create.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.vhh_tables_free.argtypes = [ctypes.c_void_p]
+        L.vhh_tables_desc.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.vhh_tables_array.restype = ctypes.c_void_p
+        L.vhh_tables_array.argtypes = [ctypes.c_void_p, ctypes.c_char_p, _i64p, ctypes.POINTER(ctypes.c_int)]
+        L.vhh_tables_sizes.argtypes = [ctypes.c_void_p, _i64p]
+        _host = L
+    return _host
+
+
+_FIELD_DTYPES = {
+    "node_global": np.int64, "node_xyz": np.float64, "cell_nodes": np.int32, "cell_global": np.int64,
+    "cell_origin": np.float64, "cell_h": np.float64, "cell_owned": np.uint8, "wall_face_cell": np.int32,
+    "wall_face_no": np.int8, "wall_face_bid": np.int8, "c_dof": np.int32, "c_ptr": np.int32, "c_master": np.int32,
+    "c_weight": np.float64, "peer_rank": np.int32, "send_ptr": np.int32, "send_nodes": np.int32, "recv_ptr": np.int32,
+    "recv_nodes": np.int32,
+}
+
+
+class RankTables:
+    """Flat per-rank tables (numpy views onto the C++ arrays) + the matching ``vh_mesh_desc`` blob."""
+
+    def __init__(self, mesh, rank):
+        L = host_lib()
+        self._mesh = mesh  # keep alive
+        self._h = L.vhh_tables_create(mesh._h, rank)
+        if not self._h:
+            raise RuntimeError(L.vhh_last_error().decode())
+        sz = (ctypes.c_int64 * 4)()
+        L.vhh_tables_sizes(self._h, sz)
+        self.degree, self.n_owned_nodes, self.n_ghost_nodes, self.n_cells = (int(v) for v in sz)
+        self.n_local_nodes = self.n_owned_nodes + self.n_ghost_nodes
+        self.rank = rank
+        n = 8 if self.degree == 1 else 27
+        for name, dt in _FIELD_DTYPES.items():
+            cnt = ctypes.c_int64()
+            es = ctypes.c_int()
+            ptr = L.vhh_tables_array(self._h, name.encode(), ctypes.byref(cnt), ctypes.byref(es))
+            assert cnt.value >= 0 and es.value == np.dtype(dt).itemsize, name
+            if cnt.value == 0:
+                arr = np.zeros(0, dtype=dt)
+            else:
+                buf = (ctypes.c_char * (cnt.value * es.value)).from_address(ptr)
+                arr = np.frombuffer(buf, dtype=dt)
+            setattr(self, name, arr)
+        self.cell_nodes = self.cell_nodes.reshape(-1, n)
+        self.node_xyz = self.node_xyz.reshape(-1, 3)
+        self.cell_origin = self.cell_origin.reshape(-1, 3)
+        self.cell_h = self.cell_h.reshape(-1, 3)
+        self._desc = ctypes.create_string_buffer(L.vhh_sizeof_mesh_desc())
+        L.vhh_tables_desc(self._h, ctypes.cast(self._desc, ctypes.c_void_p))
+
+    def desc_ptr(self):
+        return ctypes.cast(self._desc, ctypes.c_void_p)
+
+    def face_csr(self):
+        """Wall faces regrouped per cell: (face_ptr[n_cells+1], face_no[], face_bid[]) as int32."""
+        order = np.argsort(self.wall_face_cell, kind="stable")
+        cnt = np.bincount(self.wall_face_cell, minlength=self.n_cells)
+        ptr = np.zeros(self.n_cells + 1, dtype=np.int32)
+        np.cumsum(cnt, out=ptr[1:])
+        return ptr, self.wall_face_no[order].astype(np.int32), self.wall_face_bid[order].astype(np.int32)
+
+    def __del__(self):
+        try:
+            if self._h:
+                host_lib().vhh_tables_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class Mesh:
+    """Box mesh of hexahedra (hyper_cube / hyper_rectangle + refine_global, optional local refinement)."""
+
+    def __init__(self, degree, lo, hi, base=(1, 1, 1), face_bid=(1, 1, 1, 1, 4, 4), n_global_refine=0):
+        L = host_lib()
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        base = np.ascontiguousarray(base, dtype=np.int32)
+        bid = np.ascontiguousarray(face_bid, dtype=np.int32)
+        self.degree = degree
+        self._h = L.vhh_mesh_create(degree, lo.ctypes.data_as(_dp), hi.ctypes.data_as(_dp), base.ctypes.data_as(_i32p),
+                                    bid.ctypes.data_as(_i32p), n_global_refine)
+        if not self._h:
+            raise RuntimeError(L.vhh_last_error().decode())
+        self.n_ranks = 0
+
+    @property
+    def n_cells(self):
+        return int(host_lib().vhh_mesh_n_cells(self._h))
+
+    def cell_centers(self):
+        out = np.zeros((self.n_cells, 3))
+        host_lib().vhh_mesh_cell_centers(self._h, out.ctypes.data_as(_dp))
+        return out
+
+    def refine(self, flags):
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        if host_lib().vhh_mesh_refine(self._h, flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), flags.size) != 0:
+            raise RuntimeError(host_lib().vhh_last_error().decode())
+
+    def finalize(self, n_ranks=1):
+        if host_lib().vhh_mesh_finalize(self._h, n_ranks) != 0:
+            raise RuntimeError(host_lib().vhh_last_error().decode())
+        self.n_ranks = n_ranks
+        sz = (ctypes.c_int64 * 4)()
+        host_lib().vhh_mesh_global_sizes(self._h, sz)
+        self.n_nodes, _, self.n_constraint_lines, self.n_hanging_nodes = (int(v) for v in sz)
+        rb = (ctypes.c_int64 * (n_ranks + 1))()
+        host_lib().vhh_mesh_rank_node_begin(self._h, rb)
+        self.rank_node_begin = np.array(list(rb), dtype=np.int64)
+        return self
+
+    def tables(self, rank=0):
+        return RankTables(self, rank)
+
+    def __del__(self):
+        try:
+            if self._h:
+                host_lib().vhh_mesh_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def unit_cube(degree, refine, half=0.5, face_bid=(1, 1, 1, 1, 4, 4), n_ranks=1):
+    """The BASELINE configs' cube: hyper_cube(-half, half) + refine_global(refine); z faces are AdGR walls (id 4)
+    as in makegrid_cube-z-normal_AdGR.cc:164-195."""
+    return Mesh(degree, [-half] * 3, [half] * 3, (1, 1, 1), face_bid, refine).finalize(n_ranks)
+
+
+from ._capi import Context, cuda_lib, have_cuda_lib  # noqa: E402,F401

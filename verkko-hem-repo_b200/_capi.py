@@ -1,0 +1,202 @@
+"""ctypes binding of include/vh_femgl.h (lib/libvhfemgl.so).  No fallback: a missing library is an error."""
+import ctypes
+import os
+
+import numpy as np
+
+_PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "verkko-hem-repo_b200")
+if not os.path.isdir(_PKG):
+    _PKG = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_PKG, "lib", "libvhfemgl.so")
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_vp = ctypes.c_void_p
+
+VH_OK = 0
+VH_ERR_NOT_CONVERGED = -4
+
+
+class _Info(ctypes.Structure):
+    _fields_ = [("n_owned_dofs", ctypes.c_int64), ("n_local_dofs", ctypes.c_int64), ("nnzb", ctypes.c_int64),
+                ("n_fast_rows", ctypes.c_int64), ("n_slow_cells", ctypes.c_int64), ("device_bytes", ctypes.c_int64)]
+
+
+_lib = None
+
+
+def have_cuda_lib():
+    return os.path.exists(_LIB)
+
+
+def cuda_lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            raise RuntimeError("CUDA extension %s is missing: build it with __graft_entry__.build() "
+                               "(there is no CPU fallback for the hot path)" % _LIB)
+        L = ctypes.CDLL(_LIB)
+        L.vh_last_error.restype = ctypes.c_char_p
+        L.vh_last_error.argtypes = [_vp]
+        L.vh_create.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp)]
+        L.vh_destroy.argtypes = [_vp]
+        L.vh_nccl_unique_id.argtypes = [_vp]
+        L.vh_comm_init.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _vp]
+        L.vh_set_coefficients.argtypes = [_vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, _dp,
+                                          ctypes.c_double]
+        for f in ("vh_set_solution", "vh_get_solution", "vh_get_newton_update", "vh_get_rhs", "vh_get_residual"):
+            getattr(L, f).argtypes = [_vp, _dp]
+        L.vh_assemble.argtypes = [_vp, _dp]
+        L.vh_solve.argtypes = [_vp, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), _dp]
+        L.vh_line_search_trial.argtypes = [_vp, ctypes.c_double]
+        L.vh_residual.argtypes = [_vp, _dp]
+        L.vh_accept_trial.argtypes = [_vp]
+        L.vh_energy.argtypes = [_vp, ctypes.c_int, _dp]
+        L.vh_get_info.argtypes = [_vp, ctypes.POINTER(_Info)]
+        L.vh_export_matrix_bsr.argtypes = [_vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _dp]
+        L.vh_spmv.argtypes = [_vp, _dp, _dp]
+        L.vh_precondition.argtypes = [_vp, _dp, _dp]
+        L.vh_time_kernel.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+        L.vh_get_timers.argtypes = [_vp, _dp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+class Context:
+    """One GPU context for one mesh on one rank (``vh_ctx``)."""
+
+    def __init__(self, tables, device=0):
+        from . import VhError
+        self._E = VhError
+        self.L = cuda_lib()
+        self.tables = tables
+        self._h = _vp()
+        rc = self.L.vh_create(tables.desc_ptr(), device, ctypes.byref(self._h))
+        if rc != VH_OK:
+            raise VhError(rc, self.L.vh_last_error(None).decode())
+        self.n_owned = 18 * tables.n_owned_nodes
+
+    def _chk(self, rc):
+        if rc != VH_OK:
+            raise self._E(rc, self.L.vh_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self.L.vh_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- multi-GPU ---
+    @staticmethod
+    def nccl_unique_id():
+        buf = ctypes.create_string_buffer(128)
+        rc = cuda_lib().vh_nccl_unique_id(ctypes.cast(buf, _vp))
+        if rc != VH_OK:
+            raise RuntimeError("vh_nccl_unique_id failed: %s" % cuda_lib().vh_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, rank, n_ranks, unique_id):
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._chk(self.L.vh_comm_init(self._h, rank, n_ranks, ctypes.cast(buf, _vp)))
+
+    # --- coefficients / state ---
+    def set_coefficients(self, K1, K2, K3, alpha, betas, bt):
+        b = np.ascontiguousarray(betas, dtype=np.float64)
+        self._chk(self.L.vh_set_coefficients(self._h, K1, K2, K3, alpha, b.ctypes.data_as(_dp), bt))
+
+    def set_coef_vector(self, coef):
+        """coef = [K1,K2,K3,alpha,beta1..5,bt] (the oracle's layout)."""
+        self.set_coefficients(coef[0], coef[1], coef[2], coef[3], coef[4:9], coef[9])
+
+    def set_solution(self, x_owned):
+        x = np.ascontiguousarray(x_owned, dtype=np.float64)
+        assert x.size == self.n_owned
+        self._chk(self.L.vh_set_solution(self._h, x.ctypes.data_as(_dp)))
+
+    def _get(self, fn):
+        out = np.zeros(self.n_owned)
+        self._chk(fn(self._h, out.ctypes.data_as(_dp)))
+        return out
+
+    def get_solution(self):
+        return self._get(self.L.vh_get_solution)
+
+    def get_newton_update(self):
+        return self._get(self.L.vh_get_newton_update)
+
+    def get_rhs(self):
+        return self._get(self.L.vh_get_rhs)
+
+    def get_residual(self):
+        return self._get(self.L.vh_get_residual)
+
+    # --- hot path ---
+    def assemble(self):
+        v = ctypes.c_double()
+        self._chk(self.L.vh_assemble(self._h, ctypes.byref(v)))
+        return v.value
+
+    def solve(self, tol_rel, max_it=10000, restart=30):
+        its = ctypes.c_int()
+        res = ctypes.c_double()
+        self._chk(self.L.vh_solve(self._h, tol_rel, max_it, restart, ctypes.byref(its), ctypes.byref(res)))
+        return its.value, res.value
+
+    def line_search_trial(self, alpha):
+        self._chk(self.L.vh_line_search_trial(self._h, alpha))
+
+    def residual(self):
+        v = ctypes.c_double()
+        self._chk(self.L.vh_residual(self._h, ctypes.byref(v)))
+        return v.value
+
+    def accept_trial(self):
+        self._chk(self.L.vh_accept_trial(self._h))
+
+    def energy(self, which=0):
+        v = ctypes.c_double()
+        self._chk(self.L.vh_energy(self._h, which, ctypes.byref(v)))
+        return v.value
+
+    # --- introspection ---
+    def info(self):
+        i = _Info()
+        self._chk(self.L.vh_get_info(self._h, ctypes.byref(i)))
+        return {k: int(getattr(i, k)) for k, _ in _Info._fields_}
+
+    def export_matrix_bsr(self):
+        nnzb = self.info()["nnzb"]
+        nb = self.tables.n_owned_nodes
+        row_ptr = np.zeros(nb + 1, dtype=np.int32)
+        col = np.zeros(nnzb, dtype=np.int32)
+        vals = np.zeros((nnzb, 18, 18))
+        self._chk(self.L.vh_export_matrix_bsr(self._h, row_ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                              col.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), vals.ctypes.data_as(_dp)))
+        return row_ptr, col, vals
+
+    def spmv(self, x_owned):
+        x = np.ascontiguousarray(x_owned, dtype=np.float64)
+        y = np.zeros(self.n_owned)
+        self._chk(self.L.vh_spmv(self._h, x.ctypes.data_as(_dp), y.ctypes.data_as(_dp)))
+        return y
+
+    def precondition(self, x_owned):
+        x = np.ascontiguousarray(x_owned, dtype=np.float64)
+        y = np.zeros(self.n_owned)
+        self._chk(self.L.vh_precondition(self._h, x.ctypes.data_as(_dp), y.ctypes.data_as(_dp)))
+        return y
+
+    def time_kernel(self, what, reps=20, flush_l2=True):
+        ms = ctypes.c_float()
+        self._chk(self.L.vh_time_kernel(self._h, what, reps, 1 if flush_l2 else 0, ctypes.byref(ms)))
+        return ms.value
+
+    def timers(self, reset=False):
+        ms = (ctypes.c_double * 5)()
+        n = ctypes.c_int64()
+        self._chk(self.L.vh_get_timers(self._h, ms, ctypes.byref(n), 1 if reset else 0))
+        return dict(assemble=ms[0], residual=ms[1], solve=ms[2], vector=ms[3], halo=ms[4], launches=int(n.value))

@@ -1,0 +1,970 @@
+// Context lifetime and the C-ABI entry points of include/vh_femgl.h.
+//
+// vh_create turns the host's flat tables (what deal.II's DoFHandler / AffineConstraints / p4est ghost layer
+// provide for FemGL::setup_system, /root/reference/femgl/src/setup_uniform_B-phase.cc:109-341) into the device
+// layout of the hot path: BSR(18) sparsity over owned rows (make_sparsity_pattern, setup_*:264-270), the
+// row-owner / general-scatter classification of rows, reference-cell tables, and all vectors of
+// femgl.h:310-316.  Everything here runs once per mesh.
+#include "vh_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+static std::string g_create_err;
+static std::mutex  g_err_mutex;
+
+int vh_fail(vh_ctx *ctx, int code, const std::string &msg)
+{
+  if (ctx)
+    ctx->err = msg;
+  else
+    {
+      std::lock_guard<std::mutex> lk(g_err_mutex);
+      g_create_err = msg;
+    }
+  return code;
+}
+
+namespace
+{
+// ---------------- reference-cell tables (host, double) ----------------
+const int Q2_T[27][3] = {{0, 0, 0}, {2, 0, 0}, {0, 2, 0}, {2, 2, 0}, {0, 0, 2}, {2, 0, 2}, {0, 2, 2}, {2, 2, 2}, {0, 1, 0},
+                         {2, 1, 0}, {1, 0, 0}, {1, 2, 0}, {0, 1, 2}, {2, 1, 2}, {1, 0, 2}, {1, 2, 2}, {0, 0, 1}, {2, 0, 1},
+                         {0, 2, 1}, {2, 2, 1}, {0, 1, 1}, {2, 1, 1}, {1, 0, 1}, {1, 2, 1}, {1, 1, 0}, {1, 1, 2}, {1, 1, 1}};
+
+void node_t(int degree, int a, int t[3])
+{
+  if (degree == 1)
+    {
+      t[0] = a & 1, t[1] = (a >> 1) & 1, t[2] = (a >> 2) & 1;
+    }
+  else
+    {
+      t[0] = Q2_T[a][0], t[1] = Q2_T[a][1], t[2] = Q2_T[a][2];
+    }
+}
+void lag(int degree, int t, double xi, double &v, double &d)
+{
+  if (degree == 1)
+    {
+      v = t ? xi : 1.0 - xi;
+      d = t ? 1.0 : -1.0;
+    }
+  else if (t == 0)
+    {
+      v = (2 * xi - 1) * (xi - 1);
+      d = 4 * xi - 3;
+    }
+  else if (t == 1)
+    {
+      v = 4 * xi * (1 - xi);
+      d = 4 - 8 * xi;
+    }
+  else
+    {
+      v = xi * (2 * xi - 1);
+      d = 4 * xi - 1;
+    }
+}
+void gauss01(int n, double *x, double *w)
+{ // QGauss<1>(n) on [0,1]
+  if (n == 2)
+    {
+      const double d = 0.5 / std::sqrt(3.0);
+      x[0] = 0.5 - d, x[1] = 0.5 + d;
+      w[0] = w[1] = 0.5;
+    }
+  else
+    {
+      const double d = 0.5 * std::sqrt(0.6);
+      x[0] = 0.5 - d, x[1] = 0.5, x[2] = 0.5 + d;
+      w[0] = w[2] = 5.0 / 18.0, w[1] = 8.0 / 18.0;
+    }
+}
+
+struct HostTables
+{
+  int                 degree, nn, nq;
+  std::vector<double> N, dN, wq, Gref, Mf, W1;
+};
+
+HostTables make_tables(int degree)
+{
+  HostTables T;
+  T.degree      = degree;
+  const int n1  = degree + 1;
+  T.nn          = n1 * n1 * n1;
+  T.nq          = T.nn;
+  const int nn = T.nn, nq = T.nq;
+  double    gx[3], gw[3];
+  gauss01(n1, gx, gw);
+  T.N.assign((size_t)nn * nq, 0.0);
+  T.dN.assign((size_t)nn * nq * 3, 0.0);
+  T.wq.assign(nq, 0.0);
+  for (int q = 0; q < nq; ++q)
+    {
+      const int    qi[3] = {q % n1, (q / n1) % n1, q / (n1 * n1)}; // QGauss<3>: x fastest
+      T.wq[q]            = gw[qi[0]] * gw[qi[1]] * gw[qi[2]];
+      for (int a = 0; a < nn; ++a)
+        {
+          int t[3];
+          node_t(degree, a, t);
+          double v[3], d[3];
+          for (int k = 0; k < 3; ++k)
+            lag(degree, t[k], gx[qi[k]], v[k], d[k]);
+          T.N[(size_t)a * nq + q]            = v[0] * v[1] * v[2];
+          T.dN[((size_t)a * nq + q) * 3 + 0] = d[0] * v[1] * v[2];
+          T.dN[((size_t)a * nq + q) * 3 + 1] = v[0] * d[1] * v[2];
+          T.dN[((size_t)a * nq + q) * 3 + 2] = v[0] * v[1] * d[2];
+        }
+    }
+  T.Gref.assign((size_t)nn * nn * 9, 0.0);
+  for (int a = 0; a < nn; ++a)
+    for (int b = 0; b < nn; ++b)
+      for (int x = 0; x < 3; ++x)
+        for (int y = 0; y < 3; ++y)
+          {
+            double s = 0.0;
+            for (int q = 0; q < nq; ++q) // same q order as the reference's outer q loop (assemble.cc:188)
+              s += T.wq[q] * T.dN[((size_t)a * nq + q) * 3 + x] * T.dN[((size_t)b * nq + q) * 3 + y];
+            T.Gref[((size_t)a * nn + b) * 9 + 3 * x + y] = s;
+          }
+  // unit-face mass matrices with QGauss<2>(degree+1)
+  T.Mf.assign((size_t)6 * nn * nn, 0.0);
+  for (int f = 0; f < 6; ++f)
+    {
+      const int nd = f / 2, side = f % 2;
+      const int d0 = nd == 0 ? 1 : 0, d1 = nd == 2 ? 1 : 2;
+      for (int q1 = 0; q1 < n1; ++q1)
+        for (int q0 = 0; q0 < n1; ++q0)
+          {
+            double xi[3];
+            xi[nd] = side;
+            xi[d0] = gx[q0];
+            xi[d1] = gx[q1];
+            const double        wf = gw[q0] * gw[q1];
+            std::vector<double> Nf(nn);
+            for (int a = 0; a < nn; ++a)
+              {
+                int t[3];
+                node_t(degree, a, t);
+                double v = 1.0;
+                for (int k = 0; k < 3; ++k)
+                  {
+                    double vv, dd;
+                    lag(degree, t[k], xi[k], vv, dd);
+                    v *= vv;
+                  }
+                Nf[a] = v;
+              }
+            for (int a = 0; a < nn; ++a)
+              for (int b = 0; b < nn; ++b)
+                T.Mf[((size_t)f * nn + a) * nn + b] += wf * Nf[a] * Nf[b];
+          }
+    }
+  if (degree == 1)
+    {
+      T.W1.assign(512, 0.0);
+      for (int a = 0; a < 8; ++a)
+        for (int b = 0; b < 8; ++b)
+          for (int q = 0; q < 8; ++q)
+            T.W1[(a * 8 + b) * 8 + q] = T.wq[q] * T.N[a * 8 + q] * T.N[b * 8 + q];
+    }
+  return T;
+}
+
+int upload_constraints(vh_ctx *ctx, const vh_constraints &c, VhConstraintsDev &D, std::vector<int32_t> &h_line_of)
+{
+  const int64_t NL = ctx->NL;
+  h_line_of.assign((size_t)NL, -1);
+  if (c.n_lines < 0)
+    return vh_fail(ctx, VH_ERR_ARG, "constraints: n_lines < 0");
+  if (c.n_lines > 0 && (!c.dof || !c.ptr))
+    return vh_fail(ctx, VH_ERR_ARG, "constraints: null arrays");
+  for (int l = 0; l < c.n_lines; ++l)
+    {
+      if (c.dof[l] < 0 || c.dof[l] >= NL)
+        return vh_fail(ctx, VH_ERR_ARG, "constraints: DoF out of range");
+      if (c.ptr[l + 1] < c.ptr[l])
+        return vh_fail(ctx, VH_ERR_ARG, "constraints: ptr not monotone");
+      h_line_of[c.dof[l]] = l;
+    }
+  const int nent = c.n_lines ? c.ptr[c.n_lines] : 0;
+  for (int p = 0; p < nent; ++p)
+    if (c.master[p] < 0 || c.master[p] >= NL)
+      return vh_fail(ctx, VH_ERR_ARG, "constraints: master out of range");
+  for (int p = 0; p < nent; ++p)
+    if (h_line_of[c.master[p]] >= 0)
+      return vh_fail(ctx, VH_ERR_ARG, "constraints: object is not closed (a master is itself constrained)");
+  D.n_lines     = c.n_lines;
+  D.has_masters = nent > 0;
+  VH_TRY(vh_dev_upload(ctx, &D.line_of, h_line_of.data(), (size_t)NL));
+  VH_TRY(vh_dev_upload(ctx, &D.dof, c.dof, (size_t)c.n_lines));
+  std::vector<int32_t> ptr(c.n_lines + 1, 0);
+  for (int l = 0; l <= c.n_lines && c.n_lines > 0; ++l)
+    ptr[l] = c.ptr[l];
+  VH_TRY(vh_dev_upload(ctx, &D.ptr, ptr.data(), ptr.size()));
+  VH_TRY(vh_dev_upload(ctx, &D.master, c.master, (size_t)nent));
+  VH_TRY(vh_dev_upload(ctx, &D.weight, c.weight, (size_t)nent));
+  return VH_OK;
+}
+
+struct PhaseTimer
+{
+  vh_ctx *ctx;
+  int     slot;
+  PhaseTimer(vh_ctx *c, int s) : ctx(c), slot(s) { cudaEventRecord(ctx->ev0, ctx->stream); }
+  void stop()
+  {
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaEventSynchronize(ctx->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->t_ms[slot] += ms;
+  }
+};
+
+int build(vh_ctx *ctx, const vh_mesh_desc *d)
+{
+  const int nn = ctx->nn;
+  const int32_t n_owned = ctx->n_owned, n_local = ctx->n_local, n_cells = ctx->n_cells;
+
+  // ---- validate & convert cell tables ----
+  if (n_cells > 0 && (!d->cell_nodes || !d->cell_h))
+    return vh_fail(ctx, VH_ERR_ARG, "cell tables are null");
+  for (int64_t i = 0; i < (int64_t)n_cells * nn; ++i)
+    if (d->cell_nodes[i] < 0 || d->cell_nodes[i] >= n_local)
+      return vh_fail(ctx, VH_ERR_ARG, "cell_nodes entry out of range");
+  std::vector<double>   h4((size_t)n_cells * 4);
+  for (int e = 0; e < n_cells; ++e)
+    {
+      const double *h = d->cell_h + 3 * (size_t)e;
+      if (!(h[0] > 0 && h[1] > 0 && h[2] > 0))
+        return vh_fail(ctx, VH_ERR_ARG, "cell_h must be positive");
+      h4[4 * (size_t)e + 0] = h[0];
+      h4[4 * (size_t)e + 1] = h[1];
+      h4[4 * (size_t)e + 2] = h[2];
+      h4[4 * (size_t)e + 3] = h[0] * h[1] * h[2];
+    }
+  std::vector<uint32_t> faces(n_cells, 0u);
+  for (int f = 0; f < d->n_wall_faces; ++f)
+    {
+      const int e = d->wall_face_cell[f], no = d->wall_face_no[f], b = d->wall_face_bid[f];
+      if (e < 0 || e >= n_cells || no < 0 || no > 5 || b < 2 || b > 4)
+        return vh_fail(ctx, VH_ERR_ARG, "wall face table entry out of range (boundary id must be 2, 3 or 4)");
+      faces[e] |= (uint32_t)b << (4 * no);
+    }
+  std::vector<uint8_t> owned(n_cells, 1);
+  if (d->cell_owned)
+    for (int e = 0; e < n_cells; ++e)
+      owned[e] = d->cell_owned[e] ? 1 : 0;
+  VH_TRY(vh_dev_upload(ctx, &ctx->cell_nodes, d->cell_nodes, (size_t)n_cells * nn));
+  VH_TRY(vh_dev_upload(ctx, &ctx->cell_h, h4.data(), h4.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->cell_faces, faces.data(), faces.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->cell_owned, owned.data(), owned.size()));
+
+  // ---- constraints ----
+  std::vector<int32_t> line0, line1;
+  VH_TRY(upload_constraints(ctx, d->constraints_newton_update, ctx->cons[0], line0));
+  VH_TRY(upload_constraints(ctx, d->constraints_solution, ctx->cons[1], line1));
+  const vh_constraints &C = d->constraints_newton_update;
+  // node-level view: Dirichlet masks, nodes constrained to masters, and their master nodes
+  std::vector<uint32_t>             dmask(n_local, 0u);
+  std::vector<uint8_t>              has_masters(n_local, 0), is_master(n_local, 0);
+  std::vector<std::vector<int32_t>> masters_of(n_local);
+  for (int l = 0; l < C.n_lines; ++l)
+    {
+      const int nd = C.dof[l] / 18, c = C.dof[l] % 18;
+      if (C.ptr[l + 1] == C.ptr[l])
+        dmask[nd] |= 1u << c;
+      else
+        {
+          has_masters[nd] = 1;
+          for (int p = C.ptr[l]; p < C.ptr[l + 1]; ++p)
+            {
+              const int m = C.master[p] / 18;
+              is_master[m] = 1;
+              if (std::find(masters_of[nd].begin(), masters_of[nd].end(), m) == masters_of[nd].end())
+                masters_of[nd].push_back(m);
+            }
+        }
+    }
+  VH_TRY(vh_dev_upload(ctx, &ctx->dirmask, dmask.data(), dmask.size()));
+
+  // ---- rows: which (cell, local node) pairs feed owned row I  (T(a) = {a} U masters(a)) ----
+  std::vector<int32_t> inc_ptr(n_owned + 1, 0);
+  auto for_targets = [&](int node, auto &&fn) {
+    fn(node);
+    for (int m : masters_of[node])
+      fn(m);
+  };
+  for (int e = 0; e < n_cells; ++e)
+    for (int a = 0; a < nn; ++a)
+      for_targets(d->cell_nodes[(size_t)e * nn + a], [&](int I) {
+        if (I < n_owned)
+          inc_ptr[I + 1]++;
+      });
+  for (int i = 0; i < n_owned; ++i)
+    inc_ptr[i + 1] += inc_ptr[i];
+  std::vector<int32_t> inc_cell(inc_ptr[n_owned]), inc_a(inc_ptr[n_owned]), fill(inc_ptr.begin(), inc_ptr.end() - 1);
+  for (int e = 0; e < n_cells; ++e)
+    for (int a = 0; a < nn; ++a)
+      for_targets(d->cell_nodes[(size_t)e * nn + a], [&](int I) {
+        if (I < n_owned)
+          {
+            inc_cell[fill[I]] = e;
+            inc_a[fill[I]]    = a;
+            fill[I]++;
+          }
+      });
+
+  // ---- BSR pattern: columns of row I = union over feeding cells of T(b) (superset of make_sparsity_pattern) ----
+  std::vector<int32_t> &row_ptr = ctx->h_row_ptr, &col = ctx->h_col;
+  row_ptr.assign(n_owned + 1, 0);
+  col.clear();
+  col.reserve((size_t)n_owned * (ctx->degree == 1 ? 27 : 64));
+  std::vector<int32_t> tmp;
+  for (int I = 0; I < n_owned; ++I)
+    {
+      tmp.clear();
+      tmp.push_back(I); // the diagonal block always exists (constrained-diagonal rule, block-Jacobi)
+      for (int k = inc_ptr[I]; k < inc_ptr[I + 1]; ++k)
+        {
+          const int e = inc_cell[k];
+          for (int b = 0; b < nn; ++b)
+            for_targets(d->cell_nodes[(size_t)e * nn + b], [&](int J) { tmp.push_back(J); });
+        }
+      std::sort(tmp.begin(), tmp.end());
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      col.insert(col.end(), tmp.begin(), tmp.end());
+      if (col.size() > (size_t)INT32_MAX)
+        return vh_fail(ctx, VH_ERR_UNSUPPORTED, "more than 2^31 blocks on one rank");
+      row_ptr[I + 1] = (int32_t)col.size();
+    }
+  ctx->nnzb = (int64_t)col.size();
+  std::vector<int32_t> diag_pos(n_owned);
+  for (int I = 0; I < n_owned; ++I)
+    diag_pos[I] = (int32_t)(std::lower_bound(col.begin() + row_ptr[I], col.begin() + row_ptr[I + 1], I) - col.begin());
+
+  // ---- classify rows: lattice rows go to the write-once row kernel ----
+  std::vector<uint8_t> row_slow(n_owned, 1);
+  std::vector<int32_t> fast_rows, fast_cells;
+  std::vector<int8_t>  fast_slot;
+  if (ctx->degree == 1)
+    for (int I = 0; I < n_owned; ++I)
+      {
+        if (is_master[I] || has_masters[I])
+          continue;
+        int32_t cells8[8];
+        int32_t slot_node[27];
+        std::fill(cells8, cells8 + 8, -1);
+        std::fill(slot_node, slot_node + 27, -1);
+        bool ok = inc_ptr[I + 1] > inc_ptr[I];
+        for (int k = inc_ptr[I]; k < inc_ptr[I + 1] && ok; ++k)
+          {
+            const int e = inc_cell[k], a = inc_a[k], o = 7 - a;
+            if (d->cell_nodes[(size_t)e * 8 + a] != I || cells8[o] >= 0)
+              {
+                ok = false;
+                break;
+              }
+            cells8[o] = e;
+            for (int b = 0; b < 8 && ok; ++b)
+              {
+                const int J = d->cell_nodes[(size_t)e * 8 + b];
+                if (has_masters[J])
+                  ok = false;
+                const int s = ((o & 1) + (b & 1)) + 3 * (((o >> 1) & 1) + ((b >> 1) & 1)) + 9 * ((o >> 2) + (b >> 2));
+                if (slot_node[s] >= 0 && slot_node[s] != J)
+                  ok = false;
+                slot_node[s] = J;
+              }
+          }
+        if (!ok)
+          continue;
+        // slot -> position inside the (sorted) row; two slots must never map to the same node
+        int8_t pos27[32];
+        std::fill(pos27, pos27 + 32, (int8_t)-1);
+        int n_present = 0;
+        for (int s = 0; s < 27 && ok; ++s)
+          {
+            if (slot_node[s] < 0)
+              continue;
+            const auto b = col.begin() + row_ptr[I], en = col.begin() + row_ptr[I + 1];
+            const auto it = std::lower_bound(b, en, slot_node[s]);
+            if (it == en || *it != slot_node[s])
+              ok = false;
+            else
+              pos27[s] = (int8_t)(it - b);
+            ++n_present;
+          }
+        if (ok)
+          for (int s = 0; s < 27 && ok; ++s)
+            for (int s2 = s + 1; s2 < 27; ++s2)
+              if (pos27[s] >= 0 && pos27[s] == pos27[s2])
+                ok = false;
+        if (!ok || n_present != row_ptr[I + 1] - row_ptr[I])
+          continue;
+        row_slow[I] = 0;
+        fast_rows.push_back(I);
+        fast_cells.insert(fast_cells.end(), cells8, cells8 + 8);
+        fast_slot.insert(fast_slot.end(), pos27, pos27 + 32);
+      }
+  std::vector<int32_t> slow_rows, slow_cells;
+  for (int I = 0; I < n_owned; ++I)
+    if (row_slow[I])
+      slow_rows.push_back(I);
+  for (int e = 0; e < n_cells; ++e)
+    {
+      bool slow = false;
+      for (int a = 0; a < nn && !slow; ++a)
+        for_targets(d->cell_nodes[(size_t)e * nn + a], [&](int I) {
+          if (I < n_owned && row_slow[I])
+            slow = true;
+        });
+      if (slow)
+        slow_cells.push_back(e);
+    }
+  ctx->n_fast       = (int32_t)fast_rows.size();
+  ctx->n_slow_rows  = (int32_t)slow_rows.size();
+  ctx->n_slow_cells = (int32_t)slow_cells.size();
+
+  VH_TRY(vh_dev_upload(ctx, &ctx->row_ptr, row_ptr.data(), row_ptr.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->col, col.data(), col.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->diag_pos, diag_pos.data(), diag_pos.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->fast_rows, fast_rows.data(), fast_rows.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->fast_cells, fast_cells.data(), fast_cells.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->fast_slot, fast_slot.data(), fast_slot.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->slow_rows, slow_rows.data(), slow_rows.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->slow_cells, slow_cells.data(), slow_cells.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->row_slow, row_slow.data(), row_slow.size()));
+
+  // ---- reference-cell tables ----
+  HostTables T   = make_tables(ctx->degree);
+  ctx->tab.degree = ctx->degree;
+  ctx->tab.nn     = T.nn;
+  ctx->tab.nq     = T.nq;
+  VH_TRY(vh_dev_upload(ctx, &ctx->tab.N, T.N.data(), T.N.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->tab.dN, T.dN.data(), T.dN.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->tab.wq, T.wq.data(), T.wq.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->tab.Gref, T.Gref.data(), T.Gref.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->tab.Mf, T.Mf.data(), T.Mf.size()));
+  VH_TRY(vhk_upload_constants(ctx));
+  if (ctx->degree == 1)
+    VH_TRY(vhk_upload_w1(ctx, T.W1.data()));
+
+  // ---- halo plan ----
+  if (d->n_peers < 0)
+    return vh_fail(ctx, VH_ERR_ARG, "n_peers < 0");
+  if (d->n_peers > 0)
+    {
+      ctx->peer_rank.assign(d->peer_rank, d->peer_rank + d->n_peers);
+      ctx->send_ptr.assign(d->send_ptr, d->send_ptr + d->n_peers + 1);
+      ctx->recv_ptr.assign(d->recv_ptr, d->recv_ptr + d->n_peers + 1);
+      ctx->n_send = ctx->send_ptr.back();
+      ctx->n_recv = ctx->recv_ptr.back();
+      for (int64_t i = 0; i < ctx->n_send; ++i)
+        if (d->send_nodes[i] < 0 || d->send_nodes[i] >= n_owned)
+          return vh_fail(ctx, VH_ERR_ARG, "send_nodes must be owned nodes");
+      for (int64_t i = 0; i < ctx->n_recv; ++i)
+        if (d->recv_nodes[i] < n_owned || d->recv_nodes[i] >= n_local)
+          return vh_fail(ctx, VH_ERR_ARG, "recv_nodes must be ghost nodes");
+      VH_TRY(vh_dev_upload(ctx, &ctx->send_nodes, d->send_nodes, (size_t)ctx->n_send));
+      VH_TRY(vh_dev_upload(ctx, &ctx->recv_nodes, d->recv_nodes, (size_t)ctx->n_recv));
+      VH_TRY(vh_dev_alloc(ctx, &ctx->send_buf, (size_t)ctx->n_send * 18));
+      VH_TRY(vh_dev_alloc(ctx, &ctx->recv_buf, (size_t)ctx->n_recv * 18));
+    }
+  else if (ctx->n_ghost > 0)
+    return vh_fail(ctx, VH_ERR_ARG, "ghost nodes without a halo plan");
+
+  // ---- matrix, scratch, vectors ----
+  VH_TRY(vh_dev_alloc(ctx, &ctx->vals, (size_t)ctx->nnzb * VH_BLK));
+  VH_TRY(vh_dev_alloc(ctx, &ctx->minv, (size_t)n_owned * VH_BLK));
+  VH_TRY(vh_dev_alloc(ctx, &ctx->Hq, (size_t)n_cells * ctx->nq * VH_SYMP));
+  VH_TRY(vh_dev_alloc(ctx, &ctx->Rc, (size_t)n_cells * ctx->dpc));
+  VH_TRY(vh_dev_alloc(ctx, &ctx->Dc, (size_t)n_cells * ctx->dpc));
+  VH_TRY(vh_dev_alloc(ctx, &ctx->avgD, (size_t)n_cells));
+  VH_TRY(vh_dev_alloc(ctx, &ctx->Ec, (size_t)n_cells));
+  double **vl[] = {&ctx->x_sol, &ctx->x_trial, &ctx->delta, &ctx->zbuf};
+  for (double **p : vl)
+    {
+      VH_TRY(vh_dev_alloc(ctx, p, (size_t)ctx->NL));
+      VH_CUDA(cudaMemset(*p, 0, sizeof(double) * (size_t)std::max<int64_t>(ctx->NL, 1)));
+    }
+  double **vo[] = {&ctx->rhs, &ctx->resid, &ctx->w, &ctx->tmpo};
+  for (double **p : vo)
+    {
+      VH_TRY(vh_dev_alloc(ctx, p, (size_t)ctx->NO));
+      VH_CUDA(cudaMemset(*p, 0, sizeof(double) * (size_t)std::max<int64_t>(ctx->NO, 1)));
+    }
+  VH_TRY(vh_dev_alloc(ctx, &ctx->partials, VH_MAX_RED_BLOCKS));
+  VH_TRY(vh_dev_alloc(ctx, &ctx->scal, VH_SCAL_COUNT));
+  VH_TRY(vh_dev_alloc(ctx, &ctx->ticket, 4));
+  VH_CUDA(cudaMemset(ctx->ticket, 0, 4 * sizeof(unsigned int)));
+  VH_CUDA(cudaMemset(ctx->scal, 0, VH_SCAL_COUNT * sizeof(double)));
+  VH_CUDA(cudaMallocHost((void **)&ctx->h_pinned, VH_SCAL_COUNT * sizeof(double)));
+  return VH_OK;
+}
+
+int ensure_basis(vh_ctx *ctx, int restart)
+{
+  if (ctx->V && ctx->V_cap >= restart)
+    return VH_OK;
+  if (ctx->V)
+    {
+      cudaFree(ctx->V);
+      ctx->device_bytes -= (int64_t)ctx->V_cap * ctx->NO * (int64_t)sizeof(double);
+      ctx->V = nullptr;
+    }
+  VH_TRY(vh_dev_alloc(ctx, &ctx->V, (size_t)restart * (size_t)ctx->NO));
+  ctx->V_cap = restart;
+  return VH_OK;
+}
+
+int flush_l2(vh_ctx *ctx)
+{
+  if (!ctx->flush_buf)
+    {
+      ctx->flush_bytes = (size_t)256 << 20; // > 126 MB L2
+      cudaError_t e    = cudaMalloc(&ctx->flush_buf, ctx->flush_bytes);
+      if (e != cudaSuccess)
+        return vh_fail(ctx, VH_ERR_CUDA, "flush buffer allocation failed");
+    }
+  VH_CUDA(cudaMemsetAsync(ctx->flush_buf, 0, ctx->flush_bytes, ctx->stream));
+  return VH_OK;
+}
+} // namespace
+
+#define VH_REQUIRE(ctx) \
+  if (!(ctx))           \
+  return vh_fail(nullptr, VH_ERR_ARG, "null context")
+
+extern "C" {
+
+const char *vh_last_error(const vh_ctx *ctx)
+{
+  if (ctx)
+    return ctx->err.c_str();
+  std::lock_guard<std::mutex> lk(g_err_mutex);
+  static thread_local std::string copy;
+  copy = g_create_err;
+  return copy.c_str();
+}
+
+int vh_create(const vh_mesh_desc *d, int cuda_device, vh_ctx **out)
+{
+  if (!d || !out)
+    return vh_fail(nullptr, VH_ERR_ARG, "vh_create: null argument");
+  *out = nullptr;
+  if (d->degree != 1 && d->degree != 2)
+    return vh_fail(nullptr, VH_ERR_ARG, "vh_create: degree must be 1 or 2");
+  if (d->n_owned_nodes < 0 || d->n_ghost_nodes < 0 || d->n_cells < 0 || d->n_wall_faces < 0)
+    return vh_fail(nullptr, VH_ERR_ARG, "vh_create: negative size");
+  int         n_dev = 0;
+  cudaError_t e     = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return vh_fail(nullptr, VH_ERR_CUDA,
+                   std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                     " (this library has no CPU fallback)");
+  if (cuda_device < 0 || cuda_device >= n_dev)
+    return vh_fail(nullptr, VH_ERR_ARG, "vh_create: cuda_device out of range");
+  e = cudaSetDevice(cuda_device);
+  if (e != cudaSuccess)
+    return vh_fail(nullptr, VH_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cuda_device);
+  if (prop.major != 10)
+    return vh_fail(nullptr, VH_ERR_UNSUPPORTED,
+                   std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                     "; this library is built for sm_100a (B200) only");
+
+  vh_ctx *ctx  = new vh_ctx();
+  ctx->device  = cuda_device;
+  ctx->degree  = d->degree;
+  ctx->nn      = d->degree == 1 ? 8 : 27;
+  ctx->nq      = ctx->nn;
+  ctx->dpc     = 18 * ctx->nn;
+  ctx->n_owned = d->n_owned_nodes;
+  ctx->n_ghost = d->n_ghost_nodes;
+  ctx->n_local = d->n_owned_nodes + d->n_ghost_nodes;
+  ctx->n_cells = d->n_cells;
+  ctx->NO      = 18 * (int64_t)ctx->n_owned;
+  ctx->NL      = 18 * (int64_t)ctx->n_local;
+  int rc       = VH_OK;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev1) != cudaSuccess)
+    rc = vh_fail(ctx, VH_ERR_CUDA, "stream/event creation failed");
+  if (rc == VH_OK)
+    rc = build(ctx, d);
+  if (rc != VH_OK)
+    {
+      vh_fail(nullptr, rc, ctx->err);
+      vh_destroy(ctx);
+      return rc;
+    }
+  *out = ctx;
+  return VH_OK;
+}
+
+int vh_destroy(vh_ctx *ctx)
+{
+  if (!ctx)
+    return VH_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream)
+    cudaStreamSynchronize(ctx->stream);
+  vh_comm_destroy(ctx);
+  void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
+                  ctx->diag_pos, ctx->minv, ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->slow_rows, ctx->row_slow,
+                  ctx->slow_cells, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
+                  ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
+                  ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,
+                  ctx->tab.Mf};
+  for (void *p : ptrs)
+    if (p)
+      cudaFree(p);
+  for (int k = 0; k < 2; ++k)
+    {
+      void *cp[] = {ctx->cons[k].line_of, ctx->cons[k].dof, ctx->cons[k].ptr, ctx->cons[k].master, ctx->cons[k].weight};
+      for (void *p : cp)
+        if (p)
+          cudaFree(p);
+    }
+  if (ctx->h_pinned)
+    cudaFreeHost(ctx->h_pinned);
+  if (ctx->ev0)
+    cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1)
+    cudaEventDestroy(ctx->ev1);
+  if (ctx->stream)
+    cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return VH_OK;
+}
+
+int vh_set_coefficients(vh_ctx *ctx, double K1, double K2, double K3, double alpha, const double beta[5], double bt)
+{
+  VH_REQUIRE(ctx);
+  if (!beta || !(bt > 0.0))
+    return vh_fail(ctx, VH_ERR_ARG, "vh_set_coefficients: beta is null or bt <= 0");
+  ctx->coef.K1    = K1;
+  ctx->coef.K23   = K2 + K3; // always used as (K2 + K3), assemble.cc:233
+  ctx->coef.alpha = alpha;
+  for (int k = 0; k < 5; ++k)
+    ctx->coef.beta[k] = beta[k];
+  ctx->coef.bt     = bt;
+  ctx->coef_set    = true;
+  ctx->have_matrix = false;
+  return VH_OK;
+}
+
+static int upload_owned(vh_ctx *ctx, double *dev_local, const double *host_owned)
+{
+  VH_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->NO)
+    VH_CUDA(cudaMemcpyAsync(dev_local, host_owned, sizeof(double) * ctx->NO, cudaMemcpyHostToDevice, ctx->stream));
+  VH_TRY(vhk_halo_exchange(ctx, dev_local));
+  VH_CUDA(cudaStreamSynchronize(ctx->stream));
+  return VH_OK;
+}
+static int download_owned(vh_ctx *ctx, const double *dev, double *host_owned)
+{
+  VH_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->NO)
+    VH_CUDA(cudaMemcpyAsync(host_owned, dev, sizeof(double) * ctx->NO, cudaMemcpyDeviceToHost, ctx->stream));
+  VH_CUDA(cudaStreamSynchronize(ctx->stream));
+  return VH_OK;
+}
+
+int vh_set_solution(vh_ctx *ctx, const double *owned)
+{
+  VH_REQUIRE(ctx);
+  if (!owned && ctx->NO)
+    return vh_fail(ctx, VH_ERR_ARG, "vh_set_solution: null");
+  ctx->have_matrix = ctx->have_update = ctx->have_trial = false;
+  return upload_owned(ctx, ctx->x_sol, owned);
+}
+int vh_get_solution(vh_ctx *ctx, double *owned)
+{
+  VH_REQUIRE(ctx);
+  return download_owned(ctx, ctx->x_sol, owned);
+}
+int vh_get_newton_update(vh_ctx *ctx, double *owned)
+{
+  VH_REQUIRE(ctx);
+  return download_owned(ctx, ctx->delta, owned);
+}
+int vh_get_rhs(vh_ctx *ctx, double *owned)
+{
+  VH_REQUIRE(ctx);
+  return download_owned(ctx, ctx->rhs, owned);
+}
+int vh_get_residual(vh_ctx *ctx, double *owned)
+{
+  VH_REQUIRE(ctx);
+  return download_owned(ctx, ctx->resid, owned);
+}
+
+static int norm_of(vh_ctx *ctx, const double *v, double *out)
+{
+  VH_TRY(vhk_dot(ctx, v, v, ctx->scal + VH_SCAL_NRM2));
+  double s;
+  VH_TRY(vh_read_scalars(ctx, ctx->scal + VH_SCAL_NRM2, 1, &s));
+  *out = std::sqrt(s);
+  return VH_OK;
+}
+
+static int assemble_device(vh_ctx *ctx)
+{
+  VH_TRY(vhk_pointwise(ctx, ctx->x_sol, true, false));
+  VH_TRY(vhk_rows_fast(ctx));
+  VH_TRY(vhk_rhs_fast(ctx, ctx->rhs));
+  VH_TRY(vhk_rows_slow(ctx, true, ctx->rhs));
+  return VH_OK;
+}
+static int residual_device(vh_ctx *ctx, const double *x_local, double *out)
+{
+  VH_TRY(vhk_pointwise(ctx, x_local, false, false));
+  VH_TRY(vhk_rhs_fast(ctx, out));
+  VH_TRY(vhk_rows_slow(ctx, false, out));
+  return VH_OK;
+}
+
+int vh_assemble(vh_ctx *ctx, double *rhs_l2)
+{
+  VH_REQUIRE(ctx);
+  if (!ctx->coef_set)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_assemble before vh_set_coefficients");
+  VH_CUDA(cudaSetDevice(ctx->device));
+  PhaseTimer tm(ctx, 0);
+  VH_TRY(assemble_device(ctx));
+  tm.stop();
+  ctx->have_matrix = true;
+  ctx->have_update = false;
+  double nrm = 0;
+  VH_TRY(norm_of(ctx, ctx->rhs, &nrm));
+  if (rhs_l2)
+    *rhs_l2 = nrm;
+  return VH_OK;
+}
+
+int vh_solve(vh_ctx *ctx, double tol_rel, int max_it, int restart, int *iterations, double *final_residual)
+{
+  VH_REQUIRE(ctx);
+  if (!ctx->have_matrix)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_solve before vh_assemble");
+  if (restart < 2 || restart > VH_MAX_RESTART || max_it < 0)
+    return vh_fail(ctx, VH_ERR_ARG, "vh_solve: restart must be in [2,100], max_it >= 0");
+  VH_CUDA(cudaSetDevice(ctx->device));
+  VH_TRY(ensure_basis(ctx, restart));
+  PhaseTimer tm(ctx, 2);
+  VH_TRY(vhk_block_jacobi_setup(ctx)); // "Solve: setup preconditioner" (solve.cc:133)
+  double bnorm = 0;
+  VH_TRY(norm_of(ctx, ctx->rhs, &bnorm));
+  int    its = 0;
+  double res = 0;
+  int    rc  = vh_gmres(ctx, tol_rel * bnorm, max_it, restart, &its, &res); // SolverControl(max_it, tol*||rhs||), solve.cc:159-160
+  if (iterations)
+    *iterations = its;
+  if (final_residual)
+    *final_residual = res;
+  if (rc != VH_OK)
+    {
+      tm.stop();
+      return rc;
+    }
+  // constraints_newton_update.distribute + ghosted copy (solve.cc:181-183)
+  VH_TRY(vhk_halo_exchange(ctx, ctx->delta));
+  VH_TRY(vhk_distribute(ctx, 0, ctx->delta));
+  if (ctx->cons[0].has_masters)
+    VH_TRY(vhk_halo_exchange(ctx, ctx->delta));
+  tm.stop();
+  ctx->have_update = true;
+  return VH_OK;
+}
+
+int vh_line_search_trial(vh_ctx *ctx, double alpha)
+{
+  VH_REQUIRE(ctx);
+  if (!ctx->have_update)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_line_search_trial before vh_solve");
+  VH_CUDA(cudaSetDevice(ctx->device));
+  PhaseTimer tm(ctx, 3);
+  // distributed_solution = local_solution + alpha * newton_update (iteration.cc:173-177), then
+  // constraints_solution.distribute (iteration.cc:180) and the ghosted copy (iteration.cc:183)
+  VH_TRY(vhk_axpby(ctx, ctx->x_trial, 1.0, ctx->x_sol, alpha, ctx->delta, ctx->NL));
+  VH_TRY(vhk_distribute(ctx, 1, ctx->x_trial));
+  if (ctx->cons[1].has_masters)
+    VH_TRY(vhk_halo_exchange(ctx, ctx->x_trial));
+  tm.stop();
+  ctx->have_trial = true;
+  return VH_OK;
+}
+
+int vh_residual(vh_ctx *ctx, double *l2)
+{
+  VH_REQUIRE(ctx);
+  if (!ctx->coef_set)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_residual before vh_set_coefficients");
+  if (!ctx->have_trial)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_residual before vh_line_search_trial");
+  VH_CUDA(cudaSetDevice(ctx->device));
+  PhaseTimer tm(ctx, 1);
+  VH_TRY(residual_device(ctx, ctx->x_trial, ctx->resid));
+  tm.stop();
+  double nrm = 0;
+  VH_TRY(norm_of(ctx, ctx->resid, &nrm));
+  if (l2)
+    *l2 = nrm;
+  return VH_OK;
+}
+
+int vh_accept_trial(vh_ctx *ctx)
+{
+  VH_REQUIRE(ctx);
+  if (!ctx->have_trial)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_accept_trial before vh_line_search_trial");
+  VH_CUDA(cudaSetDevice(ctx->device));
+  VH_CUDA(cudaMemcpyAsync(ctx->x_sol, ctx->x_trial, sizeof(double) * ctx->NL, cudaMemcpyDeviceToDevice, ctx->stream));
+  VH_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->have_matrix = false;
+  return VH_OK;
+}
+
+int vh_energy(vh_ctx *ctx, int which, double *energy)
+{
+  VH_REQUIRE(ctx);
+  if (!ctx->coef_set || !energy)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_energy: coefficients not set or null output");
+  if (which == 1 && !ctx->have_trial)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_energy(trial) before vh_line_search_trial");
+  VH_CUDA(cudaSetDevice(ctx->device));
+  // the pointwise kernel overwrites the cell-rhs scratch only; the matrix stays valid
+  VH_TRY(vhk_pointwise(ctx, which == 1 ? ctx->x_trial : ctx->x_sol, false, true));
+  VH_TRY(vhk_sum(ctx, ctx->Ec, nullptr, ctx->n_cells, ctx->scal + VH_SCAL_NRM2));
+  VH_TRY(vh_read_scalars(ctx, ctx->scal + VH_SCAL_NRM2, 1, energy));
+  return VH_OK;
+}
+
+int vh_get_info(vh_ctx *ctx, vh_info *info)
+{
+  VH_REQUIRE(ctx);
+  info->n_owned_dofs = ctx->NO;
+  info->n_local_dofs = ctx->NL;
+  info->nnzb         = ctx->nnzb;
+  info->n_fast_rows  = ctx->n_fast;
+  info->n_slow_cells = ctx->n_slow_cells;
+  info->device_bytes = ctx->device_bytes;
+  return VH_OK;
+}
+
+int vh_export_matrix_bsr(vh_ctx *ctx, int32_t *row_ptr, int32_t *col, double *vals)
+{
+  VH_REQUIRE(ctx);
+  if (!ctx->have_matrix)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_export_matrix_bsr before vh_assemble");
+  VH_CUDA(cudaSetDevice(ctx->device));
+  std::memcpy(row_ptr, ctx->h_row_ptr.data(), sizeof(int32_t) * ctx->h_row_ptr.size());
+  std::memcpy(col, ctx->h_col.data(), sizeof(int32_t) * ctx->h_col.size());
+  VH_CUDA(cudaStreamSynchronize(ctx->stream));
+  VH_CUDA(cudaMemcpy(vals, ctx->vals, sizeof(double) * (size_t)ctx->nnzb * VH_BLK, cudaMemcpyDeviceToHost));
+  return VH_OK;
+}
+
+int vh_spmv(vh_ctx *ctx, const double *x_owned, double *y_owned)
+{
+  VH_REQUIRE(ctx);
+  if (!ctx->have_matrix)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_spmv before vh_assemble");
+  VH_TRY(upload_owned(ctx, ctx->zbuf, x_owned));
+  VH_TRY(vhk_spmv(ctx, ctx->zbuf, ctx->tmpo));
+  return download_owned(ctx, ctx->tmpo, y_owned);
+}
+
+int vh_precondition(vh_ctx *ctx, const double *x_owned, double *y_owned)
+{
+  VH_REQUIRE(ctx);
+  if (!ctx->have_matrix)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_precondition before vh_assemble");
+  VH_TRY(upload_owned(ctx, ctx->zbuf, x_owned));
+  VH_TRY(vhk_block_jacobi_setup(ctx));
+  VH_TRY(vhk_block_jacobi_apply(ctx, ctx->zbuf, ctx->tmpo));
+  return download_owned(ctx, ctx->tmpo, y_owned);
+}
+
+int vh_time_kernel(vh_ctx *ctx, int what, int reps, int do_flush, float *ms_avg)
+{
+  VH_REQUIRE(ctx);
+  if (reps < 1 || !ms_avg)
+    return vh_fail(ctx, VH_ERR_ARG, "vh_time_kernel: reps < 1");
+  if (!ctx->coef_set)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_time_kernel before vh_set_coefficients");
+  if ((what == 0 || what == 3 || what == 4 || what == 6) && !ctx->have_matrix)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_time_kernel: needs an assembled matrix");
+  VH_CUDA(cudaSetDevice(ctx->device));
+  if (what == 3)
+    VH_TRY(vhk_block_jacobi_setup(ctx));
+  if (what == 4)
+    VH_TRY(ensure_basis(ctx, 2));
+  double total = 0.0;
+  for (int r = 0; r < reps; ++r)
+    {
+      if (do_flush)
+        VH_TRY(flush_l2(ctx));
+      VH_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+      switch (what)
+        {
+        case 0:
+          VH_TRY(vhk_spmv(ctx, ctx->x_sol, ctx->tmpo));
+          break;
+        case 1:
+          VH_TRY(assemble_device(ctx));
+          break;
+        case 2:
+          VH_TRY(residual_device(ctx, ctx->x_sol, ctx->resid));
+          break;
+        case 3:
+          VH_TRY(vhk_block_jacobi_apply(ctx, ctx->x_sol, ctx->tmpo));
+          break;
+        case 4:
+          VH_CUDA(cudaMemsetAsync(ctx->scal + VH_SCAL_MISC + 1, 0, sizeof(double), ctx->stream));
+          VH_TRY(vhk_add_and_dot(ctx, ctx->w, ctx->scal + VH_SCAL_MISC + 1, ctx->V, ctx->V + ctx->NO, ctx->scal + VH_SCAL_MISC + 2));
+          break;
+        case 5:
+          VH_TRY(vhk_pointwise(ctx, ctx->x_sol, true, false));
+          break;
+        case 6:
+          VH_TRY(vhk_rows_fast(ctx));
+          break;
+        default:
+          return vh_fail(ctx, VH_ERR_ARG, "vh_time_kernel: unknown kernel id");
+        }
+      VH_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+      VH_CUDA(cudaEventSynchronize(ctx->ev1));
+      float ms = 0;
+      VH_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      total += ms;
+    }
+  *ms_avg = (float)(total / reps);
+  return VH_OK;
+}
+
+int vh_get_timers(vh_ctx *ctx, double ms[5], int64_t *n_launches, int reset)
+{
+  VH_REQUIRE(ctx);
+  for (int i = 0; i < 5; ++i)
+    ms[i] = ctx->t_ms[i];
+  if (n_launches)
+    *n_launches = ctx->n_launches;
+  if (reset)
+    {
+      for (int i = 0; i < 5; ++i)
+        ctx->t_ms[i] = 0;
+      ctx->n_launches = 0;
+    }
+  return VH_OK;
+}
+
+} // extern "C"

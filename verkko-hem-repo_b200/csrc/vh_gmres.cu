@@ -1,0 +1,196 @@
+// Restarted GMRES with right nodal block-Jacobi preconditioning — the GPU replacement of
+//   SolverFGMRES<LA::MPI::Vector>::solve(system_matrix, update, system_rhs, preconditioner)
+//   (/root/reference/femgl/src/solve.cc:156-176; ML-AMG replaced by block-Jacobi as the north star prescribes).
+//
+// Iteration semantics are deal.II's SolverFGMRES ([deal.II-internal]):
+//   * x0 = 0, r = b - A x, beta = ||r||; SolverControl is checked with (accumulated_iterations, beta) first;
+//   * inner step j: v_j = r/a, z_j = M^-1 v_j, w = A z_j, modified Gram-Schmidt through
+//     H(0,j) = w.v_0, H(i,j) = add_and_dot(-H(i-1,j), v_{i-1}, v_i), H(j+1,j) = a = sqrt(add_and_dot(-H(j,j), v_j, w));
+//   * from j > 0 on, the (j+1) x j leading Hessenberg block is solved in the least-squares sense
+//     (Householder QR) and its residual is checked with ++accumulated_iterations;
+//   * at restart / exit x += sum_{i < y.size()} y_i z_i.
+// Because M is a fixed linear operator here, z_i is not stored: sum y_i z_i = M^-1 (sum y_i v_i), which is
+// what keeps 38M-DoF problems inside 180 GB (SURVEY.md §7 hard part 5).
+//
+// Device/host split: vectors and all O(N) work stay on the device; the Gram-Schmidt coefficients are produced
+// by device-side reductions and consumed by the next fused kernel straight from device memory.  The host reads
+// one Hessenberg column per inner step (a single small D2H) to run the tiny QR and the stopping test.
+#include "vh_internal.h"
+
+#include <cmath>
+#include <vector>
+
+namespace
+{
+// min || rhs - H1 y ||_2 for the (rows x cols) column-major-free dense H1 (row-major, ld = cols), Householder QR.
+// Returns the residual norm (deal.II Householder::least_squares).
+double least_squares(std::vector<double> H1, int rows, int cols, std::vector<double> rhs, std::vector<double> &y)
+{
+  for (int k = 0; k < cols; ++k)
+    {
+      double sigma = 0.0;
+      for (int i = k; i < rows; ++i)
+        sigma += H1[i * cols + k] * H1[i * cols + k];
+      const double nrm = std::sqrt(sigma);
+      if (nrm == 0.0)
+        continue;
+      const double akk = H1[k * cols + k];
+      const double s   = akk >= 0 ? -nrm : nrm;
+      // v = a_k - s e_k, beta = 1/(s*(s - akk)) hmm: use standard form  Hh = I - v v^T / (v^T v / 2)
+      std::vector<double> v(rows, 0.0);
+      for (int i = k; i < rows; ++i)
+        v[i] = H1[i * cols + k];
+      v[k] -= s;
+      double vtv = 0.0;
+      for (int i = k; i < rows; ++i)
+        vtv += v[i] * v[i];
+      if (vtv == 0.0)
+        continue;
+      for (int c = k; c < cols; ++c)
+        {
+          double d = 0.0;
+          for (int i = k; i < rows; ++i)
+            d += v[i] * H1[i * cols + c];
+          d *= 2.0 / vtv;
+          for (int i = k; i < rows; ++i)
+            H1[i * cols + c] -= d * v[i];
+        }
+      double d = 0.0;
+      for (int i = k; i < rows; ++i)
+        d += v[i] * rhs[i];
+      d *= 2.0 / vtv;
+      for (int i = k; i < rows; ++i)
+        rhs[i] -= d * v[i];
+    }
+  y.assign(cols, 0.0);
+  for (int k = cols - 1; k >= 0; --k)
+    {
+      double s = rhs[k];
+      for (int c = k + 1; c < cols; ++c)
+        s -= H1[k * cols + c] * y[c];
+      y[k] = H1[k * cols + k] != 0.0 ? s / H1[k * cols + k] : 0.0;
+    }
+  double res = 0.0;
+  for (int i = cols; i < rows; ++i)
+    res += rhs[i] * rhs[i];
+  return std::sqrt(res);
+}
+} // namespace
+
+int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iterations, double *final_res)
+{
+  const int64_t NO = ctx->NO;
+  const int     m  = restart;
+  double       *aux = ctx->w;
+  double       *hcol  = ctx->scal + VH_SCAL_HCOL; // device: H(0..j+1, j) of the current inner step (last entry squared)
+  double       *ycoef = ctx->scal + VH_SCAL_Y;    // device: y for the solution update
+  double       *nrm2  = ctx->scal + VH_SCAL_NRM2;
+
+  // x0 = 0 (solve.cc:131: freshly constructed distributed_newton_update)
+  VH_CUDA(cudaMemsetAsync(ctx->delta, 0, sizeof(double) * ctx->NL, ctx->stream));
+
+  enum
+  {
+    ITERATE,
+    SUCCESS,
+    FAILURE
+  };
+  auto check = [&](int step, double val) {
+    if (val <= tol_abs)
+      return (int)SUCCESS;
+    if (step >= max_it || std::isnan(val))
+      return (int)FAILURE;
+    return (int)ITERATE;
+  };
+
+  int                 accumulated = 0;
+  double              res = 0.0;
+  int                 state = ITERATE;
+  bool                x_is_zero = true;
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), y;
+  do
+    {
+      // aux = b - A x
+      if (x_is_zero)
+        VH_CUDA(cudaMemcpyAsync(aux, ctx->rhs, sizeof(double) * NO, cudaMemcpyDeviceToDevice, ctx->stream));
+      else
+        {
+          VH_TRY(vhk_halo_exchange(ctx, ctx->delta));
+          VH_TRY(vhk_spmv(ctx, ctx->delta, ctx->tmpo));
+          VH_TRY(vhk_axpby(ctx, aux, 1.0, ctx->rhs, -1.0, ctx->tmpo, NO));
+        }
+      VH_TRY(vhk_dot(ctx, aux, aux, nrm2));
+      double beta2;
+      VH_TRY(vh_read_scalars(ctx, nrm2, 1, &beta2));
+      const double beta = std::sqrt(beta2);
+      res               = beta;
+      state             = check(accumulated, res);
+      if (state == SUCCESS)
+        break;
+      std::fill(H.begin(), H.end(), 0.0);
+      y.clear();
+      double        a    = beta;
+      const double *a2_d = nrm2; // device location of a^2
+      for (int j = 0; j < m; ++j)
+        {
+          double *vj = ctx->V + (size_t)j * NO;
+          if (a != 0.0)
+            VH_TRY(vhk_scale_to(ctx, vj, aux, a2_d));
+          else
+            VH_CUDA(cudaMemsetAsync(vj, 0, sizeof(double) * NO, ctx->stream));
+          // z = M^-1 v_j (owned part of zbuf), ghosts refreshed, aux = A z
+          VH_TRY(vhk_block_jacobi_apply(ctx, vj, ctx->zbuf));
+          VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
+          VH_TRY(vhk_spmv(ctx, ctx->zbuf, aux));
+          // modified Gram-Schmidt, coefficients stay on the device between the fused kernels
+          VH_TRY(vhk_dot(ctx, aux, ctx->V, hcol + 0));
+          for (int i = 1; i <= j; ++i)
+            VH_TRY(vhk_add_and_dot(ctx, aux, hcol + (i - 1), ctx->V + (size_t)(i - 1) * NO, ctx->V + (size_t)i * NO, hcol + i));
+          VH_TRY(vhk_add_and_dot(ctx, aux, hcol + j, vj, aux, hcol + j + 1));
+          std::vector<double> hc(j + 2);
+          VH_TRY(vh_read_scalars(ctx, hcol, j + 2, hc.data()));
+          for (int i = 0; i <= j; ++i)
+            H[(size_t)i * m + j] = hc[i];
+          a                          = std::sqrt(hc[j + 1]);
+          H[(size_t)(j + 1) * m + j] = a;
+          a2_d                       = hcol + j + 1;
+          // keep a^2 where the next inner step's scaling kernel reads it, before hcol is overwritten
+          VH_CUDA(cudaMemcpyAsync(nrm2, hcol + j + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+          a2_d = nrm2;
+          if (j > 0)
+            {
+              const int           rows = j + 1, cols = j;
+              std::vector<double> H1((size_t)rows * cols), prhs(rows, 0.0);
+              for (int r = 0; r < rows; ++r)
+                for (int c = 0; c < cols; ++c)
+                  H1[(size_t)r * cols + c] = H[(size_t)r * m + c];
+              prhs[0] = beta;
+              res     = least_squares(H1, rows, cols, prhs, y);
+              state   = check(++accumulated, res);
+              if (state != ITERATE)
+                break;
+            }
+        }
+      // x += sum_i y_i z_i = M^-1 (sum_i y_i v_i)
+      if (!y.empty())
+        {
+          for (size_t i = 0; i < y.size(); ++i)
+            ctx->h_pinned[i] = y[i];
+          VH_CUDA(cudaMemcpyAsync(ycoef, ctx->h_pinned, sizeof(double) * y.size(), cudaMemcpyHostToDevice, ctx->stream));
+          VH_CUDA(cudaMemsetAsync(ctx->tmpo, 0, sizeof(double) * NO, ctx->stream));
+          VH_TRY(vhk_axpy_dev(ctx, ctx->tmpo, ycoef, (int)y.size(), ctx->V, NO));
+          VH_TRY(vhk_block_jacobi_apply(ctx, ctx->tmpo, ctx->zbuf));
+          VH_TRY(vhk_axpby(ctx, ctx->delta, 1.0, ctx->delta, 1.0, ctx->zbuf, NO));
+          VH_CUDA(cudaStreamSynchronize(ctx->stream)); // h_pinned is reused by the next read
+          x_is_zero = false;
+        }
+    }
+  while (state == ITERATE);
+
+  *iterations = accumulated;
+  *final_res  = res;
+  if (state != SUCCESS)
+    return vh_fail(ctx, VH_ERR_NOT_CONVERGED,
+                   "GMRES: no convergence after " + std::to_string(accumulated) + " iterations, residual " + std::to_string(res));
+  return VH_OK;
+}

@@ -1,0 +1,216 @@
+// Internal declarations of the CUDA hot-path library (not installed; the public surface is include/vh_femgl.h).
+#ifndef VH_INTERNAL_H
+#define VH_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "vh_femgl.h"
+
+#define VH_NCOMP 18
+#define VH_BLK 324   /* 18*18 doubles per matrix block */
+#define VH_SYM 171   /* unique entries of a symmetric 18x18 */
+#define VH_SYMP 172  /* padded to a multiple of 2 doubles so a double2 never straddles quadrature points */
+
+// ---- reference-cell tables (unit cell [0,1]^3), built on the host at vh_create and uploaded once ----
+// Q1: nn = nq = 8, nqf = 4.  Q2: nn = nq = 27, nqf = 9.
+struct VhTables
+{
+  int     degree, nn, nq;
+  double *N;    // [nn][nq]           shape values at QGauss<3>(degree+1) points
+  double *dN;   // [nn][nq][3]        unit-cell gradients
+  double *wq;   // [nq]
+  double *Gref; // [nn][nn][3][3]     sum_q wq d_x N_a d_y N_b   (gradient forms are geometry-only)
+  double *Mf;   // [6][nn][nn]        unit-face mass  sum_qf wf Nf_a Nf_b  for face_no 0..5
+};
+
+struct VhCoef
+{
+  double K1, K23, alpha, beta[5], bt;
+};
+
+struct VhConstraintsDev
+{
+  int32_t  n_lines  = 0;
+  int32_t *line_of  = nullptr; // [n_local_dofs] line index or -1
+  int32_t *dof      = nullptr; // [n_lines]
+  int32_t *ptr      = nullptr; // [n_lines+1]
+  int32_t *master   = nullptr;
+  double  *weight   = nullptr;
+  bool     has_masters = false;
+};
+
+struct vh_ctx
+{
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  std::string  err;
+
+  // sizes
+  int     degree = 1, nn = 8, nq = 8, dpc = 144;
+  int32_t n_owned = 0, n_ghost = 0, n_local = 0, n_cells = 0;
+  int64_t NO = 0, NL = 0; // owned / local DoFs
+  int64_t nnzb = 0;
+
+  // mesh tables (device)
+  int32_t  *cell_nodes = nullptr; // [n_cells][nn]
+  double   *cell_h     = nullptr; // [n_cells][4]  hx,hy,hz,vol
+  uint32_t *cell_faces = nullptr; // [n_cells]     4 bits per face: boundary id (0 = none)
+  uint8_t  *cell_owned = nullptr;
+  uint32_t *dirmask    = nullptr; // [n_local] bit c: DoF (node,c) is homogeneous Dirichlet in constraints_newton_update
+  VhConstraintsDev cons[2];       // 0: newton update, 1: solution
+  VhTables tab{};
+  VhCoef   coef{};
+  bool     coef_set = false;
+
+  // BSR(18) matrix over owned rows
+  int32_t *row_ptr  = nullptr; // [n_owned+1]
+  int32_t *col      = nullptr; // [nnzb] local node ids, ascending inside a row
+  double  *vals     = nullptr; // [nnzb][18][18]
+  int32_t *diag_pos = nullptr; // [n_owned] block index of (I,I)
+  double  *minv     = nullptr; // [n_owned][18][18] inverse diagonal blocks (block-Jacobi)
+  std::vector<int32_t> h_row_ptr, h_col;
+
+  // row classification
+  int32_t  n_fast = 0, n_slow_rows = 0, n_slow_cells = 0;
+  int32_t *fast_rows  = nullptr; // [n_fast]
+  int32_t *fast_cells = nullptr; // [n_fast][8]   cell in octant o (row node is local vertex 7-o), -1 = absent
+  int8_t  *fast_slot  = nullptr; // [n_fast][32]  stencil slot (dx+1)+3(dy+1)+9(dz+1) -> position in the row, -1 = absent
+  int32_t *slow_rows  = nullptr; // [n_slow_rows]
+  uint8_t *row_slow   = nullptr; // [n_owned]
+  int32_t *slow_cells = nullptr; // [n_slow_cells]
+  // node -> incident (cell, local node) lists for the deterministic rhs gather of fast rows
+  // (fast rows use fast_cells; kept for Q2 later)
+
+  // per-cell scratch written by the pointwise kernel
+  double *Hq   = nullptr; // [n_cells][nq][172]  symmetric bulk Hessian at every quadrature point
+  double *Rc   = nullptr; // [n_cells][dpc]      cell rhs (= -cell residual)
+  double *Dc   = nullptr; // [n_cells][dpc]      cell matrix diagonal (for the constrained-diagonal rule)
+  double *avgD = nullptr; // [n_cells]           mean |diag| of the cell matrix
+  double *Ec   = nullptr; // [n_cells]           cell energy
+
+  // vectors
+  double *x_sol = nullptr, *x_trial = nullptr, *delta = nullptr, *zbuf = nullptr; // [NL]
+  double *rhs = nullptr, *resid = nullptr, *w = nullptr, *tmpo = nullptr;          // [NO]
+  double *V   = nullptr;                                                           // [(restart+1)][NO]
+  int     V_cap = 0;
+  // reductions
+  double *partials = nullptr; // [VH_MAX_RED_BLOCKS]
+  double *scal     = nullptr; // device scalars [VH_SCAL_COUNT]
+  unsigned int *ticket = nullptr;
+  double *h_pinned = nullptr; // pinned host scratch [VH_SCAL_COUNT]
+
+  // halo
+  int                  rank = 0, n_ranks = 1;
+  void                *nccl_comm = nullptr;
+  std::vector<int32_t> peer_rank, send_ptr, recv_ptr;
+  int32_t             *send_nodes = nullptr, *recv_nodes = nullptr; // device lists
+  double              *send_buf = nullptr, *recv_buf = nullptr;
+  int64_t              n_send = 0, n_recv = 0;
+
+  // state flags
+  bool have_matrix = false, have_update = false, have_trial = false;
+
+  // accounting
+  int64_t     n_launches = 0;
+  double      t_ms[5]    = {0, 0, 0, 0, 0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t     device_bytes = 0;
+  void       *flush_buf   = nullptr;
+  size_t      flush_bytes = 0;
+};
+
+#define VH_MAX_RED_BLOCKS 2048
+// layout of the device scalar scratch ctx->scal
+#define VH_MAX_RESTART 100
+#define VH_SCAL_HCOL 0    /* Hessenberg column of the current GMRES inner step (<= VH_MAX_RESTART+1) */
+#define VH_SCAL_NRM2 120  /* squared norm feeding the next basis-vector scaling */
+#define VH_SCAL_Y 128     /* least-squares solution for the GMRES update (<= VH_MAX_RESTART) */
+#define VH_SCAL_MISC 250
+#define VH_SCAL_COUNT 256
+
+// ---- error plumbing ----
+int vh_fail(vh_ctx *ctx, int code, const std::string &msg);
+#define VH_CUDA(call)                                                                                        \
+  do                                                                                                         \
+    {                                                                                                        \
+      cudaError_t e__ = (call);                                                                              \
+      if (e__ != cudaSuccess)                                                                                \
+        return vh_fail(ctx, VH_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));               \
+    }                                                                                                        \
+  while (0)
+#define VH_TRY(call)           \
+  do                           \
+    {                          \
+      int rc__ = (call);       \
+      if (rc__ != VH_OK)       \
+        return rc__;           \
+    }                          \
+  while (0)
+#define VH_LAUNCH_CHECK()                                                                                    \
+  do                                                                                                         \
+    {                                                                                                        \
+      ctx->n_launches++;                                                                                     \
+      cudaError_t e__ = cudaGetLastError();                                                                  \
+      if (e__ != cudaSuccess)                                                                                \
+        return vh_fail(ctx, VH_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__));          \
+    }                                                                                                        \
+  while (0)
+
+// ---- assembly (vh_assemble.cu) ----
+int vhk_pointwise(vh_ctx *ctx, const double *x_local, bool want_hessian, bool want_energy);
+int vhk_rows_fast(vh_ctx *ctx);
+int vhk_rows_slow(vh_ctx *ctx, bool want_matrix, double *rhs_out);
+int vhk_rhs_fast(vh_ctx *ctx, double *rhs_out);
+int vhk_upload_constants(vh_ctx *ctx);
+int vhk_upload_w1(vh_ctx *ctx, const double *W1);
+
+// ---- linear algebra (vh_linalg.cu) ----
+int vhk_spmv(vh_ctx *ctx, const double *x_local, double *y_owned);
+int vhk_block_jacobi_setup(vh_ctx *ctx);
+int vhk_block_jacobi_apply(vh_ctx *ctx, const double *x_owned, double *y_owned);
+// out_scalar[0] = sum_i a[i]*b[i] over owned DoFs (all-reduced over ranks); stream-ordered, result on device
+int vhk_dot(vh_ctx *ctx, const double *a, const double *b, double *out_scalar);
+// w += (-*coef) * v ; out = dot(w, u)   (deal.II Vector::add_and_dot with a = -coef)
+int vhk_add_and_dot(vh_ctx *ctx, double *w, const double *coef_dev, const double *v, const double *u, double *out_scalar);
+int vhk_scale_to(vh_ctx *ctx, double *dst, const double *src, const double *norm_sq_dev); // dst = src / sqrt(*norm_sq)
+int vhk_axpy_dev(vh_ctx *ctx, double *y, const double *coefs_dev, int k, const double *V, int64_t ld); // y += sum_j c_j V_j
+int vhk_axpby(vh_ctx *ctx, double *z, double a, const double *x, double b, const double *y, int64_t n); // z = a x + b y
+int vhk_distribute(vh_ctx *ctx, int which, double *x_local); // AffineConstraints::distribute on owned constrained DoFs
+int vhk_sum(vh_ctx *ctx, const double *a, const uint8_t *mask, int64_t n, double *out_scalar); // masked sum, all-reduced
+int vh_read_scalars(vh_ctx *ctx, const double *dev, int n, double *host);                     // D2H + sync
+
+// ---- halo (vh_halo.cu) ----
+int vhk_halo_exchange(vh_ctx *ctx, double *x_local);
+int vhk_allreduce_sum(vh_ctx *ctx, double *dev, int n);
+void vh_comm_destroy(vh_ctx *ctx);
+
+// ---- GMRES (vh_gmres.cu) ----
+int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iterations, double *final_res);
+
+// ---- helpers ----
+template <typename T>
+int vh_dev_alloc(vh_ctx *ctx, T **p, size_t count)
+{
+  *p = nullptr;
+  if (count == 0)
+    count = 1;
+  cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+  if (e != cudaSuccess)
+    return vh_fail(ctx, VH_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(count * sizeof(T)) + " B): " + cudaGetErrorString(e));
+  ctx->device_bytes += (int64_t)(count * sizeof(T));
+  return VH_OK;
+}
+template <typename T>
+int vh_dev_upload(vh_ctx *ctx, T **p, const T *host, size_t count)
+{
+  VH_TRY(vh_dev_alloc(ctx, p, count));
+  if (count)
+    VH_CUDA(cudaMemcpy(*p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+  return VH_OK;
+}
+
+#endif

@@ -1,0 +1,179 @@
+// Pointwise bulk terms of the GL functional for the 3x3 complex order parameter A = u + i v.
+//
+// Replaces, in closed form, the reference's per-(q,i,j) evaluation through 3x3 FullMatrix products:
+//   vec_rhs_alpha / vec_rhs_beta1..5   /root/reference/femgl/src/cell_mat_vec/cell_vec_rhs_{alpha,beta1..5}.cc:108-216
+//   mat_lhs_alpha / mat_lhs_beta1..5   /root/reference/femgl/src/cell_mat_vec/cell_mat_lhs_{alpha,beta1..5}.cc:108-342
+// with  g = alpha A + 2 sum_k beta_k G_k   (the explicit 2.0 is at assemble.cc:237,265),
+//   G1 = tr(AA^T) A*, G2 = tr(AA^+) A, G3 = A A^T A*, G4 = A A^+ A, G5 = A* A^T A,
+// and H = dg/dA (18x18 real, symmetric).  Because every test direction is a unit matrix s*e_nu e_k^T
+// (s = 1 or i), each column of H needs only the four 3x3 products R = AA^T, Q = AA^+, P = A^+A, S = A^T A.
+//
+// Layout: A[18] = {u row-major (9), v row-major (9)}; prod[72] = {R,Q,P,S} x 9 entries x (re,im).
+// All functions are __host__ __device__ so the same source is unit-tested on the CPU (tests/native).
+#ifndef VH_POINTWISE_CUH
+#define VH_POINTWISE_CUH
+
+#ifndef __CUDACC__
+#define VH_HD inline
+#else
+#define VH_HD __host__ __device__ __forceinline__
+#endif
+
+struct vh_cx
+{
+  double re, im;
+};
+VH_HD vh_cx vh_cmul(vh_cx a, vh_cx b) { return vh_cx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+VH_HD vh_cx vh_conj(vh_cx a) { return vh_cx{a.re, -a.im}; }
+VH_HD vh_cx vh_ld(const double *A, int mu, int j) { return vh_cx{A[3 * mu + j], A[9 + 3 * mu + j]}; }
+VH_HD vh_cx vh_ldp(const double *prod, int m, int i, int j)
+{
+  const double *p = prod + 18 * m + 2 * (3 * i + j);
+  return vh_cx{p[0], p[1]};
+}
+
+// One entry e in [0,36) of the product table: matrix m = e/9, (i,j) = ((e%9)/3, e%3).
+VH_HD void vh_product_entry(const double *A, int e, double *out2)
+{
+  const int m = e / 9, i = (e % 9) / 3, j = e % 3;
+  double    re = 0, im = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    {
+      vh_cx x, y;
+      if (m == 0) // R = A A^T
+        x = vh_ld(A, i, k), y = vh_ld(A, j, k);
+      else if (m == 1) // Q = A A^+
+        x = vh_ld(A, i, k), y = vh_conj(vh_ld(A, j, k));
+      else if (m == 2) // P = A^+ A
+        x = vh_conj(vh_ld(A, k, i)), y = vh_ld(A, k, j);
+      else // S = A^T A
+        x = vh_ld(A, k, i), y = vh_ld(A, k, j);
+      const vh_cx z = vh_cmul(x, y);
+      re += z.re;
+      im += z.im;
+    }
+  out2[0] = re;
+  out2[1] = im;
+}
+
+// Component c of the bulk residual density g (c<9: Re g_{mu j}, c>=9: Im g_{mu j}).
+VH_HD double vh_g_component(const double *A, const double *prod, int c, double alpha, const double *beta)
+{
+  const int   mu = (c % 9) / 3, j = c % 3;
+  const vh_cx a = vh_ld(A, mu, j);
+  const vh_cx T{prod[0] + prod[8] + prod[16], prod[1] + prod[9] + prod[17]}; // tr R
+  const double Sr = prod[18 + 0] + prod[18 + 8] + prod[18 + 16];             // tr Q (real)
+  vh_cx        g  = vh_cmul(T, vh_conj(a));
+  g.re *= beta[0];
+  g.im *= beta[0];
+  g.re += beta[1] * Sr * a.re;
+  g.im += beta[1] * Sr * a.im;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    {
+      const vh_cx akj = vh_ld(A, k, j);
+      const vh_cx t3  = vh_cmul(vh_ldp(prod, 0, mu, k), vh_conj(akj));              // R A*
+      const vh_cx t4  = vh_cmul(vh_ldp(prod, 1, mu, k), akj);                       // Q A
+      const vh_cx t5  = vh_cmul(vh_conj(vh_ld(A, mu, k)), vh_ldp(prod, 3, k, j));   // A* S
+      g.re += beta[2] * t3.re + beta[3] * t4.re + beta[4] * t5.re;
+      g.im += beta[2] * t3.im + beta[3] * t4.im + beta[4] * t5.im;
+    }
+  const double re = alpha * a.re + 2.0 * g.re, im = alpha * a.im + 2.0 * g.im;
+  return c < 9 ? re : im;
+}
+
+// Column d of H = dg/dA: out[c], c = 0..17.  Direction E = s e_nu e_k^T, s = 1 (d<9) or i (d>=9).
+VH_HD void vh_hessian_column(const double *A, const double *prod, int d, double alpha, const double *beta, double *out)
+{
+  const int   nu = (d % 9) / 3, k = d % 3;
+  const bool  imag = d >= 9;
+  const vh_cx s  = imag ? vh_cx{0.0, 1.0} : vh_cx{1.0, 0.0};
+  const vh_cx sc = vh_conj(s);
+  const vh_cx T{prod[0] + prod[8] + prod[16], prod[1] + prod[9] + prod[17]};
+  const double Sr = prod[18 + 0] + prod[18 + 8] + prod[18 + 16];
+  const vh_cx  ank = vh_ld(A, nu, k);
+  vh_cx        dT  = vh_cmul(s, ank); // d tr(AA^T) = 2 s A_{nu k}
+  dT.re *= 2.0;
+  dT.im *= 2.0;
+  const double dS = 2.0 * A[d]; // d tr(AA^+) = 2 Re(conj(A_{nu k}) s)
+  const double b1 = 2.0 * beta[0], b2 = 2.0 * beta[1], b3 = 2.0 * beta[2], b4 = 2.0 * beta[3], b5 = 2.0 * beta[4];
+#pragma unroll
+  for (int mu = 0; mu < 3; ++mu)
+    {
+      const vh_cx amk = vh_ld(A, mu, k);
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        {
+          const vh_cx amj = vh_ld(A, mu, j), anj = vh_ld(A, nu, j);
+          // dense part
+          vh_cx       t  = vh_cmul(dT, vh_conj(amj));
+          double      re = b1 * t.re + b2 * dS * amj.re, im = b1 * t.im + b2 * dS * amj.im;
+          t  = vh_cmul(s, vh_cmul(amk, vh_conj(anj))); // A E^T A*
+          re += b3 * t.re;
+          im += b3 * t.im;
+          t = vh_cmul(sc, vh_cmul(amk, anj)); // A E^+ A
+          re += b4 * t.re;
+          im += b4 * t.im;
+          t = vh_cmul(s, vh_cmul(vh_conj(amk), anj)); // A* E^T A
+          re += b5 * t.re;
+          im += b5 * t.im;
+          if (mu == nu)
+            { // E A^T A*, E A^+ A, E* A^T A : only row nu
+              const vh_cx p = vh_ldp(prod, 2, k, j);
+              t  = vh_cmul(s, vh_conj(p));
+              re += b3 * t.re;
+              im += b3 * t.im;
+              t = vh_cmul(s, p);
+              re += b4 * t.re;
+              im += b4 * t.im;
+              t = vh_cmul(sc, vh_ldp(prod, 3, k, j));
+              re += b5 * t.re;
+              im += b5 * t.im;
+            }
+          if (j == k)
+            { // A A^T E*, A A^+ E, A* A^T E : only column k
+              const vh_cx q = vh_ldp(prod, 1, mu, nu);
+              t = vh_cmul(sc, vh_ldp(prod, 0, mu, nu));
+              re += b3 * t.re;
+              im += b3 * t.im;
+              t = vh_cmul(s, q);
+              re += b4 * t.re;
+              im += b4 * t.im;
+              t = vh_cmul(s, vh_conj(q));
+              re += b5 * t.re;
+              im += b5 * t.im;
+              if (mu == nu)
+                { // alpha E + 2 beta1 T E* + 2 beta2 tr(AA^+) E
+                  t = vh_cmul(T, sc);
+                  re += alpha * s.re + b1 * t.re + b2 * Sr * s.re;
+                  im += alpha * s.im + b1 * t.im + b2 * Sr * s.im;
+                }
+            }
+          out[3 * mu + j]     = re;
+          out[9 + 3 * mu + j] = im;
+        }
+    }
+}
+
+// Bulk free-energy density  alpha I0 + sum beta_k I_k   from the product table.
+VH_HD double vh_bulk_energy(const double *prod, double alpha, const double *beta)
+{
+  const vh_cx  T{prod[0] + prod[8] + prod[16], prod[1] + prod[9] + prod[17]};
+  const double Sr = prod[18 + 0] + prod[18 + 8] + prod[18 + 16];
+  double       I3 = 0, I4 = 0, I5 = 0;
+#pragma unroll
+  for (int e = 0; e < 9; ++e)
+    {
+      const double rr = prod[2 * e], ri = prod[2 * e + 1], qr = prod[18 + 2 * e], qi = prod[18 + 2 * e + 1];
+      I3 += rr * rr + ri * ri;
+      I4 += qr * qr + qi * qi;
+      I5 += qr * qr - qi * qi;
+    }
+  return alpha * Sr + beta[0] * (T.re * T.re + T.im * T.im) + beta[1] * Sr * Sr + beta[2] * I3 + beta[3] * I4 + beta[4] * I5;
+}
+
+// index of (c,d), c<=d, in the row-major packed upper triangle of a symmetric 18x18
+VH_HD int vh_sym_index(int c, int d) { return c * 18 - (c * (c - 1)) / 2 + (d - c); }
+
+#endif
