@@ -54,7 +54,7 @@ __device__ __forceinline__ double block_sum(double v, double *s_red)
 // 1. pointwise kernel
 // ------------------------------------------------------------------------------------------------
 template <int NN, int NQ>
-__global__ void k_pointwise(const int32_t *__restrict__ cell_nodes, const double *__restrict__ cell_h,
+__global__ void __launch_bounds__(NQ == 8 ? 160 : 512) k_pointwise(const int32_t *__restrict__ cell_nodes, const double *__restrict__ cell_h,
                             const uint32_t *__restrict__ cell_faces, const uint8_t *__restrict__ cell_owned,
                             const double *__restrict__ x, VhTables tab, VhCoef cf, int want_h, int want_e,
                             double *__restrict__ Hq, double *__restrict__ Rc, double *__restrict__ Dc,
