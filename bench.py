@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — the femgl Newton step (assembly + GMRES(30)/block-Jacobi + line search) on N B200s of one box.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code (oracle/_ref) on the host cores
+
+A "step" is one Newton step of run.cc:214-218 (assemble_system, solve(tol), newton_iteration) on the synthetic
+cube of BASELINE.json configs[1]: Q1, hyper_cube(-20,20), global refinement 5, 646 866 DoFs per GPU
+(weak scaling: N GPUs solve an N-times taller box, partitioned along the Morton curve).
+The W warm-up steps and the K timed steps both start from the uniform B-phase initial condition
+(setup_uniform_B-phase.cc:245-259), so the timed region is Newton iterations 1..K of a real run.
+
+Prints ONE JSON line.  `value` = DoFs advanced one Newton step per second, whole job (ms_per_step is the
+Newton-step wall time the BASELINE metric names); `roofline` is the SpMV kernel (HBM-bound) timed live with CUDA
+events; `assembly` and `kernels` break the step down; `e2e` repeats the step through the C ABI with host
+buffers in and out every step; `cpu_baseline` is the reference's literal term code on a bounded cell sample.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+K123 = 0.42072
+# Matep(p = 25 bar, t = 0.5, SCC on): tests/golden/matep.json, SURVEY.md App. B KAT-1
+COEF = dict(alpha=-0.5, beta=(-0.010850915879921348, 0.020598836429398658, 0.02117724292551364, 0.019780381922869742,
+                              -0.023091499302424053), gapB=3.9900156313155422, bt=2.0)
+LIN_TOL = 1e-1       # "Cycle 0 linear solver tol" default, declare.cc:203
+LS_STEP = 0.83       # "primary step length of dampped newton iteration" default, declare.cc:287
+MAX_LIN_IT = 10000   # declare.cc:277
+RESTART = 30         # SolverFGMRES default max_basis_size
+
+
+def coef_vector():
+    return np.array([K123, K123, K123, COEF["alpha"], *COEF["beta"], COEF["bt"]])
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu),
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([s.strip() for s in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_mesh(n_gpus, refine, degree):
+    import verkko_hem_repo_b200 as vh
+    # weak scaling: N root cubes stacked along z, each refined `refine` times; Morton order keeps each root
+    # contiguous, so rank r owns root r (the p4est partition of a 1 x 1 x N brick).
+    L = 20.0  # "cube half side length" default (declare.cc:159)
+    m = vh.Mesh(degree, [-L, -L, -L], [L, L, -L + 2 * L * n_gpus], base=(1, 1, n_gpus), face_bid=(1, 1, 1, 1, 4, 4),
+                n_global_refine=refine)
+    m.finalize(n_gpus)
+    return m
+
+
+def initial_state(T):
+    from helpers import b_phase_state, MATEP_SCC_ON
+    return b_phase_state(T, MATEP_SCC_ON, noise=0.0)
+
+
+def newton_step(ctx):
+    """run.cc:214-218 + iteration.cc:128-210 through the C ABI.  Returns (lin_its, n_trials, res_norm)."""
+    bn = ctx.assemble()
+    its, _ = ctx.solve(LIN_TOL, MAX_LIN_IT, RESTART)
+    n_trials = 0
+    cur = bn
+    for i in range(100):
+        ctx.line_search_trial(LS_STEP ** i)
+        cur = ctx.residual()
+        n_trials += 1
+        if cur < bn:
+            break
+    ctx.accept_trial()
+    return its, n_trials, cur
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's own term files (oracle/_ref) on the host cores
+# ------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    seed, n_cells_each, h, coef = args
+    import femgl_oracle as O
+    rng = np.random.default_rng(seed)
+    amp = COEF["gapB"] * float(np.float32(0.577350269))
+    t0 = time.time()
+    for _ in range(n_cells_each):
+        U = np.zeros((8, 18))
+        U[:, [0, 4, 8]] = amp
+        U += 0.05 * COEF["gapB"] * rng.uniform(-1, 1, U.shape)
+        O.ref_cell(1, [0, 0, 0], h, U.ravel(), coef, [(4, 4)], want_matrix=True)   # assemble_system cell
+        O.ref_cell(1, [0, 0, 0], h, U.ravel(), coef, [(4, 4)], want_matrix=False)  # one compute_residual cell
+    return time.time() - t0
+
+
+def reference_sample(refine, cells_per_core=1):
+    """Time the reference's literal (q,i,j) loops + term functions on `cores * cells_per_core` Q1 cells, one worker
+    process per host core (the reference is 1 thread per MPI rank, sol/src/main.cc:108)."""
+    import femgl_oracle as O
+    if not O.have_ref():
+        return None
+    cores = os.cpu_count() or 1
+    n_side = 2 ** refine
+    h = [40.0 / n_side] * 3
+    coef = coef_vector()
+    t0 = time.time()
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_ref_worker, [(1000 + k, cells_per_core, h, coef) for k in range(cores)])
+    wall = time.time() - t0
+    n_cells = cores * cells_per_core
+    return dict(cores=cores, cells=n_cells, wall_s=wall, cells_per_s=n_cells / wall)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_nodes = (2 ** args.refine + 1) ** 2 * (2 ** args.refine * args.gpus + 1)
+    n_cells = (2 ** args.refine) ** 3 * args.gpus
+    n_dofs = 18 * n_nodes
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        reference_sample(args.refine, 1)
+    t_list, last = [], None
+    for _ in range(args.steps):
+        last = reference_sample(args.refine, 2)
+        if last is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvhref.so not built"}))
+            return
+        t_list.append(last["wall_s"])
+    cps = last["cells"] * len(t_list) / sum(t_list)
+    # one Newton step of the reference = one assembly + >= 1 residual evaluation over all cells; its ML-AMG solve is
+    # not reproducible here and is left out, so this is an UPPER bound on the reference's throughput.
+    step_s = n_cells / cps
+    val = n_dofs / step_s
+    out = {"impl": "reference", "metric": "femgl Newton-step throughput",
+           "value": val, "unit": "DoF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": "femgl Q1 cube r%d x %d (%d DoFs), extrapolated from a %d-cell sample per step"
+                      % (args.refine, args.gpus, n_dofs, last["cells"])},
+           "cpu_baseline": {"value": val, "unit": "DoF/s", "cores": last["cores"], "kind": "reference",
+                            "sample": "%d Q1 cells/step (Jacobian + 1 residual) by the reference's verbatim cell_mat_vec "
+                                      "term files driven by its literal (q,i,j) loops; %.2f cells/s on %d cores, "
+                                      "extrapolated linearly to %d cells" % (last["cells"], cps, last["cores"], n_cells)},
+           "e2e": {"value": val, "unit": "DoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import verkko_hem_repo_b200 as vh
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    mesh = build_mesh(world, args.refine, args.degree)
+    T = mesh.tables(rank)
+    ctx = vh.Context(T, device=local_rank)
+    if world > 1:
+        uid = [vh.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+    ctx.set_coef_vector(coef_vector())
+    x0 = initial_state(T)[:18 * T.n_owned_nodes]
+    n_dofs = 18 * mesh.n_nodes
+    info = ctx.info()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up ----
+    ctx.set_solution(x0)
+    for _ in range(args.warmup):
+        newton_step(ctx)
+
+    # ---- timed: K Newton steps from the initial condition, state resident in HBM ----
+    ctx.set_solution(x0)
+    ctx.timers(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    hist = []
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        hist.append(newton_step(ctx))
+    ms = ctx.timer_stop()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    tm = ctx.timers()
+    ms = max_over_ranks(ms)
+    ms_per_step = ms / args.steps
+    value = n_dofs / (ms_per_step * 1e-3)
+
+    # ---- e2e: same steps, host buffers in and out of the C ABI every step (pinned host memory) ----
+    xh = torch.from_numpy(x0.copy()).pin_memory().numpy()
+    barrier()
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        ctx.set_solution(xh)          # H2D of the step's input
+        newton_step(ctx)
+        xh[:] = ctx.get_solution()    # D2H of the step's result
+    ms_e2e = max_over_ranks(ctx.timer_stop())
+    wall_e2e = time.perf_counter() - t0
+    barrier()
+    e2e_val = n_dofs / (ms_e2e / args.steps * 1e-3)
+
+    # ---- live kernel timings for the roofline (rank 0's kernels; inputs larger than L2 or L2 flushed) ----
+    ctx.set_solution(x0)
+    ctx.assemble()
+    nnzb, nb = info["nnzb"], T.n_owned_nodes
+    spmv_bytes = 8 * 324 * nnzb + 4 * nnzb + 4 * (nb + 1) + 16 * 18 * nb
+    t_spmv = ctx.time_kernel(0, reps=20, flush_l2=True)
+    t_asm = ctx.time_kernel(1, reps=5, flush_l2=True)
+    t_pw = ctx.time_kernel(5, reps=5, flush_l2=True)
+    t_rows = ctx.time_kernel(6, reps=5, flush_l2=True)
+    t_res = ctx.time_kernel(2, reps=5, flush_l2=True)
+    t_bj = ctx.time_kernel(3, reps=10, flush_l2=True)
+    fp64_peak = ctx.measure_fp64_peak()
+    hbm_peak, peak_src = peaks()
+    n = 8 if args.degree == 1 else 27
+    asm_flops = 2.0 * n * n * n * 336 * T.n_cells
+    asm_bytes = 8 * 324 * nnzb + 8 * 18 * n * T.n_cells
+    spmv_gbs = spmv_bytes / (t_spmv * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_spmv_bsr18", "achieved": spmv_gbs, "peak": hbm_peak, "unit": "GB/s",
+            "frac": spmv_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": t_spmv,
+            "algorithmic_bytes_per_launch": spmv_bytes}
+    asm = {"ms": t_asm, "dofs_per_s": 18 * nb / (t_asm * 1e-3), "tflops_fp64": asm_flops / (t_asm * 1e-3) / 1e12,
+           "fp64_peak_tflops_measured": fp64_peak, "frac_fp64": asm_flops / (t_asm * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
+           "store_gbs": asm_bytes / (t_asm * 1e-3) / 1e9, "frac_hbm": asm_bytes / (t_asm * 1e-3) / 1e9 / hbm_peak,
+           "pointwise_ms": t_pw, "rows_ms": t_rows, "algorithmic_flops": asm_flops, "algorithmic_bytes": asm_bytes}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        s = reference_sample(args.refine, 1)
+        if s is not None:
+            n_cells = mesh.n_cells
+            step_s = n_cells / s["cells_per_s"]
+            cpu = {"value": n_dofs / step_s, "unit": "DoF/s", "cores": s["cores"], "kind": "reference",
+                   "sample": "%d Q1 cells (Jacobian + 1 residual each) through the reference's verbatim term files and literal "
+                             "(q,i,j) loops in %.1f s on %d cores; extrapolated linearly to %d cells; solve excluded"
+                             % (s["cells"], s["wall_s"], s["cores"], n_cells)}
+
+    if rank == 0:
+        out = {"metric": "femgl Newton-step throughput",
+               "value": value, "unit": "DoF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": "femgl 3D cube Q%d, global refinement %d per GPU (%d DoFs total, %d cells), B-phase IC, "
+                                      "z walls AdGR diffuse (bt=2), p=25 bar t=0.5 SCC on, linear tol 1e-1, damped Newton 0.83"
+                                      % (args.degree, args.refine, n_dofs, mesh.n_cells),
+                          "l2": "matrix (%.2f GB/GPU) exceeds the 126 MB L2; kernel timings flush L2 between launches"
+                                % (8 * 324 * nnzb / 1e9),
+                          "parallelism": "subdomain x%d (Morton partition, NCCL halo + all-reduce)" % world},
+               "newton_history": [{"gmres_its": h[0], "line_search_trials": h[1], "residual": h[2]} for h in hist],
+               "phase_ms_per_step": {k: tm[k] / args.steps for k in ("assemble", "residual", "solve", "vector")},
+               "roofline": roof, "assembly": asm,
+               "kernels": {"spmv_ms": t_spmv, "spmv_gbs": spmv_gbs, "residual_ms": t_res, "block_jacobi_apply_ms": t_bj},
+               "e2e": {"value": e2e_val, "unit": "DoF/s", "h2d_bytes_per_step": int(8 * 18 * T.n_owned_nodes),
+                       "d2h_bytes_per_step": int(8 * 18 * T.n_owned_nodes), "ms_per_step": ms_e2e / args.steps,
+                       "wall_ms_per_step": wall_e2e / args.steps * 1e3},
+               "gpu_launches": tm["launches"], "clocks": clocks, "cpu_baseline": cpu,
+               "matrix": {"nnzb": nnzb, "fast_rows": info["n_fast_rows"], "slow_cells": info["n_slow_cells"],
+                          "device_bytes": info["device_bytes"]}}
+        print(json.dumps(out))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--refine", type=int, default=5)
+    ap.add_argument("--degree", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

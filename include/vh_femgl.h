@@ -142,11 +142,17 @@ int vh_spmv(vh_ctx *ctx, const double *x_owned, double *y_owned);
 /* y = M^-1 x with M = nodal 18x18 diagonal blocks of system_matrix; host buffers */
 int vh_precondition(vh_ctx *ctx, const double *x_owned, double *y_owned);
 /* Device-timed kernels (CUDA events on the launching stream; average ms per launch over `reps`):
- *   what: 0 SpMV, 1 Jacobian+rhs assembly, 2 residual assembly, 3 block-Jacobi apply, 4 fused add_and_dot */
+ *   what: 0 SpMV, 1 Jacobian+rhs assembly, 2 residual assembly, 3 block-Jacobi apply, 4 fused add_and_dot,
+ *         5 pointwise kernel only, 6 row-owner Jacobian kernel only */
 int vh_time_kernel(vh_ctx *ctx, int what, int reps, int flush_l2, float *ms_avg);
 /* Cumulative device time (ms) and launch counts since the last reset:
  *   [0] assemble [1] residual [2] solve [3] line search vector ops [4] halo; n_launches = kernels launched */
 int vh_get_timers(vh_ctx *ctx, double ms[5], int64_t *n_launches, int reset);
+/* CUDA-event stopwatch on the library's stream (the stream every kernel of this context is launched on). */
+int vh_timer_start(vh_ctx *ctx);
+int vh_timer_stop(vh_ctx *ctx, float *ms);
+/* FP64 DFMA peak of the device this context lives on, measured by a register-resident FMA chain (TFLOP/s). */
+int vh_measure_fp64_peak(vh_ctx *ctx, double *tflops);
 
 #ifdef __cplusplus
 }

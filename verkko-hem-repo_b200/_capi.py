@@ -57,6 +57,9 @@ def cuda_lib():
         L.vh_precondition.argtypes = [_vp, _dp, _dp]
         L.vh_time_kernel.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
         L.vh_get_timers.argtypes = [_vp, _dp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
+        L.vh_timer_start.argtypes = [_vp]
+        L.vh_timer_stop.argtypes = [_vp, ctypes.POINTER(ctypes.c_float)]
+        L.vh_measure_fp64_peak.argtypes = [_vp, _dp]
         _lib = L
     return _lib
 
@@ -194,6 +197,19 @@ class Context:
         ms = ctypes.c_float()
         self._chk(self.L.vh_time_kernel(self._h, what, reps, 1 if flush_l2 else 0, ctypes.byref(ms)))
         return ms.value
+
+    def timer_start(self):
+        self._chk(self.L.vh_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        self._chk(self.L.vh_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def measure_fp64_peak(self):
+        v = ctypes.c_double()
+        self._chk(self.L.vh_measure_fp64_peak(self._h, ctypes.byref(v)))
+        return v.value
 
     def timers(self, reset=False):
         ms = (ctypes.c_double * 5)()

@@ -594,7 +594,8 @@ int vh_create(const vh_mesh_desc *d, int cuda_device, vh_ctx **out)
   ctx->NL      = 18 * (int64_t)ctx->n_local;
   int rc       = VH_OK;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev1) != cudaSuccess)
+      cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreate(&ctx->ev2) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev3) != cudaSuccess)
     rc = vh_fail(ctx, VH_ERR_CUDA, "stream/event creation failed");
   if (rc == VH_OK)
     rc = build(ctx, d);
@@ -638,6 +639,10 @@ int vh_destroy(vh_ctx *ctx)
     cudaEventDestroy(ctx->ev0);
   if (ctx->ev1)
     cudaEventDestroy(ctx->ev1);
+  if (ctx->ev2)
+    cudaEventDestroy(ctx->ev2);
+  if (ctx->ev3)
+    cudaEventDestroy(ctx->ev3);
   if (ctx->stream)
     cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -964,6 +969,67 @@ int vh_get_timers(vh_ctx *ctx, double ms[5], int64_t *n_launches, int reset)
         ctx->t_ms[i] = 0;
       ctx->n_launches = 0;
     }
+  return VH_OK;
+}
+
+int vh_timer_start(vh_ctx *ctx)
+{
+  VH_REQUIRE(ctx);
+  VH_CUDA(cudaSetDevice(ctx->device));
+  VH_CUDA(cudaStreamSynchronize(ctx->stream));
+  VH_CUDA(cudaEventRecord(ctx->ev2, ctx->stream));
+  return VH_OK;
+}
+int vh_timer_stop(vh_ctx *ctx, float *ms)
+{
+  VH_REQUIRE(ctx);
+  VH_CUDA(cudaEventRecord(ctx->ev3, ctx->stream));
+  VH_CUDA(cudaEventSynchronize(ctx->ev3));
+  VH_CUDA(cudaEventElapsedTime(ms, ctx->ev2, ctx->ev3));
+  return VH_OK;
+}
+
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters)
+{
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    a[k] = 1.0 + 1e-9 * (threadIdx.x + k);
+  const double m = 1.0 + 1e-12, b = 1e-12;
+  for (int i = 0; i < iters; ++i)
+    {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        a[k] = fma(a[k], m, b);
+    }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    s += a[k];
+  if (s == 12345.678)
+    out[0] = s; // keep the chain alive
+}
+
+int vh_measure_fp64_peak(vh_ctx *ctx, double *tflops)
+{
+  VH_REQUIRE(ctx);
+  VH_CUDA(cudaSetDevice(ctx->device));
+  const int grid = 148 * 8, iters = 1 << 15;
+  double    best = 0.0;
+  for (int rep = 0; rep < 4; ++rep)
+    {
+      VH_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+      k_dfma_peak<<<grid, 256, 0, ctx->stream>>>(ctx->scal + VH_SCAL_MISC + 4, iters);
+      VH_LAUNCH_CHECK();
+      VH_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+      VH_CUDA(cudaEventSynchronize(ctx->ev1));
+      float ms = 0;
+      VH_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      const double tf = 2.0 * 8.0 * (double)iters * grid * 256 / (ms * 1e-3) * 1e-12;
+      if (rep > 0 && tf > best)
+        best = tf;
+    }
+  *tflops = best;
   return VH_OK;
 }
 
