@@ -55,31 +55,50 @@ def peaks():
 
 
 class ClockSampler:
+    """Polls nvidia-smi (one-shot queries, ~5 Hz) from a thread while the timed region runs."""
+
     def __init__(self, gpu_index):
         self.rows = []
-        self.proc = None
         self.gpu = gpu_index
+        self.family = "clocks_event_reasons"
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _query(self):
+        f = self.family
+        return ("clocks.sm,clocks.max.sm,power.draw,%s.hw_slowdown,%s.hw_thermal_slowdown,%s.sw_thermal_slowdown,"
+                "%s.sw_power_cap" % (f, f, f, f))
+
+    def _once(self):
+        p = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self._query(), "--format=csv,noheader,nounits"],
+                           capture_output=True, text=True, timeout=20)
+        return p.returncode, p.stdout.strip()
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                rc, out = self._once()
+                if rc == 0 and out:
+                    self.rows.append([s.strip() for s in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.15)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu),
-                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            rc, out = self._once()
+            if rc != 0 or "not a valid" in out.lower():
+                self.family = "clocks_throttle_reasons"
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([s.strip() for s in line.split(",")])
+            self._thr = None
 
     def stop(self):
-        if self.proc is None:
+        if self._thr is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        self._stop.set()
+        self._thr.join(timeout=30)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:

@@ -20,4 +20,16 @@ extern "C" void vht_pointwise(const double *A, const double *coef, double *g18, 
     }
   *f = vh_bulk_energy(prod, alpha, beta);
 }
+// same outputs through the table-driven single-entry evaluation the kernels use
+extern "C" void vht_hessian_entries(const double *A, const double *coef, double *H324)
+{
+  double prod[72], ztab[324];
+  for (int e = 0; e < 36; ++e)
+    vh_product_entry(A, e, prod + 2 * e);
+  for (int e = 0; e < 162; ++e)
+    vh_ztable_entry(A, e, ztab);
+  for (int c = 0; c < 18; ++c)
+    for (int d = 0; d < 18; ++d)
+      H324[18 * c + d] = vh_hessian_entry(A, prod, ztab, c, d, coef[3], coef + 4);
+}
 extern "C" int vht_sym_index(int c, int d) { return vh_sym_index(c, d); }

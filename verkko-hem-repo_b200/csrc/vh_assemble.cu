@@ -54,23 +54,24 @@ __device__ __forceinline__ double block_sum(double v, double *s_red)
 // 1. pointwise kernel
 // ------------------------------------------------------------------------------------------------
 template <int NN, int NQ>
-__global__ void __launch_bounds__(NQ == 8 ? 160 : 512) k_pointwise(const int32_t *__restrict__ cell_nodes, const double *__restrict__ cell_h,
-                            const uint32_t *__restrict__ cell_faces, const uint8_t *__restrict__ cell_owned,
-                            const double *__restrict__ x, VhTables tab, VhCoef cf, int want_h, int want_e,
-                            double *__restrict__ Hq, double *__restrict__ Rc, double *__restrict__ Dc,
-                            double *__restrict__ avgD, double *__restrict__ Ec)
+__global__ void __launch_bounds__(NQ == 8 ? 160 : 512)
+  k_pointwise(const int32_t *__restrict__ cell_nodes, const double *__restrict__ cell_h, const uint32_t *__restrict__ cell_faces,
+              const uint8_t *__restrict__ cell_owned, const double *__restrict__ x, VhTables tab, VhCoef cf, int want_h, int want_e,
+              double *__restrict__ Hq, double *__restrict__ Rc, double *__restrict__ Dc, double *__restrict__ avgD,
+              double *__restrict__ Ec)
 {
   extern __shared__ double sm[];
-  double *sU  = sm;               // [NN*18]
-  double *sA  = sU + NN * 18;     // [NQ*18]
-  double *sdA = sA + NQ * 18;     // [NQ*18*3]
-  double *sP  = sdA + NQ * 54;    // [NQ*72]
-  double *sg  = sP + NQ * 72;     // [NQ*18]
-  double *sN  = sg + NQ * 18;     // [NN*NQ]
-  double *sdN = sN + NN * NQ;     // [NN*NQ*3]
-  double *swq = sdN + NN * NQ * 3; // [NQ]
-  double *sred = swq + NQ;        // [32]
-  double *sH  = sred + 32;        // [NQ*324] (only touched when want_h)
+  double *sU   = sm;                // [NN*18]
+  double *sA   = sU + NN * 18;      // [NQ*18]
+  double *sdA  = sA + NQ * 18;      // [NQ*18*3]
+  double *sP   = sdA + NQ * 54;     // [NQ*72]   products R,Q,P,S
+  double *sg   = sP + NQ * 72;      // [NQ*18]
+  double *sHd  = sg + NQ * 18;      // [NQ*18]   diagonal of H_q (unscaled)
+  double *sN   = sHd + NQ * 18;     // [NN*NQ]
+  double *sdN  = sN + NN * NQ;      // [NN*NQ*3]
+  double *swq  = sdN + NN * NQ * 3; // [NQ]
+  double *sred = swq + NQ;          // [32]
+  double *sZ   = sred + 32;         // [NQ*324]  Z1,Z2 tables (only touched when want_h)
 
   const int     t    = threadIdx.x;
   const int64_t cell = blockIdx.x;
@@ -103,44 +104,49 @@ __global__ void __launch_bounds__(NQ == 8 ? 160 : 512) k_pointwise(const int32_t
           d1 += sdN[(a * NQ + q) * 3 + 1] * u;
           d2 += sdN[(a * NQ + q) * 3 + 2] * u;
         }
-      sA[t]           = A;
-      sdA[3 * t + 0]  = d0 * ih[0];
-      sdA[3 * t + 1]  = d1 * ih[1];
-      sdA[3 * t + 2]  = d2 * ih[2];
+      sA[t]          = A;
+      sdA[3 * t + 0] = d0 * ih[0];
+      sdA[3 * t + 1] = d1 * ih[1];
+      sdA[3 * t + 2] = d2 * ih[2];
     }
   __syncthreads();
-  for (int i = t; i < NQ * 36; i += blockDim.x)
-    {
-      const int q = i / 36, e = i - 36 * q;
-      vh_product_entry(sA + q * 18, e, sP + q * 72 + 2 * e);
-    }
+  // per quadrature point: 36 product entries (+ 162 Z-table entries for the Hessian)
+  {
+    const int per_q = want_h ? 198 : 36;
+    for (int i = t; i < NQ * per_q; i += blockDim.x)
+      {
+        const int q = i / per_q, e = i - per_q * q;
+        if (e < 36)
+          vh_product_entry(sA + q * 18, e, sP + q * 72 + 2 * e);
+        else
+          vh_ztable_entry(sA + q * 18, e - 36, sZ + q * VH_BLK);
+      }
+  }
   __syncthreads();
   if (t < 18 * NQ)
     {
       const int q = t / 18, c = t - 18 * q;
       sg[t]       = vh_g_component(sA + q * 18, sP + q * 72, c, cf.alpha, cf.beta);
-      if (want_h)
-        {
-          double col[18];
-          vh_hessian_column(sA + q * 18, sP + q * 72, c, cf.alpha, cf.beta, col);
-#pragma unroll
-          for (int cc = 0; cc < 18; ++cc)
-            sH[q * VH_BLK + cc * 18 + c] = col[cc];
-        }
     }
-  __syncthreads();
   if (want_h)
-    {
+    { // the 171 unique entries of every H_q, stored pre-multiplied by the cell volume (JxW = w_q * vol)
       double *dst = Hq + cell * (int64_t)(NQ * VH_SYMP);
       for (int i = t; i < NQ * VH_SYMP; i += blockDim.x)
         {
-          const int q = i / VH_SYMP, s = i - VH_SYMP * q;
+          const int q = i / VH_SYMP, sidx = i - VH_SYMP * q;
           double    v = 0.0;
-          if (s < VH_SYM)
-            v = sH[q * VH_BLK + c_symc[s] * 18 + c_symd[s]];
+          if (sidx < VH_SYM)
+            {
+              const int c = c_symc[sidx], d = c_symd[sidx];
+              v           = vh_hessian_entry(sA + q * 18, sP + q * 72, sZ + q * VH_BLK, c, d, cf.alpha, cf.beta);
+              if (c == d)
+                sHd[q * 18 + c] = v;
+              v *= vol;
+            }
           dst[i] = v;
         }
     }
+  __syncthreads();
 
   // cell rhs (assemble.cc:257-276) and cell-matrix diagonal
   const uint32_t faces = cell_faces[cell];
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(NQ == 8 ? 160 : 512) k_pointwise(const int32_t
           const double  gxc = xc == 0 ? gx : (xc == 1 ? gy : gz);
           r += JxW * (Na * sg[q * 18 + c] + cf.K1 * (gx * dA[0] + gy * dA[1] + gz * dA[2]) + cf.K23 * gxc * div);
           if (want_h)
-            dg += JxW * Na * Na * sH[q * VH_BLK + c * 18 + c];
+            dg += JxW * Na * Na * sHd[q * 18 + c];
         }
       if (want_h)
         {
@@ -246,19 +252,54 @@ __global__ void __launch_bounds__(NQ == 8 ? 160 : 512) k_pointwise(const int32_t
 // ------------------------------------------------------------------------------------------------
 #define VH_FAST_THREADS 96
 #define VH_FAST_ACTIVE 86 /* 86 threads x 2 packed entries = 172 */
+#define VH_FAST_STAGES 4
+#define VH_CELL_H_BYTES (8 * VH_SYMP * 8) /* one cell's 8 x 172 doubles: 11008 B, a multiple of 16 */
+#define VH_FAST_SMEM (VH_FAST_STAGES * VH_CELL_H_BYTES + 2 * VH_BLK * 8 + VH_BLK * 8 + VH_FAST_STAGES * 8 + 36 * 4)
 
-__global__ void __launch_bounds__(VH_FAST_THREADS)
-  k_rows_fast_q1(const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells,
-                 const int8_t *__restrict__ fast_slot, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
-                 const uint32_t *__restrict__ dirmask, const double *__restrict__ cell_h,
-                 const uint32_t *__restrict__ cell_faces, const double *__restrict__ Hq, const double *__restrict__ Dc,
-                 const double *__restrict__ avgD, VhTables tab, VhCoef cf, double *__restrict__ vals)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-  __shared__ __align__(16) double s_tile[2][VH_BLK];
-  __shared__ double               s_GS[27 * 9];
-  __shared__ double               s_FS[27 * 3];
-  __shared__ int                  s_cells[8];
-  __shared__ int                  s_pos[27];
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "VH_WAIT_%=:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra VH_DONE_%=;\n"
+               "bra VH_WAIT_%=;\n"
+               "VH_DONE_%=:\n"
+               "}" ::"r"(smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(VH_FAST_THREADS, 4)
+  k_rows_fast_q1(const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells,
+                 const int8_t *__restrict__ fast_slot, const int32_t *__restrict__ fast_class,
+                 const double *__restrict__ class_tab, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                 const uint32_t *__restrict__ dirmask, const double *__restrict__ Hq, const double *__restrict__ Dc,
+                 const double *__restrict__ avgD, VhCoef cf, double *__restrict__ vals)
+{
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double   *s_H    = reinterpret_cast<double *>(smraw);                                     // [4][8*172]
+  double   *s_tile = reinterpret_cast<double *>(smraw + VH_FAST_STAGES * VH_CELL_H_BYTES);  // [2][324]
+  double   *s_cls  = s_tile + 2 * VH_BLK;                                                   // [27][12]: GS(9), FS(3)
+  uint64_t *s_bar  = reinterpret_cast<uint64_t *>(s_cls + VH_BLK);                          // [4]
+  int      *s_cells = reinterpret_cast<int *>(s_bar + VH_FAST_STAGES);                      // [8]
+  int      *s_pos   = s_cells + 8;                                                          // [27]
 
   const int t = threadIdx.x;
   const int r = blockIdx.x;
@@ -267,158 +308,177 @@ __global__ void __launch_bounds__(VH_FAST_THREADS)
     s_cells[t] = fast_cells[(size_t)r * 8 + t];
   if (t >= 32 && t < 59)
     s_pos[t - 32] = fast_slot[(size_t)r * 32 + (t - 32)];
+  if (t == 64)
+    {
+#pragma unroll
+      for (int k = 0; k < VH_FAST_STAGES; ++k)
+        mbar_init(s_bar + k, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  {
+    const double *cls = class_tab + (size_t)fast_class[r] * VH_BLK;
+    for (int i = t; i < VH_BLK; i += VH_FAST_THREADS)
+      s_cls[i] = cls[i];
+  }
   __syncthreads();
 
-  // geometry-only terms per stencil slot:  GS[s][x][y] = sum_(o,b)->s vol_o Gref[7-o][b][x][y] / (h_x h_y)
-  for (int i = t; i < 27 * 9; i += VH_FAST_THREADS)
+  // TMA producer: thread 0 streams the incident cells' pre-scaled H_q tables (11 KB each, contiguous) into the ring
+  auto issue = [&](int o) {
+    const int e = s_cells[o];
+    if (e >= 0)
+      {
+        uint64_t *bar = s_bar + (o & (VH_FAST_STAGES - 1));
+        mbar_expect_tx(bar, VH_CELL_H_BYTES);
+        bulk_g2s(s_H + (size_t)(o & (VH_FAST_STAGES - 1)) * (8 * VH_SYMP), Hq + (size_t)e * (8 * VH_SYMP), VH_CELL_H_BYTES, bar);
+      }
+  };
+  if (t == 0)
     {
-      const int s = i / 9, xy = i - 9 * s, xx = xy / 3, yy = xy - 3 * xx;
-      const int sx = s % 3, sy = (s / 3) % 3, sz = s / 9;
-      double    acc = 0.0;
-      for (int o = 0; o < 8; ++o)
-        {
-          const int e = s_cells[o];
-          const int bx = sx - (o & 1), by = sy - ((o >> 1) & 1), bz = sz - (o >> 2);
-          if (e < 0 || bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1)
-            continue;
-          const int     b = bx + 2 * by + 4 * bz, a = 7 - o;
-          const double *h = cell_h + 4 * (size_t)e;
-          acc += h[3] / (h[xx] * h[yy]) * tab.Gref[(size_t)(a * 8 + b) * 9 + xy];
-        }
-      s_GS[i] = acc;
-    }
-  const bool robin = cf.bt < 1e10;
-  for (int i = t; i < 27 * 3; i += VH_FAST_THREADS)
-    {
-      const int s = i / 3, xx = i - 3 * s;
-      const int sx = s % 3, sy = (s / 3) % 3, sz = s / 9;
-      double    acc = 0.0;
-      if (robin)
-        for (int o = 0; o < 8; ++o)
-          {
-            const int e = s_cells[o];
-            const int bx = sx - (o & 1), by = sy - ((o >> 1) & 1), bz = sz - (o >> 2);
-            if (e < 0 || bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1)
-              continue;
-            const uint32_t faces = cell_faces[e];
-            if (!faces)
-              continue;
-            const int     b = bx + 2 * by + 4 * bz, a = 7 - o;
-            const double *h = cell_h + 4 * (size_t)e;
-            for (int f = 0; f < 6; ++f)
-              {
-                const int bid = (faces >> (4 * f)) & 15u;
-                if (bid < 2 || bid > 4 || xx == bid - 2)
-                  continue;
-                acc += cf.K1 / cf.bt * (h[3] / h[f / 2]) * tab.Mf[(size_t)(f * 8 + a) * 8 + b];
-              }
-          }
-      s_FS[i] = acc;
+#pragma unroll
+      for (int o = 0; o < VH_FAST_STAGES; ++o)
+        issue(o);
     }
 
-  // bulk part:  acc[s](c,d) = sum_o sum_q sum_b->s  vol_o w_q N_a(q) N_b(q) H_{o,q}(c,d)
+  // bulk part:  acc[s](c,d) = sum_o sum_q sum_b->s  w_q N_a(q) N_b(q) (vol_o H_{o,q})(c,d)
   double acc0[27], acc1[27];
 #pragma unroll
   for (int s = 0; s < 27; ++s)
     acc0[s] = acc1[s] = 0.0;
-  if (t < VH_FAST_ACTIVE)
-    {
+  uint32_t uses = 0; // bit k: parity of the next completed phase of stage k
 #pragma unroll
-      for (int o = 0; o < 8; ++o)
-        {
-          const int e = s_cells[o];
-          if (e >= 0)
+  for (int o = 0; o < 8; ++o)
+    {
+      if (o == 2 || o == 4)
+        { // stages {0,1} (resp. {2,3}) have been consumed by every thread: refill them with cells o+2, o+3
+          __syncthreads();
+          if (t == 0)
             {
-              const double   vol = cell_h[4 * (size_t)e + 3];
-              const double2 *Hp  = reinterpret_cast<const double2 *>(Hq + (size_t)e * (8 * VH_SYMP)) + t;
+              issue(o + 2);
+              issue(o + 3);
+            }
+        }
+      const int e = s_cells[o];
+      if (e >= 0)
+        {
+          const int st = o & (VH_FAST_STAGES - 1);
+          mbar_wait(s_bar + st, (uses >> st) & 1u);
+          uses ^= 1u << st;
+          if (t < VH_FAST_ACTIVE)
+            {
+              const double2 *Hp = reinterpret_cast<const double2 *>(s_H + (size_t)st * (8 * VH_SYMP)) + t;
 #pragma unroll
               for (int q = 0; q < 8; ++q)
                 {
-                  const double2 hv = __ldg(Hp + q * (VH_SYMP / 2));
-                  const double  hx = hv.x * vol, hy = hv.y * vol;
+                  const double2 hv = Hp[q * (VH_SYMP / 2)];
 #pragma unroll
                   for (int b = 0; b < 8; ++b)
                     {
                       const int    s = ((o & 1) + (b & 1)) + 3 * (((o >> 1) & 1) + ((b >> 1) & 1)) + 9 * ((o >> 2) + (b >> 2));
                       const double w = c_W1[((7 - o) * 8 + b) * 8 + q];
-                      acc0[s]        = fma(w, hx, acc0[s]);
-                      acc1[s]        = fma(w, hy, acc1[s]);
+                      acc0[s]        = fma(w, hv.x, acc0[s]);
+                      acc1[s]        = fma(w, hv.y, acc1[s]);
                     }
                 }
             }
         }
     }
-  __syncthreads();
 
+  // ---- write the block row: geometry-only terms, Dirichlet masks, coalesced 16-byte stores ----
   const uint32_t maskI = dirmask[I];
   const int      rp    = row_ptr[I];
-  const int      p0    = 2 * t, p1 = 2 * t + 1;
-  int            c0 = 0, d0 = 0, c1 = 0, d1 = 0;
-  if (t < VH_FAST_ACTIVE)
-    {
-      c0 = c_symc[p0], d0 = c_symd[p0];
-      c1 = c_symc[p1], d1 = c_symd[p1];
-    }
-  const bool have1 = t < VH_FAST_ACTIVE && p1 < VH_SYM;
-  int        n_done = 0;
+  const double   kf    = cf.bt < 1e10 ? cf.K1 / cf.bt : 0.0;
+  const bool     act   = t < VH_FAST_ACTIVE;
+  const int      c0 = c_symc[act ? 2 * t : 0], d0 = c_symd[act ? 2 * t : 0];
+  const int      c1 = c_symc[act ? 2 * t + 1 : 0], d1 = c_symd[act ? 2 * t + 1 : 0];
+  const bool     have1 = act && (2 * t + 1 < VH_SYM);
+  const int      x0c = c0 % 3, x0d = d0 % 3, x1c = c1 % 3, x1d = d1 % 3;
+  const bool     same0 = (c0 / 3 == d0 / 3), same1 = (c1 / 3 == d1 / 3), diag0 = (c0 == d0), diag1 = (c1 == d1);
+  const int      g0cd = x0c * 3 + x0d, g0dc = x0d * 3 + x0c, g1cd = x1c * 3 + x1d, g1dc = x1d * 3 + x1c;
+  const int      o0cd = c0 * 18 + d0, o0dc = d0 * 18 + c0, o1cd = c1 * 18 + d1, o1dc = d1 * 18 + c1;
+  const bool     rI0c = (maskI >> c0) & 1u, rI0d = (maskI >> d0) & 1u, rI1c = (maskI >> c1) & 1u, rI1d = (maskI >> d1) & 1u;
+  int            n_done = 0;
 #pragma unroll
   for (int s = 0; s < 27; ++s)
     {
       const int pos = s_pos[s];
       if (pos < 0)
         continue; // block-uniform
-      double        *tile  = s_tile[n_done & 1];
-      const int      J     = col[rp + pos];
-      const uint32_t maskJ = dirmask[J];
-      const double   trG   = cf.K1 * (s_GS[s * 9 + 0] + s_GS[s * 9 + 4] + s_GS[s * 9 + 8]);
-      if (t < VH_FAST_ACTIVE)
+      double        *tile  = s_tile + (n_done & 1) * VH_BLK;
+      const uint32_t maskJ = dirmask[col[rp + pos]];
+      const double  *G     = s_cls + s * 12;
+      if (act)
         {
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
+          {
+            double vcd = acc0[s], vdc = acc0[s];
+            if (diag0)
+              vcd += cf.K1 * (G[0] + G[4] + G[8]) + kf * G[9 + x0c];
+            if (same0)
+              {
+                vcd += cf.K23 * G[g0cd];
+                vdc += cf.K23 * G[g0dc];
+              }
+            if (rI0c || ((maskJ >> d0) & 1u))
+              vcd = 0.0;
+            if (rI0d || ((maskJ >> c0) & 1u))
+              vdc = 0.0;
+            if (s == 13 && diag0 && rI0c)
+              { // constrained diagonal: sum over cells of |a_ii| (mean |diag| of the cell if a_ii == 0)
+                double dsum = 0.0;
+                for (int o = 0; o < 8; ++o)
+                  {
+                    const int e = s_cells[o];
+                    if (e < 0)
+                      continue;
+                    double dv = fabs(Dc[(size_t)e * 144 + (7 - o) * 18 + c0]);
+                    if (dv == 0.0)
+                      dv = avgD[e];
+                    dsum += dv;
+                  }
+                vcd = dsum;
+              }
+            tile[o0cd] = vcd;
+            if (!diag0)
+              tile[o0dc] = vdc;
+          }
+          if (have1)
             {
-              if (k == 1 && !have1)
-                break;
-              const int    c = k ? c1 : c0, d = k ? d1 : d0;
-              const double a = k ? acc1[s] : acc0[s];
-              const int    xc = c % 3, xd = d % 3;
-              double       vcd = a, vdc = a;
-              if (c == d)
-                vcd += trG + s_FS[s * 3 + xc];
-              if (c / 3 == d / 3)
+              double vcd = acc1[s], vdc = acc1[s];
+              if (diag1)
+                vcd += cf.K1 * (G[0] + G[4] + G[8]) + kf * G[9 + x1c];
+              if (same1)
                 {
-                  vcd += cf.K23 * s_GS[s * 9 + xc * 3 + xd];
-                  vdc += cf.K23 * s_GS[s * 9 + xd * 3 + xc];
+                  vcd += cf.K23 * G[g1cd];
+                  vdc += cf.K23 * G[g1dc];
                 }
-              // component-masked Dirichlet DoFs: row and column dropped (distribute_local_to_global)
-              if (((maskI >> c) & 1u) || ((maskJ >> d) & 1u))
+              if (rI1c || ((maskJ >> d1) & 1u))
                 vcd = 0.0;
-              if (((maskI >> d) & 1u) || ((maskJ >> c) & 1u))
+              if (rI1d || ((maskJ >> c1) & 1u))
                 vdc = 0.0;
-              if (s == 13 && c == d && ((maskI >> c) & 1u))
-                { // constrained diagonal: sum over cells of |a_ii| (mean |diag| of the cell if a_ii == 0)
+              if (s == 13 && diag1 && rI1c)
+                {
                   double dsum = 0.0;
                   for (int o = 0; o < 8; ++o)
                     {
                       const int e = s_cells[o];
                       if (e < 0)
                         continue;
-                      double dv = fabs(Dc[(size_t)e * 144 + (7 - o) * 18 + c]);
+                      double dv = fabs(Dc[(size_t)e * 144 + (7 - o) * 18 + c1]);
                       if (dv == 0.0)
                         dv = avgD[e];
                       dsum += dv;
                     }
                   vcd = dsum;
                 }
-              tile[c * 18 + d] = vcd;
-              if (c != d)
-                tile[d * 18 + c] = vdc;
+              tile[o1cd] = vcd;
+              if (!diag1)
+                tile[o1dc] = vdc;
             }
         }
       __syncthreads();
       double2       *dst = reinterpret_cast<double2 *>(vals + (size_t)(rp + pos) * VH_BLK);
       const double2 *src = reinterpret_cast<const double2 *>(tile);
       for (int i = t; i < VH_BLK / 2; i += VH_FAST_THREADS)
-        dst[i] = src[i];
+        __stcs(dst + i, src[i]); // streaming store: the block is not re-read by this kernel
       ++n_done;
     }
 }
@@ -529,8 +589,7 @@ __global__ void k_cells_slow(SlowArgs A, VhTables tab, VhCoef cf, int want_matri
             const int sidx = c <= d ? vh_sym_index(c, d) : vh_sym_index(d, c);
             double    v = 0.0;
             for (int q = 0; q < NQ; ++q)
-              v += swq[q] * sN[a * NQ + q] * sN[b * NQ + q] * sH[q * VH_SYMP + sidx];
-            v *= vol;
+              v += swq[q] * sN[a * NQ + q] * sN[b * NQ + q] * sH[q * VH_SYMP + sidx]; // H_q is stored pre-scaled by vol
             if (c == d)
               v += vol * cf.K1 * (G[0] * ih[0] * ih[0] + G[4] * ih[1] * ih[1] + G[8] * ih[2] * ih[2]);
             if (c / 3 == d / 3)
@@ -598,7 +657,7 @@ __global__ void k_cells_slow(SlowArgs A, VhTables tab, VhCoef cf, int want_matri
 template <int NN, int NQ>
 size_t pointwise_smem(bool want_h)
 {
-  size_t n = (size_t)NN * 18 + NQ * 18 + NQ * 54 + NQ * 72 + NQ * 18 + NN * NQ + NN * NQ * 3 + NQ + 32;
+  size_t n = (size_t)NN * 18 + NQ * 18 + NQ * 54 + NQ * 72 + NQ * 18 + NQ * 18 + NN * NQ + NN * NQ * 3 + NQ + 32;
   if (want_h)
     n += (size_t)NQ * VH_BLK;
   return n * sizeof(double);
@@ -663,9 +722,16 @@ int vhk_rows_fast(vh_ctx *ctx)
 {
   if (ctx->n_fast == 0)
     return VH_OK;
-  k_rows_fast_q1<<<ctx->n_fast, VH_FAST_THREADS, 0, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->row_ptr,
-                                                                  ctx->col, ctx->dirmask, ctx->cell_h, ctx->cell_faces, ctx->Hq,
-                                                                  ctx->Dc, ctx->avgD, ctx->tab, ctx->coef, ctx->vals);
+  static bool attr_set = false;
+  if (!attr_set)
+    {
+      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
+      attr_set = true;
+    }
+  k_rows_fast_q1<<<ctx->n_fast, VH_FAST_THREADS, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot,
+                                                                             ctx->fast_class, ctx->class_tab, ctx->row_ptr, ctx->col,
+                                                                             ctx->dirmask, ctx->Hq, ctx->Dc, ctx->avgD, ctx->coef,
+                                                                             ctx->vals);
   VH_LAUNCH_CHECK();
   return VH_OK;
 }

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <mutex>
 
 static std::string g_create_err;
@@ -348,6 +349,8 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   for (int I = 0; I < n_owned; ++I)
     diag_pos[I] = (int32_t)(std::lower_bound(col.begin() + row_ptr[I], col.begin() + row_ptr[I + 1], I) - col.begin());
 
+  HostTables T = make_tables(ctx->degree);
+
   // ---- classify rows: lattice rows go to the write-once row kernel ----
   std::vector<uint8_t> row_slow(n_owned, 1);
   std::vector<int32_t> fast_rows, fast_cells;
@@ -412,6 +415,64 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
         fast_cells.insert(fast_cells.end(), cells8, cells8 + 8);
         fast_slot.insert(fast_slot.end(), pos27, pos27 + 32);
       }
+  // geometry classes of the fast rows: the gradient (K1, K2+K3) and Robin-face forms depend only on the shapes of
+  // the incident cells, so rows with identical stencils share one 27 x 12 table (a uniform mesh has a few dozen).
+  std::vector<int32_t> fast_class(fast_rows.size());
+  std::vector<double>  class_tab;
+  {
+    std::map<std::string, int32_t> class_of;
+    for (size_t r = 0; r < fast_rows.size(); ++r)
+      {
+        const int32_t *c8 = &fast_cells[8 * r];
+        std::string    sig;
+        for (int o = 0; o < 8; ++o)
+          {
+            if (c8[o] < 0)
+              {
+                sig.push_back('-');
+                continue;
+              }
+            sig.push_back('+');
+            sig.append(reinterpret_cast<const char *>(&h4[4 * (size_t)c8[o]]), 3 * sizeof(double));
+            sig.append(reinterpret_cast<const char *>(&faces[c8[o]]), sizeof(uint32_t));
+          }
+        auto it = class_of.find(sig);
+        if (it == class_of.end())
+          {
+            const int32_t id = (int32_t)class_of.size();
+            class_of[sig]    = id;
+            class_tab.resize((size_t)(id + 1) * VH_BLK, 0.0);
+            double *tab = &class_tab[(size_t)id * VH_BLK];
+            for (int o = 0; o < 8; ++o)
+              {
+                const int e = c8[o];
+                if (e < 0)
+                  continue;
+                const double *h = &h4[4 * (size_t)e];
+                const int     a = 7 - o;
+                for (int b = 0; b < 8; ++b)
+                  {
+                    const int sl = ((o & 1) + (b & 1)) + 3 * (((o >> 1) & 1) + ((b >> 1) & 1)) + 9 * ((o >> 2) + (b >> 2));
+                    for (int x = 0; x < 3; ++x)
+                      for (int y = 0; y < 3; ++y)
+                        tab[sl * 12 + 3 * x + y] += h[3] / (h[x] * h[y]) * T.Gref[((size_t)a * 8 + b) * 9 + 3 * x + y];
+                    for (int f = 0; f < 6; ++f)
+                      {
+                        const int bid = (faces[e] >> (4 * f)) & 15u;
+                        if (bid < 2 || bid > 4)
+                          continue;
+                        for (int x = 0; x < 3; ++x)
+                          if (x != bid - 2)
+                            tab[sl * 12 + 9 + x] += (h[3] / h[f / 2]) * T.Mf[((size_t)f * 8 + a) * 8 + b];
+                      }
+                  }
+              }
+            it = class_of.find(sig);
+          }
+        fast_class[r] = it->second;
+      }
+    ctx->n_classes = (int32_t)class_of.size();
+  }
   std::vector<int32_t> slow_rows, slow_cells;
   for (int I = 0; I < n_owned; ++I)
     if (row_slow[I])
@@ -437,12 +498,13 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   VH_TRY(vh_dev_upload(ctx, &ctx->fast_rows, fast_rows.data(), fast_rows.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->fast_cells, fast_cells.data(), fast_cells.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->fast_slot, fast_slot.data(), fast_slot.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->fast_class, fast_class.data(), fast_class.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->class_tab, class_tab.data(), class_tab.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->slow_rows, slow_rows.data(), slow_rows.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->slow_cells, slow_cells.data(), slow_cells.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->row_slow, row_slow.data(), row_slow.size()));
 
   // ---- reference-cell tables ----
-  HostTables T   = make_tables(ctx->degree);
   ctx->tab.degree = ctx->degree;
   ctx->tab.nn     = T.nn;
   ctx->tab.nq     = T.nq;
@@ -618,7 +680,7 @@ int vh_destroy(vh_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
   vh_comm_destroy(ctx);
   void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
-                  ctx->diag_pos, ctx->minv, ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->slow_rows, ctx->row_slow,
+                  ctx->diag_pos, ctx->minv, ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->slow_rows, ctx->row_slow,
                   ctx->slow_cells, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
                   ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
                   ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,

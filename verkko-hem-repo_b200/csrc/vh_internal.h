@@ -79,6 +79,9 @@ struct vh_ctx
   int32_t *fast_rows  = nullptr; // [n_fast]
   int32_t *fast_cells = nullptr; // [n_fast][8]   cell in octant o (row node is local vertex 7-o), -1 = absent
   int8_t  *fast_slot  = nullptr; // [n_fast][32]  stencil slot (dx+1)+3(dy+1)+9(dz+1) -> position in the row, -1 = absent
+  int32_t *fast_class = nullptr; // [n_fast]      geometry class of the row's stencil
+  double  *class_tab  = nullptr; // [n_classes][27][12] per slot: GS[3][3] = sum vol/(h_x h_y) Gref, FS[3] = sum area Mf (x != normal)
+  int32_t  n_classes  = 0;
   int32_t *slow_rows  = nullptr; // [n_slow_rows]
   uint8_t *row_slow   = nullptr; // [n_owned]
   int32_t *slow_cells = nullptr; // [n_slow_cells]

@@ -41,20 +41,36 @@ __global__ void __launch_bounds__(VH_SPMV_WARPS * 32)
   for (int r = 0; r < 6; ++r)
     xoff[r] = 2 * ((lane + 32 * r) % 9);
   const bool last = lane < 2; // round 5 covers double2 160,161 only
-  for (int b = b0; b < b1; ++b)
+  for (int base = b0; base < b1; base += 32)
     {
-      const double2 *B  = reinterpret_cast<const double2 *>(vals + (size_t)b * VH_BLK);
-      const double  *xj = x + 18 * (size_t)__ldg(col + b);
-      double2        v[6];
-#pragma unroll
-      for (int r = 0; r < 5; ++r)
-        v[r] = __ldcs(B + lane + 32 * r); // streaming: every matrix byte is used exactly once per SpMV
-      v[5] = last ? __ldcs(B + lane + 160) : make_double2(0.0, 0.0);
-#pragma unroll
-      for (int r = 0; r < 6; ++r)
+      // the row's block-column indices, one per lane, handed out by shuffle (no dependent global load per block)
+      const int nchunk = min(32, b1 - base);
+      const int mycol  = lane < nchunk ? __ldg(col + base + lane) : 0;
+      for (int j = 0; j < nchunk; j += 2)
         {
-          const double2 xv = *reinterpret_cast<const double2 *>(xj + xoff[r]);
-          acc[r]           = fma(v[r].x, xv.x, fma(v[r].y, xv.y, acc[r]));
+          const bool     two = j + 1 < nchunk;
+          const double2 *B0  = reinterpret_cast<const double2 *>(vals + (size_t)(base + j) * VH_BLK);
+          const double2 *B1  = B0 + (two ? VH_BLK / 2 : 0);
+          double2        v0[6], v1[6];
+          // 12 independent 16-byte streaming loads per lane in flight (every matrix byte is used once per SpMV)
+#pragma unroll
+          for (int r = 0; r < 5; ++r)
+            v0[r] = __ldcs(B0 + lane + 32 * r);
+          v0[5] = last ? __ldcs(B0 + lane + 160) : make_double2(0.0, 0.0);
+#pragma unroll
+          for (int r = 0; r < 5; ++r)
+            v1[r] = two ? __ldcs(B1 + lane + 32 * r) : make_double2(0.0, 0.0);
+          v1[5] = (two && last) ? __ldcs(B1 + lane + 160) : make_double2(0.0, 0.0);
+          const double *x0 = x + 18 * (size_t)__shfl_sync(0xffffffffu, mycol, j);
+          const double *x1 = x + 18 * (size_t)__shfl_sync(0xffffffffu, mycol, two ? j + 1 : j);
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+            {
+              const double2 xa = *reinterpret_cast<const double2 *>(x0 + xoff[r]);
+              const double2 xb = *reinterpret_cast<const double2 *>(x1 + xoff[r]);
+              acc[r]           = fma(v0[r].x, xa.x, fma(v0[r].y, xa.y, acc[r]));
+              acc[r]           = fma(v1[r].x, xb.x, fma(v1[r].y, xb.y, acc[r]));
+            }
         }
     }
 #pragma unroll
@@ -78,35 +94,38 @@ __global__ void __launch_bounds__(128)
   k_block_invert(int n_rows, const int32_t *__restrict__ diag_pos, const double *__restrict__ vals, double *__restrict__ minv,
                  int *__restrict__ n_singular)
 {
-  __shared__ double s_M[4][18][37]; // [A | I], padded
+  // Register-resident Gauss-Jordan: lane r < 18 keeps row r of [A | I] in registers, the pivot row is broadcast by
+  // shuffles, and rows are never swapped physically: the lane that pivots on column k ends up holding row k of A^-1.
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int row  = blockIdx.x * 4 + wid;
   if (row >= n_rows)
     return;
-  double(*M)[37]   = s_M[wid];
   const double *B  = vals + (size_t)diag_pos[row] * VH_BLK;
-  for (int i = lane; i < VH_BLK; i += 32)
+  const int     rr = lane < 18 ? lane : 17;
+  double        a[36];
+#pragma unroll
+  for (int c = 0; c < 18; ++c)
     {
-      const int r = i / 18, c = i - 18 * r;
-      M[r][c]      = B[i];
-      M[r][18 + c] = (r == c) ? 1.0 : 0.0;
+      a[c]      = __ldg(B + rr * 18 + c);
+      a[18 + c] = (c == rr) ? 1.0 : 0.0;
     }
-  __syncwarp();
+  bool used     = lane >= 18;
+  int  mycol    = -1;
   bool singular = false;
+#pragma unroll
   for (int k = 0; k < 18; ++k)
     {
-      // pivot search over rows k..17 (lanes own rows)
-      double pv = (lane >= k && lane < 18) ? fabs(M[lane][k]) : -1.0;
-      int    pi = lane;
+      double pv = used ? -1.0 : fabs(a[k]);
+      int    pl = lane;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1)
         {
           const double ov = __shfl_xor_sync(0xffffffffu, pv, o);
-          const int    oi = __shfl_xor_sync(0xffffffffu, pi, o);
-          if (ov > pv || (ov == pv && oi < pi))
+          const int    ol = __shfl_xor_sync(0xffffffffu, pl, o);
+          if (ov > pv || (ov == pv && ol < pl))
             {
               pv = ov;
-              pi = oi;
+              pl = ol;
             }
         }
       if (!(pv > 0.0))
@@ -114,27 +133,21 @@ __global__ void __launch_bounds__(128)
           singular = true;
           break;
         }
-      if (pi != k)
-        for (int c = lane; c < 36; c += 32)
-          {
-            const double tmp = M[k][c];
-            M[k][c]          = M[pi][c];
-            M[pi][c]         = tmp;
-          }
-      __syncwarp();
-      const double inv = 1.0 / M[k][k];
-      __syncwarp();
-      for (int c = lane; c < 36; c += 32)
-        M[k][c] *= inv;
-      __syncwarp();
-      if (lane < 18 && lane != k)
+      const double inv = 1.0 / __shfl_sync(0xffffffffu, a[k], pl);
+      const bool   me  = lane == pl;
+      const double f   = me ? 0.0 : a[k];
+#pragma unroll
+      for (int c = k + 1; c < 36; ++c)
         {
-          const double f = M[lane][k];
-          if (f != 0.0)
-            for (int c = 0; c < 36; ++c)
-              M[lane][c] -= f * M[k][c];
+          const double p = __shfl_sync(0xffffffffu, a[c], pl) * inv;
+          a[c]           = me ? p : fma(-f, p, a[c]);
         }
-      __syncwarp();
+      a[k] = me ? 1.0 : 0.0;
+      if (me)
+        {
+          used  = true;
+          mycol = k;
+        }
     }
   if (singular)
     {
@@ -144,8 +157,13 @@ __global__ void __launch_bounds__(128)
         minv[(size_t)row * VH_BLK + i] = (i / 18 == i % 18) ? 1.0 : 0.0;
       return;
     }
-  for (int i = lane; i < VH_BLK; i += 32)
-    minv[(size_t)row * VH_BLK + i] = M[i / 18][18 + i % 18];
+  if (lane < 18)
+    {
+      double *out = minv + (size_t)row * VH_BLK + mycol * 18;
+#pragma unroll
+      for (int c = 0; c < 18; ++c)
+        out[c] = a[18 + c];
+    }
 }
 
 // y = blockdiag(minv) x : same streaming scheme as the SpMV with exactly one block per row

@@ -173,6 +173,98 @@ VH_HD double vh_bulk_energy(const double *prod, double alpha, const double *beta
   return alpha * Sr + beta[0] * (T.re * T.re + T.im * T.im) + beta[1] * Sr * Sr + beta[2] * I3 + beta[3] * I4 + beta[4] * I5;
 }
 
+
+// ---- table-driven evaluation of single Hessian entries (what the kernels use) -------------------------
+// Every dense term of dg[E] is one entry of   Z1[x,y] = A_x conj(A_y)   or   Z2[x,y] = A_x A_y
+// (x,y = 3*mu+j matrix positions), so H_q costs 162 complex products + a handful of adds per entry instead
+// of ~7 complex products per entry.  ztab[324] = {Z1 (81 x (re,im)), Z2 (81 x (re,im))}.
+VH_HD void vh_ztable_entry(const double *A, int e, double *ztab)
+{
+  const int   which = e / 81, xy = e - 81 * which, x = xy / 9, y = xy - 9 * x;
+  const vh_cx ax{A[x], A[9 + x]}, ay{A[y], A[9 + y]};
+  const vh_cx z = vh_cmul(ax, which ? ay : vh_conj(ay));
+  ztab[2 * e]     = z.re;
+  ztab[2 * e + 1] = z.im;
+}
+
+// H[c][d] from the tables; identical (to rounding) to vh_hessian_column(..., d, ...)[c].
+VH_HD double vh_hessian_entry(const double *A, const double *prod, const double *ztab, int c, int d, double alpha,
+                              const double *beta)
+{
+  const int  pc = c / 9, mu = (c % 9) / 3, j = c % 3;
+  const bool pd = d >= 9;
+  const int  nu = (d % 9) / 3, k = d % 3;
+  const int  x_nk = 3 * nu + k, x_mj = 3 * mu + j, x_mk = 3 * mu + k, x_nj = 3 * nu + j;
+  double     re = 0.0, im = 0.0;
+  // G += w * s * z   and   G += w * conj(s) * z   with s = 1 (d<9) or i (d>=9)
+#define VH_ADD_S(zr, zi, w)        \
+  do                               \
+    {                              \
+      if (!pd)                     \
+        {                          \
+          re += (w) * (zr);        \
+          im += (w) * (zi);        \
+        }                          \
+      else                         \
+        {                          \
+          re -= (w) * (zi);        \
+          im += (w) * (zr);        \
+        }                          \
+    }                              \
+  while (0)
+#define VH_ADD_SB(zr, zi, w)       \
+  do                               \
+    {                              \
+      if (!pd)                     \
+        {                          \
+          re += (w) * (zr);        \
+          im += (w) * (zi);        \
+        }                          \
+      else                         \
+        {                          \
+          re += (w) * (zi);        \
+          im -= (w) * (zr);        \
+        }                          \
+    }                              \
+  while (0)
+  const double  b1 = 2.0 * beta[0], b2 = 2.0 * beta[1], b3 = 2.0 * beta[2], b4 = 2.0 * beta[3], b5 = 2.0 * beta[4];
+  const double *z1a = ztab + 2 * (9 * x_nk + x_mj);       // A_{nu k} conj(A_{mu j})
+  const double *z1b = ztab + 2 * (9 * x_mk + x_nj);       // A_{mu k} conj(A_{nu j})
+  const double *z2b = ztab + 162 + 2 * (9 * x_mk + x_nj); // A_{mu k} A_{nu j}
+  VH_ADD_S(z1a[0], z1a[1], 2.0 * b1);
+  re += 2.0 * b2 * A[d] * A[x_mj];
+  im += 2.0 * b2 * A[d] * A[9 + x_mj];
+  VH_ADD_S(z1b[0], z1b[1], b3);
+  VH_ADD_SB(z2b[0], z2b[1], b4);
+  VH_ADD_S(z1b[0], -z1b[1], b5);
+  if (mu == nu)
+    {
+      const double *p = prod + 36 + 2 * (3 * k + j); // P = A^+ A
+      const double *q = prod + 54 + 2 * (3 * k + j); // S = A^T A
+      VH_ADD_S(p[0], -p[1], b3);
+      VH_ADD_S(p[0], p[1], b4);
+      VH_ADD_SB(q[0], q[1], b5);
+    }
+  if (j == k)
+    {
+      const double *r = prod + 0 + 2 * (3 * mu + nu);  // R = A A^T
+      const double *q = prod + 18 + 2 * (3 * mu + nu); // Q = A A^+
+      VH_ADD_SB(r[0], r[1], b3);
+      VH_ADD_S(q[0], q[1], b4);
+      VH_ADD_S(q[0], -q[1], b5);
+      if (mu == nu)
+        {
+          const double Tr = prod[0] + prod[8] + prod[16], Ti = prod[1] + prod[9] + prod[17];
+          const double Sr = prod[18 + 0] + prod[18 + 8] + prod[18 + 16];
+          VH_ADD_S(alpha + b2 * Sr, 0.0, 1.0);
+          VH_ADD_SB(Tr, Ti, b1);
+        }
+    }
+#undef VH_ADD_S
+#undef VH_ADD_SB
+  return pc ? im : re;
+}
+
 // index of (c,d), c<=d, in the row-major packed upper triangle of a symmetric 18x18
 VH_HD int vh_sym_index(int c, int d) { return c * 18 - (c * (c - 1)) / 2 + (d - c); }
 
