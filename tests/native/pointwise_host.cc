@@ -32,4 +32,22 @@ extern "C" void vht_hessian_entries(const double *A, const double *coef, double 
     for (int d = 0; d < 18; ++d)
       H324[18 * c + d] = vh_hessian_entry(A, prod, ztab, c, d, coef[3], coef + 4);
 }
+// ... and through the per-thread term lists (16 loads + 16 FMAs per entry and quadrature point)
+extern "C" void vht_hessian_terms(const double *A, const double *coef, double *H324)
+{
+  double tab[VH_TQ];
+  for (int i = 0; i < 18; ++i)
+    tab[VH_TQ_A + i] = A[i];
+  for (int e = 0; e < 36; ++e)
+    vh_product_entry(A, e, tab + VH_TQ_P + 2 * e);
+  for (int e = 0; e < 162; ++e)
+    vh_ztable_entry(A, e, tab + VH_TQ_Z);
+  for (int c = 0; c < 18; ++c)
+    for (int d = 0; d < 18; ++d)
+      {
+        vh_terms T;
+        vh_entry_terms(c, d, coef[3], coef + 4, T);
+        H324[18 * c + d] = vh_entry_eval(tab, T);
+      }
+}
 extern "C" int vht_sym_index(int c, int d) { return vh_sym_index(c, d); }

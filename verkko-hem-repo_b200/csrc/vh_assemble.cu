@@ -54,7 +54,7 @@ __device__ __forceinline__ double block_sum(double v, double *s_red)
 // 1. pointwise kernel
 // ------------------------------------------------------------------------------------------------
 template <int NN, int NQ>
-__global__ void __launch_bounds__(NQ == 8 ? 160 : 512)
+__global__ void __launch_bounds__(NQ == 8 ? 192 : 512)
   k_pointwise(const int32_t *__restrict__ cell_nodes, const double *__restrict__ cell_h, const uint32_t *__restrict__ cell_faces,
               const uint8_t *__restrict__ cell_owned, const double *__restrict__ x, VhTables tab, VhCoef cf, int want_h, int want_e,
               double *__restrict__ Hq, double *__restrict__ Rc, double *__restrict__ Dc, double *__restrict__ avgD,
@@ -62,16 +62,14 @@ __global__ void __launch_bounds__(NQ == 8 ? 160 : 512)
 {
   extern __shared__ double sm[];
   double *sU   = sm;                // [NN*18]
-  double *sA   = sU + NN * 18;      // [NQ*18]
-  double *sdA  = sA + NQ * 18;      // [NQ*18*3]
-  double *sP   = sdA + NQ * 54;     // [NQ*72]   products R,Q,P,S
-  double *sg   = sP + NQ * 72;      // [NQ*18]
+  double *sT   = sU + NN * 18;      // [NQ][VH_TQ]  per quadrature point: A(18) | products R,Q,P,S (72) | Z1,Z2 (324)
+  double *sdA  = sT + NQ * VH_TQ;   // [NQ*18*3]
+  double *sg   = sdA + NQ * 54;     // [NQ*18]
   double *sHd  = sg + NQ * 18;      // [NQ*18]   diagonal of H_q (unscaled)
   double *sN   = sHd + NQ * 18;     // [NN*NQ]
   double *sdN  = sN + NN * NQ;      // [NN*NQ*3]
   double *swq  = sdN + NN * NQ * 3; // [NQ]
   double *sred = swq + NQ;          // [32]
-  double *sZ   = sred + 32;         // [NQ*324]  Z1,Z2 tables (only touched when want_h)
 
   const int     t    = threadIdx.x;
   const int64_t cell = blockIdx.x;
@@ -104,10 +102,10 @@ __global__ void __launch_bounds__(NQ == 8 ? 160 : 512)
           d1 += sdN[(a * NQ + q) * 3 + 1] * u;
           d2 += sdN[(a * NQ + q) * 3 + 2] * u;
         }
-      sA[t]          = A;
-      sdA[3 * t + 0] = d0 * ih[0];
-      sdA[3 * t + 1] = d1 * ih[1];
-      sdA[3 * t + 2] = d2 * ih[2];
+      sT[q * VH_TQ + VH_TQ_A + c] = A;
+      sdA[3 * t + 0]              = d0 * ih[0];
+      sdA[3 * t + 1]              = d1 * ih[1];
+      sdA[3 * t + 2]              = d2 * ih[2];
     }
   __syncthreads();
   // per quadrature point: 36 product entries (+ 162 Z-table entries for the Hessian)
@@ -116,34 +114,42 @@ __global__ void __launch_bounds__(NQ == 8 ? 160 : 512)
     for (int i = t; i < NQ * per_q; i += blockDim.x)
       {
         const int q = i / per_q, e = i - per_q * q;
+        double   *T = sT + q * VH_TQ;
         if (e < 36)
-          vh_product_entry(sA + q * 18, e, sP + q * 72 + 2 * e);
+          vh_product_entry(T + VH_TQ_A, e, T + VH_TQ_P + 2 * e);
         else
-          vh_ztable_entry(sA + q * 18, e - 36, sZ + q * VH_BLK);
+          vh_ztable_entry(T + VH_TQ_A, e - 36, T + VH_TQ_Z);
       }
   }
   __syncthreads();
   if (t < 18 * NQ)
     {
       const int q = t / 18, c = t - 18 * q;
-      sg[t]       = vh_g_component(sA + q * 18, sP + q * 72, c, cf.alpha, cf.beta);
+      sg[t]       = vh_g_component(sT + q * VH_TQ + VH_TQ_A, sT + q * VH_TQ + VH_TQ_P, c, cf.alpha, cf.beta);
     }
   if (want_h)
-    { // the 171 unique entries of every H_q, stored pre-multiplied by the cell volume (JxW = w_q * vol)
-      double *dst = Hq + cell * (int64_t)(NQ * VH_SYMP);
-      for (int i = t; i < NQ * VH_SYMP; i += blockDim.x)
+    { // the 171 unique entries of every H_q, stored pre-multiplied by the cell volume (JxW = w_q * vol).
+      // A thread owns ONE packed entry (c,d): its 16-term list is set up once and reused for every quadrature point.
+      const int n_groups = blockDim.x / VH_SYMP, grp = t / VH_SYMP, sidx = t - VH_SYMP * grp;
+      if (grp < n_groups)
         {
-          const int q = i / VH_SYMP, sidx = i - VH_SYMP * q;
-          double    v = 0.0;
+          double *dst = Hq + cell * (int64_t)(NQ * VH_SYMP) + sidx;
           if (sidx < VH_SYM)
             {
               const int c = c_symc[sidx], d = c_symd[sidx];
-              v           = vh_hessian_entry(sA + q * 18, sP + q * 72, sZ + q * VH_BLK, c, d, cf.alpha, cf.beta);
-              if (c == d)
-                sHd[q * 18 + c] = v;
-              v *= vol;
+              vh_terms  T;
+              vh_entry_terms(c, d, cf.alpha, cf.beta, T);
+              for (int q = grp; q < NQ; q += n_groups)
+                {
+                  const double v = vh_entry_eval(sT + q * VH_TQ, T);
+                  if (c == d)
+                    sHd[q * 18 + c] = v;
+                  dst[q * VH_SYMP] = v * vol;
+                }
             }
-          dst[i] = v;
+          else
+            for (int q = grp; q < NQ; q += n_groups)
+              dst[q * VH_SYMP] = 0.0;
         }
     }
   __syncthreads();
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(NQ == 8 ? 160 : 512)
               e += cf.K23 * div * div;
             }
           if (c == 6)
-            e += vh_bulk_energy(sP + q * 72, cf.alpha, cf.beta);
+            e += vh_bulk_energy(sT + q * VH_TQ + VH_TQ_P, cf.alpha, cf.beta);
           e *= JxW;
         }
       if (robin && t < 18 && cell_owned[cell])
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(NQ == 8 ? 160 : 512)
 #define VH_FAST_ACTIVE 86 /* 86 threads x 2 packed entries = 172 */
 #define VH_FAST_STAGES 4
 #define VH_CELL_H_BYTES (8 * VH_SYMP * 8) /* one cell's 8 x 172 doubles: 11008 B, a multiple of 16 */
-#define VH_FAST_SMEM (VH_FAST_STAGES * VH_CELL_H_BYTES + 2 * VH_BLK * 8 + VH_BLK * 8 + VH_FAST_STAGES * 8 + 36 * 4)
+#define VH_FAST_SMEM (VH_FAST_STAGES * VH_CELL_H_BYTES + VH_BLK * 8 + 32 * 8 + VH_FAST_STAGES * 8 + (36 + 28) * 4)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
@@ -294,12 +300,13 @@ __global__ void __launch_bounds__(VH_FAST_THREADS, 4)
                  const double *__restrict__ avgD, VhCoef cf, double *__restrict__ vals)
 {
   extern __shared__ __align__(128) unsigned char smraw[];
-  double   *s_H    = reinterpret_cast<double *>(smraw);                                     // [4][8*172]
-  double   *s_tile = reinterpret_cast<double *>(smraw + VH_FAST_STAGES * VH_CELL_H_BYTES);  // [2][324]
-  double   *s_cls  = s_tile + 2 * VH_BLK;                                                   // [27][12]: GS(9), FS(3)
-  uint64_t *s_bar  = reinterpret_cast<uint64_t *>(s_cls + VH_BLK);                          // [4]
+  double   *s_H    = reinterpret_cast<double *>(smraw);                                     // [4][8*172], later [27][172]
+  double   *s_cls  = reinterpret_cast<double *>(smraw + VH_FAST_STAGES * VH_CELL_H_BYTES);  // [27][12]: GS(9), FS(3)
+  double   *s_tr   = s_cls + VH_BLK;                                                        // [27] tr(GS), padded to 32
+  uint64_t *s_bar  = reinterpret_cast<uint64_t *>(s_tr + 32);                               // [4]
   int      *s_cells = reinterpret_cast<int *>(s_bar + VH_FAST_STAGES);                      // [8]
-  int      *s_pos   = s_cells + 8;                                                          // [27]
+  int      *s_pos   = s_cells + 8;                                                          // [27] (+1 pad)
+  uint32_t *s_maskJ = reinterpret_cast<uint32_t *>(s_pos + 28);                             // [27]
 
   const int t = threadIdx.x;
   const int r = blockIdx.x;
@@ -383,103 +390,93 @@ __global__ void __launch_bounds__(VH_FAST_THREADS, 4)
         }
     }
 
-  // ---- write the block row: geometry-only terms, Dirichlet masks, coalesced 16-byte stores ----
+  // ---- write the block row ----
+  // 1. dump the packed symmetric accumulators of all 27 slots into the (now idle) TMA ring: [27][172] doubles
+  __syncthreads();
+  double *s_sym = s_H;
+  if (t < VH_FAST_ACTIVE)
+    {
+#pragma unroll
+      for (int s = 0; s < 27; ++s)
+        reinterpret_cast<double2 *>(s_sym + s * VH_SYMP)[t] = make_double2(acc0[s], acc1[s]);
+    }
   const uint32_t maskI = dirmask[I];
   const int      rp    = row_ptr[I];
-  const double   kf    = cf.bt < 1e10 ? cf.K1 / cf.bt : 0.0;
-  const bool     act   = t < VH_FAST_ACTIVE;
-  const int      c0 = c_symc[act ? 2 * t : 0], d0 = c_symd[act ? 2 * t : 0];
-  const int      c1 = c_symc[act ? 2 * t + 1 : 0], d1 = c_symd[act ? 2 * t + 1 : 0];
-  const bool     have1 = act && (2 * t + 1 < VH_SYM);
-  const int      x0c = c0 % 3, x0d = d0 % 3, x1c = c1 % 3, x1d = d1 % 3;
-  const bool     same0 = (c0 / 3 == d0 / 3), same1 = (c1 / 3 == d1 / 3), diag0 = (c0 == d0), diag1 = (c1 == d1);
-  const int      g0cd = x0c * 3 + x0d, g0dc = x0d * 3 + x0c, g1cd = x1c * 3 + x1d, g1dc = x1d * 3 + x1c;
-  const int      o0cd = c0 * 18 + d0, o0dc = d0 * 18 + c0, o1cd = c1 * 18 + d1, o1dc = d1 * 18 + c1;
-  const bool     rI0c = (maskI >> c0) & 1u, rI0d = (maskI >> d0) & 1u, rI1c = (maskI >> c1) & 1u, rI1d = (maskI >> d1) & 1u;
-  int            n_done = 0;
+  if (t < 27)
+    { // per-slot column Dirichlet masks and tr(GS), so the store loop has no dependent global loads
+      const int pos = s_pos[t];
+      s_maskJ[t]    = pos >= 0 ? dirmask[col[rp + pos]] : 0u;
+      s_tr[t]       = s_cls[t * 12 + 0] + s_cls[t * 12 + 4] + s_cls[t * 12 + 8];
+    }
+  __syncthreads();
+  // 2. every thread owns two fixed 16-byte pieces of the 18x18 block (double2 #t and #t+96): its four entries'
+  //    packed offsets, geometry selectors and row masks are loop invariants; the slot loop is rolled and barrier-free.
+  const double kf = cf.bt < 1e10 ? cf.K1 / cf.bt : 0.0;
+  int          soff[4], gsel[4], fsel[4], ecol[4];
+  double       wK1[4], wF[4], wK23[4];
+  bool         rmask[4], isdiag[4];
 #pragma unroll
+  for (int k = 0; k < 4; ++k)
+    {
+      const int i = t + VH_FAST_THREADS * (k >> 1);           // double2 index inside the block
+      const int c = min((2 * i) / 18, 17), d = (2 * i) % 18 + (k & 1);
+      soff[k]   = c <= d ? vh_sym_index(c, d) : vh_sym_index(d, c);
+      gsel[k]   = (c % 3) * 3 + d % 3;
+      fsel[k]   = 9 + c % 3;
+      ecol[k]   = d;
+      isdiag[k] = c == d;
+      wK1[k]    = c == d ? cf.K1 : 0.0;
+      wF[k]     = c == d ? kf : 0.0;
+      wK23[k]   = (c / 3 == d / 3) ? cf.K23 : 0.0;
+      rmask[k]  = (maskI >> c) & 1u;
+    }
+  const bool second = t + VH_FAST_THREADS < VH_BLK / 2;
   for (int s = 0; s < 27; ++s)
     {
       const int pos = s_pos[s];
       if (pos < 0)
         continue; // block-uniform
-      double        *tile  = s_tile + (n_done & 1) * VH_BLK;
-      const uint32_t maskJ = dirmask[col[rp + pos]];
+      const double  *sy    = s_sym + s * VH_SYMP;
       const double  *G     = s_cls + s * 12;
-      if (act)
+      const double   trG   = s_tr[s];
+      const uint32_t maskJ = s_maskJ[s];
+      double         v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
         {
-          {
-            double vcd = acc0[s], vdc = acc0[s];
-            if (diag0)
-              vcd += cf.K1 * (G[0] + G[4] + G[8]) + kf * G[9 + x0c];
-            if (same0)
+          double val = sy[soff[k]];
+          val        = fma(wK1[k], trG, val);
+          val        = fma(wF[k], G[fsel[k]], val);
+          val        = fma(wK23[k], G[gsel[k]], val);
+          // component-masked Dirichlet DoFs: row and column dropped (distribute_local_to_global)
+          if (rmask[k] || ((maskJ >> ecol[k]) & 1u))
+            val = 0.0;
+          v[k] = val;
+        }
+      if (s == 13 && maskI != 0u)
+        { // constrained diagonal: sum over cells of |a_ii| (mean |diag| of the cell if a_ii == 0)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (isdiag[k] && rmask[k])
               {
-                vcd += cf.K23 * G[g0cd];
-                vdc += cf.K23 * G[g0dc];
-              }
-            if (rI0c || ((maskJ >> d0) & 1u))
-              vcd = 0.0;
-            if (rI0d || ((maskJ >> c0) & 1u))
-              vdc = 0.0;
-            if (s == 13 && diag0 && rI0c)
-              { // constrained diagonal: sum over cells of |a_ii| (mean |diag| of the cell if a_ii == 0)
                 double dsum = 0.0;
                 for (int o = 0; o < 8; ++o)
                   {
                     const int e = s_cells[o];
                     if (e < 0)
                       continue;
-                    double dv = fabs(Dc[(size_t)e * 144 + (7 - o) * 18 + c0]);
+                    double dv = fabs(Dc[(size_t)e * 144 + (7 - o) * 18 + ecol[k]]);
                     if (dv == 0.0)
                       dv = avgD[e];
                     dsum += dv;
                   }
-                vcd = dsum;
+                v[k] = dsum;
               }
-            tile[o0cd] = vcd;
-            if (!diag0)
-              tile[o0dc] = vdc;
-          }
-          if (have1)
-            {
-              double vcd = acc1[s], vdc = acc1[s];
-              if (diag1)
-                vcd += cf.K1 * (G[0] + G[4] + G[8]) + kf * G[9 + x1c];
-              if (same1)
-                {
-                  vcd += cf.K23 * G[g1cd];
-                  vdc += cf.K23 * G[g1dc];
-                }
-              if (rI1c || ((maskJ >> d1) & 1u))
-                vcd = 0.0;
-              if (rI1d || ((maskJ >> c1) & 1u))
-                vdc = 0.0;
-              if (s == 13 && diag1 && rI1c)
-                {
-                  double dsum = 0.0;
-                  for (int o = 0; o < 8; ++o)
-                    {
-                      const int e = s_cells[o];
-                      if (e < 0)
-                        continue;
-                      double dv = fabs(Dc[(size_t)e * 144 + (7 - o) * 18 + c1]);
-                      if (dv == 0.0)
-                        dv = avgD[e];
-                      dsum += dv;
-                    }
-                  vcd = dsum;
-                }
-              tile[o1cd] = vcd;
-              if (!diag1)
-                tile[o1dc] = vdc;
-            }
         }
-      __syncthreads();
-      double2       *dst = reinterpret_cast<double2 *>(vals + (size_t)(rp + pos) * VH_BLK);
-      const double2 *src = reinterpret_cast<const double2 *>(tile);
-      for (int i = t; i < VH_BLK / 2; i += VH_FAST_THREADS)
-        __stcs(dst + i, src[i]); // streaming store: the block is not re-read by this kernel
-      ++n_done;
+      double2 *dst = reinterpret_cast<double2 *>(vals + (size_t)(rp + pos) * VH_BLK);
+      __stcs(dst + t, make_double2(v[0], v[1])); // streaming stores: the block is not re-read by this kernel
+      if (second)
+        __stcs(dst + t + VH_FAST_THREADS, make_double2(v[2], v[3]));
     }
 }
 
@@ -657,9 +654,8 @@ __global__ void k_cells_slow(SlowArgs A, VhTables tab, VhCoef cf, int want_matri
 template <int NN, int NQ>
 size_t pointwise_smem(bool want_h)
 {
-  size_t n = (size_t)NN * 18 + NQ * 18 + NQ * 54 + NQ * 72 + NQ * 18 + NQ * 18 + NN * NQ + NN * NQ * 3 + NQ + 32;
-  if (want_h)
-    n += (size_t)NQ * VH_BLK;
+  (void)want_h;
+  size_t n = (size_t)NN * 18 + (size_t)NQ * VH_TQ + NQ * 54 + NQ * 18 + NQ * 18 + NN * NQ + NN * NQ * 3 + NQ + 32;
   return n * sizeof(double);
 }
 } // namespace
@@ -696,7 +692,7 @@ int vhk_pointwise(vh_ctx *ctx, const double *x_local, bool want_h, bool want_e)
   if (ctx->degree == 1)
     {
       const size_t smem = pointwise_smem<8, 8>(want_h);
-      k_pointwise<8, 8><<<ctx->n_cells, 160, smem, ctx->stream>>>(ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned,
+      k_pointwise<8, 8><<<ctx->n_cells, 192, smem, ctx->stream>>>(ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned,
                                                                  x_local, ctx->tab, ctx->coef, want_h, want_e, ctx->Hq, ctx->Rc,
                                                                  ctx->Dc, ctx->avgD, ctx->Ec);
     }

@@ -14,6 +14,7 @@
 #define VH_POINTWISE_CUH
 
 #ifndef __CUDACC__
+#include <cmath>
 #define VH_HD inline
 #else
 #define VH_HD __host__ __device__ __forceinline__
@@ -263,6 +264,96 @@ VH_HD double vh_hessian_entry(const double *A, const double *prod, const double 
 #undef VH_ADD_S
 #undef VH_ADD_SB
   return pc ? im : re;
+}
+
+
+// ---- per-thread term lists: H[c][d] = cst + wprod*tab[pa]*tab[pb] + sum_{k<16} w[k]*tab[off[k]] ---------------
+// tab is the per-quadrature-point table {A[18] | prod[72] | Z1[162] | Z2[162]} (VH_TQ doubles).  For a fixed (c,d)
+// every term of vh_hessian_entry reads ONE table entry with a fixed signed weight, so a thread that owns (c,d)
+// sets the list up once and then spends 16 loads + 16 FMAs per quadrature point.
+#define VH_TQ_A 0
+#define VH_TQ_P 18
+#define VH_TQ_Z 90
+#define VH_TQ 414
+#define VH_NTERMS 16
+
+struct vh_terms
+{
+  int    off[VH_NTERMS];
+  double w[VH_NTERMS];
+  double cst, wprod;
+  int    pa, pb;
+};
+
+// G += wt * (s or conj(s)) * (z or conj(z)), z = tab[o], tab[o+1]; only component pc of G is wanted.
+VH_HD void vh_term(vh_terms &T, int &n, int o, double wt, bool sbar, bool cj, int pc, bool pd)
+{
+  // (sign, component) of z that lands in component pc of the result
+  int    comp;
+  double sg = 1.0;
+  if (!pd)
+    comp = pc; // s = 1: re -> re, im -> im
+  else if (!sbar)
+    { // s = i: re = -zi, im = +zr
+      comp = 1 - pc;
+      if (pc == 0)
+        sg = -1.0;
+    }
+  else
+    { // conj(s) = -i: re = +zi, im = -zr
+      comp = 1 - pc;
+      if (pc == 1)
+        sg = -1.0;
+    }
+  if (cj && comp == 1)
+    sg = -sg;
+  T.off[n] = o + comp;
+  T.w[n]   = wt * sg;
+  ++n;
+}
+
+VH_HD void vh_entry_terms(int c, int d, double alpha, const double *beta, vh_terms &T)
+{
+  const int  pc = c / 9, mu = (c % 9) / 3, j = c % 3;
+  const bool pd = d >= 9;
+  const int  nu = (d % 9) / 3, k = d % 3;
+  const int  x_nk = 3 * nu + k, x_mj = 3 * mu + j, x_mk = 3 * mu + k, x_nj = 3 * nu + j;
+  const double b1 = 2.0 * beta[0], b2 = 2.0 * beta[1], b3 = 2.0 * beta[2], b4 = 2.0 * beta[3], b5 = 2.0 * beta[4];
+  int        n = 0;
+  const int  Z1 = VH_TQ_Z, Z2 = VH_TQ_Z + 162, P = VH_TQ_P;
+  vh_term(T, n, Z1 + 2 * (9 * x_nk + x_mj), 2.0 * b1, false, false, pc, pd);
+  vh_term(T, n, Z1 + 2 * (9 * x_mk + x_nj), b3, false, false, pc, pd);
+  vh_term(T, n, Z2 + 2 * (9 * x_mk + x_nj), b4, true, false, pc, pd);
+  vh_term(T, n, Z1 + 2 * (9 * x_mk + x_nj), b5, false, true, pc, pd);
+  const bool rowm = mu == nu, colm = j == k;
+  // row nu only:  E A^T A* (conj P), E A^+ A (P), E* A^T A (S)
+  vh_term(T, n, P + 36 + 2 * (3 * k + j), rowm ? b3 : 0.0, false, true, pc, pd);
+  vh_term(T, n, P + 36 + 2 * (3 * k + j), rowm ? b4 : 0.0, false, false, pc, pd);
+  vh_term(T, n, P + 54 + 2 * (3 * k + j), rowm ? b5 : 0.0, true, false, pc, pd);
+  // column k only:  A A^T E* (R), A A^+ E (Q), A* A^T E (conj Q)
+  vh_term(T, n, P + 0 + 2 * (3 * mu + nu), colm ? b3 : 0.0, true, false, pc, pd);
+  vh_term(T, n, P + 18 + 2 * (3 * mu + nu), colm ? b4 : 0.0, false, false, pc, pd);
+  vh_term(T, n, P + 18 + 2 * (3 * mu + nu), colm ? b5 : 0.0, false, true, pc, pd);
+  // both:  (alpha + 2 beta2 tr(AA^+)) E  and  2 beta1 tr(AA^T) E*
+  const bool both = rowm && colm;
+  for (int i = 0; i < 3; ++i)
+    vh_term(T, n, P + 18 + 8 * i, both ? b2 : 0.0, false, false, pc, pd); // Q_ii (imaginary parts are 0 up to rounding)
+  for (int i = 0; i < 3; ++i)
+    vh_term(T, n, P + 0 + 8 * i, both ? b1 : 0.0, true, false, pc, pd); // R_ii
+  // alpha * s lands in component pc only if pc == pd
+  T.cst   = (both && (pc == (pd ? 1 : 0))) ? alpha : 0.0;
+  T.wprod = 2.0 * b2; // 4 beta2 a_d * (component pc of A_{mu j}) = 2 b2 a_c a_d
+  T.pa    = VH_TQ_A + c;
+  T.pb    = VH_TQ_A + d;
+}
+
+VH_HD double vh_entry_eval(const double *tab, const vh_terms &T)
+{
+  double v = fma(T.wprod * tab[T.pa], tab[T.pb], T.cst);
+#pragma unroll
+  for (int k = 0; k < VH_NTERMS; ++k)
+    v = fma(T.w[k], tab[T.off[k]], v);
+  return v;
 }
 
 // index of (c,d), c<=d, in the row-major packed upper triangle of a symmetric 18x18
