@@ -221,6 +221,10 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------
 def run_ours(args):
+    # NCCL / torch print banners on stdout; the contract is ONE JSON line there, so everything else goes to stderr.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import verkko_hem_repo_b200 as vh
 
@@ -358,7 +362,10 @@ def run_ours(args):
                "gpu_launches": tm["launches"], "clocks": clocks, "cpu_baseline": cpu,
                "matrix": {"nnzb": nnzb, "fast_rows": info["n_fast_rows"], "slow_cells": info["n_slow_cells"],
                           "device_bytes": info["device_bytes"]}}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -1,0 +1,134 @@
+"""GPU tests of the host driver mirror (FemGL::run through the C ABI), multi-GPU parity, and size-independent
+properties at the BASELINE size C2 (Q1 r5, 646 866 DoFs)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import femgl_oracle as O
+import verkko_hem_repo_b200 as vh
+from helpers import MATEP_SCC_ON, b_phase_state, coef_vector
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+PRM = """
+subsection physical parameters
+  set pressure in bar = 25.0
+  set t_reduced = 0.5
+  set AdGR diffuse length = 2.0
+  set trun on Strong Coupling Correction = true
+end
+subsection control parameters
+  set cube half side length = 2.0
+  set Number of initial global refinments = %d
+  set Number of refinements = %d
+  set Number of interations = %d
+  set Cycle 0 refinement threshold = %g
+  set converge accuracy = 1e-7
+end
+"""
+
+
+def test_femgl_run_matches_oracle_newton_loop():
+    """C1-shaped run through FemGL::run() (C++ driver mirror): the per-step record (||rhs||, GMRES iterations, line-search
+    trials, ||R||, energy) equals the oracle's Newton loop with the stop logic of run.cc:234-250."""
+    out = vh.run_prm(PRM % (3, 0, 5, 1e-12))
+    hist = out["history"]
+    T = vh.unit_cube(1, 3, half=2.0).tables(0)
+    coef = coef_vector(MATEP_SCC_ON, 2.0)
+    x = b_phase_state(T, noise=0.0)
+    assert len(hist) >= 3
+    for rec in hist:
+        o = O.newton_step(T, x, coef, 1e-1)
+        assert abs(rec["rhs_norm"] - o["rhs_norm"]) <= 1e-10 * o["rhs_norm"]
+        assert rec["linear_its"] == o["lin_its"] and rec["trials"] == o["n_trials"]
+        assert abs(rec["residual"] - o["res_norm"]) <= 1e-10 * o["res_norm"]
+        e = O.energy_global(T, o["x"], coef)
+        assert abs(rec["energy"] - e) <= 1e-10 * abs(e)
+        x = o["x"]
+    assert np.abs(out["solution"] - x).max() <= 1e-9 * np.abs(x).max()
+    # the reference's observable lines are preserved
+    assert "Refinement Cycle is 0" in out["log"] and "Solved in" in out["log"] and "step length alpha is:" in out["log"]
+
+
+def test_femgl_run_with_adaptive_cycles_converges_and_refines():
+    """Two adaptive cycles (hanging nodes -> general scatter path + solution transfer): the run completes, the mesh
+    grows, and the residual of the transferred solution keeps decreasing inside each cycle."""
+    out = vh.run_prm(PRM % (2, 2, 3, 1e3))
+    hist = out["history"]
+    cycles = sorted(set(h["cycle"] for h in hist))
+    assert cycles == [0, 1, 2]
+    for c in cycles:
+        rs = [h["residual"] for h in hist if h["cycle"] == c]
+        assert all(np.isfinite(rs)) and rs[-1] <= rs[0] * 1.0000001
+    assert out["solution"].size > 18 * 125  # refined beyond the 5^3-node start mesh
+    assert "adaptive_refine_grid() call is done !" in out["log"]
+
+
+def test_error_propagates_like_solvercontrol_noconvergence():
+    with pytest.raises(RuntimeError) as e:
+        vh.run_prm((PRM % (2, 0, 2, 1e-12)).replace("set converge accuracy = 1e-7",
+                                                    "set converge accuracy = 1e-7\n  set maximum linear iteration number = 1\n"
+                                                    "  set Cycle 0 linear solver tol = 1e-12"))
+    assert "no convergence" in str(e.value)
+
+
+def test_c2_size_properties():
+    """BASELINE config C2 (Q1 r5): properties that hold at any size — symmetry of the Jacobian, Jacobian = derivative of
+    the residual, residual = -1/2 gradient of the energy, constrained rows decoupled."""
+    m = vh.unit_cube(1, 5, half=20.0)
+    T = m.tables(0)
+    assert 18 * m.n_nodes == 646866
+    coef = coef_vector(MATEP_SCC_ON, 2.0)
+    x = b_phase_state(T)
+    ctx = vh.Context(T)
+    ctx.set_coef_vector(coef)
+    ctx.set_solution(x)
+    ctx.assemble()
+    info = ctx.info()
+    assert info["nnzb"] == 912673 and info["n_fast_rows"] == m.n_nodes and info["n_slow_cells"] == 0
+    rng = np.random.default_rng(3)
+    con = np.zeros(x.size, dtype=bool)
+    con[T.c_dof] = True
+    u = rng.uniform(-1, 1, x.size)
+    v = rng.uniform(-1, 1, x.size)
+    Au, Av = ctx.spmv(u), ctx.spmv(v)
+    assert abs(v @ Au - u @ Av) <= 1e-11 * abs(v @ Au)             # symmetric operator
+    z = np.where(con, 1.0, 0.0)
+    Az = ctx.spmv(z)
+    assert np.abs(Az[~con]).max() == 0.0 and (Az[con] > 0).all()    # constrained DoFs: positive diagonal only
+    rhs0 = ctx.get_rhs()
+    assert np.abs(rhs0[con]).max() == 0.0
+    # directional derivative of the residual along a constraint-compatible direction d
+    d = np.where(con, 0.0, rng.uniform(-1, 1, x.size))
+    eps = 1e-5
+    ctx2 = vh.Context(T)
+    ctx2.set_coef_vector(coef)
+    rp = []
+    en = []
+    for s in (+1, -1):
+        ctx2.set_solution(x + s * eps * d)
+        ctx2.assemble()
+        rp.append(ctx2.get_rhs())
+        en.append(ctx2.energy(0))
+    Ad = ctx.spmv(d)
+    fd = -(rp[0] - rp[1]) / (2 * eps)
+    assert np.abs(fd[~con] - Ad[~con]).max() <= 1e-6 * np.abs(Ad).max()
+    # rhs = -R = -1/2 dF/dx
+    assert abs((en[0] - en[1]) / (2 * eps) - (-2.0 * (rhs0 @ d))) <= 1e-6 * abs(2.0 * (rhs0 @ d))
+    ctx.close()
+    ctx2.close()
+
+
+def test_two_gpu_run_equals_one_gpu_run():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "multigpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MULTIGPU PARITY OK" in r.stdout

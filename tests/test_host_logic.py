@@ -1,0 +1,207 @@
+"""CPU tests of the host side: Matep / confreader mirrors, mesh + constraint + partition tables, C-ABI surface."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import femgl_oracle as O
+import verkko_hem_repo_b200 as vh
+from helpers import b_phase_state, coef_vector
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+REFERENCE_KEYS = {  # SURVEY.md App. D == /root/reference/confreader/src/declare.cc:115-291 (misspellings included)
+    "physical parameters": ["pressure in bar", "t_reduced", "AdGR diffuse length", "gaussian random mean value", "gaussian random STD",
+                            "trun on Strong Coupling Correction", "amplitude u parameter"],
+    "control parameters": ["cube half side length", "half x length of retangle", "half y length of retangle",
+                           "half z length of retangle", "B-phase inner plate radius ratio", "B-phase ball radius ratio",
+                           "A-phase block range ratio", "Number of refinements", "Number of interations",
+                           "Cycle 0 refinement threshold", "Cycle 0 linear solver tol", "Cycle 1 refinement threshold",
+                           "Cycle 1 do global refinement", "Cycle 1 linear solver tol", "Cycle 2 refinement threshold",
+                           "Cycle 2 do global refinement", "Cycle 2 linear solver tol", "Cycle 3 refinement threshold",
+                           "Cycle 3 do global refinement", "Cycle 3 linear solver tol", "Cycle 4 do global refinement",
+                           "Cycle 4 linear solver tol", "converge accuracy", "adaptive refinment ratio", "adaptive coarsen ratio",
+                           "Number of initial global refinments", "Number of n-cycle in AdditionalData",
+                           "maximum linear iteration number", "Using dampped Newton iteration",
+                           "primary step length of dampped newton iteration"],
+}
+
+
+def test_matep_restatement_is_bit_exact(golden_dir):
+    with open(os.path.join(golden_dir, "matep.json")) as f:
+        grid = json.load(f)
+    for row in grid:
+        got = vh.matep(row["p"], row["t"], row["scc"])
+        for k, v in got.items():
+            assert v == row[k], (row["p"], row["t"], row["scc"], k)
+
+
+def test_confreader_declares_every_reference_key_with_its_default():
+    d = vh.parse_prm("")
+    n = 0
+    for sec, keys in REFERENCE_KEYS.items():
+        for k in keys:
+            assert sec + "/" + k in d, k
+            n += 1
+    assert n == 37
+    assert d["physical parameters/AdGR diffuse length"] == "1.0e10"
+    assert d["control parameters/primary step length of dampped newton iteration"] == "0.83"
+    assert d["control parameters/Cycle 0 linear solver tol"] == "1.0e-1"
+    # additive GPU-side keys have defaults, so a reference configuration.prm parses unchanged
+    assert d["control parameters/GMRES restart length"] == "30"
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/confreader"), reason="reference tree not present")
+def test_confreader_keys_match_reference_source():
+    src = "\n".join(l for l in open("/root/reference/confreader/src/declare.cc").read().splitlines()
+                    if not l.lstrip().startswith("//"))
+    ref = re.findall(r'declare_entry\("([^"]+)",\s*"([^"]*)"', src)
+    assert len(ref) == 37
+    d = vh.parse_prm("")
+    flat = {k.split("/", 1)[1]: v for k, v in d.items()}
+    for key, default in ref:
+        assert flat[key] == default, key
+
+
+def test_prm_parsing_and_errors():
+    d = vh.parse_prm("# comment\nsubsection physical parameters\n  set pressure in bar = 25.0 # trailing\n  set t_reduced=0.5\nend\n"
+                     "subsection control parameters\n set Number of initial global refinments = 3\nend\n")
+    assert d["physical parameters/pressure in bar"] == "25.0" and d["physical parameters/t_reduced"] == "0.5"
+    assert d["control parameters/Number of initial global refinments"] == "3"
+    with pytest.raises(RuntimeError):
+        vh.parse_prm("subsection physical parameters\n set no such key = 1\nend\n")
+    with pytest.raises(RuntimeError):
+        vh.parse_prm("subsection physical parameters\n set t_reduced = 0.5\n")
+
+
+@pytest.mark.parametrize("degree,refine", [(1, 3), (2, 2)])
+def test_uniform_cube_tables(degree, refine):
+    m = vh.unit_cube(degree, refine, half=0.5)
+    T = m.tables(0)
+    nc1 = 2 ** refine
+    n1 = degree * nc1 + 1
+    assert m.n_cells == nc1 ** 3 and m.n_nodes == n1 ** 3 and T.n_ghost_nodes == 0
+    # every cell's nodes sit where the FE_Q support points of that box are
+    _, _, _, xi = O.fe_tables(degree)
+    want = T.cell_origin[:, None, :] + xi[None, :, :] * T.cell_h[:, None, :]
+    got = T.node_xyz[T.cell_nodes]
+    assert np.abs(want - got).max() < 1e-13
+    # z faces carry boundary id 4 -> 6 masked components on the two wall planes (femgl.h:300-301)
+    assert T.c_dof.size == 2 * n1 * n1 * 6 and T.c_master.size == 0
+    assert set((T.c_dof % 18).tolist()) == {2, 5, 8, 11, 14, 17}
+    wall = np.abs(np.abs(T.node_xyz[T.c_dof // 18, 2]) - 0.5) < 1e-13
+    assert wall.all()
+    assert T.wall_face_cell.size == 2 * nc1 * nc1 and set(T.wall_face_bid.tolist()) == {4} and set(T.wall_face_no.tolist()) == {4, 5}
+
+
+def test_morton_order_and_partition_cover():
+    m = vh.unit_cube(1, 3, n_ranks=4)
+    owned = np.zeros(m.n_nodes, dtype=int)
+    cells_owned = 0
+    for r in range(4):
+        T = m.tables(r)
+        owned[T.node_global[:T.n_owned_nodes]] += 1
+        cells_owned += int(T.cell_owned.sum())
+        # ghosts are grouped by owner: receive lists are contiguous ascending runs
+        assert (np.diff(T.recv_nodes) > 0).all() if T.recv_nodes.size else True
+        # every visited cell touches an owned node
+        assert (T.cell_nodes < T.n_owned_nodes).any(axis=1).all()
+    assert (owned == 1).all() and cells_owned == m.n_cells
+    # halo plans are mutually consistent: what r sends to p is what p expects from r, in the same order
+    tabs = [m.tables(r) for r in range(4)]
+    for r, T in enumerate(tabs):
+        for k, p in enumerate(T.peer_rank):
+            send = T.node_global[T.send_nodes[T.send_ptr[k]:T.send_ptr[k + 1]]]
+            Tp = tabs[p]
+            kk = list(Tp.peer_rank).index(r)
+            recv = Tp.node_global[Tp.recv_nodes[Tp.recv_ptr[kk]:Tp.recv_ptr[kk + 1]]]
+            assert np.array_equal(send, recv)
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_hanging_node_constraints_reproduce_polynomials(degree):
+    m = vh.Mesh(degree, [-1, -1, -1], [1, 1, 1], n_global_refine=1 if degree == 2 else 2)
+    c = m.cell_centers()
+    m.refine((c[:, 0] < 0) & (c[:, 2] > 0))
+    m.finalize(1)
+    T = m.tables(0)
+    assert m.n_hanging_nodes > 0
+    cnt = np.diff(T.c_ptr)
+    # hanging-node lines of components that are not Dirichlet-masked anywhere (c % 3 != 2 with z walls): no master is
+    # ever dropped by closing the constraints, so the weights are the plain FE interpolation weights
+    lines = np.nonzero((cnt > 0) & (T.c_dof % 3 != 2))[0]
+    assert lines.size > 0
+    x, y, z = T.node_xyz.T
+    f = (1 + 2 * x - y + 0.5 * z) if degree == 1 else (1 + x * y - 2 * z * z + x * x + 0.3 * y)
+    field = np.repeat(f[:, None], 18, axis=1).ravel()
+    for l in lines:
+        s = slice(T.c_ptr[l], T.c_ptr[l + 1])
+        assert abs(T.c_weight[s].sum() - 1.0) < 1e-13                       # partition of unity
+        assert (T.c_master[s] % 18 == T.c_dof[l] % 18).all()                # same component
+        # a polynomial of the element degree, sampled at the nodes, already satisfies the constraint
+        assert abs((T.c_weight[s] * field[T.c_master[s]]).sum() - field[T.c_dof[l]]) < 1e-12
+    # masked components of hanging nodes: masters on the wall are Dirichlet DoFs and drop out when the object is closed
+    masked = np.nonzero((T.c_dof % 3 == 2) & (np.abs(np.abs(T.node_xyz[T.c_dof // 18, 2]) - 1.0) < 1e-12))[0]
+    assert (cnt[masked] == 0).all()
+
+
+def test_solution_transfer_reproduces_trilinear_field():
+    old = vh.Mesh(1, [-1, -1, -1], [1, 1, 1], n_global_refine=2).finalize(1)
+    new = old.clone()
+    c = new.cell_centers()
+    new.refine(c[:, 1] > 0.2)
+    new.finalize(1)
+    f = lambda X: 0.5 + X[:, 0] - 2 * X[:, 1] * X[:, 2] + X[:, 0] * X[:, 1] * X[:, 2]  # noqa: E731
+    ov = np.repeat(f(old.node_xyz())[:, None], 18, axis=1) * np.arange(1, 19)[None, :]
+    nv = new.interpolate_from(old, ov.ravel()).reshape(-1, 18)
+    want = f(new.node_xyz())[:, None] * np.arange(1, 19)[None, :]
+    assert np.abs(nv - want).max() < 1e-13
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """include/vh_femgl.h is the drop-in boundary: the built library must export exactly those entry points."""
+    hdr = open(os.path.join(ROOT, "include", "vh_femgl.h")).read()
+    names = sorted(set(re.findall(r"\b(vh_[a-z0-9_]+)\s*\(", hdr)))
+    assert "vh_assemble" in names and "vh_solve" in names and "vh_residual" in names and len(names) >= 25
+    lib = os.path.join(ROOT, "verkko-hem-repo_b200", "lib", "libvhfemgl.so")
+    if not os.path.exists(lib):
+        vh.build(cuda=True, host=False)
+    L = ctypes.CDLL(lib)  # loads without a GPU (no compute call is made)
+    for n in names:
+        assert hasattr(L, n), "missing export " + n
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    T = vh.unit_cube(1, 1).tables(0)
+    with pytest.raises(vh.VhError) as e:
+        vh.Context(T)
+    assert "no CPU fallback" in str(e.value) or e.value.code in (-2, -5)
+
+
+def test_oracle_partition_independence():
+    """Rows assembled per rank from its owned + ghost-layer cells equal the rows of the 1-rank assembly (the reason the
+    GPU path needs no compress(add) exchange)."""
+    coef = coef_vector(bt=2.0)
+    m1 = vh.unit_cube(1, 2, half=2.0)
+    T1 = m1.tables(0)
+    mP = vh.unit_cube(1, 2, half=2.0, n_ranks=3)
+    # global numbering differs between the two partitions: compare through coordinates
+    key1 = {tuple(np.round(p, 9)): i for i, p in enumerate(T1.node_xyz)}
+    x1 = b_phase_state(T1, seed=5)
+    A1, r1 = O.assemble_global(T1, x1, coef, True)
+    A1 = A1.tocsr()
+    for r in range(3):
+        T = mP.tables(r)
+        perm = np.array([key1[tuple(np.round(p, 9))] for p in T.node_xyz])
+        x = x1.reshape(-1, 18)[perm].ravel()
+        A, rhs = O.assemble_global(T, x, coef, True)
+        dof_perm = (18 * perm[:, None] + np.arange(18)[None, :]).ravel()
+        want = A1[dof_perm[:18 * T.n_owned_nodes]][:, dof_perm]
+        assert abs(A - want).max() <= 1e-13 * abs(A1).max()
+        assert np.abs(rhs - r1[dof_perm[:18 * T.n_owned_nodes]]).max() <= 1e-13 * np.abs(r1).max()

@@ -32,7 +32,7 @@ class VhError(RuntimeError):
 
 def build(cuda=True, host=True, verbose=False):
     """Compile the in-tree libraries (nvcc cross-compiles sm_100a without a GPU)."""
-    targets = (["host"] if host else []) + (["cuda"] if cuda else [])
+    targets = (["host"] if host else []) + (["cuda", "driver"] if cuda else [])
     cmd = ["make", "-C", _PKG, "-j8"] + targets
     if not verbose:
         cmd.insert(1, "-s")
@@ -70,6 +70,13 @@ def host_lib():
         L.vhh_tables_array.restype = ctypes.c_void_p
         L.vhh_tables_array.argtypes = [ctypes.c_void_p, ctypes.c_char_p, _i64p, ctypes.POINTER(ctypes.c_int)]
         L.vhh_tables_sizes.argtypes = [ctypes.c_void_p, _i64p]
+        L.vhh_matep.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_int, _dp]
+        L.vhh_prm_dump.restype = ctypes.c_char_p
+        L.vhh_prm_dump.argtypes = [ctypes.c_char_p]
+        L.vhh_mesh_interpolate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, _dp, _dp]
+        L.vhh_mesh_clone.restype = ctypes.c_void_p
+        L.vhh_mesh_clone.argtypes = [ctypes.c_void_p]
+        L.vhh_mesh_node_xyz.argtypes = [ctypes.c_void_p, _dp]
         _host = L
     return _host
 
@@ -181,6 +188,26 @@ class Mesh:
     def tables(self, rank=0):
         return RankTables(self, rank)
 
+    def clone(self):
+        m = Mesh.__new__(Mesh)
+        m.degree = self.degree
+        m._h = host_lib().vhh_mesh_clone(self._h)
+        m.n_ranks = 0
+        return m
+
+    def node_xyz(self):
+        out = np.zeros((self.n_nodes, 3))
+        host_lib().vhh_mesh_node_xyz(self._h, out.ctypes.data_as(_dp))
+        return out
+
+    def interpolate_from(self, old_mesh, old_values):
+        """SolutionTransfer stand-in: FE-interpolate old_values (old mesh, global node order) onto this mesh."""
+        ov = np.ascontiguousarray(old_values, dtype=np.float64)
+        nv = np.zeros(18 * self.n_nodes)
+        if host_lib().vhh_mesh_interpolate(self._h, old_mesh._h, ov.ctypes.data_as(_dp), nv.ctypes.data_as(_dp)) != 0:
+            raise RuntimeError(host_lib().vhh_last_error().decode())
+        return nv
+
     def __del__(self):
         try:
             if self._h:
@@ -190,10 +217,26 @@ class Mesh:
             pass
 
 
+def matep(p, t, scc):
+    """Material coefficients from the host-side Matep restatement (host/matep.cc)."""
+    out = np.zeros(12)
+    host_lib().vhh_matep(float(p), float(t), int(bool(scc)), out.ctypes.data_as(_dp))
+    keys = ["alpha", "beta1", "beta2", "beta3", "beta4", "beta5", "gapA", "gapB", "fA", "fB", "Tcp_mK", "tAB_RWS"]
+    return dict(zip(keys, out.tolist()))
+
+
+def parse_prm(text=""):
+    """Parse .prm text with the confreader mirror; returns {"subsection/key": value-string}."""
+    r = host_lib().vhh_prm_dump(text.encode())
+    if r is None:
+        raise RuntimeError(host_lib().vhh_last_error().decode())
+    return dict(line.split("=", 1) for line in r.decode().splitlines() if line)
+
+
 def unit_cube(degree, refine, half=0.5, face_bid=(1, 1, 1, 1, 4, 4), n_ranks=1):
     """The BASELINE configs' cube: hyper_cube(-half, half) + refine_global(refine); z faces are AdGR walls (id 4)
     as in makegrid_cube-z-normal_AdGR.cc:164-195."""
     return Mesh(degree, [-half] * 3, [half] * 3, (1, 1, 1), face_bid, refine).finalize(n_ranks)
 
 
-from ._capi import Context, cuda_lib, have_cuda_lib  # noqa: E402,F401
+from ._capi import Context, cuda_lib, have_cuda_lib, run_prm  # noqa: E402,F401

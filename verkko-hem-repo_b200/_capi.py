@@ -216,3 +216,60 @@ class Context:
         n = ctypes.c_int64()
         self._chk(self.L.vh_get_timers(self._h, ms, ctypes.byref(n), 1 if reset else 0))
         return dict(assemble=ms[0], residual=ms[1], solve=ms[2], vector=ms[3], halo=ms[4], launches=int(n.value))
+
+
+# ------------------------------------------------------------------------------------------
+# FemGL driver mirror (host/femgl.cc) through lib/libvhdriver.so
+# ------------------------------------------------------------------------------------------
+_drv = None
+
+
+def driver_lib():
+    global _drv
+    if _drv is None:
+        p = os.path.join(_PKG, "lib", "libvhdriver.so")
+        if not os.path.exists(p):
+            raise RuntimeError("%s is missing: build it with __graft_entry__.build()" % p)
+        L = ctypes.CDLL(p)
+        L.vhd_run.restype = _vp
+        L.vhd_run.argtypes = [ctypes.c_char_p]
+        L.vhd_error.restype = ctypes.c_char_p
+        L.vhd_error.argtypes = [_vp]
+        L.vhd_log.restype = ctypes.c_char_p
+        L.vhd_log.argtypes = [_vp]
+        L.vhd_n_steps.argtypes = [_vp]
+        L.vhd_step.argtypes = [_vp, ctypes.c_int, _dp]
+        L.vhd_solution_size.restype = ctypes.c_longlong
+        L.vhd_solution_size.argtypes = [_vp]
+        L.vhd_solution.argtypes = [_vp, _dp]
+        L.vhd_free.argtypes = [_vp]
+        _drv = L
+    return _drv
+
+
+def run_prm(prm_text):
+    """FemGL<3>(degree, prm).run() of the C++ driver mirror on cuda:0, configured by .prm text.
+    Returns dict(history=[{...}], log=str, solution=ndarray); raises RuntimeError with the driver's exception text."""
+    L = driver_lib()
+    h = L.vhd_run(prm_text.encode())
+    try:
+        err = L.vhd_error(h).decode()
+        log = L.vhd_log(h).decode()
+        if err:
+            raise RuntimeError(err + "\n--- log ---\n" + log[-2000:])
+        keys = ["cycle", "iteration", "rhs_norm", "linear_its", "residual", "alpha", "trials", "energy", "t_assemble_ms",
+                "t_solve_ms", "t_newton_ms"]
+        hist = []
+        buf = np.zeros(11)
+        for i in range(L.vhd_n_steps(h)):
+            L.vhd_step(h, i, buf.ctypes.data_as(_dp))
+            d = dict(zip(keys, buf.tolist()))
+            for k in ("cycle", "iteration", "linear_its", "trials"):
+                d[k] = int(d[k])
+            hist.append(d)
+        sol = np.zeros(L.vhd_solution_size(h))
+        if sol.size:
+            L.vhd_solution(h, sol.ctypes.data_as(_dp))
+        return dict(history=hist, log=log, solution=sol)
+    finally:
+        L.vhd_free(h)

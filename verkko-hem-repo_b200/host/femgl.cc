@@ -1,0 +1,430 @@
+// See femgl.h.  Control flow and printed lines follow the reference:
+//   ctor                 /root/reference/femgl/src/femgl.cc:107-203
+//   run()                /root/reference/femgl/src/run.cc:108-260
+//   assemble_system()    /root/reference/femgl/src/assemble.cc:108-372      -> vh_assemble
+//   solve(tol)           /root/reference/femgl/src/solve.cc:108-187         -> vh_solve
+//   newton_iteration()   /root/reference/femgl/src/iteration.cc:109-215     -> vh_line_search_trial / vh_residual / vh_accept_trial
+//   compute_residual()   /root/reference/femgl/src/residual.cc:109-297      -> vh_residual
+//   make_grid()          /root/reference/femgl/src/makegrid_cube-z-normal_AdGR.cc:140-197,
+//                        makegrid_retangle-z-AdGR-xy-HomoNeumann.cc:159-192
+//   setup_system()       /root/reference/femgl/src/setup_uniform_B-phase.cc:109-341,
+//                        setup_uniform_BnA-flatwall-configuration.cc:201-245
+//   refine_grid()        /root/reference/femgl/src/refine.cc:109-181
+#include "femgl.h"
+
+#include "../../include/vh_femgl.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+
+namespace vhhost
+{
+namespace
+{
+double now_ms()
+{
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+} // namespace
+
+template <int dim>
+void FemGL<dim>::check(int rc, const char *what) const
+{
+  if (rc != VH_OK)
+    throw std::runtime_error(std::string(what) + ": " + vh_last_error(gpu)); // reaches main()'s handler, main.cc:120-145
+}
+
+template <int dim>
+FemGL<dim>::FemGL(unsigned int Q_degree, ParameterHandler &prmHandler)
+  : degree(Q_degree), cycle(0), iteration_loop(0), conf(prmHandler), out(&std::cout)
+{
+  static_assert(dim == 3, "femgl is three-dimensional");
+  conf.enter_subsection("physical parameters");
+  p         = conf.get_double("pressure in bar");
+  reduced_t = conf.get_double("t_reduced");
+  bt        = conf.get_double("AdGR diffuse length");
+  SCC_key   = conf.get_bool("trun on Strong Coupling Correction");
+  conf.leave_subsection();
+
+  mat.with_SCC(SCC_key);
+  alpha = mat.alpha_td(reduced_t);
+  beta1 = mat.beta1_td(p, reduced_t);
+  beta2 = mat.beta2_td(p, reduced_t);
+  beta3 = mat.beta3_td(p, reduced_t);
+  beta4 = mat.beta4_td(p, reduced_t);
+  beta5 = mat.beta5_td(p, reduced_t);
+
+  std::ostream &pcout = *out;
+  pcout << "------------------------------------------------------" << "\n"
+        << ">>>>>>>>>>  Physical Parameters in this run  <<<<<<<<<" << "\n"
+        << "------------------------------------------------------" << "\n"
+        << " Number of MPI processes is " << 1 << "\n"
+        << " p is " << p << ", t is " << reduced_t << ", T is " << (reduced_t * mat.Tcp_mK(p)) << "\n"
+        << " AdGR expolation lenghtn bt is " << bt << ", SCC_key is " << SCC_key << "\n"
+        << " gapA is " << mat.gap_A_td(p, reduced_t) << ", gapB is " << mat.gap_B_td(p, reduced_t) << "\n"
+        << " f_A is " << mat.f_A_td(p, reduced_t) << ", f_B is " << mat.f_B_td(p, reduced_t) << "\n"
+        << " alpha is " << alpha << ", beta1 is " << beta1 << ", beta2 is " << beta2 << "\n"
+        << " beta3 is " << beta3 << ", beta4 is " << beta4 << ", beta5 is " << beta5 << "\n"
+        << "------------------------------------------------------" << "\n"
+        << ">>>>>>>>>>  Physical Parameters in this run  <<<<<<<<<" << "\n"
+        << "------------------------------------------------------" << "\n"
+        << std::endl;
+}
+
+template <int dim>
+FemGL<dim>::~FemGL()
+{
+  if (gpu)
+    vh_destroy(gpu);
+}
+
+// The reference selects geometry and initial condition at compile time by (un)commenting one makegrid_*.cc and one
+// setup_*.cc in femgl/CMakeLists.txt:42-64.  Here the two box geometries and two initial conditions the BASELINE
+// configs use are selected by the additive key "geometry" (cube | retangle).
+template <int dim>
+void FemGL<dim>::make_grid()
+{
+  conf.enter_subsection("control parameters");
+  const int         number_global_refine = (int)conf.get_integer("Number of initial global refinments");
+  const double      half_length          = conf.get_double("cube half side length");
+  const double      hx = conf.get_double("half x length of retangle"), hy = conf.get_double("half y length of retangle"),
+               hz        = conf.get_double("half z length of retangle");
+  const std::string geom = conf.get("geometry");
+  conf.leave_subsection();
+  // boundary ids: x and y faces natural (1), z faces AdGR walls with normal z (4)
+  const int face_bid[6] = {1, 1, 1, 1, 4, 4};
+  const int base[3]     = {1, 1, 1};
+  if (geom == "retangle")
+    { // GridGenerator::hyper_rectangle(-h, +h), makegrid_retangle-z-AdGR-xy-HomoNeumann.cc:159-192
+      const double lo[3] = {-hx, -hy, -hz}, hi[3] = {hx, hy, hz};
+      triangulation.reset(new Mesh((int)degree, lo, hi, base, face_bid, number_global_refine));
+    }
+  else
+    { // GridGenerator::hyper_cube(-half, +half), makegrid_cube-z-normal_AdGR.cc:151-160
+      const double lo[3] = {-half_length, -half_length, -half_length}, hi[3] = {half_length, half_length, half_length};
+      triangulation.reset(new Mesh((int)degree, lo, hi, base, face_bid, number_global_refine));
+    }
+}
+
+template <int dim>
+void FemGL<dim>::setup_system()
+{
+  std::ostream &pcout = *out;
+  triangulation->finalize(1);
+  tables.reset(new RankTables(triangulation->tables(0)));
+  pcout << "   Number of degrees of freedom: " << 18 * triangulation->n_nodes << std::endl;
+
+  if (gpu)
+    {
+      vh_destroy(gpu);
+      gpu = nullptr;
+    }
+  vh_mesh_desc d;
+  std::memset(&d, 0, sizeof(d));
+  RankTables &T    = *tables;
+  d.degree         = T.degree;
+  d.n_owned_nodes  = T.n_owned_nodes;
+  d.n_ghost_nodes  = T.n_ghost_nodes;
+  d.node_global    = T.node_global.data();
+  d.n_cells        = T.n_cells;
+  d.cell_nodes     = T.cell_nodes.data();
+  d.cell_origin    = T.cell_origin.data();
+  d.cell_h         = T.cell_h.data();
+  d.cell_owned     = T.cell_owned.data();
+  d.n_wall_faces   = (int32_t)T.wall_face_cell.size();
+  d.wall_face_cell = T.wall_face_cell.data();
+  d.wall_face_no   = T.wall_face_no.data();
+  d.wall_face_bid  = T.wall_face_bid.data();
+  vh_constraints c;
+  c.n_lines                   = (int32_t)T.c_dof.size();
+  c.dof                       = T.c_dof.data();
+  c.ptr                       = T.c_ptr.data();
+  c.master                    = T.c_master.data();
+  c.weight                    = T.c_weight.data();
+  d.constraints_newton_update = c; // identical structure: both use zero Dirichlet values (dirichlet.h:110-169)
+  d.constraints_solution      = c;
+  int rc                      = vh_create(&d, 0, &gpu);
+  if (rc != VH_OK)
+    throw std::runtime_error(std::string("vh_create: ") + vh_last_error(nullptr));
+  const double beta[5] = {beta1, beta2, beta3, beta4, beta5};
+  check(vh_set_coefficients(gpu, K1, K2, K3, alpha, beta, bt), "vh_set_coefficients");
+
+  if (cycle == 0)
+    { // initial condition
+      conf.enter_subsection("control parameters");
+      const std::string ic           = conf.get("initial condition");
+      const double      rangeA_ratio = conf.get_double("A-phase block range ratio");
+      const double      z_half       = conf.get_double("half z length of retangle");
+      conf.leave_subsection();
+      host_solution.assign((size_t)18 * T.n_owned_nodes, 0.0);
+      if (ic == "BnA")
+        { // flat A/B wall at z = ratio*Lz: BnA.h:130-163, setup_uniform_BnA-flatwall-configuration.cc:228-235
+          const double z_ofA     = rangeA_ratio * z_half;
+          const double matelem_A = mat.gap_A_td(p, reduced_t) * 0.7071067811865475f;
+          const double matelem_B = mat.gap_B_td(p, reduced_t) * 0.5773502691896258f;
+          for (int n = 0; n < T.n_owned_nodes; ++n)
+            {
+              double *v = &host_solution[(size_t)18 * n];
+              if (T.node_xyz[(size_t)3 * n + 2] >= z_ofA)
+                v[0] = v[4] = v[8] = matelem_B;
+              else
+                v[0] = v[10] = matelem_A;
+            }
+        }
+      else
+        { // uniform B phase, setup_uniform_B-phase.cc:245-259
+          const double amp = mat.gap_B_td(p, reduced_t) * 0.577350269f;
+          for (int n = 0; n < T.n_owned_nodes; ++n)
+            {
+              double *v = &host_solution[(size_t)18 * n];
+              v[0] = v[4] = v[8] = amp;
+            }
+        }
+      // constraints_solution.distribute (setup_uniform_B-phase.cc:262): zero the Dirichlet DoFs, interpolate hanging ones
+      for (size_t l = 0; l < T.c_dof.size(); ++l)
+        {
+          double s = 0.0;
+          for (int q = T.c_ptr[l]; q < T.c_ptr[l + 1]; ++q)
+            s += T.c_weight[q] * host_solution[T.c_master[q]];
+          host_solution[T.c_dof[l]] = s;
+        }
+    }
+  check(vh_set_solution(gpu, host_solution.data()), "vh_set_solution");
+}
+
+template <int dim>
+void FemGL<dim>::assemble_system()
+{
+  check(vh_assemble(gpu, &system_rhs_l2), "assemble_system");
+}
+
+template <int dim>
+void FemGL<dim>::compute_residual()
+{
+  check(vh_residual(gpu, &residual_l2), "compute_residual");
+}
+
+template <int dim>
+void FemGL<dim>::solve(const double &tol)
+{
+  std::ostream &pcout = *out;
+  conf.enter_subsection("control parameters");
+  const unsigned int no_n_cycles = (unsigned int)conf.get_integer("Number of n-cycle in AdditionalData"); // AMG only
+  const unsigned int max_linear_solver_iterations = (unsigned int)conf.get_integer("maximum linear iteration number");
+  const int          restart                      = (int)conf.get_integer("GMRES restart length");
+  conf.leave_subsection();
+  (void)no_n_cycles;
+  pcout << " start to build block-Jacobi preconditioner." << std::endl;
+  pcout << " system_rhs.l2_norm() is " << system_rhs_l2 << std::endl;
+  pcout << " Starting linear solving." << std::endl;
+  double final_res = 0;
+  check(vh_solve(gpu, tol, (int)max_linear_solver_iterations, restart, &last_linear_its, &final_res), "solve");
+  pcout << "   Solved in " << last_linear_its << " iterations." << std::endl;
+}
+
+template <int dim>
+void FemGL<dim>::newton_iteration()
+{
+  std::ostream &pcout = *out;
+  conf.enter_subsection("control parameters");
+  const double line_search_step = conf.get_double("primary step length of dampped newton iteration");
+  const bool   dampped_newton   = conf.get_bool("Using dampped Newton iteration");
+  conf.leave_subsection();
+
+  const double previous_residual = system_rhs_l2; // iteration.cc:130
+  last_trials                    = 0;
+  if (dampped_newton == false)
+    {
+      check(vh_line_search_trial(gpu, 1.0), "newton_iteration");
+      compute_residual();
+      last_trials = 1;
+      last_alpha  = 1.0;
+      pcout << " we are in full newton-iteration " << ", residual is: " << residual_l2 << ", previous_residual is: " << previous_residual
+            << std::endl;
+      if (residual_l2 < previous_residual)
+        pcout << " ohh! current_residual < previous_residual, we get better solution ! " << std::endl;
+      else
+        pcout << " Humm ! current_residual >= previous_residual, maybe you need a better guess ! This is full-newton" << std::endl;
+    }
+  else
+    {
+      for (unsigned int i = 0; i < 100; ++i)
+        {
+          const double a = std::pow(line_search_step, static_cast<double>(i));
+          check(vh_line_search_trial(gpu, a), "newton_iteration");
+          compute_residual();
+          ++last_trials;
+          last_alpha = a;
+          pcout << " step length alpha is: " << a << ", residual is: " << residual_l2 << ", previous_residual is: " << previous_residual
+                << std::endl;
+          if (residual_l2 < previous_residual)
+            {
+              pcout << " ohh! current_residual < previous_residual, we get better solution ! " << std::endl;
+              break;
+            }
+          else
+            pcout << " haa! current_residual >= previous_residual, more line search ! " << std::endl;
+        }
+    }
+  check(vh_accept_trial(gpu), "newton_iteration"); // local_solution = distributed_solution (iteration.cc:210)
+}
+
+template <int dim>
+void FemGL<dim>::refine_grid(std::string &refinement_strategy)
+{
+  std::ostream &pcout = *out;
+  // keep the old mesh and solution for the transfer
+  check(vh_get_solution(gpu, host_solution.data()), "refine_grid");
+  std::unique_ptr<Mesh>       old_mesh(new Mesh(*triangulation));
+  std::unique_ptr<RankTables> old_tab(new RankTables(*tables));
+  const std::vector<double>   old_sol = host_solution;
+
+  std::vector<uint8_t> flags((size_t)triangulation->n_cells(), 0);
+  if (refinement_strategy == "global")
+    std::fill(flags.begin(), flags.end(), 1);
+  else
+    { // The reference uses deal.II's KellyErrorEstimator + refine_and_coarsen_fixed_number (refine.cc:144-153), which is
+      // not available here.  Surrogate with the same interface semantics (a fixed FRACTION of cells): the indicator is
+      // the jump-free cell quantity h * |grad A|_cell estimated from the nodal values.
+      conf.enter_subsection("control parameters");
+      const double refine_ratio = conf.get_double("adaptive refinment ratio");
+      conf.leave_subsection();
+      const int           n  = degree == 1 ? 8 : 27;
+      const int64_t       nc = triangulation->n_cells();
+      std::vector<double> ind(nc, 0.0);
+      for (int64_t e = 0; e < nc; ++e)
+        {
+          double s = 0.0;
+          for (int c = 0; c < 18; ++c)
+            {
+              double lo = 1e300, hi = -1e300;
+              for (int a = 0; a < n; ++a)
+                {
+                  const double v = old_sol[(size_t)18 * old_tab->cell_nodes[(size_t)e * n + a] + c];
+                  lo             = std::min(lo, v);
+                  hi             = std::max(hi, v);
+                }
+              s += (hi - lo) * (hi - lo);
+            }
+          ind[e] = s;
+        }
+      std::vector<double> sorted(ind);
+      std::sort(sorted.begin(), sorted.end());
+      const int64_t n_ref = (int64_t)std::floor(refine_ratio * (double)nc);
+      const double  thr   = n_ref > 0 ? sorted[nc - n_ref] : 1e300;
+      for (int64_t e = 0; e < nc; ++e)
+        flags[e] = ind[e] >= thr && ind[e] > 0.0;
+    }
+  triangulation->refine(flags);
+  // SolutionTransfer::interpolate (refine.cc:128-130,171-175): FE interpolation of the old field at the new nodes
+  triangulation->finalize(1);
+  std::vector<double> new_sol;
+  triangulation->interpolate_from(*old_mesh, old_sol, new_sol);
+  host_solution = new_sol;
+  setup_system(); // re-creates the GPU context for the new mesh and uploads host_solution (cycle > 0 keeps it)
+  pcout << (refinement_strategy == "global" ? "setup_system() call is done ! this is global refinment" : "setup_system() call is done !")
+        << std::endl;
+  if (refinement_strategy != "global")
+    pcout << "adaptive_refine_grid() call is done !" << std::endl;
+}
+
+template <int dim>
+void FemGL<dim>::output_results(const std::string &dirc) const
+{
+  // VTU/PVTU output (io.cc:106-170) is out of scope; the solution is available through solution().
+  (void)dirc;
+}
+
+template <int dim>
+void FemGL<dim>::run()
+{
+  std::ostream &pcout = *out;
+  pcout << "Running using the B200 CUDA hot path (vh_femgl)." << std::endl;
+  conf.enter_subsection("control parameters");
+  const unsigned int n_cycles    = (unsigned int)conf.get_integer("Number of refinements");
+  const unsigned int n_iteration = (unsigned int)conf.get_integer("Number of interations");
+  std::vector<double> cycleX_refine_threshold = {conf.get_double("Cycle 0 refinement threshold"), conf.get_double("Cycle 1 refinement threshold"),
+                                                 conf.get_double("Cycle 2 refinement threshold"), conf.get_double("Cycle 3 refinement threshold")};
+  std::vector<bool>   cycleX_refine_strategy  = {conf.get_bool("Cycle 1 do global refinement"), conf.get_bool("Cycle 2 do global refinement"),
+                                                 conf.get_bool("Cycle 3 do global refinement"), conf.get_bool("Cycle 4 do global refinement")};
+  std::vector<double> cycleX_solve_tol        = {conf.get_double("Cycle 0 linear solver tol"), conf.get_double("Cycle 1 linear solver tol"),
+                                                 conf.get_double("Cycle 2 linear solver tol"), conf.get_double("Cycle 3 linear solver tol"),
+                                                 conf.get_double("Cycle 4 linear solver tol")};
+  const double        converge_acc            = conf.get_double("converge accuracy");
+  conf.leave_subsection();
+  if (n_cycles > 4)
+    throw std::runtime_error("Number of refinements > 4: the reference declares tolerances for cycles 0..4 only");
+
+  std::string ref_str;
+  for (cycle = 0; cycle <= n_cycles; ++cycle)
+    {
+      pcout << "\n" << "Refinement Cycle is " << cycle << "\n"
+            << "------------------------------------------------------" << "\n"
+            << "------------------------------------------------------" << "\n" << std::endl;
+      if (cycle == 0)
+        {
+          pcout << " cycle 0 will be globally refined in make_grid() call " << "\n" << std::endl;
+          make_grid();
+          setup_system();
+          output_results("./setup_config/");
+        }
+      else
+        {
+          pcout << " 0th rank has active cells : " << triangulation->n_cells() << " cycleX_refine_strategy[cycle-1] is "
+                << cycleX_refine_strategy[cycle - 1] << "\n" << std::endl;
+          ref_str = cycleX_refine_strategy[cycle - 1] ? "global" : "adaptive";
+          refine_grid(ref_str);
+        }
+      double residual_last_iter = 0.0;
+      for (iteration_loop = 0; iteration_loop <= n_iteration; ++iteration_loop)
+        {
+          pcout << "Refinement cycle : " << cycle << ", " << "iteration_loop: " << iteration_loop << std::endl;
+          StepRecord rec{};
+          rec.cycle     = cycle;
+          rec.iteration = iteration_loop;
+          double t0     = now_ms();
+          assemble_system();
+          rec.t_assemble_ms = now_ms() - t0;
+          pcout << " assembly is done !" << std::endl;
+          t0 = now_ms();
+          solve(cycleX_solve_tol[cycle]);
+          rec.t_solve_ms = now_ms() - t0;
+          pcout << " block-Jacobi preconditioned solving is done ! With solver_tol " << cycleX_solve_tol[cycle] << std::endl;
+          t0 = now_ms();
+          newton_iteration();
+          rec.t_newton_ms = now_ms() - t0;
+          pcout << " newton iteration is done !" << std::endl;
+          output_results("./refine-cycle_" + std::to_string(cycle) + "/");
+          rec.rhs_norm   = system_rhs_l2;
+          rec.linear_its = last_linear_its;
+          rec.residual   = residual_l2;
+          rec.alpha      = last_alpha;
+          rec.trials     = last_trials;
+          check(vh_energy(gpu, 0, &rec.energy), "energy");
+          records.push_back(rec);
+          pcout << " timings [ms]: assembly " << rec.t_assemble_ms << ", solve " << rec.t_solve_ms << ", newton_iteration "
+                << rec.t_newton_ms << ", free energy " << rec.energy << "\n" << std::endl;
+
+          const double residual_l2_norm = residual_l2; // run.cc:234-250
+          if ((std::fabs(residual_l2_norm - residual_last_iter) < cycleX_refine_threshold[cycle < 4 ? cycle : 3]) &&
+              (residual_l2_norm > converge_acc) && (cycle < n_cycles))
+            break;
+          else if (residual_l2_norm <= converge_acc)
+            break;
+          else
+            residual_last_iter = residual_l2_norm;
+        }
+      if (residual_l2 <= converge_acc)
+        break;
+    }
+  if (gpu)
+    check(vh_get_solution(gpu, host_solution.data()), "get_solution");
+}
+
+template class FemGL<3>;
+} // namespace vhhost

@@ -1,6 +1,8 @@
 // C entry points over the host-side mesh tables (mesh.h), for ctypes (tests, bench.py) and for C callers.
 // Not part of the GPU drop-in boundary (that is include/vh_femgl.h); this is the stand-in for what deal.II
 // hands to the adapter.
+#include "confreader.h"
+#include "matep.h"
 #include "mesh.h"
 
 #include "../../include/vh_femgl.h"
@@ -172,6 +174,76 @@ void vhh_tables_sizes(void *t, int64_t *out)
   out[1]        = T->n_owned_nodes;
   out[2]        = T->n_ghost_nodes;
   out[3]        = T->n_cells;
+}
+
+// ---- Matep restatement: out12 = alpha, beta1..5, gapA, gapB, fA, fB, Tcp_mK, tAB_RWS ----
+void vhh_matep(double p, double t, int scc, double *out12)
+{
+  vhhost::Matep mat;
+  bool          key = scc != 0;
+  mat.with_SCC(key);
+  out12[0]  = mat.alpha_td(t);
+  out12[1]  = mat.beta1_td(p, t);
+  out12[2]  = mat.beta2_td(p, t);
+  out12[3]  = mat.beta3_td(p, t);
+  out12[4]  = mat.beta4_td(p, t);
+  out12[5]  = mat.beta5_td(p, t);
+  out12[6]  = mat.gap_A_td(p, t);
+  out12[7]  = mat.gap_B_td(p, t);
+  out12[8]  = mat.f_A_td(p, t);
+  out12[9]  = mat.f_B_td(p, t);
+  out12[10] = mat.Tcp_mK(p);
+  out12[11] = mat.tAB_RWS(p);
+}
+
+// ---- confreader / ParameterHandler: parse prm text, return "subsection/key=value" lines (newline separated) ----
+const char *vhh_prm_dump(const char *prm_text)
+{
+  static thread_local std::string out;
+  out.clear();
+  try
+    {
+      vhhost::ParameterHandler prm;
+      vhhost::confreader       cr(prm);
+      prm.parse_input_from_string(prm_text ? prm_text : "");
+      for (const std::string &k : prm.declared_keys())
+        {
+          const size_t slash = k.find('/');
+          prm.enter_subsection(k.substr(0, slash));
+          out += k + "=" + prm.get(k.substr(slash + 1)) + "\n";
+          prm.leave_subsection();
+        }
+    }
+  catch (const std::exception &e)
+    {
+      g_err = e.what();
+      return nullptr;
+    }
+  return out.c_str();
+}
+
+// ---- solution transfer between two finalized meshes (single rank: global node order) ----
+int vhh_mesh_interpolate(void *new_mesh, void *old_mesh, const double *old_values, double *new_values)
+{
+  try
+    {
+      Mesh               *N = static_cast<Mesh *>(new_mesh), *O = static_cast<Mesh *>(old_mesh);
+      std::vector<double> ov(old_values, old_values + 18 * O->n_nodes), nv;
+      N->interpolate_from(*O, ov, nv);
+      std::memcpy(new_values, nv.data(), nv.size() * sizeof(double));
+      return 0;
+    }
+  catch (const std::exception &e)
+    {
+      g_err = e.what();
+      return -1;
+    }
+}
+void *vhh_mesh_clone(void *m) { return new Mesh(*static_cast<Mesh *>(m)); }
+void  vhh_mesh_node_xyz(void *m, double *out)
+{
+  Mesh *M = static_cast<Mesh *>(m);
+  std::memcpy(out, M->node_xyz.data(), M->node_xyz.size() * sizeof(double));
 }
 
 } // extern "C"

@@ -294,6 +294,8 @@ void Mesh::finalize(int n_ranks_)
           node_xyz[(size_t)j * 3 + d] = lo[d] + (hi[d] - lo[d]) * ((double)node_X[(size_t)i * 3 + d] / (double)(base[d] * U));
         }
     }
+  node_lattice = nX;
+  lattice_U    = U;
   for (auto &kv : node_of)
     kv.second = newid[kv.second];
   cell_nodes.resize(tmp_cell_nodes.size());
@@ -507,6 +509,62 @@ void Mesh::finalize(int n_ranks_)
         std::sort(gh.begin(), gh.end()); // rank-major global numbering => sorted by (owner, id)
       }
   }
+}
+
+void Mesh::interpolate_from(const Mesh &old_mesh, const std::vector<double> &old_values, std::vector<double> &new_values) const
+{
+  if (n_ranks < 1 || old_mesh.n_ranks < 1)
+    throw std::runtime_error("Mesh::interpolate_from: both meshes must be finalized");
+  if (old_mesh.degree != degree || (int64_t)old_values.size() != 18 * old_mesh.n_nodes)
+    throw std::invalid_argument("Mesh::interpolate_from: incompatible meshes / value array");
+  const int n = degree == 1 ? 8 : 27;
+  std::unordered_map<uint64_t, int64_t> where;
+  where.reserve(old_mesh.leaves.size() * 2);
+  auto pack = [](int level, const int64_t g[3]) {
+    return ((uint64_t)level << 58) | ((uint64_t)g[0] << 38) | ((uint64_t)g[1] << 19) | (uint64_t)g[2];
+  };
+  for (int64_t e = 0; e < old_mesh.n_cells(); ++e)
+    {
+      const Leaf   &l    = old_mesh.leaves[e];
+      const int64_t g[3] = {l.g[0], l.g[1], l.g[2]};
+      where[pack(l.level, g)] = e;
+    }
+  new_values.assign((size_t)18 * n_nodes, 0.0);
+  for (int64_t nd = 0; nd < n_nodes; ++nd)
+    {
+      const int64_t *X = &node_lattice[(size_t)3 * nd];
+      int64_t        cell = -1;
+      double         xi[3] = {0, 0, 0};
+      for (int lev = old_mesh.Lmax; lev >= 0 && cell < 0; --lev)
+        {
+          const int64_t cs = lattice_U >> lev;
+          int64_t       g[3];
+          for (int d = 0; d < 3; ++d)
+            {
+              g[d] = X[d] / cs;
+              if (g[d] > ((int64_t)base[d] << lev) - 1)
+                g[d] = ((int64_t)base[d] << lev) - 1;
+              xi[d] = (double)(X[d] - g[d] * cs) / (double)cs;
+            }
+          auto it = where.find(pack(lev, g));
+          if (it != where.end())
+            cell = it->second;
+        }
+      if (cell < 0)
+        throw std::runtime_error("Mesh::interpolate_from: node outside the old mesh");
+      for (int a = 0; a < n; ++a)
+        {
+          int t[3];
+          node_t(degree, a, t);
+          const double w = lagrange(degree, t[0], xi[0]) * lagrange(degree, t[1], xi[1]) * lagrange(degree, t[2], xi[2]);
+          if (w == 0.0)
+            continue;
+          const double *src = &old_values[(size_t)18 * old_mesh.cell_nodes[(size_t)cell * n + a]];
+          double       *dst = &new_values[(size_t)18 * nd];
+          for (int c = 0; c < 18; ++c)
+            dst[c] += w * src[c];
+        }
+    }
 }
 
 RankTables Mesh::tables(int r) const

@@ -66,6 +66,11 @@ public:
 
   RankTables tables(int rank) const;
 
+  // SolutionTransfer::interpolate stand-in (refine.cc:128-130,171-175): FE interpolation of a field given on the
+  // nodes of `old_mesh` (global node order, 18 values per node) at this mesh's nodes.  Both meshes must be finalized
+  // and this mesh must be a refinement of old_mesh.
+  void interpolate_from(const Mesh &old_mesh, const std::vector<double> &old_values, std::vector<double> &new_values) const;
+
   // ---- global data, valid after finalize() ----
   int                  degree;
   int                  n_ranks = 0;
@@ -80,6 +85,8 @@ public:
   std::vector<int64_t> c_dof, c_ptr, c_master;
   std::vector<double>  c_weight;
   int64_t              n_hanging_nodes = 0;
+  std::vector<int64_t> node_lattice;        // [n_nodes][3] integer lattice coordinates, root cell side = lattice_U units
+  int64_t              lattice_U = 0;
 
   void cell_box(int64_t e, double origin[3], double h[3]) const;
 
