@@ -35,19 +35,8 @@ void *vhd_run(const char *prm_text)
       r->prm.enter_subsection("control parameters");
       const unsigned int degree = (unsigned int)r->prm.get_integer("polynomial degree");
       r->prm.leave_subsection();
-      std::streambuf *old = std::cout.rdbuf(r->log.rdbuf()); // the ctor prints its banner through std::cout
-      try
-        {
-          r->femgl.reset(new FemGL<3>(degree, r->prm));
-          r->femgl->set_output_stream(&r->log);
-          r->femgl->run();
-        }
-      catch (...)
-        {
-          std::cout.rdbuf(old);
-          throw;
-        }
-      std::cout.rdbuf(old);
+      r->femgl.reset(new FemGL<3>(degree, r->prm, &r->log));
+      r->femgl->run();
     }
   catch (const std::exception &e)
     {

@@ -40,8 +40,8 @@ void FemGL<dim>::check(int rc, const char *what) const
 }
 
 template <int dim>
-FemGL<dim>::FemGL(unsigned int Q_degree, ParameterHandler &prmHandler)
-  : degree(Q_degree), cycle(0), iteration_loop(0), conf(prmHandler), out(&std::cout)
+FemGL<dim>::FemGL(unsigned int Q_degree, ParameterHandler &prmHandler, std::ostream *log)
+  : degree(Q_degree), cycle(0), iteration_loop(0), conf(prmHandler), out(log ? log : &std::cout)
 {
   static_assert(dim == 3, "femgl is three-dimensional");
   conf.enter_subsection("physical parameters");

@@ -25,7 +25,8 @@ template <int dim>
 class FemGL
 {
 public:
-  FemGL(unsigned int Q_degree, ParameterHandler &);
+  // `log` is where the reference's pcout lines go (default std::cout, as in the reference)
+  FemGL(unsigned int Q_degree, ParameterHandler &, std::ostream *log = nullptr);
   ~FemGL();
 
   void run();
