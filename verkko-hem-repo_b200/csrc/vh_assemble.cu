@@ -295,7 +295,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 __global__ void __launch_bounds__(VH_FAST_THREADS, 4)
   k_rows_fast_q1(const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells,
                  const int8_t *__restrict__ fast_slot, const int32_t *__restrict__ fast_class,
-                 const double *__restrict__ class_tab, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                 const double *__restrict__ class_M, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                  const uint32_t *__restrict__ dirmask, const double *__restrict__ Hq, const double *__restrict__ Dc,
                  const double *__restrict__ avgD, VhCoef cf, double *__restrict__ vals)
 {
@@ -322,9 +322,9 @@ __global__ void __launch_bounds__(VH_FAST_THREADS, 4)
         mbar_init(s_bar + k, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-  {
-    const double *cls = class_tab + (size_t)fast_class[r] * VH_BLK;
-    for (int i = t; i < VH_BLK; i += VH_FAST_THREADS)
+  { // geometry-only part of every block of this row's stencil: block += kron(I_6, M_s), M_s 3x3 (stride 10, [9] = 0)
+    const double *cls = class_M + (size_t)fast_class[r] * 270;
+    for (int i = t; i < 270; i += VH_FAST_THREADS)
       s_cls[i] = cls[i];
   }
   __syncthreads();
@@ -403,32 +403,24 @@ __global__ void __launch_bounds__(VH_FAST_THREADS, 4)
   const uint32_t maskI = dirmask[I];
   const int      rp    = row_ptr[I];
   if (t < 27)
-    { // per-slot column Dirichlet masks and tr(GS), so the store loop has no dependent global loads
+    { // per-slot column Dirichlet masks, so the store loop has no dependent global loads
       const int pos = s_pos[t];
       s_maskJ[t]    = pos >= 0 ? dirmask[col[rp + pos]] : 0u;
-      s_tr[t]       = s_cls[t * 12 + 0] + s_cls[t * 12 + 4] + s_cls[t * 12 + 8];
     }
   __syncthreads();
-  // 2. every thread owns two fixed 16-byte pieces of the 18x18 block (double2 #t and #t+96): its four entries'
-  //    packed offsets, geometry selectors and row masks are loop invariants; the slot loop is rolled and barrier-free.
-  const double kf = cf.bt < 1e10 ? cf.K1 / cf.bt : 0.0;
-  int          soff[4], gsel[4], fsel[4], ecol[4];
-  double       wK1[4], wF[4], wK23[4];
-  bool         rmask[4], isdiag[4];
+  // 2. every thread owns two fixed 16-byte pieces of the 18x18 block (double2 #t and #t+96): the packed offsets and
+  //    geometry selectors of its four entries are loop invariants; the slot loop is rolled and barrier-free.
+  int      soff[4], gsel[4];
+  uint32_t rbit[4], cbit[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     {
-      const int i = t + VH_FAST_THREADS * (k >> 1);           // double2 index inside the block
+      const int i = t + VH_FAST_THREADS * (k >> 1); // double2 index inside the block
       const int c = min((2 * i) / 18, 17), d = (2 * i) % 18 + (k & 1);
-      soff[k]   = c <= d ? vh_sym_index(c, d) : vh_sym_index(d, c);
-      gsel[k]   = (c % 3) * 3 + d % 3;
-      fsel[k]   = 9 + c % 3;
-      ecol[k]   = d;
-      isdiag[k] = c == d;
-      wK1[k]    = c == d ? cf.K1 : 0.0;
-      wF[k]     = c == d ? kf : 0.0;
-      wK23[k]   = (c / 3 == d / 3) ? cf.K23 : 0.0;
-      rmask[k]  = (maskI >> c) & 1u;
+      soff[k] = c <= d ? vh_sym_index(c, d) : vh_sym_index(d, c);
+      gsel[k] = (c / 3 == d / 3) ? (c % 3) * 3 + d % 3 : 9; // entry 9 of every M_s is 0
+      rbit[k] = 1u << c;
+      cbit[k] = 1u << d;
     }
   const bool second = t + VH_FAST_THREADS < VH_BLK / 2;
   for (int s = 0; s < 27; ++s)
@@ -437,41 +429,39 @@ __global__ void __launch_bounds__(VH_FAST_THREADS, 4)
       if (pos < 0)
         continue; // block-uniform
       const double  *sy    = s_sym + s * VH_SYMP;
-      const double  *G     = s_cls + s * 12;
-      const double   trG   = s_tr[s];
+      const double  *M     = s_cls + s * 10;
       const uint32_t maskJ = s_maskJ[s];
       double         v[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        {
-          double val = sy[soff[k]];
-          val        = fma(wK1[k], trG, val);
-          val        = fma(wF[k], G[fsel[k]], val);
-          val        = fma(wK23[k], G[gsel[k]], val);
-          // component-masked Dirichlet DoFs: row and column dropped (distribute_local_to_global)
-          if (rmask[k] || ((maskJ >> ecol[k]) & 1u))
-            val = 0.0;
-          v[k] = val;
-        }
-      if (s == 13 && maskI != 0u)
-        { // constrained diagonal: sum over cells of |a_ii| (mean |diag| of the cell if a_ii == 0)
+        v[k] = sy[soff[k]] + M[gsel[k]];
+      if ((maskI | maskJ) != 0u)
+        { // component-masked Dirichlet DoFs (block-uniform branch): row and column dropped (distribute_local_to_global)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (isdiag[k] && rmask[k])
-              {
-                double dsum = 0.0;
-                for (int o = 0; o < 8; ++o)
+            if ((maskI & rbit[k]) || (maskJ & cbit[k]))
+              v[k] = 0.0;
+          if (s == 13)
+            { // constrained diagonal: sum over cells of |a_ii| (mean |diag| of the cell if a_ii == 0)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (rbit[k] == cbit[k] && (maskI & rbit[k]))
                   {
-                    const int e = s_cells[o];
-                    if (e < 0)
-                      continue;
-                    double dv = fabs(Dc[(size_t)e * 144 + (7 - o) * 18 + ecol[k]]);
-                    if (dv == 0.0)
-                      dv = avgD[e];
-                    dsum += dv;
+                    const int c    = 31 - __clz(rbit[k]);
+                    double    dsum = 0.0;
+                    for (int o = 0; o < 8; ++o)
+                      {
+                        const int e = s_cells[o];
+                        if (e < 0)
+                          continue;
+                        double dv = fabs(Dc[(size_t)e * 144 + (7 - o) * 18 + c]);
+                        if (dv == 0.0)
+                          dv = avgD[e];
+                        dsum += dv;
+                      }
+                    v[k] = dsum;
                   }
-                v[k] = dsum;
-              }
+            }
         }
       double2 *dst = reinterpret_cast<double2 *>(vals + (size_t)(rp + pos) * VH_BLK);
       __stcs(dst + t, make_double2(v[0], v[1])); // streaming stores: the block is not re-read by this kernel
@@ -725,7 +715,7 @@ int vhk_rows_fast(vh_ctx *ctx)
       attr_set = true;
     }
   k_rows_fast_q1<<<ctx->n_fast, VH_FAST_THREADS, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot,
-                                                                             ctx->fast_class, ctx->class_tab, ctx->row_ptr, ctx->col,
+                                                                             ctx->fast_class, ctx->class_M, ctx->row_ptr, ctx->col,
                                                                              ctx->dirmask, ctx->Hq, ctx->Dc, ctx->avgD, ctx->coef,
                                                                              ctx->vals);
   VH_LAUNCH_CHECK();

@@ -500,6 +500,8 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   VH_TRY(vh_dev_upload(ctx, &ctx->fast_slot, fast_slot.data(), fast_slot.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->fast_class, fast_class.data(), fast_class.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->class_tab, class_tab.data(), class_tab.size()));
+  VH_TRY(vh_dev_alloc(ctx, &ctx->class_M, (size_t)ctx->n_classes * 270));
+  ctx->h_class_tab = class_tab;
   VH_TRY(vh_dev_upload(ctx, &ctx->slow_rows, slow_rows.data(), slow_rows.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->slow_cells, slow_cells.data(), slow_cells.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->row_slow, row_slow.data(), row_slow.size()));
@@ -680,7 +682,7 @@ int vh_destroy(vh_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
   vh_comm_destroy(ctx);
   void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
-                  ctx->diag_pos, ctx->minv, ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->slow_rows, ctx->row_slow,
+                  ctx->diag_pos, ctx->minv, ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->slow_rows, ctx->row_slow,
                   ctx->slow_cells, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
                   ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
                   ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,
@@ -724,6 +726,24 @@ int vh_set_coefficients(vh_ctx *ctx, double K1, double K2, double K3, double alp
   ctx->coef.bt     = bt;
   ctx->coef_set    = true;
   ctx->have_matrix = false;
+  // Geometry-only part of the Jacobian per stencil class and slot:  block += kron(I_6, M_s) with
+  //   M_s[x][y] = (K2+K3) GS[x][y] + delta_xy (K1 tr GS + (K1/bt) FS[x])        (Robin term only if bt < 1e10)
+  if (ctx->n_classes > 0)
+    {
+      VH_CUDA(cudaSetDevice(ctx->device));
+      const double        kf = bt < 1e10 ? K1 / bt : 0.0;
+      std::vector<double> M((size_t)ctx->n_classes * 270, 0.0);
+      for (int cl = 0; cl < ctx->n_classes; ++cl)
+        for (int s = 0; s < 27; ++s)
+          {
+            const double *G  = &ctx->h_class_tab[(size_t)cl * VH_BLK + s * 12];
+            const double  tr = G[0] + G[4] + G[8];
+            for (int x = 0; x < 3; ++x)
+              for (int y = 0; y < 3; ++y)
+                M[(size_t)cl * 270 + s * 10 + 3 * x + y] = (K2 + K3) * G[3 * x + y] + (x == y ? K1 * tr + kf * G[9 + x] : 0.0);
+          }
+      VH_CUDA(cudaMemcpy(ctx->class_M, M.data(), M.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
   return VH_OK;
 }
 
