@@ -114,8 +114,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_mesh(n_gpus, refine, degree):
+def build_mesh(n_gpus, refine, degree, global_refine=None):
     import verkko_hem_repo_b200 as vh
+    if global_refine is not None:
+        # strong scaling (BASELINE configs[4]): ONE cube refined `global_refine` times, Morton-partitioned over the ranks
+        L = 20.0
+        m = vh.Mesh(degree, [-L, -L, -L], [L, L, L], base=(1, 1, 1), face_bid=(1, 1, 1, 1, 4, 4), n_global_refine=global_refine)
+        m.finalize(n_gpus)
+        return m
     # weak scaling: N root cubes stacked along z, each refined `refine` times; Morton order keeps each root
     # contiguous, so rank r owns root r (the p4est partition of a 1 x 1 x N brick).
     L = 20.0  # "cube half side length" default (declare.cc:159)
@@ -242,7 +248,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    mesh = build_mesh(world, args.refine, args.degree)
+    mesh = build_mesh(world, args.refine, args.degree, args.global_refine)
     T = mesh.tables(rank)
     ctx = vh.Context(T, device=local_rank)
     if world > 1:
@@ -344,11 +350,12 @@ def run_ours(args):
     if rank == 0:
         out = {"metric": "femgl Newton-step throughput",
                "value": value, "unit": "DoF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.global_refine is None else "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
-               "config": {"workload": "femgl 3D cube Q%d, global refinement %d per GPU (%d DoFs total, %d cells), B-phase IC, "
+               "config": {"workload": "femgl 3D cube Q%d, global refinement %s (%d DoFs total, %d cells), B-phase IC, "
                                       "z walls AdGR diffuse (bt=2), p=25 bar t=0.5 SCC on, linear tol 1e-1, damped Newton 0.83"
-                                      % (args.degree, args.refine, n_dofs, mesh.n_cells),
+                                      % (args.degree, ("%d per GPU" % args.refine) if args.global_refine is None
+                                         else ("%d, one cube split over the GPUs" % args.global_refine), n_dofs, mesh.n_cells),
                           "l2": "matrix (%.2f GB/GPU) exceeds the 126 MB L2; kernel timings flush L2 between launches"
                                 % (8 * 324 * nnzb / 1e9),
                           "parallelism": "subdomain x%d (Morton partition, NCCL halo + all-reduce)" % world},
@@ -380,6 +387,8 @@ def main():
     ap.add_argument("--refine", type=int, default=5)
     ap.add_argument("--degree", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--global-refine", type=int, default=None,
+                    help="strong scaling: one cube with this many global refinements split over the GPUs (7 = BASELINE C5, 38.6M DoFs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
