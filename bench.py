@@ -328,8 +328,17 @@ def run_ours(args):
     asm_flops = 2.0 * n * n * n * 336 * T.n_cells
     asm_bytes = 8 * 324 * nnzb + 8 * 18 * n * T.n_cells
     spmv_gbs = spmv_bytes / (t_spmv * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes per launch measured once with `ncu --set full` for this exact workload (profiles/traffic.json)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        key = "q%d_r%d_%dgpu" % (args.degree, args.refine, world)
+        if args.global_refine is None and key in tj:
+            traffic = tj[key]["k_spmv_bsr18"]["read_bytes"] + tj[key]["k_spmv_bsr18"]["write_bytes"]
+    except Exception:
+        traffic = None
     roof = {"bound": "hbm", "kernel": "k_spmv_bsr18", "achieved": spmv_gbs, "peak": hbm_peak, "unit": "GB/s",
-            "frac": spmv_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": t_spmv,
+            "frac": spmv_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src, "ms_per_launch": t_spmv,
             "algorithmic_bytes_per_launch": spmv_bytes}
     asm = {"ms": t_asm, "dofs_per_s": 18 * nb / (t_asm * 1e-3), "tflops_fp64": asm_flops / (t_asm * 1e-3) / 1e12,
            "fp64_peak_tflops_measured": fp64_peak, "frac_fp64": asm_flops / (t_asm * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,

@@ -19,6 +19,7 @@
 #include "vh_pointwise.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 __constant__ double  c_W1[512];   // Q1: w_q N_a(q) N_b(q), index (a*8+b)*8+q
 __constant__ uint8_t c_symc[VH_SYMP], c_symd[VH_SYMP];
@@ -256,8 +257,6 @@ __global__ void __launch_bounds__(NQ == 8 ? 192 : 512)
 // ------------------------------------------------------------------------------------------------
 // 2. row-owner Jacobian kernel for Q1 rows whose neighbourhood is a piece of a structured lattice
 // ------------------------------------------------------------------------------------------------
-#define VH_FAST_THREADS 96
-#define VH_FAST_ACTIVE 86 /* 86 threads x 2 packed entries = 172 */
 #define VH_FAST_STAGES 4
 #define VH_CELL_H_BYTES (8 * VH_SYMP * 8) /* one cell's 8 x 172 doubles: 11008 B, a multiple of 16 */
 #define VH_FAST_SMEM (VH_FAST_STAGES * VH_CELL_H_BYTES + VH_BLK * 8 + 32 * 8 + VH_FAST_STAGES * 8 + (36 + 28) * 4)
@@ -292,7 +291,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                : "memory");
 }
 
-__global__ void __launch_bounds__(VH_FAST_THREADS, 4)
+// EPT = packed Hessian entries per thread: 2 -> 96 threads/row (86 active), 108 accumulator registers, 12 warps/SM;
+//                                          1 -> 192 threads/row (172 active), 54 accumulator registers, 24 warps/SM.
+template <int EPT>
+__global__ void __launch_bounds__(192 / EPT, 4)
   k_rows_fast_q1(const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells,
                  const int8_t *__restrict__ fast_slot, const int32_t *__restrict__ fast_class,
                  const double *__restrict__ class_M, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
@@ -308,23 +310,34 @@ __global__ void __launch_bounds__(VH_FAST_THREADS, 4)
   int      *s_pos   = s_cells + 8;                                                          // [27] (+1 pad)
   uint32_t *s_maskJ = reinterpret_cast<uint32_t *>(s_pos + 28);                             // [27]
 
-  const int t = threadIdx.x;
-  const int r = blockIdx.x;
-  const int I = fast_rows[r];
-  if (t < 8)
-    s_cells[t] = fast_cells[(size_t)r * 8 + t];
-  if (t >= 32 && t < 59)
-    s_pos[t - 32] = fast_slot[(size_t)r * 32 + (t - 32)];
-  if (t == 64)
-    {
+  constexpr int NT = 192 / EPT, ACT = VH_SYMP / EPT;
+  const int     t = threadIdx.x;
+  const int     r = blockIdx.x;
+  const int     I = fast_rows[r];
+  if (t == 0)
+    { // TMA producer, first thing in the CTA: the DRAM/L2 latency of the first four cells' tables overlaps the prologue
 #pragma unroll
       for (int k = 0; k < VH_FAST_STAGES; ++k)
         mbar_init(s_bar + k, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+      for (int o = 0; o < VH_FAST_STAGES; ++o)
+        {
+          const int e = fast_cells[(size_t)r * 8 + o];
+          if (e >= 0)
+            {
+              mbar_expect_tx(s_bar + o, VH_CELL_H_BYTES);
+              bulk_g2s(s_H + (size_t)o * (8 * VH_SYMP), Hq + (size_t)e * (8 * VH_SYMP), VH_CELL_H_BYTES, s_bar + o);
+            }
+        }
     }
+  if (t >= 64 && t < 72)
+    s_cells[t - 64] = fast_cells[(size_t)r * 8 + (t - 64)];
+  if (t >= 32 && t < 59)
+    s_pos[t - 32] = fast_slot[(size_t)r * 32 + (t - 32)];
   { // geometry-only part of every block of this row's stencil: block += kron(I_6, M_s), M_s 3x3 (stride 10, [9] = 0)
     const double *cls = class_M + (size_t)fast_class[r] * 270;
-    for (int i = t; i < 270; i += VH_FAST_THREADS)
+    for (int i = t; i < 270; i += NT)
       s_cls[i] = cls[i];
   }
   __syncthreads();
@@ -339,18 +352,13 @@ __global__ void __launch_bounds__(VH_FAST_THREADS, 4)
         bulk_g2s(s_H + (size_t)(o & (VH_FAST_STAGES - 1)) * (8 * VH_SYMP), Hq + (size_t)e * (8 * VH_SYMP), VH_CELL_H_BYTES, bar);
       }
   };
-  if (t == 0)
-    {
-#pragma unroll
-      for (int o = 0; o < VH_FAST_STAGES; ++o)
-        issue(o);
-    }
-
   // bulk part:  acc[s](c,d) = sum_o sum_q sum_b->s  w_q N_a(q) N_b(q) (vol_o H_{o,q})(c,d)
-  double acc0[27], acc1[27];
+  double acc[EPT][27];
 #pragma unroll
   for (int s = 0; s < 27; ++s)
-    acc0[s] = acc1[s] = 0.0;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k)
+      acc[k][s] = 0.0;
   uint32_t uses = 0; // bit k: parity of the next completed phase of stage k
 #pragma unroll
   for (int o = 0; o < 8; ++o)
@@ -370,20 +378,28 @@ __global__ void __launch_bounds__(VH_FAST_THREADS, 4)
           const int st = o & (VH_FAST_STAGES - 1);
           mbar_wait(s_bar + st, (uses >> st) & 1u);
           uses ^= 1u << st;
-          if (t < VH_FAST_ACTIVE)
+          if (t < ACT)
             {
-              const double2 *Hp = reinterpret_cast<const double2 *>(s_H + (size_t)st * (8 * VH_SYMP)) + t;
+              const double *Hs = s_H + (size_t)st * (8 * VH_SYMP) + EPT * t;
 #pragma unroll
               for (int q = 0; q < 8; ++q)
                 {
-                  const double2 hv = Hp[q * (VH_SYMP / 2)];
+                  double hv[EPT];
+                  if constexpr (EPT == 2)
+                    {
+                      const double2 h2 = *reinterpret_cast<const double2 *>(Hs + q * VH_SYMP);
+                      hv[0] = h2.x, hv[1] = h2.y;
+                    }
+                  else
+                    hv[0] = Hs[q * VH_SYMP];
 #pragma unroll
                   for (int b = 0; b < 8; ++b)
                     {
                       const int    s = ((o & 1) + (b & 1)) + 3 * (((o >> 1) & 1) + ((b >> 1) & 1)) + 9 * ((o >> 2) + (b >> 2));
                       const double w = c_W1[((7 - o) * 8 + b) * 8 + q];
-                      acc0[s]        = fma(w, hv.x, acc0[s]);
-                      acc1[s]        = fma(w, hv.y, acc1[s]);
+#pragma unroll
+                      for (int k = 0; k < EPT; ++k)
+                        acc[k][s] = fma(w, hv[k], acc[k][s]);
                     }
                 }
             }
@@ -394,11 +410,16 @@ __global__ void __launch_bounds__(VH_FAST_THREADS, 4)
   // 1. dump the packed symmetric accumulators of all 27 slots into the (now idle) TMA ring: [27][172] doubles
   __syncthreads();
   double *s_sym = s_H;
-  if (t < VH_FAST_ACTIVE)
+  if (t < ACT)
     {
 #pragma unroll
       for (int s = 0; s < 27; ++s)
-        reinterpret_cast<double2 *>(s_sym + s * VH_SYMP)[t] = make_double2(acc0[s], acc1[s]);
+        {
+          if constexpr (EPT == 2)
+            reinterpret_cast<double2 *>(s_sym + s * VH_SYMP)[t] = make_double2(acc[0][s], acc[1][s]);
+          else
+            s_sym[s * VH_SYMP + t] = acc[0][s];
+        }
     }
   const uint32_t maskI = dirmask[I];
   const int      rp    = row_ptr[I];
@@ -408,21 +429,23 @@ __global__ void __launch_bounds__(VH_FAST_THREADS, 4)
       s_maskJ[t]    = pos >= 0 ? dirmask[col[rp + pos]] : 0u;
     }
   __syncthreads();
-  // 2. every thread owns two fixed 16-byte pieces of the 18x18 block (double2 #t and #t+96): the packed offsets and
-  //    geometry selectors of its four entries are loop invariants; the slot loop is rolled and barrier-free.
-  int      soff[4], gsel[4];
-  uint32_t rbit[4], cbit[4];
+  // 2. every thread owns EPT fixed 16-byte pieces of the 18x18 block (double2 #t [and #t+96]): the packed offsets and
+  //    geometry selectors of its entries are loop invariants; the slot loop is rolled and barrier-free.
+  constexpr int NE = 2 * EPT;
+  int           soff[NE], gsel[NE];
+  uint32_t      rbit[NE], cbit[NE];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < NE; ++k)
     {
-      const int i = t + VH_FAST_THREADS * (k >> 1); // double2 index inside the block
+      const int i = t + NT * (k >> 1); // double2 index inside the block
       const int c = min((2 * i) / 18, 17), d = (2 * i) % 18 + (k & 1);
       soff[k] = c <= d ? vh_sym_index(c, d) : vh_sym_index(d, c);
       gsel[k] = (c / 3 == d / 3) ? (c % 3) * 3 + d % 3 : 9; // entry 9 of every M_s is 0
       rbit[k] = 1u << c;
       cbit[k] = 1u << d;
     }
-  const bool second = t + VH_FAST_THREADS < VH_BLK / 2;
+  const bool first = t < VH_BLK / 2, second = EPT == 2 && t + NT < VH_BLK / 2;
+#pragma unroll 3
   for (int s = 0; s < 27; ++s)
     {
       const int pos = s_pos[s];
@@ -431,20 +454,20 @@ __global__ void __launch_bounds__(VH_FAST_THREADS, 4)
       const double  *sy    = s_sym + s * VH_SYMP;
       const double  *M     = s_cls + s * 10;
       const uint32_t maskJ = s_maskJ[s];
-      double         v[4];
+      double         v[NE];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < NE; ++k)
         v[k] = sy[soff[k]] + M[gsel[k]];
       if ((maskI | maskJ) != 0u)
         { // component-masked Dirichlet DoFs (block-uniform branch): row and column dropped (distribute_local_to_global)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
+          for (int k = 0; k < NE; ++k)
             if ((maskI & rbit[k]) || (maskJ & cbit[k]))
               v[k] = 0.0;
           if (s == 13)
             { // constrained diagonal: sum over cells of |a_ii| (mean |diag| of the cell if a_ii == 0)
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
+              for (int k = 0; k < NE; ++k)
                 if (rbit[k] == cbit[k] && (maskI & rbit[k]))
                   {
                     const int c    = 31 - __clz(rbit[k]);
@@ -464,9 +487,30 @@ __global__ void __launch_bounds__(VH_FAST_THREADS, 4)
             }
         }
       double2 *dst = reinterpret_cast<double2 *>(vals + (size_t)(rp + pos) * VH_BLK);
-      __stcs(dst + t, make_double2(v[0], v[1])); // streaming stores: the block is not re-read by this kernel
-      if (second)
-        __stcs(dst + t + VH_FAST_THREADS, make_double2(v[2], v[3]));
+      if (first)
+        __stcs(dst + t, make_double2(v[0], v[1])); // streaming stores: the block is not re-read by this kernel
+      if constexpr (EPT == 2)
+        if (second)
+          __stcs(dst + t + NT, make_double2(v[2], v[3]));
+    }
+}
+
+// Store-bandwidth probe with the row kernel's write pattern (one CTA per block row, 16-byte stores, no other work):
+// what the write-once matrix store costs on its own.  Used by vh_time_kernel(what=7) only.
+__global__ void __launch_bounds__(192) k_store_probe(int n_rows, const int32_t *__restrict__ row_ptr, double *__restrict__ vals, int mode)
+{
+  const int r = blockIdx.x;
+  if (r >= n_rows)
+    return;
+  double2      *dst = reinterpret_cast<double2 *>(vals + (size_t)row_ptr[r] * VH_BLK);
+  const int     n2  = (row_ptr[r + 1] - row_ptr[r]) * (VH_BLK / 2);
+  const double2 v   = make_double2(1.0, 2.0);
+  for (int i = threadIdx.x; i < n2; i += blockDim.x)
+    {
+      if (mode == 0)
+        __stcs(dst + i, v);
+      else
+        dst[i] = v;
     }
 }
 
@@ -708,16 +752,29 @@ int vhk_rows_fast(vh_ctx *ctx)
 {
   if (ctx->n_fast == 0)
     return VH_OK;
-  static bool attr_set = false;
-  if (!attr_set)
+  static int ept = 0;
+  if (!ept)
     {
-      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
-      attr_set = true;
+      const char *e = getenv("VH_ROWS_EPT"); // tuning knob: packed entries per thread (1 or 2)
+      ept           = (e && e[0] == '2') ? 2 : 1;
+      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
+      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
     }
-  k_rows_fast_q1<<<ctx->n_fast, VH_FAST_THREADS, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot,
-                                                                             ctx->fast_class, ctx->class_M, ctx->row_ptr, ctx->col,
-                                                                             ctx->dirmask, ctx->Hq, ctx->Dc, ctx->avgD, ctx->coef,
-                                                                             ctx->vals);
+  if (ept == 2)
+    k_rows_fast_q1<2><<<ctx->n_fast, 96, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class,
+                                                                     ctx->class_M, ctx->row_ptr, ctx->col, ctx->dirmask, ctx->Hq,
+                                                                     ctx->Dc, ctx->avgD, ctx->coef, ctx->vals);
+  else
+    k_rows_fast_q1<1><<<ctx->n_fast, 192, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class,
+                                                                      ctx->class_M, ctx->row_ptr, ctx->col, ctx->dirmask, ctx->Hq,
+                                                                      ctx->Dc, ctx->avgD, ctx->coef, ctx->vals);
+  VH_LAUNCH_CHECK();
+  return VH_OK;
+}
+
+int vhk_store_probe(vh_ctx *ctx, int mode)
+{
+  k_store_probe<<<ctx->n_owned, 192, 0, ctx->stream>>>(ctx->n_owned, ctx->row_ptr, ctx->vals, mode);
   VH_LAUNCH_CHECK();
   return VH_OK;
 }

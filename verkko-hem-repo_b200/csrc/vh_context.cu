@@ -1025,6 +1025,11 @@ int vh_time_kernel(vh_ctx *ctx, int what, int reps, int do_flush, float *ms_avg)
         case 6:
           VH_TRY(vhk_rows_fast(ctx));
           break;
+        case 7: // destroys the matrix values: bandwidth probe only
+        case 8:
+          VH_TRY(vhk_store_probe(ctx, what - 7));
+          ctx->have_matrix = false;
+          break;
         default:
           return vh_fail(ctx, VH_ERR_ARG, "vh_time_kernel: unknown kernel id");
         }

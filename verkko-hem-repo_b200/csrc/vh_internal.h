@@ -170,6 +170,7 @@ int vhk_pointwise(vh_ctx *ctx, const double *x_local, bool want_hessian, bool wa
 int vhk_rows_fast(vh_ctx *ctx);
 int vhk_rows_slow(vh_ctx *ctx, bool want_matrix, double *rhs_out);
 int vhk_rhs_fast(vh_ctx *ctx, double *rhs_out);
+int vhk_store_probe(vh_ctx *ctx, int mode);
 int vhk_upload_constants(vh_ctx *ctx);
 int vhk_upload_w1(vh_ctx *ctx, const double *W1);
 

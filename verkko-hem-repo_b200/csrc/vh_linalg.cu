@@ -94,8 +94,10 @@ __global__ void __launch_bounds__(128)
   k_block_invert(int n_rows, const int32_t *__restrict__ diag_pos, const double *__restrict__ vals, double *__restrict__ minv,
                  int *__restrict__ n_singular)
 {
-  // Register-resident Gauss-Jordan: lane r < 18 keeps row r of [A | I] in registers, the pivot row is broadcast by
-  // shuffles, and rows are never swapped physically: the lane that pivots on column k ends up holding row k of A^-1.
+  // Register-resident Gauss-Jordan: lane r < 18 keeps row r of [A | I] in registers; the scaled pivot row is broadcast
+  // through shared memory (shuffles would be the bottleneck: ~1000 per block), and rows are never swapped physically:
+  // the lane that pivots on column k ends up holding row k of A^-1.
+  __shared__ __align__(16) double s_row[4][36];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int row  = blockIdx.x * 4 + wid;
   if (row >= n_rows)
@@ -135,13 +137,24 @@ __global__ void __launch_bounds__(128)
         }
       const double inv = 1.0 / __shfl_sync(0xffffffffu, a[k], pl);
       const bool   me  = lane == pl;
-      const double f   = me ? 0.0 : a[k];
-#pragma unroll
-      for (int c = k + 1; c < 36; ++c)
+      const double f   = a[k];
+      if (me)
         {
-          const double p = __shfl_sync(0xffffffffu, a[c], pl) * inv;
-          a[c]           = me ? p : fma(-f, p, a[c]);
+#pragma unroll
+          for (int c = k + 1; c < 36; ++c)
+            {
+              a[c] *= inv;
+              s_row[wid][c] = a[c];
+            }
         }
+      __syncwarp();
+      if (!me)
+        {
+#pragma unroll
+          for (int c = k + 1; c < 36; ++c)
+            a[c] = fma(-f, s_row[wid][c], a[c]);
+        }
+      __syncwarp();
       a[k] = me ? 1.0 : 0.0;
       if (me)
         {
