@@ -347,7 +347,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        s = reference_sample(args.refine, 1)
+        s = reference_sample(args.refine, 6)
         if s is not None:
             n_cells = mesh.n_cells
             step_s = n_cells / s["cells_per_s"]

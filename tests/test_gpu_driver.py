@@ -132,3 +132,57 @@ def test_two_gpu_run_equals_one_gpu_run():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTIGPU PARITY OK" in r.stdout
+
+
+SLAB_PRM = """
+subsection physical parameters
+  set pressure in bar = 25.0
+  set t_reduced = 0.5
+  set AdGR diffuse length = 2.0
+end
+subsection control parameters
+  set geometry = retangle
+  set initial condition = BnA
+  set half x length of retangle = 3.0
+  set half y length of retangle = 2.0
+  set half z length of retangle = 4.0
+  set A-phase block range ratio = 0.1
+  set Number of initial global refinments = 2
+  set Number of refinements = %d
+  set Number of interations = 2
+  set Cycle 0 refinement threshold = %g
+end
+"""
+
+
+def test_slab_with_ab_interface_matches_oracle_first_steps():
+    """C4-shaped configuration (hyper_rectangle slab, flat A/B wall initial condition BnA.h:130-163, AdGR z walls):
+    the first Newton steps through FemGL::run() equal the oracle's on the same anisotropic mesh."""
+    out = vh.run_prm(SLAB_PRM % (0, 1e-12))
+    m = vh.Mesh(1, [-3, -2, -4], [3, 2, 4], n_global_refine=2).finalize(1)
+    T = m.tables(0)
+    mat = vh.matep(25.0, 0.5, True)
+    coef = np.array([0.42072] * 3 + [mat["alpha"], mat["beta1"], mat["beta2"], mat["beta3"], mat["beta4"], mat["beta5"], 2.0])
+    x = np.zeros((T.n_local_nodes, 18))
+    isB = T.node_xyz[:, 2] >= 0.1 * 4.0
+    eA = mat["gapA"] * float(np.float32(0.7071067811865475))
+    eB = mat["gapB"] * float(np.float32(0.5773502691896258))
+    x[isB, 0] = x[isB, 4] = x[isB, 8] = eB
+    x[~isB, 0] = x[~isB, 10] = eA
+    x = O.distribute(T, x.ravel())
+    for rec in out["history"]:
+        o = O.newton_step(T, x, coef, 1e-1)
+        assert abs(rec["rhs_norm"] - o["rhs_norm"]) <= 1e-10 * o["rhs_norm"]
+        assert rec["linear_its"] == o["lin_its"] and rec["trials"] == o["n_trials"]
+        assert abs(rec["residual"] - o["res_norm"]) <= 1e-10 * o["res_norm"]
+        x = o["x"]
+
+
+def test_slab_adaptive_cycles_run_to_completion():
+    out = vh.run_prm(SLAB_PRM % (2, 1e3))
+    hist = out["history"]
+    assert sorted(set(h["cycle"] for h in hist)) == [0, 1, 2]
+    assert all(np.isfinite(h["residual"]) and np.isfinite(h["energy"]) for h in hist)
+    # the refinement concentrates on the A/B interface: the mesh grows but stays far below uniform refinement
+    n0 = 18 * 5 * 5 * 5
+    assert n0 < out["solution"].size < 18 * 17 ** 3
