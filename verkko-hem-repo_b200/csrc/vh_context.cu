@@ -563,7 +563,7 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
       VH_TRY(vh_dev_alloc(ctx, p, (size_t)ctx->NO));
       VH_CUDA(cudaMemset(*p, 0, sizeof(double) * (size_t)std::max<int64_t>(ctx->NO, 1)));
     }
-  VH_TRY(vh_dev_alloc(ctx, &ctx->partials, VH_MAX_RED_BLOCKS));
+  VH_TRY(vh_dev_alloc(ctx, &ctx->partials, (size_t)VH_MAX_RED_BLOCKS * 32));
   VH_TRY(vh_dev_alloc(ctx, &ctx->scal, VH_SCAL_COUNT));
   VH_TRY(vh_dev_alloc(ctx, &ctx->ticket, 4));
   VH_CUDA(cudaMemset(ctx->ticket, 0, 4 * sizeof(unsigned int)));

@@ -134,19 +134,26 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
       for (int j = 0; j < m; ++j)
         {
           double *vj = ctx->V + (size_t)j * NO;
+          // v_j = aux / a and z = M^-1 v_j (owned part of zbuf) in one pass; ghosts refreshed; aux = A z
           if (a != 0.0)
-            VH_TRY(vhk_scale_to(ctx, vj, aux, a2_d));
+            VH_TRY(vhk_block_jacobi_apply_scaled(ctx, aux, a2_d, vj, ctx->zbuf));
           else
-            VH_CUDA(cudaMemsetAsync(vj, 0, sizeof(double) * NO, ctx->stream));
-          // z = M^-1 v_j (owned part of zbuf), ghosts refreshed, aux = A z
-          VH_TRY(vhk_block_jacobi_apply(ctx, vj, ctx->zbuf));
+            {
+              VH_CUDA(cudaMemsetAsync(vj, 0, sizeof(double) * NO, ctx->stream));
+              VH_CUDA(cudaMemsetAsync(ctx->zbuf, 0, sizeof(double) * NO, ctx->stream));
+            }
           VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
           VH_TRY(vhk_spmv(ctx, ctx->zbuf, aux));
-          // modified Gram-Schmidt, coefficients stay on the device between the fused kernels
-          VH_TRY(vhk_dot(ctx, aux, ctx->V, hcol + 0));
-          for (int i = 1; i <= j; ++i)
-            VH_TRY(vhk_add_and_dot(ctx, aux, hcol + (i - 1), ctx->V + (size_t)(i - 1) * NO, ctx->V + (size_t)i * NO, hcol + i));
-          VH_TRY(vhk_add_and_dot(ctx, aux, hcol + j, vj, aux, hcol + j + 1));
+          // modified Gram-Schmidt; the coefficients never leave the device between the fused steps
+          bool fused = false;
+          VH_TRY(vhk_mgs_fused(ctx, aux, ctx->V, NO, j, hcol, &fused));
+          if (!fused)
+            {
+              VH_TRY(vhk_dot(ctx, aux, ctx->V, hcol + 0));
+              for (int i = 1; i <= j; ++i)
+                VH_TRY(vhk_add_and_dot(ctx, aux, hcol + (i - 1), ctx->V + (size_t)(i - 1) * NO, ctx->V + (size_t)i * NO, hcol + i));
+              VH_TRY(vhk_add_and_dot(ctx, aux, hcol + j, vj, aux, hcol + j + 1));
+            }
           std::vector<double> hc(j + 2);
           VH_TRY(vh_read_scalars(ctx, hcol, j + 2, hc.data()));
           for (int i = 0; i <= j; ++i)

@@ -128,7 +128,7 @@ struct vh_ctx
   size_t      flush_bytes = 0;
 };
 
-#define VH_MAX_RED_BLOCKS 2048
+#define VH_MAX_RED_BLOCKS 2048 /* ctx->partials holds 32x this many doubles (fused Gram-Schmidt: one set per step) */
 // layout of the device scalar scratch ctx->scal
 #define VH_MAX_RESTART 100
 #define VH_SCAL_HCOL 0    /* Hessenberg column of the current GMRES inner step (<= VH_MAX_RESTART+1) */
@@ -178,6 +178,8 @@ int vhk_upload_w1(vh_ctx *ctx, const double *W1);
 int vhk_spmv(vh_ctx *ctx, const double *x_local, double *y_owned);
 int vhk_block_jacobi_setup(vh_ctx *ctx);
 int vhk_block_jacobi_apply(vh_ctx *ctx, const double *x_owned, double *y_owned);
+int vhk_block_jacobi_apply_scaled(vh_ctx *ctx, const double *x_owned, const double *nsq_dev, double *v_out, double *y_owned);
+int vhk_mgs_fused(vh_ctx *ctx, double *w, const double *V, int64_t ld, int j, double *hcol_dev, bool *used);
 // out_scalar[0] = sum_i a[i]*b[i] over owned DoFs (all-reduced over ranks); stream-ordered, result on device
 int vhk_dot(vh_ctx *ctx, const double *a, const double *b, double *out_scalar);
 // w += (-*coef) * v ; out = dot(w, u)   (deal.II Vector::add_and_dot with a = -coef)

@@ -8,6 +8,9 @@
 // two-stage reductions whose results stay on the device (no host round trip inside the Gram-Schmidt loop).
 #include "vh_internal.h"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace
 {
 __device__ __forceinline__ double warp_sum(double v)
@@ -214,6 +217,147 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// v = x / sqrt(*nsq) (written out: it is the next Krylov basis vector) and y = blockdiag(minv) v, in one pass
+__global__ void __launch_bounds__(256)
+  k_block_apply_scaled(int n_rows, const double *__restrict__ minv, const double *__restrict__ x, const double *__restrict__ nsq,
+                       double *__restrict__ v_out, double *__restrict__ y)
+{
+  __shared__ double s_part[8][6 * 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row  = blockIdx.x * 8 + wid;
+  if (row >= n_rows)
+    return;
+  const double   nrm = sqrt(*nsq);
+  const double   inv = nrm != 0.0 ? 1.0 / nrm : 0.0;
+  const double2 *B   = reinterpret_cast<const double2 *>(minv + (size_t)row * VH_BLK);
+  const double  *xj  = x + 18 * (size_t)row;
+  if (lane < 9)
+    {
+      double2 xv = *reinterpret_cast<const double2 *>(xj + 2 * lane);
+      xv.x *= inv;
+      xv.y *= inv;
+      *reinterpret_cast<double2 *>(v_out + 18 * (size_t)row + 2 * lane) = xv;
+    }
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+    {
+      const int k = lane + 32 * r;
+      double    a = 0.0;
+      if (k < 162)
+        {
+          const double2 m  = __ldg(B + k);
+          const double2 xv = *reinterpret_cast<const double2 *>(xj + 2 * (k % 9));
+          a                = fma(m.x, xv.x * inv, m.y * (xv.y * inv));
+        }
+      s_part[wid][k] = a;
+    }
+  __syncwarp();
+  if (lane < 18)
+    {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        s += s_part[wid][9 * lane + k];
+      y[(size_t)row * 18 + lane] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Whole modified Gram-Schmidt step of GMRES in ONE cooperative kernel (single-rank contexts):
+//   h_0 = w.v_0;  for i = 1..j: w -= h_{i-1} v_{i-1}, h_i = w.v_i;  w -= h_j v_j, h_{j+1} = w.w
+// (deal.II's add_and_dot chain).  j+2 grid-wide barriers replace j+2 kernel launches; each thread keeps
+// its slice of w in registers, so w is read and written exactly once.  Reductions are deterministic: per-block partials
+// are summed in the same fixed order by every block.
+// ------------------------------------------------------------------------------------------------
+#define VH_MGS_THREADS 256
+#define VH_MGS_EPT 8 /* elements of w per thread held in registers (as double2 x 4) */
+__global__ void __launch_bounds__(VH_MGS_THREADS)
+  k_mgs_fused(int64_t n, double *__restrict__ w, const double *__restrict__ V, int64_t ld, int j, double *__restrict__ hcol,
+              double *__restrict__ partials)
+{
+  cg::grid_group    grid = cg::this_grid();
+  __shared__ double s_w[VH_MGS_THREADS / 32];
+  __shared__ double s_tot;
+  const int         lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t     base = ((int64_t)blockIdx.x * VH_MGS_THREADS + threadIdx.x) * 2;
+  const int64_t     stride = (int64_t)gridDim.x * VH_MGS_THREADS * 2;
+  double2           wr[VH_MGS_EPT / 2];
+#pragma unroll
+  for (int k = 0; k < VH_MGS_EPT / 2; ++k)
+    {
+      const int64_t i = base + k * stride;
+      wr[k]           = make_double2(0.0, 0.0);
+      if (i + 1 < n)
+        wr[k] = *reinterpret_cast<const double2 *>(w + i);
+      else if (i < n)
+        wr[k].x = w[i];
+    }
+  double hprev = 0.0;
+  for (int step = 0; step <= j + 1; ++step)
+    {
+      const double *vp = step > 0 ? V + (size_t)(step - 1) * ld : nullptr; // subtract hprev * v_{step-1}
+      const double *vu = step <= j ? V + (size_t)step * ld : nullptr;      // dot with v_step (or with w itself)
+      double        s  = 0.0;
+#pragma unroll
+      for (int k = 0; k < VH_MGS_EPT / 2; ++k)
+        {
+          const int64_t i = base + k * stride;
+          if (i >= n)
+            continue;
+          const bool two = i + 1 < n;
+          if (vp)
+            {
+              const double2 pv = two ? *reinterpret_cast<const double2 *>(vp + i) : make_double2(vp[i], 0.0);
+              wr[k].x          = fma(-hprev, pv.x, wr[k].x);
+              wr[k].y          = fma(-hprev, pv.y, wr[k].y);
+            }
+          double2 uv = wr[k];
+          if (vu)
+            uv = two ? *reinterpret_cast<const double2 *>(vu + i) : make_double2(vu[i], 0.0);
+          s = fma(wr[k].x, uv.x, fma(wr[k].y, uv.y, s));
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0)
+        s_w[wid] = s;
+      __syncthreads();
+      if (threadIdx.x == 0)
+        {
+          double b = 0.0;
+          for (int k = 0; k < VH_MGS_THREADS / 32; ++k)
+            b += s_w[k];
+          partials[(size_t)step * gridDim.x + blockIdx.x] = b;
+        }
+      grid.sync();
+      if (wid == 0)
+        { // every block sums all partials of this step in the same order
+          double t = 0.0;
+          for (int b = lane; b < (int)gridDim.x; b += 32)
+            t += partials[(size_t)step * gridDim.x + b];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+            t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0)
+            s_tot = t;
+        }
+      __syncthreads();
+      hprev = s_tot;
+      if (blockIdx.x == 0 && threadIdx.x == 0)
+        hcol[step] = hprev;
+      __syncthreads();
+    }
+#pragma unroll
+  for (int k = 0; k < VH_MGS_EPT / 2; ++k)
+    {
+      const int64_t i = base + k * stride;
+      if (i + 1 < n)
+        *reinterpret_cast<double2 *>(w + i) = wr[k];
+      else if (i < n)
+        w[i] = wr[k].x;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused vector kernels with deterministic device-side reductions
 // ------------------------------------------------------------------------------------------------
@@ -410,6 +554,47 @@ int vhk_block_jacobi_apply(vh_ctx *ctx, const double *x_owned, double *y_owned)
     return VH_OK;
   k_block_apply<<<(ctx->n_owned + 7) / 8, 256, 0, ctx->stream>>>(ctx->n_owned, ctx->minv, x_owned, y_owned);
   VH_LAUNCH_CHECK();
+  return VH_OK;
+}
+
+int vhk_block_jacobi_apply_scaled(vh_ctx *ctx, const double *x_owned, const double *nsq_dev, double *v_out, double *y_owned)
+{
+  if (ctx->n_owned == 0)
+    return VH_OK;
+  k_block_apply_scaled<<<(ctx->n_owned + 7) / 8, 256, 0, ctx->stream>>>(ctx->n_owned, ctx->minv, x_owned, nsq_dev, v_out, y_owned);
+  VH_LAUNCH_CHECK();
+  return VH_OK;
+}
+
+// Returns VH_OK and sets *used = true when the fused cooperative kernel ran; *used = false means "not applicable here"
+// (multi-rank context, vector too long for the register-resident slice, or no cooperative launch): use the kernel chain.
+int vhk_mgs_fused(vh_ctx *ctx, double *w, const double *V, int64_t ld, int j, double *hcol_dev, bool *used)
+{
+  *used = false;
+  if (ctx->n_ranks != 1 || ctx->NO == 0)
+    return VH_OK;
+  static int coop = -1, max_blocks = 0;
+  if (coop < 0)
+    {
+      int dev = ctx->device, sms = 0, per_sm = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mgs_fused, VH_MGS_THREADS, 0);
+      max_blocks = sms * (per_sm < 4 ? per_sm : 4);
+    }
+  if (!coop || max_blocks < 1)
+    return VH_OK;
+  const int64_t per_block = (int64_t)VH_MGS_THREADS * VH_MGS_EPT;
+  int64_t       grid      = (ctx->NO + per_block - 1) / per_block;
+  if (grid > max_blocks || (int64_t)(j + 2) * grid > VH_MAX_RED_BLOCKS * 32)
+    return VH_OK;
+  int64_t n     = ctx->NO;
+  void   *args[] = {&n, &w, (void *)&V, &ld, &j, &hcol_dev, &ctx->partials};
+  cudaError_t e = cudaLaunchCooperativeKernel((void *)k_mgs_fused, dim3((unsigned)grid), dim3(VH_MGS_THREADS), args, 0, ctx->stream);
+  if (e != cudaSuccess)
+    return vh_fail(ctx, VH_ERR_CUDA, std::string("cooperative launch: ") + cudaGetErrorString(e));
+  ctx->n_launches++;
+  *used = true;
   return VH_OK;
 }
 
