@@ -495,6 +495,218 @@ __global__ void __launch_bounds__(192 / EPT, 4)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 2c. row-owner kernel with the contraction on the FP64 tensor cores (mma.sync m8n8k4 -> SASS DMMA.8x8x4).
+//     For one incident cell o the row's contribution is the GEMM  out[b][entry] = sum_q W_o[b][q] * H_o[q][entry]
+//     with M = 8 column nodes b, K = 8 quadrature points (two k-steps of 4), N = 172 packed entries (22 tiles of 8).
+//     On B200 DMMA has the same FLOP/s as DFMA (measured 37.1 vs 36.7 TFLOP/s, tools/dmma_peak.cu) but needs 8x fewer
+//     issue slots, which is what the scalar kernel is short of.
+//     Row permutation: MMA row m of octant o holds column node b = m XOR o, so that row m always accumulates slots of
+//     parity m (slot coordinate s_d = 1 if m_d else 2*o_d): contributions of different cells to one slot stay in the
+//     same lane and are reduced in registers; no cross-lane traffic, no atomics.  C fragments: one set per octant.
+//     6 warps x 4 tiles; A fragments (weights) come from a 4 KB shared table, B fragments from the TMA ring.
+// ------------------------------------------------------------------------------------------------
+#define VH_MMA_THREADS 192
+#define VH_MMA_STAGES 8 /* all incident cells' tables in flight at once: 88 KB ring, two CTAs per SM */
+#define VH_MMA_SMEM (VH_MMA_STAGES * VH_CELL_H_BYTES + 272 * 8 + 512 * 8 + VH_MMA_STAGES * 8 + 64 * 4)
+
+__global__ void __launch_bounds__(VH_MMA_THREADS, 2)
+  k_rows_mma_q1(const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells, const int8_t *__restrict__ fast_slot,
+                const int32_t *__restrict__ fast_class, const double *__restrict__ class_M, const double *__restrict__ afrag,
+                const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, const uint32_t *__restrict__ dirmask,
+                const double *__restrict__ Hq, const double *__restrict__ Dc, const double *__restrict__ avgD,
+                double *__restrict__ vals)
+{
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double   *s_H     = reinterpret_cast<double *>(smraw);                                   // [8][8*172], later [27][172]
+  double   *s_cls   = reinterpret_cast<double *>(smraw + VH_MMA_STAGES * VH_CELL_H_BYTES); // [27][10] (+2)
+  double   *s_A     = s_cls + 272;                                                         // [8 o][2 kstep][32 lanes]
+  uint64_t *s_bar   = reinterpret_cast<uint64_t *>(s_A + 512);                             // [8]
+  int      *s_cells = reinterpret_cast<int *>(s_bar + VH_MMA_STAGES);                      // [8]
+  int      *s_pos   = s_cells + 8;                                                         // [27] (+1)
+  uint32_t *s_maskJ = reinterpret_cast<uint32_t *>(s_pos + 28);                            // [27]
+
+  constexpr int NT = VH_MMA_THREADS;
+  const int     t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int     r = blockIdx.x;
+  const int     I = fast_rows[r];
+  if (t == 0)
+    { // TMA producer, first thing in the CTA: every incident cell's table (11 KB each) is requested at once
+#pragma unroll
+      for (int k = 0; k < VH_MMA_STAGES; ++k)
+        mbar_init(s_bar + k, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        {
+          const int e = fast_cells[(size_t)r * 8 + o];
+          if (e >= 0)
+            {
+              mbar_expect_tx(s_bar + o, VH_CELL_H_BYTES);
+              bulk_g2s(s_H + (size_t)o * (8 * VH_SYMP), Hq + (size_t)e * (8 * VH_SYMP), VH_CELL_H_BYTES, s_bar + o);
+            }
+        }
+    }
+  // all row metadata is fetched now, behind the TMA latency: nothing global is touched again until the stores
+  const uint32_t maskI = dirmask[I];
+  const int      rp    = row_ptr[I];
+  if (t >= 64 && t < 72)
+    s_cells[t - 64] = fast_cells[(size_t)r * 8 + (t - 64)];
+  if (t >= 32 && t < 59)
+    {
+      const int pos     = fast_slot[(size_t)r * 32 + (t - 32)];
+      s_pos[t - 32]     = pos;
+      s_maskJ[t - 32]   = pos >= 0 ? dirmask[col[rp + pos]] : 0u;
+    }
+  {
+    const double *cls = class_M + (size_t)fast_class[r] * 270;
+    for (int i = t; i < 270; i += NT)
+      s_cls[i] = cls[i];
+    for (int i = t; i < 512; i += NT)
+      s_A[i] = afrag[i];
+  }
+  __syncthreads();
+
+  // B-fragment offsets of this lane inside a cell table: row q = 4*kstep + lane%4, column = packed entry of tile + lane/4
+  int boff[4];
+#pragma unroll
+  for (int tl = 0; tl < 4; ++tl)
+    {
+      const int e = 8 * (4 * warp + tl) + (lane >> 2);
+      boff[tl]    = (lane & 3) * VH_SYMP + (e < VH_SYMP ? e : VH_SYMP - 1); // clamped to the zero pad entry
+    }
+  double acc[8][4][2];
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+#pragma unroll
+    for (int tl = 0; tl < 4; ++tl)
+      acc[o][tl][0] = acc[o][tl][1] = 0.0;
+
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+    {
+      const int e = s_cells[o];
+      if (e >= 0)
+        {
+          mbar_wait(s_bar + o, 0u);
+          const double *Hs = s_H + (size_t)o * (8 * VH_SYMP);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            {
+              const double a = s_A[(o * 2 + ks) * 32 + lane];
+#pragma unroll
+              for (int tl = 0; tl < 4; ++tl)
+                {
+                  const double b = Hs[ks * 4 * VH_SYMP + boff[tl]];
+                  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                               : "+d"(acc[o][tl][0]), "+d"(acc[o][tl][1])
+                               : "d"(a), "d"(b));
+                }
+            }
+        }
+    }
+
+  // ---- reduce the octant sets inside each lane and dump the packed accumulators: [27][172] in the idle TMA ring ----
+  __syncthreads();
+  double   *s_sym = s_H;
+  const int m = lane >> 2; // MMA row = slot parity class (m_x, m_y, m_z)
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    if ((m >> d) & 1)
+      { // coordinate d of the slot is 1 whatever the octant: octants o and o|(1<<d) feed the same slot
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+          if (!((o >> d) & 1))
+#pragma unroll
+            for (int tl = 0; tl < 4; ++tl)
+              {
+                acc[o][tl][0] += acc[o | (1 << d)][tl][0];
+                acc[o][tl][1] += acc[o | (1 << d)][tl][1];
+              }
+      }
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+    if ((o & m) == 0)
+      {
+        const int sx = (m & 1) ? 1 : 2 * (o & 1), sy = (m & 2) ? 1 : 2 * ((o >> 1) & 1), sz = (m & 4) ? 1 : 2 * (o >> 2);
+        double   *dst = s_sym + (sx + 3 * sy + 9 * sz) * VH_SYMP;
+#pragma unroll
+        for (int tl = 0; tl < 4; ++tl)
+          {
+            const int e = 8 * (4 * warp + tl) + 2 * (lane & 3);
+            if (e < VH_SYMP)
+              *reinterpret_cast<double2 *>(dst + e) = make_double2(acc[o][tl][0], acc[o][tl][1]);
+          }
+      }
+  __syncthreads();
+
+  // ---- store: thread t < 162 owns double2 #t of every 18x18 block ----
+  if (t < VH_BLK / 2)
+    {
+      int      soff[2], gsel[2];
+      uint32_t rbit[2], cbit[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        {
+          const int c = (2 * t) / 18, d = (2 * t) % 18 + k;
+          soff[k] = c <= d ? vh_sym_index(c, d) : vh_sym_index(d, c);
+          gsel[k] = (c / 3 == d / 3) ? (c % 3) * 3 + d % 3 : 9;
+          rbit[k] = 1u << c;
+          cbit[k] = 1u << d;
+        }
+      // fully unrolled: the 108 shared-memory loads of the 27 slots are batched ahead of the adds and the stores
+      double2 v[27];
+#pragma unroll
+      for (int s = 0; s < 27; ++s)
+        {
+          const double *sy = s_sym + s * VH_SYMP;
+          const double *G  = s_cls + s * 10;
+          v[s]             = make_double2(sy[soff[0]] + G[gsel[0]], sy[soff[1]] + G[gsel[1]]);
+        }
+#pragma unroll
+      for (int s = 0; s < 27; ++s)
+        {
+          const int pos = s_pos[s];
+          if (pos < 0)
+            continue; // block-uniform
+          const uint32_t maskJ = s_maskJ[s];
+          double         v0 = v[s].x, v1 = v[s].y;
+          if ((maskI | maskJ) != 0u)
+            {
+              if ((maskI & rbit[0]) || (maskJ & cbit[0]))
+                v0 = 0.0;
+              if ((maskI & rbit[1]) || (maskJ & cbit[1]))
+                v1 = 0.0;
+              if (s == 13)
+                {
+#pragma unroll
+                  for (int k = 0; k < 2; ++k)
+                    if (rbit[k] == cbit[k] && (maskI & rbit[k]))
+                      { // constrained diagonal: sum over cells of |a_ii| (mean |diag| of the cell if a_ii == 0)
+                        const int c    = 31 - __clz(rbit[k]);
+                        double    dsum = 0.0;
+                        for (int o = 0; o < 8; ++o)
+                          {
+                            const int e = s_cells[o];
+                            if (e < 0)
+                              continue;
+                            double dv = fabs(Dc[(size_t)e * 144 + (7 - o) * 18 + c]);
+                            if (dv == 0.0)
+                              dv = avgD[e];
+                            dsum += dv;
+                          }
+                        if (k == 0)
+                          v0 = dsum;
+                        else
+                          v1 = dsum;
+                      }
+                }
+            }
+          __stcs(reinterpret_cast<double2 *>(vals + (size_t)(rp + pos) * VH_BLK) + t, make_double2(v0, v1));
+        }
+    }
+}
+
 // Store-bandwidth probe with the row kernel's write pattern (one CTA per block row, 16-byte stores, no other work):
 // what the write-once matrix store costs on its own.  Used by vh_time_kernel(what=7) only.
 __global__ void __launch_bounds__(192) k_store_probe(int n_rows, const int32_t *__restrict__ row_ptr, double *__restrict__ vals, int mode)
@@ -760,7 +972,19 @@ int vhk_rows_fast(vh_ctx *ctx)
       VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
       VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
     }
-  if (ept == 2)
+  static int use_mma = -1;
+  if (use_mma < 0)
+    {
+      const char *e = getenv("VH_ROWS_MMA"); // tuning knob: 1 = FP64 tensor-core kernel (default), 0 = scalar DFMA kernel
+      use_mma       = (e && e[0] == '0') ? 0 : 1;
+      VH_CUDA(cudaFuncSetAttribute(k_rows_mma_q1, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_MMA_SMEM));
+    }
+  if (use_mma)
+    k_rows_mma_q1<<<ctx->n_fast, VH_MMA_THREADS, VH_MMA_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot,
+                                                                           ctx->fast_class, ctx->class_M, ctx->afrag, ctx->row_ptr,
+                                                                           ctx->col, ctx->dirmask, ctx->Hq, ctx->Dc, ctx->avgD,
+                                                                           ctx->vals);
+  else if (ept == 2)
     k_rows_fast_q1<2><<<ctx->n_fast, 96, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class,
                                                                      ctx->class_M, ctx->row_ptr, ctx->col, ctx->dirmask, ctx->Hq,
                                                                      ctx->Dc, ctx->avgD, ctx->coef, ctx->vals);

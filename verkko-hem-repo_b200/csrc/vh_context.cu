@@ -517,7 +517,17 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   VH_TRY(vh_dev_upload(ctx, &ctx->tab.Mf, T.Mf.data(), T.Mf.size()));
   VH_TRY(vhk_upload_constants(ctx));
   if (ctx->degree == 1)
-    VH_TRY(vhk_upload_w1(ctx, T.W1.data()));
+    {
+      VH_TRY(vhk_upload_w1(ctx, T.W1.data()));
+      // A fragments of mma.m8n8k4 (row-major 8x4: lane holds row lane/4, column lane%4) for every octant and k-step:
+      // row m of octant o carries column node b = m XOR o, the row node is local vertex a = 7 - o.
+      std::vector<double> af(512);
+      for (int o = 0; o < 8; ++o)
+        for (int ks = 0; ks < 2; ++ks)
+          for (int l = 0; l < 32; ++l)
+            af[(o * 2 + ks) * 32 + l] = T.W1[((7 - o) * 8 + ((l >> 2) ^ o)) * 8 + 4 * ks + (l & 3)];
+      VH_TRY(vh_dev_upload(ctx, &ctx->afrag, af.data(), af.size()));
+    }
 
   // ---- halo plan ----
   if (d->n_peers < 0)
@@ -682,7 +692,7 @@ int vh_destroy(vh_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
   vh_comm_destroy(ctx);
   void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
-                  ctx->diag_pos, ctx->minv, ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->slow_rows, ctx->row_slow,
+                  ctx->diag_pos, ctx->minv, ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->row_slow,
                   ctx->slow_cells, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
                   ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
                   ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,

@@ -82,6 +82,7 @@ struct vh_ctx
   int32_t *fast_class = nullptr; // [n_fast]      geometry class of the row's stencil
   double  *class_tab  = nullptr; // [n_classes][27][12] per slot: GS[3][3] = sum vol/(h_x h_y) Gref, FS[3] = sum area Mf (x != normal)
   int32_t  n_classes  = 0;
+  double  *afrag      = nullptr; // [8 octants][2 k-steps][32 lanes] A fragments of the DMMA row kernel (weights w_q N_a N_b)
   double  *class_M    = nullptr; // [n_classes][27][10] coefficient-dependent 3x3 geometry block per slot (entry 9 = 0)
   std::vector<double> h_class_tab;
   int32_t *slow_rows  = nullptr; // [n_slow_rows]
