@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(NQ == 8 ? 192 : 512)
       if (grp < n_groups)
         {
           double *dst = Hq + cell * (int64_t)(NQ * VH_SYMP) + sidx;
-          if (sidx < VH_SYM)
+          if (c_symd[sidx] >= c_symc[sidx])
             {
               const int c = c_symc[sidx], d = c_symd[sidx];
               vh_terms  T;
@@ -293,7 +293,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 
 // EPT = packed Hessian entries per thread: 2 -> 96 threads/row (86 active), 108 accumulator registers, 12 warps/SM;
 //                                          1 -> 192 threads/row (172 active), 54 accumulator registers, 24 warps/SM.
-template <int EPT>
+// PACK = true: the row is stored as packed symmetric blocks (172 doubles each): the accumulators go straight from
+//               registers to global memory with coalesced stores; geometry terms and Dirichlet masks are applied by the
+//               consumers (SpMV, block-Jacobi setup, export), so the expansion stage disappears.
+template <int EPT, bool PACK>
 __global__ void __launch_bounds__(192 / EPT, 4)
   k_rows_fast_q1(const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells,
                  const int8_t *__restrict__ fast_slot, const int32_t *__restrict__ fast_class,
@@ -335,11 +338,12 @@ __global__ void __launch_bounds__(192 / EPT, 4)
     s_cells[t - 64] = fast_cells[(size_t)r * 8 + (t - 64)];
   if (t >= 32 && t < 59)
     s_pos[t - 32] = fast_slot[(size_t)r * 32 + (t - 32)];
-  { // geometry-only part of every block of this row's stencil: block += kron(I_6, M_s), M_s 3x3 (stride 10, [9] = 0)
-    const double *cls = class_M + (size_t)fast_class[r] * 270;
-    for (int i = t; i < 270; i += NT)
-      s_cls[i] = cls[i];
-  }
+  if constexpr (!PACK)
+    { // geometry-only part of every block of this row's stencil: block += kron(I_6, M_s), M_s 3x3 (stride 10, [9] = 0)
+      const double *cls = class_M + (size_t)fast_class[r] * 270;
+      for (int i = t; i < 270; i += NT)
+        s_cls[i] = cls[i];
+    }
   __syncthreads();
 
   // TMA producer: thread 0 streams the incident cells' pre-scaled H_q tables (11 KB each, contiguous) into the ring
@@ -404,6 +408,27 @@ __global__ void __launch_bounds__(192 / EPT, 4)
                 }
             }
         }
+    }
+
+  if constexpr (PACK)
+    { // packed storage: block (rp+pos) holds the 172 packed entries contiguously; thread t owns entries EPT*t..
+      const int rp = row_ptr[I];
+      if (t < ACT)
+        {
+#pragma unroll
+          for (int s = 0; s < 27; ++s)
+            {
+              const int pos = s_pos[s];
+              if (pos < 0)
+                continue;
+              double *dst = vals + (size_t)(rp + pos) * VH_SYMP + EPT * t;
+              if constexpr (EPT == 2)
+                __stcs(reinterpret_cast<double2 *>(dst), make_double2(acc[0][s], acc[1][s]));
+              else
+                __stcs(dst, acc[0][s]);
+            }
+        }
+      return;
     }
 
   // ---- write the block row ----
@@ -573,7 +598,7 @@ __global__ void __launch_bounds__(VH_MMA_THREADS, 2)
   for (int tl = 0; tl < 4; ++tl)
     {
       const int e = 8 * (4 * warp + tl) + (lane >> 2);
-      boff[tl]    = (lane & 3) * VH_SYMP + (e < VH_SYMP ? e : VH_SYMP - 1); // clamped to the zero pad entry
+      boff[tl]    = (lane & 3) * VH_SYMP + (e < VH_SYMP ? e : 18); // out-of-range columns read the zero dummy entry (1,0)
     }
   double acc[8][4][2];
 #pragma unroll
@@ -728,7 +753,8 @@ __global__ void __launch_bounds__(192) k_store_probe(int n_rows, const int32_t *
 
 // rhs of fast rows: deterministic gather of the cell rhs over the incident cells (no atomics)
 __global__ void k_rhs_fast_q1(int n_fast, const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells,
-                              const uint32_t *__restrict__ dirmask, const double *__restrict__ Rc, double *__restrict__ rhs)
+                              const uint32_t *__restrict__ dirmask, const double *__restrict__ Rc, double *__restrict__ rhs,
+                              const double *__restrict__ Dc, const double *__restrict__ avgD, double *__restrict__ cdiag)
 {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (int64_t)n_fast * 18)
@@ -743,9 +769,57 @@ __global__ void k_rhs_fast_q1(int n_fast, const int32_t *__restrict__ fast_rows,
       if (e >= 0)
         s += Rc[(size_t)e * 144 + (7 - o) * 18 + c];
     }
-  if ((dirmask[I] >> c) & 1u)
+  const bool masked = (dirmask[I] >> c) & 1u;
+  if (masked)
     s = 0.0;
   rhs[(size_t)I * 18 + c] = s;
+  if (cdiag)
+    { // packed storage keeps the constrained-diagonal values sum_cells |a_ii| (distribute_local_to_global) beside the blocks
+      double dsum = 0.0;
+      if (masked)
+        for (int o = 0; o < 8; ++o)
+          {
+            const int e = fast_cells[(size_t)r * 8 + o];
+            if (e < 0)
+              continue;
+            double dv = fabs(Dc[(size_t)e * 144 + (7 - o) * 18 + c]);
+            if (dv == 0.0)
+              dv = avgD[e];
+            dsum += dv;
+          }
+      cdiag[(size_t)I * 18 + c] = dsum;
+    }
+}
+
+// Expansion of the packed rows into full 18x18 blocks (export / diagnostics): block = Sym(P) + kron(I_6, M_slot), Dirichlet
+// rows and columns zeroed, constrained diagonal from cdiag.
+__global__ void k_expand_packed(int n_fast, const int32_t *__restrict__ fast_rows, const uint8_t *__restrict__ fast_posslot,
+                                const int32_t *__restrict__ fast_class, const double *__restrict__ class_M,
+                                const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                                const uint32_t *__restrict__ dirmask, const double *__restrict__ pvals,
+                                const double *__restrict__ cdiag, double *__restrict__ full)
+{
+  const int r = blockIdx.x;
+  if (r >= n_fast)
+    return;
+  const int      I = fast_rows[r], rp = row_ptr[I], nb = row_ptr[I + 1] - rp;
+  const uint32_t maskI = dirmask[I];
+  const double  *M0 = class_M + (size_t)fast_class[r] * 270;
+  for (int i = threadIdx.x; i < nb * VH_BLK; i += blockDim.x)
+    {
+      const int      pos = i / VH_BLK, e = i - VH_BLK * pos, c = e / 18, d = e - 18 * c;
+      const int      J = col[rp + pos];
+      const uint32_t maskJ = dirmask[J];
+      const double  *P = pvals + (size_t)(rp + pos) * VH_SYMP;
+      double         v = P[c <= d ? vh_sym_index(c, d) : vh_sym_index(d, c)];
+      if (c / 3 == d / 3)
+        v += M0[fast_posslot[(size_t)r * 32 + pos] * 10 + (c % 3) * 3 + d % 3];
+      if (((maskI >> c) & 1u) || ((maskJ >> d) & 1u))
+        v = 0.0;
+      if (J == I && c == d && ((maskI >> c) & 1u))
+        v = cdiag[(size_t)I * 18 + c];
+      full[(size_t)(rp + pos) * VH_BLK + e] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -910,16 +984,7 @@ int vhk_upload_constants(vh_ctx *ctx)
 {
   // symmetric packing tables
   uint8_t sc[VH_SYMP], sd[VH_SYMP];
-  int     k = 0;
-  for (int c = 0; c < 18; ++c)
-    for (int d = c; d < 18; ++d)
-      {
-        sc[k] = (uint8_t)c;
-        sd[k] = (uint8_t)d;
-        ++k;
-      }
-  sc[VH_SYM] = 17;
-  sd[VH_SYM] = 17; // padding slot (never written back)
+  vh_sym_tables(sc, sd); // dummies (d < c) are written as 0 by the pointwise kernel and never read back as entries
   VH_CUDA(cudaMemcpyToSymbol(c_symc, sc, sizeof(sc)));
   VH_CUDA(cudaMemcpyToSymbol(c_symd, sd, sizeof(sd)));
   return VH_OK;
@@ -969,29 +1034,54 @@ int vhk_rows_fast(vh_ctx *ctx)
     {
       const char *e = getenv("VH_ROWS_EPT"); // tuning knob: packed entries per thread (1 or 2)
       ept           = (e && e[0] == '2') ? 2 : 1;
-      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
-      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
+      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
+      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
+      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
+      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
     }
   static int use_mma = -1;
   if (use_mma < 0)
     {
-      const char *e = getenv("VH_ROWS_MMA"); // tuning knob: 1 = FP64 tensor-core kernel (default), 0 = scalar DFMA kernel
-      use_mma       = (e && e[0] == '0') ? 0 : 1;
+      const char *e = getenv("VH_ROWS_MMA"); // tuning knob (full-format storage only): 1 = FP64 tensor-core kernel, 0 = scalar DFMA kernel (default, faster)
+      use_mma       = (e && e[0] == '1') ? 1 : 0;
       VH_CUDA(cudaFuncSetAttribute(k_rows_mma_q1, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_MMA_SMEM));
     }
-  if (use_mma)
+  if (ctx->packed)
+    { // packed symmetric storage: no expansion stage, half the bytes
+      if (ept == 2)
+        k_rows_fast_q1<2, true><<<ctx->n_fast, 96, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot,
+                                                                               ctx->fast_class, ctx->class_M, ctx->row_ptr, ctx->col,
+                                                                               ctx->dirmask, ctx->Hq, ctx->Dc, ctx->avgD, ctx->coef,
+                                                                               ctx->pvals);
+      else
+        k_rows_fast_q1<1, true><<<ctx->n_fast, 192, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot,
+                                                                                ctx->fast_class, ctx->class_M, ctx->row_ptr, ctx->col,
+                                                                                ctx->dirmask, ctx->Hq, ctx->Dc, ctx->avgD, ctx->coef,
+                                                                                ctx->pvals);
+    }
+  else if (use_mma)
     k_rows_mma_q1<<<ctx->n_fast, VH_MMA_THREADS, VH_MMA_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot,
                                                                            ctx->fast_class, ctx->class_M, ctx->afrag, ctx->row_ptr,
                                                                            ctx->col, ctx->dirmask, ctx->Hq, ctx->Dc, ctx->avgD,
                                                                            ctx->vals);
   else if (ept == 2)
-    k_rows_fast_q1<2><<<ctx->n_fast, 96, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class,
+    k_rows_fast_q1<2, false><<<ctx->n_fast, 96, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class,
                                                                      ctx->class_M, ctx->row_ptr, ctx->col, ctx->dirmask, ctx->Hq,
                                                                      ctx->Dc, ctx->avgD, ctx->coef, ctx->vals);
   else
-    k_rows_fast_q1<1><<<ctx->n_fast, 192, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class,
+    k_rows_fast_q1<1, false><<<ctx->n_fast, 192, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class,
                                                                       ctx->class_M, ctx->row_ptr, ctx->col, ctx->dirmask, ctx->Hq,
                                                                       ctx->Dc, ctx->avgD, ctx->coef, ctx->vals);
+  VH_LAUNCH_CHECK();
+  return VH_OK;
+}
+
+int vhk_expand_packed(vh_ctx *ctx, double *full_vals)
+{
+  if (!ctx->packed || ctx->n_fast == 0)
+    return VH_OK;
+  k_expand_packed<<<ctx->n_fast, 256, 0, ctx->stream>>>(ctx->n_fast, ctx->fast_rows, ctx->fast_posslot, ctx->fast_class, ctx->class_M,
+                                                       ctx->row_ptr, ctx->col, ctx->dirmask, ctx->pvals, ctx->cdiag, full_vals);
   VH_LAUNCH_CHECK();
   return VH_OK;
 }
@@ -1003,13 +1093,15 @@ int vhk_store_probe(vh_ctx *ctx, int mode)
   return VH_OK;
 }
 
-int vhk_rhs_fast(vh_ctx *ctx, double *rhs_out)
+int vhk_rhs_fast(vh_ctx *ctx, double *rhs_out, bool with_cdiag)
 {
   if (ctx->n_fast == 0)
     return VH_OK;
   const int64_t n = (int64_t)ctx->n_fast * 18;
+  // the constrained-diagonal values are (re)computed whenever the Jacobian was (the cell diagonals Dc are fresh then)
   k_rhs_fast_q1<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n_fast, ctx->fast_rows, ctx->fast_cells, ctx->dirmask,
-                                                                     ctx->Rc, rhs_out);
+                                                                     ctx->Rc, rhs_out, ctx->Dc, ctx->avgD,
+                                                                     (ctx->packed && with_cdiag) ? ctx->cdiag : nullptr);
   VH_LAUNCH_CHECK();
   return VH_OK;
 }

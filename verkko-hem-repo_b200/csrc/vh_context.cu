@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -355,6 +356,7 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   std::vector<uint8_t> row_slow(n_owned, 1);
   std::vector<int32_t> fast_rows, fast_cells;
   std::vector<int8_t>  fast_slot;
+  std::vector<uint8_t> fast_posslot;
   if (ctx->degree == 1)
     for (int I = 0; I < n_owned; ++I)
       {
@@ -414,6 +416,12 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
         fast_rows.push_back(I);
         fast_cells.insert(fast_cells.end(), cells8, cells8 + 8);
         fast_slot.insert(fast_slot.end(), pos27, pos27 + 32);
+        uint8_t ps[32];
+        std::fill(ps, ps + 32, (uint8_t)13);
+        for (int sl = 0; sl < 27; ++sl)
+          if (pos27[sl] >= 0)
+            ps[pos27[sl]] = (uint8_t)sl;
+        fast_posslot.insert(fast_posslot.end(), ps, ps + 32);
       }
   // geometry classes of the fast rows: the gradient (K1, K2+K3) and Robin-face forms depend only on the shapes of
   // the incident cells, so rows with identical stencils share one 27 x 12 table (a uniform mesh has a few dozen).
@@ -498,6 +506,13 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   VH_TRY(vh_dev_upload(ctx, &ctx->fast_rows, fast_rows.data(), fast_rows.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->fast_cells, fast_cells.data(), fast_cells.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->fast_slot, fast_slot.data(), fast_slot.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->fast_posslot, fast_posslot.data(), fast_posslot.size()));
+  {
+    std::vector<int32_t> fidx(n_owned, -1);
+    for (size_t r = 0; r < fast_rows.size(); ++r)
+      fidx[fast_rows[r]] = (int32_t)r;
+    VH_TRY(vh_dev_upload(ctx, &ctx->fast_index, fidx.data(), fidx.size()));
+  }
   VH_TRY(vh_dev_upload(ctx, &ctx->fast_class, fast_class.data(), fast_class.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->class_tab, class_tab.data(), class_tab.size()));
   VH_TRY(vh_dev_alloc(ctx, &ctx->class_M, (size_t)ctx->n_classes * 270));
@@ -554,7 +569,17 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
     return vh_fail(ctx, VH_ERR_ARG, "ghost nodes without a halo plan");
 
   // ---- matrix, scratch, vectors ----
-  VH_TRY(vh_dev_alloc(ctx, &ctx->vals, (size_t)ctx->nnzb * VH_BLK));
+  // storage format: packed symmetric blocks for the lattice rows unless VH_FULL_BSR=1 (A/B switch, full 18x18 blocks)
+  ctx->packed = ctx->degree == 1 && ctx->n_fast > 0 && !(getenv("VH_FULL_BSR") && getenv("VH_FULL_BSR")[0] == '1');
+  if (ctx->packed)
+    {
+      VH_TRY(vh_dev_alloc(ctx, &ctx->pvals, (size_t)ctx->nnzb * VH_SYMP));
+      VH_TRY(vh_dev_alloc(ctx, &ctx->cdiag, (size_t)n_owned * 18));
+      VH_CUDA(cudaMemset(ctx->cdiag, 0, sizeof(double) * (size_t)std::max(n_owned, 1) * 18));
+    }
+  if (!ctx->packed || ctx->n_slow_rows > 0)
+    VH_TRY(vh_dev_alloc(ctx, &ctx->vals, (size_t)ctx->nnzb * VH_BLK));
+  VH_TRY(vhk_upload_linalg_constants(ctx));
   VH_TRY(vh_dev_alloc(ctx, &ctx->minv, (size_t)n_owned * VH_BLK));
   VH_TRY(vh_dev_alloc(ctx, &ctx->Hq, (size_t)n_cells * ctx->nq * VH_SYMP));
   VH_TRY(vh_dev_alloc(ctx, &ctx->Rc, (size_t)n_cells * ctx->dpc));
@@ -692,7 +717,7 @@ int vh_destroy(vh_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
   vh_comm_destroy(ctx);
   void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
-                  ctx->diag_pos, ctx->minv, ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->row_slow,
+                  ctx->diag_pos, ctx->minv, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->row_slow,
                   ctx->slow_cells, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
                   ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
                   ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,
@@ -817,14 +842,14 @@ static int assemble_device(vh_ctx *ctx)
 {
   VH_TRY(vhk_pointwise(ctx, ctx->x_sol, true, false));
   VH_TRY(vhk_rows_fast(ctx));
-  VH_TRY(vhk_rhs_fast(ctx, ctx->rhs));
+  VH_TRY(vhk_rhs_fast(ctx, ctx->rhs, true));
   VH_TRY(vhk_rows_slow(ctx, true, ctx->rhs));
   return VH_OK;
 }
 static int residual_device(vh_ctx *ctx, const double *x_local, double *out)
 {
   VH_TRY(vhk_pointwise(ctx, x_local, false, false));
-  VH_TRY(vhk_rhs_fast(ctx, out));
+  VH_TRY(vhk_rhs_fast(ctx, out, false));
   VH_TRY(vhk_rows_slow(ctx, false, out));
   return VH_OK;
 }
@@ -966,8 +991,26 @@ int vh_export_matrix_bsr(vh_ctx *ctx, int32_t *row_ptr, int32_t *col, double *va
   std::memcpy(row_ptr, ctx->h_row_ptr.data(), sizeof(int32_t) * ctx->h_row_ptr.size());
   std::memcpy(col, ctx->h_col.data(), sizeof(int32_t) * ctx->h_col.size());
   VH_CUDA(cudaStreamSynchronize(ctx->stream));
-  VH_CUDA(cudaMemcpy(vals, ctx->vals, sizeof(double) * (size_t)ctx->nnzb * VH_BLK, cudaMemcpyDeviceToHost));
-  return VH_OK;
+  if (!ctx->packed)
+    {
+      VH_CUDA(cudaMemcpy(vals, ctx->vals, sizeof(double) * (size_t)ctx->nnzb * VH_BLK, cudaMemcpyDeviceToHost));
+      return VH_OK;
+    }
+  // packed storage: expand into a temporary full-format copy (tests / diagnostics only)
+  double     *tmp = nullptr;
+  cudaError_t e   = cudaMalloc((void **)&tmp, sizeof(double) * (size_t)ctx->nnzb * VH_BLK);
+  if (e != cudaSuccess)
+    return vh_fail(ctx, VH_ERR_CUDA, "vh_export_matrix_bsr: cannot allocate the expanded copy");
+  int rc = VH_OK;
+  if (ctx->vals)
+    cudaMemcpyAsync(tmp, ctx->vals, sizeof(double) * (size_t)ctx->nnzb * VH_BLK, cudaMemcpyDeviceToDevice, ctx->stream);
+  rc = vhk_expand_packed(ctx, tmp);
+  if (rc == VH_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    rc = vh_fail(ctx, VH_ERR_CUDA, "vh_export_matrix_bsr: expansion failed");
+  if (rc == VH_OK && cudaMemcpy(vals, tmp, sizeof(double) * (size_t)ctx->nnzb * VH_BLK, cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = vh_fail(ctx, VH_ERR_CUDA, "vh_export_matrix_bsr: copy failed");
+  cudaFree(tmp);
+  return rc;
 }
 
 int vh_spmv(vh_ctx *ctx, const double *x_owned, double *y_owned)
@@ -976,7 +1019,7 @@ int vh_spmv(vh_ctx *ctx, const double *x_owned, double *y_owned)
   if (!ctx->have_matrix)
     return vh_fail(ctx, VH_ERR_STATE, "vh_spmv before vh_assemble");
   VH_TRY(upload_owned(ctx, ctx->zbuf, x_owned));
-  VH_TRY(vhk_spmv(ctx, ctx->zbuf, ctx->tmpo));
+  VH_TRY(vhk_spmv(ctx, ctx->zbuf, ctx->tmpo, false));
   return download_owned(ctx, ctx->tmpo, y_owned);
 }
 
@@ -1014,7 +1057,7 @@ int vh_time_kernel(vh_ctx *ctx, int what, int reps, int do_flush, float *ms_avg)
       switch (what)
         {
         case 0:
-          VH_TRY(vhk_spmv(ctx, ctx->x_sol, ctx->tmpo));
+          VH_TRY(vhk_spmv(ctx, ctx->x_sol, ctx->tmpo, true)); // timing only: masking is a separate, tiny kernel
           break;
         case 1:
           VH_TRY(assemble_device(ctx));
@@ -1037,6 +1080,8 @@ int vh_time_kernel(vh_ctx *ctx, int what, int reps, int do_flush, float *ms_avg)
           break;
         case 7: // destroys the matrix values: bandwidth probe only
         case 8:
+          if (!ctx->vals)
+            return vh_fail(ctx, VH_ERR_STATE, "store probe needs full-format storage (VH_FULL_BSR=1)");
           VH_TRY(vhk_store_probe(ctx, what - 7));
           ctx->have_matrix = false;
           break;

@@ -116,7 +116,7 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
       else
         {
           VH_TRY(vhk_halo_exchange(ctx, ctx->delta));
-          VH_TRY(vhk_spmv(ctx, ctx->delta, ctx->tmpo));
+          VH_TRY(vhk_spmv(ctx, ctx->delta, ctx->tmpo, true)); // delta = M^-1 (V y): zero at Dirichlet DoFs
           VH_TRY(vhk_axpby(ctx, aux, 1.0, ctx->rhs, -1.0, ctx->tmpo, NO));
         }
       VH_TRY(vhk_dot(ctx, aux, aux, nrm2));
@@ -143,7 +143,7 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
               VH_CUDA(cudaMemsetAsync(ctx->zbuf, 0, sizeof(double) * NO, ctx->stream));
             }
           VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
-          VH_TRY(vhk_spmv(ctx, ctx->zbuf, aux));
+          VH_TRY(vhk_spmv(ctx, ctx->zbuf, aux, true)); // z = M^-1 v_j: zero at Dirichlet DoFs because v_j is
           // modified Gram-Schmidt; the coefficients never leave the device between the fused steps
           bool fused = false;
           VH_TRY(vhk_mgs_fused(ctx, aux, ctx->V, NO, j, hcol, &fused));

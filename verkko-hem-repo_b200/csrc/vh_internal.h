@@ -9,11 +9,11 @@
 #include <vector>
 
 #include "vh_femgl.h"
+#include "vh_pointwise.cuh"
 
 #define VH_NCOMP 18
 #define VH_BLK 324   /* 18*18 doubles per matrix block */
-#define VH_SYM 171   /* unique entries of a symmetric 18x18 */
-#define VH_SYMP 172  /* padded to a multiple of 2 doubles so a double2 never straddles quadrature points */
+/* VH_SYMP = 180: packed symmetric 18x18, see vh_pointwise.cuh (171 unique entries + 9 zero dummies, even row starts) */
 
 // ---- reference-cell tables (unit cell [0,1]^3), built on the host at vh_create and uploaded once ----
 // Q1: nn = nq = 8, nqf = 4.  Q2: nn = nq = 27, nqf = 9.
@@ -69,7 +69,15 @@ struct vh_ctx
   // BSR(18) matrix over owned rows
   int32_t *row_ptr  = nullptr; // [n_owned+1]
   int32_t *col      = nullptr; // [nnzb] local node ids, ascending inside a row
-  double  *vals     = nullptr; // [nnzb][18][18]
+  double  *vals     = nullptr; // [nnzb][18][18]  full blocks (general-scatter rows; all rows when !packed)
+  // Packed storage of the lattice ("fast") rows: block = Sym(P) + kron(I_6, M_slot) with Dirichlet masks applied on
+  // the fly, P = 171 unique entries of the symmetric bulk part (+1 pad): 1376 B per block instead of 2592 B.
+  bool     packed   = false;
+  double  *pvals    = nullptr; // [nnzb][172]
+  uint32_t *spmv_lane_tab   = nullptr; // [3][32]  lane constants of k_spmv_sym18
+  uint16_t *spmv_gather_tab = nullptr; // [26][18] row-end gather lists of k_spmv_sym18
+  double   *xmask   = nullptr; // [NL] scratch: Dirichlet-masked copy of an SpMV input (public vh_spmv only)
+  double  *cdiag    = nullptr; // [n_owned][18] constrained-diagonal values sum_cells |a_ii| (0 for unconstrained DoFs)
   int32_t *diag_pos = nullptr; // [n_owned] block index of (I,I)
   double  *minv     = nullptr; // [n_owned][18][18] inverse diagonal blocks (block-Jacobi)
   std::vector<int32_t> h_row_ptr, h_col;
@@ -79,6 +87,8 @@ struct vh_ctx
   int32_t *fast_rows  = nullptr; // [n_fast]
   int32_t *fast_cells = nullptr; // [n_fast][8]   cell in octant o (row node is local vertex 7-o), -1 = absent
   int8_t  *fast_slot  = nullptr; // [n_fast][32]  stencil slot (dx+1)+3(dy+1)+9(dz+1) -> position in the row, -1 = absent
+  uint8_t *fast_posslot = nullptr; // [n_fast][32] position in the row -> stencil slot
+  int32_t *fast_index = nullptr; // [n_owned]     index into fast_rows or -1
   int32_t *fast_class = nullptr; // [n_fast]      geometry class of the row's stencil
   double  *class_tab  = nullptr; // [n_classes][27][12] per slot: GS[3][3] = sum vol/(h_x h_y) Gref, FS[3] = sum area Mf (x != normal)
   int32_t  n_classes  = 0;
@@ -170,13 +180,16 @@ int vh_fail(vh_ctx *ctx, int code, const std::string &msg);
 int vhk_pointwise(vh_ctx *ctx, const double *x_local, bool want_hessian, bool want_energy);
 int vhk_rows_fast(vh_ctx *ctx);
 int vhk_rows_slow(vh_ctx *ctx, bool want_matrix, double *rhs_out);
-int vhk_rhs_fast(vh_ctx *ctx, double *rhs_out);
+int vhk_rhs_fast(vh_ctx *ctx, double *rhs_out, bool with_cdiag);
 int vhk_store_probe(vh_ctx *ctx, int mode);
 int vhk_upload_constants(vh_ctx *ctx);
 int vhk_upload_w1(vh_ctx *ctx, const double *W1);
 
 // ---- linear algebra (vh_linalg.cu) ----
-int vhk_spmv(vh_ctx *ctx, const double *x_local, double *y_owned);
+// x_is_masked: the caller guarantees zeros at the homogeneous-Dirichlet DoFs of x (all Krylov vectors satisfy this)
+int vhk_spmv(vh_ctx *ctx, const double *x_local, double *y_owned, bool x_is_masked);
+int vhk_upload_linalg_constants(vh_ctx *ctx);
+int vhk_expand_packed(vh_ctx *ctx, double *full_vals);
 int vhk_block_jacobi_setup(vh_ctx *ctx);
 int vhk_block_jacobi_apply(vh_ctx *ctx, const double *x_owned, double *y_owned);
 int vhk_block_jacobi_apply_scaled(vh_ctx *ctx, const double *x_owned, const double *nsq_dev, double *v_out, double *y_owned);

@@ -11,6 +11,8 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
+                  // SpMV row-end reduction: partial-sum slots per component
+
 namespace
 {
 __device__ __forceinline__ double warp_sum(double v)
@@ -29,14 +31,15 @@ __device__ __forceinline__ double warp_sum(double v)
 // ------------------------------------------------------------------------------------------------
 #define VH_SPMV_WARPS 8
 __global__ void __launch_bounds__(VH_SPMV_WARPS * 32)
-  k_spmv_bsr18(int n_rows, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+  k_spmv_bsr18(int n_rows, const int32_t *__restrict__ rows, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y)
 {
   __shared__ double s_part[VH_SPMV_WARPS][6 * 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int row  = blockIdx.x * VH_SPMV_WARPS + wid;
-  if (row >= n_rows)
+  const int ridx = blockIdx.x * VH_SPMV_WARPS + wid;
+  if (ridx >= n_rows)
     return;
+  const int row = rows ? rows[ridx] : ridx; // rows != nullptr: only the general-scatter rows (packed storage elsewhere)
   const int b0 = row_ptr[row], b1 = row_ptr[row + 1];
   double    acc[6] = {0, 0, 0, 0, 0, 0};
   int       xoff[6];
@@ -91,11 +94,146 @@ __global__ void __launch_bounds__(VH_SPMV_WARPS * 32)
 }
 
 // ------------------------------------------------------------------------------------------------
+// SpMV over the PACKED rows: block = Sym(P) + kron(I_6, M_slot), Dirichlet columns/rows masked on the fly.
+// One warp per row; a block is 90 double2 (1440 B, layout P180 of vh_pointwise.cuh): lane l streams double2 l, l+32,
+// l+64.  A double2 holds (c,d),(c,d+1) with d even, so it needs ONE aligned 16-byte load of x_J[d..d+1] plus x_J[c]:
+//     y_c += S0 x_d + S1 x_{d+1};   y_d += S0 x_c;   y_{d+1} += S1 x_c        (mirror terms, off the diagonal)
+// (c,d) are lane constants, identical in every block: nine private partial sums per lane, gathered once per row through a
+// constant index table.  The geometry part is three FMAs per block for lanes 0..17.  Four blocks are in flight.
+// ------------------------------------------------------------------------------------------------
+#define VH_PSPMV_WARPS 8
+#define VH_PSPMV_NPART 9
+// xg: vector the blocks are applied to.  Its Dirichlet DoFs must already be zero (true for every Krylov vector; the
+// public vh_spmv masks a copy first), so no mask logic sits in the streaming loop.  xo: the unmasked vector, used only
+// for the constrained diagonal  y_c = (sum_cells |a_ii|) x_c.
+// lane_tab[3][32]: per (slot k, lane) packed  c | d_even<<8 | m0<<16 | m1<<17;  gather_tab[26][18]: partial-sum indices.
+__global__ void __launch_bounds__(VH_PSPMV_WARPS * 32, 2)
+  k_spmv_sym18(int n_fast, const int32_t *__restrict__ fast_rows, const uint8_t *__restrict__ fast_posslot,
+               const int32_t *__restrict__ fast_class, const double *__restrict__ class_M, const int32_t *__restrict__ row_ptr,
+               const int32_t *__restrict__ col, const uint32_t *__restrict__ dirmask, const double *__restrict__ pvals,
+               const double *__restrict__ cdiag, const uint32_t *__restrict__ lane_tab, const uint16_t *__restrict__ gather_tab,
+               const double *__restrict__ xg, const double *__restrict__ xo, double *__restrict__ y)
+{
+  __shared__ double s_part[VH_PSPMV_WARPS][VH_PSPMV_NPART * 32 + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r    = blockIdx.x * VH_PSPMV_WARPS + wid;
+  if (r >= n_fast)
+    return;
+  const int     I = fast_rows[r], b0 = row_ptr[I], b1 = row_ptr[I + 1];
+  const double *M0 = class_M + (size_t)fast_class[r] * 270;
+  const bool    third = lane < (VH_SYMP / 2 - 64); // double2 #(lane+64) exists for lanes 0..25
+  int           pc[3], pd[3];
+  double        m0[3], m1[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    {
+      const uint32_t w = __ldg(lane_tab + 32 * k + lane);
+      pc[k]            = w & 0xff;
+      pd[k]            = (w >> 8) & 0xff;
+      m0[k]            = (w >> 16) & 1u ? 1.0 : 0.0;
+      m1[k]            = (w >> 17) & 1u ? 1.0 : 0.0;
+    }
+  double    ac[3] = {0, 0, 0}, a0[3] = {0, 0, 0}, a1[3] = {0, 0, 0};
+  double    geo   = 0.0;
+  const int gc = lane < 18 ? lane : 0, gg = 3 * (gc / 3), gx = gc % 3; // geometry: lane c, group base, orbital index
+
+  // one block: 3 x 16 B of matrix, 3 x (16 B + 8 B) of x through L1, 12 FMAs (+3 for the geometry part in lanes 0..17)
+#define VH_PSPMV_BLOCK(V, JJ, SL)                                                        \
+  {                                                                                      \
+    const double *xj = xg + 18 * (size_t)(JJ);                                           \
+    _Pragma("unroll") for (int k = 0; k < 3; ++k)                                        \
+    {                                                                                    \
+      const double2 xd = *reinterpret_cast<const double2 *>(xj + pd[k]);                 \
+      const double  xc = xj[pc[k]];                                                      \
+      ac[k]            = fma((V)[k].x, xd.x, fma((V)[k].y, xd.y, ac[k]));                \
+      a0[k]            = fma((V)[k].x, xc, a0[k]);                                       \
+      a1[k]            = fma((V)[k].y, xc, a1[k]);                                       \
+    }                                                                                    \
+    if (lane < 18)                                                                       \
+      {                                                                                  \
+        const double *M = M0 + (SL)*10 + 3 * gx;                                         \
+        geo             = fma(M[0], xj[gg], fma(M[1], xj[gg + 1], fma(M[2], xj[gg + 2], geo))); \
+      }                                                                                  \
+  }
+
+  for (int base = b0; base < b1; base += 32)
+    {
+      const int nchunk = min(32, b1 - base);
+      const int mycol  = lane < nchunk ? __ldg(col + base + lane) : 0;
+      const int myslot = lane < nchunk ? (int)fast_posslot[(size_t)r * 32 + (base - b0) + lane] : 13;
+      int       j      = 0;
+      for (; j + 4 <= nchunk; j += 4)
+        { // four blocks (12 x 16 B per lane) in flight, no tail logic here
+          double2 v[4][3];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            {
+              const double2 *B = reinterpret_cast<const double2 *>(pvals + (size_t)(base + j + u) * VH_SYMP);
+              v[u][0]          = __ldcs(B + lane);
+              v[u][1]          = __ldcs(B + lane + 32);
+              v[u][2]          = third ? __ldcs(B + lane + 64) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            {
+              const int J  = __shfl_sync(0xffffffffu, mycol, j + u);
+              const int sl = __shfl_sync(0xffffffffu, myslot, j + u);
+              VH_PSPMV_BLOCK(v[u], J, sl)
+            }
+        }
+      for (; j < nchunk; ++j)
+        {
+          double2        v[3];
+          const double2 *B = reinterpret_cast<const double2 *>(pvals + (size_t)(base + j) * VH_SYMP);
+          v[0]             = __ldcs(B + lane);
+          v[1]             = __ldcs(B + lane + 32);
+          v[2]             = third ? __ldcs(B + lane + 64) : make_double2(0.0, 0.0);
+          const int J      = __shfl_sync(0xffffffffu, mycol, j);
+          const int sl     = __shfl_sync(0xffffffffu, myslot, j);
+          VH_PSPMV_BLOCK(v, J, sl)
+        }
+    }
+#undef VH_PSPMV_BLOCK
+  // row end: nine partial sums per lane -> 18 components (fixed gather order: deterministic)
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    {
+      s_part[wid][(3 * k + 0) * 32 + lane] = ac[k];
+      s_part[wid][(3 * k + 1) * 32 + lane] = a0[k] * m0[k];
+      s_part[wid][(3 * k + 2) * 32 + lane] = a1[k] * m1[k];
+    }
+  if (lane == 0)
+    s_part[wid][VH_PSPMV_NPART * 32] = 0.0; // padding target of the gather lists
+  __syncwarp();
+  if (lane < 18)
+    {
+      double sum = geo;
+#pragma unroll
+      for (int i = 0; i < 26; ++i)
+        sum += s_part[wid][__ldg(gather_tab + i * 18 + lane)];
+      const uint32_t mI = dirmask[I];
+      if ((mI >> lane) & 1u) // constrained row: only the diagonal entry sum_cells |a_ii|
+        sum = cdiag[(size_t)I * 18 + lane] * xo[18 * (size_t)I + lane];
+      y[(size_t)I * 18 + lane] = sum;
+    }
+}
+
+// x~ = x with the homogeneous-Dirichlet DoFs zeroed (their matrix columns are empty)
+__global__ void k_mask_dirichlet(int64_t n, const uint32_t *__restrict__ dirmask, const double *__restrict__ x, double *__restrict__ xm)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    xm[i] = ((dirmask[i / 18] >> (i % 18)) & 1u) ? 0.0 : x[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // block-Jacobi: invert the 18x18 diagonal blocks (Gauss-Jordan, partial pivoting), one warp per block
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
   k_block_invert(int n_rows, const int32_t *__restrict__ diag_pos, const double *__restrict__ vals, double *__restrict__ minv,
-                 int *__restrict__ n_singular)
+                 int *__restrict__ n_singular, const double *__restrict__ pvals, const int32_t *__restrict__ fast_index,
+                 const int32_t *__restrict__ fast_class, const double *__restrict__ class_M, const uint32_t *__restrict__ dirmask,
+                 const double *__restrict__ cdiag)
 {
   // Register-resident Gauss-Jordan: lane r < 18 keeps row r of [A | I] in registers; the scaled pivot row is broadcast
   // through shared memory (shuffles would be the bottleneck: ~1000 per block), and rows are never swapped physically:
@@ -105,14 +243,35 @@ __global__ void __launch_bounds__(128)
   const int row  = blockIdx.x * 4 + wid;
   if (row >= n_rows)
     return;
-  const double *B  = vals + (size_t)diag_pos[row] * VH_BLK;
-  const int     rr = lane < 18 ? lane : 17;
-  double        a[36];
+  const int rr = lane < 18 ? lane : 17;
+  double    a[36];
+  const int fi = pvals ? fast_index[row] : -1;
+  if (fi >= 0)
+    { // packed row: diagonal block = Sym(P) + kron(I_6, M_13), Dirichlet rows/columns -> sum_cells |a_ii| on the diagonal
+      const double  *P  = pvals + (size_t)diag_pos[row] * VH_SYMP;
+      const double  *M  = class_M + (size_t)fast_class[fi] * 270 + 13 * 10;
+      const uint32_t mI = dirmask[row];
 #pragma unroll
-  for (int c = 0; c < 18; ++c)
+      for (int c = 0; c < 18; ++c)
+        {
+          double v = __ldg(P + (rr <= c ? vh_sym_index(rr, c) : vh_sym_index(c, rr)));
+          if (rr / 3 == c / 3)
+            v += M[(rr % 3) * 3 + c % 3];
+          if (((mI >> rr) & 1u) || ((mI >> c) & 1u))
+            v = (rr == c) ? cdiag[(size_t)row * 18 + c] : 0.0;
+          a[c]      = v;
+          a[18 + c] = (c == rr) ? 1.0 : 0.0;
+        }
+    }
+  else
     {
-      a[c]      = __ldg(B + rr * 18 + c);
-      a[18 + c] = (c == rr) ? 1.0 : 0.0;
+      const double *B = vals + (size_t)diag_pos[row] * VH_BLK;
+#pragma unroll
+      for (int c = 0; c < 18; ++c)
+        {
+          a[c]      = __ldg(B + rr * 18 + c);
+          a[18 + c] = (c == rr) ? 1.0 : 0.0;
+        }
     }
   bool used     = lane >= 18;
   int  mycol    = -1;
@@ -522,12 +681,77 @@ inline unsigned red_grid(int64_t n)
 }
 } // namespace
 
-int vhk_spmv(vh_ctx *ctx, const double *x_local, double *y_owned)
+int vhk_upload_linalg_constants(vh_ctx *ctx)
+{
+  uint8_t sc[VH_SYMP], sd[VH_SYMP];
+  vh_sym_tables(sc, sd);
+  // Lane table and gather lists of k_spmv_sym18.  double2 #p (entries e = 2p, 2p+1) lives in lane p%32, slot k = p/32 and
+  // produces three partials: [3k+0] -> y_c, [3k+1] -> y_d (mirror of the first entry), [3k+2] -> y_{d+1} (mirror of the
+  // second).  Component comp collects at most 9 + 17 = 26 of them; unused list positions point at a zero slot.
+  std::vector<uint32_t> lt(96, 0u);
+  std::vector<uint16_t> g(26 * 18, (uint16_t)(9 * 32));
+  std::vector<int>      cnt(18, 0);
+  for (int p = 0; p < 96; ++p)
+    {
+      const int pp = p < VH_SYMP / 2 ? p : VH_SYMP / 2 - 1; // lanes without a third double2 mirror the last one (their v is 0)
+      const int c = sc[2 * pp], d = 2 * (sd[2 * pp + 1] >> 1);
+      const int mir0 = (d != c && sd[2 * pp] >= sc[2 * pp]) ? 1 : 0, mir1 = (d + 1 != c) ? 1 : 0;
+      lt[(p / 32) * 32 + p % 32] = (uint32_t)c | ((uint32_t)d << 8) | ((uint32_t)mir0 << 16) | ((uint32_t)mir1 << 17);
+      if (p >= VH_SYMP / 2)
+        continue;
+      const int lane = p % 32, k = p / 32;
+      auto      add = [&](int comp, int slot) {
+        if (cnt[comp] < 26)
+          g[(size_t)cnt[comp] * 18 + comp] = (uint16_t)(slot * 32 + lane);
+        cnt[comp]++;
+      };
+      add(c, 3 * k + 0);
+      if (mir0)
+        add(d, 3 * k + 1);
+      if (mir1)
+        add(d + 1, 3 * k + 2);
+    }
+  for (int comp = 0; comp < 18; ++comp)
+    if (cnt[comp] > 26)
+      return vh_fail(ctx, VH_ERR_ARG, "internal: SpMV gather list overflow");
+  VH_TRY(vh_dev_upload(ctx, &ctx->spmv_lane_tab, lt.data(), lt.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->spmv_gather_tab, g.data(), g.size()));
+  return VH_OK;
+}
+
+int vhk_spmv(vh_ctx *ctx, const double *x_local, double *y_owned, bool x_is_masked)
 {
   if (ctx->n_owned == 0)
     return VH_OK;
+  if (ctx->packed)
+    {
+      const unsigned grid = (ctx->n_fast + VH_PSPMV_WARPS - 1) / VH_PSPMV_WARPS;
+      const double *xg = x_local;
+      if (!x_is_masked)
+        { // arbitrary input: the blocks are applied to a copy whose Dirichlet DoFs are zeroed
+          if (!ctx->xmask)
+            VH_TRY(vh_dev_alloc(ctx, &ctx->xmask, (size_t)ctx->NL));
+          k_mask_dirichlet<<<(unsigned)((ctx->NL + 255) / 256), 256, 0, ctx->stream>>>(ctx->NL, ctx->dirmask, x_local, ctx->xmask);
+          VH_LAUNCH_CHECK();
+          xg = ctx->xmask;
+        }
+      k_spmv_sym18<<<grid, VH_PSPMV_WARPS * 32, 0, ctx->stream>>>(ctx->n_fast, ctx->fast_rows, ctx->fast_posslot, ctx->fast_class,
+                                                                 ctx->class_M, ctx->row_ptr, ctx->col, ctx->dirmask, ctx->pvals,
+                                                                 ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, xg, x_local,
+                                                                 y_owned);
+      VH_LAUNCH_CHECK();
+      if (ctx->n_slow_rows > 0)
+        {
+          const unsigned gs = (ctx->n_slow_rows + VH_SPMV_WARPS - 1) / VH_SPMV_WARPS;
+          k_spmv_bsr18<<<gs, VH_SPMV_WARPS * 32, 0, ctx->stream>>>(ctx->n_slow_rows, ctx->slow_rows, ctx->row_ptr, ctx->col, ctx->vals,
+                                                                  x_local, y_owned);
+          VH_LAUNCH_CHECK();
+        }
+      return VH_OK;
+    }
   const unsigned grid = (ctx->n_owned + VH_SPMV_WARPS - 1) / VH_SPMV_WARPS;
-  k_spmv_bsr18<<<grid, VH_SPMV_WARPS * 32, 0, ctx->stream>>>(ctx->n_owned, ctx->row_ptr, ctx->col, ctx->vals, x_local, y_owned);
+  k_spmv_bsr18<<<grid, VH_SPMV_WARPS * 32, 0, ctx->stream>>>(ctx->n_owned, nullptr, ctx->row_ptr, ctx->col, ctx->vals, x_local,
+                                                            y_owned);
   VH_LAUNCH_CHECK();
   return VH_OK;
 }
@@ -538,7 +762,9 @@ int vhk_block_jacobi_setup(vh_ctx *ctx)
     return VH_OK;
   int *d_sing = reinterpret_cast<int *>(ctx->scal + VH_SCAL_MISC);
   VH_CUDA(cudaMemsetAsync(d_sing, 0, sizeof(int), ctx->stream));
-  k_block_invert<<<(ctx->n_owned + 3) / 4, 128, 0, ctx->stream>>>(ctx->n_owned, ctx->diag_pos, ctx->vals, ctx->minv, d_sing);
+  k_block_invert<<<(ctx->n_owned + 3) / 4, 128, 0, ctx->stream>>>(ctx->n_owned, ctx->diag_pos, ctx->vals, ctx->minv, d_sing,
+                                                                  ctx->packed ? ctx->pvals : nullptr, ctx->fast_index, ctx->fast_class,
+                                                                  ctx->class_M, ctx->dirmask, ctx->cdiag);
   VH_LAUNCH_CHECK();
   int h_sing = 0;
   VH_CUDA(cudaMemcpyAsync(&h_sing, d_sing, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

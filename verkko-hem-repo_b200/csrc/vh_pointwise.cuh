@@ -356,7 +356,28 @@ VH_HD double vh_entry_eval(const double *tab, const vh_terms &T)
   return v;
 }
 
-// index of (c,d), c<=d, in the row-major packed upper triangle of a symmetric 18x18
-VH_HD int vh_sym_index(int c, int d) { return c * 18 - (c * (c - 1)) / 2 + (d - c); }
+// Packed layout of a symmetric 18x18 ("P180"): row c stores the entries (c,d) for d = 2*(c/2) .. 17, so every row
+// starts at an EVEN column and every 16-byte pair (d, d+1) of the packed array belongs to one row and pairs with an
+// aligned 16-byte pair of the vector in the SpMV.  For odd c the first stored entry (c, c-1) is a dummy that is always 0.
+// 180 doubles per matrix (171 unique + 9 dummies).
+#define VH_SYMP 180
+VH_HD int vh_sym_rowstart(int c)
+{
+  const int m = c >> 1;
+  return (c & 1) ? 36 * m - 2 * m * m + 18 : 38 * m - 2 * m * m;
+}
+// index of (c,d), c <= d
+VH_HD int vh_sym_index(int c, int d) { return vh_sym_rowstart(c) + d - 2 * (c >> 1); }
+// fills c[e], d[e] for e in [0,180); dummies have d[e] = c[e] - 1 (i.e. d < c)
+inline void vh_sym_tables(unsigned char *tc, unsigned char *td)
+{
+  int e = 0;
+  for (int c = 0; c < 18; ++c)
+    for (int d = 2 * (c >> 1); d < 18; ++d, ++e)
+      {
+        tc[e] = (unsigned char)c;
+        td[e] = (unsigned char)d;
+      }
+}
 
 #endif
