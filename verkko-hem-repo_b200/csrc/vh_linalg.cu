@@ -8,6 +8,8 @@
 // two-stage reductions whose results stay on the device (no host round trip inside the Gram-Schmidt loop).
 #include "vh_internal.h"
 
+#include <cstdlib>
+
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -107,7 +109,8 @@ __global__ void __launch_bounds__(VH_SPMV_WARPS * 32)
 // public vh_spmv masks a copy first), so no mask logic sits in the streaming loop.  xo: the unmasked vector, used only
 // for the constrained diagonal  y_c = (sum_cells |a_ii|) x_c.
 // lane_tab[3][32]: per (slot k, lane) packed  c | d_even<<8 | m0<<16 | m1<<17;  gather_tab[26][18]: partial-sum indices.
-__global__ void __launch_bounds__(VH_PSPMV_WARPS * 32, 2)
+template <int NB, int MINB> // NB blocks in flight per warp, MINB resident CTAs per SM
+__global__ void __launch_bounds__(VH_PSPMV_WARPS * 32, MINB)
   k_spmv_sym18(int n_fast, const int32_t *__restrict__ fast_rows, const uint8_t *__restrict__ fast_posslot,
                const int32_t *__restrict__ fast_class, const double *__restrict__ class_M, const int32_t *__restrict__ row_ptr,
                const int32_t *__restrict__ col, const uint32_t *__restrict__ dirmask, const double *__restrict__ pvals,
@@ -162,11 +165,11 @@ __global__ void __launch_bounds__(VH_PSPMV_WARPS * 32, 2)
       const int mycol  = lane < nchunk ? __ldg(col + base + lane) : 0;
       const int myslot = lane < nchunk ? (int)fast_posslot[(size_t)r * 32 + (base - b0) + lane] : 13;
       int       j      = 0;
-      for (; j + 4 <= nchunk; j += 4)
-        { // four blocks (12 x 16 B per lane) in flight, no tail logic here
-          double2 v[4][3];
+      for (; j + NB <= nchunk; j += NB)
+        { // NB blocks (NB x 3 x 16 B per lane) in flight, no tail logic here
+          double2 v[NB][3];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < NB; ++u)
             {
               const double2 *B = reinterpret_cast<const double2 *>(pvals + (size_t)(base + j + u) * VH_SYMP);
               v[u][0]          = __ldcs(B + lane);
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(VH_PSPMV_WARPS * 32, 2)
               v[u][2]          = third ? __ldcs(B + lane + 64) : make_double2(0.0, 0.0);
             }
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < NB; ++u)
             {
               const int J  = __shfl_sync(0xffffffffu, mycol, j + u);
               const int sl = __shfl_sync(0xffffffffu, myslot, j + u);
@@ -735,10 +738,26 @@ int vhk_spmv(vh_ctx *ctx, const double *x_local, double *y_owned, bool x_is_mask
           VH_LAUNCH_CHECK();
           xg = ctx->xmask;
         }
-      k_spmv_sym18<<<grid, VH_PSPMV_WARPS * 32, 0, ctx->stream>>>(ctx->n_fast, ctx->fast_rows, ctx->fast_posslot, ctx->fast_class,
-                                                                 ctx->class_M, ctx->row_ptr, ctx->col, ctx->dirmask, ctx->pvals,
-                                                                 ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, xg, x_local,
-                                                                 y_owned);
+      static int variant = -1;
+      if (variant < 0)
+        {
+          const char *e = getenv("VH_SPMV_VARIANT"); // tuning knob: blocks in flight / resident CTAs
+          variant       = e ? atoi(e) : 0;
+        }
+#define VH_LAUNCH_PSPMV(NB, MINB)                                                                                                  \
+  k_spmv_sym18<NB, MINB><<<grid, VH_PSPMV_WARPS * 32, 0, ctx->stream>>>(ctx->n_fast, ctx->fast_rows, ctx->fast_posslot,            \
+                                                                       ctx->fast_class, ctx->class_M, ctx->row_ptr, ctx->col,      \
+                                                                       ctx->dirmask, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab,   \
+                                                                       ctx->spmv_gather_tab, xg, x_local, y_owned)
+      if (variant == 1)
+        VH_LAUNCH_PSPMV(3, 3);
+      else if (variant == 2)
+        VH_LAUNCH_PSPMV(2, 4);
+      else if (variant == 3)
+        VH_LAUNCH_PSPMV(6, 2);
+      else
+        VH_LAUNCH_PSPMV(4, 2);
+#undef VH_LAUNCH_PSPMV
       VH_LAUNCH_CHECK();
       if (ctx->n_slow_rows > 0)
         {
