@@ -51,3 +51,17 @@ extern "C" void vht_hessian_terms(const double *A, const double *coef, double *H
       }
 }
 extern "C" int vht_sym_index(int c, int d) { return vh_sym_index(c, d); }
+// ... and through the register-resident evaluation of k_points_q1 (unique products, compile-time entry formulas)
+extern "C" void vht_points_q1(const double *A, const double *coef, double *g18, double *H324, double *f)
+{
+  vh_prods p;
+  vh_prods_compute(A, p);
+  const vh_hweights w  = vh_make_hweights(coef[3], coef + 4);
+  const vh_hdiag    hd = vh_make_hdiag(p, w);
+  vh_g_all(A, p, w, g18);
+  for (int c = 0; c < 18; ++c)
+    for (int d = 0; d < 18; ++d)
+      H324[18 * c + d] = vh_h_entry(A, p, w, hd, c, d);
+  *f = vh_bulk_energy_u(p, coef[3], coef + 4);
+}
+extern "C" int vht_hq8_index(int q, int e) { return vh_hq8_index(q, e); }

@@ -205,3 +205,42 @@ def test_oracle_partition_independence():
         want = A1[dof_perm[:18 * T.n_owned_nodes]][:, dof_perm]
         assert abs(A - want).max() <= 1e-13 * abs(A1).max()
         assert np.abs(rhs - r1[dof_perm[:18 * T.n_owned_nodes]]).max() <= 1e-13 * np.abs(r1).max()
+
+
+def _native_pointwise_lib():
+    """Host build of the product's __host__ __device__ pointwise math (csrc/vh_pointwise.cuh) — test-only."""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "native", "pointwise_host.cc")
+    out = os.path.join(ROOT, "tests", "native", "_build", "libvhpw.so")
+    hdr = os.path.join(ROOT, "verkko-hem-repo_b200", "csrc", "vh_pointwise.cuh")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-shared", "-fPIC", "-o", out, src])
+    return ctypes.CDLL(out)
+
+
+@pytest.mark.parametrize("entry", ["vht_pointwise", "vht_points_q1"])
+def test_device_pointwise_math_matches_oracle_on_host(entry):
+    """The closed forms the kernels evaluate (column form and the register-resident per-entry form of k_points_q1)
+    agree with the oracle's restatement of cell_mat_lhs_*/cell_vec_rhs_* to rounding for random complex A."""
+    L = _native_pointwise_lib()
+    P = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(7)
+    coef = coef_vector()
+    for trial in range(20):
+        A = rng.standard_normal(18) * (1.0 if trial else 0.0) + (0.3 if trial == 0 else 0.0)
+        g = np.zeros(18); H = np.zeros((18, 18)); f = np.zeros(1)
+        getattr(L, entry)(A.ctypes.data_as(P), coef.ctypes.data_as(P), g.ctypes.data_as(P), H.ctypes.data_as(P), f.ctypes.data_as(P))
+        g0, H0, f0 = O.pointwise(A, coef)
+        assert np.abs(g - g0).max() <= 1e-13 * max(1.0, np.abs(g0).max())
+        assert np.abs(H - H0).max() <= 1e-13 * max(1.0, np.abs(H0).max())
+        assert abs(f[0] - f0) <= 1e-13 * max(1.0, abs(f0))
+        assert np.abs(H - H.T).max() <= 1e-13 * max(1.0, np.abs(H0).max())
+
+
+def test_hq8_layout_is_a_bijection():
+    L = _native_pointwise_lib()
+    seen = {L.vht_hq8_index(q, e) for q in range(8) for e in range(180)}
+    assert seen == set(range(1440))
+    for p in range(90):  # the eight quadrature points of one pair share one 128-byte line
+        assert {L.vht_hq8_index(q, 2 * p) // 16 for q in range(8)} == {p}

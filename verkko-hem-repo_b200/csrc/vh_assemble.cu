@@ -255,6 +255,310 @@ __global__ void __launch_bounds__(NQ == 8 ? 192 : 512)
 }
 
 // ------------------------------------------------------------------------------------------------
+// 1b. pointwise kernel for Q1, one THREAD per quadrature point
+// ------------------------------------------------------------------------------------------------
+// A warp owns 4 cells x 8 quadrature points (lane = 8*g + q).  The thread interpolates A and grad A at its point, keeps A
+// and the 42 unique product entries in registers and evaluates g (18) and the packed H_q (171 entries) with fully
+// unrolled, compile-time specialised formulas (vh_h_entry): ~12 FP64 instructions per entry and no index arithmetic,
+// against ~75 instructions per entry of the table-driven k_pointwise.  H_q leaves the registers with 16-byte stores in the
+// [pair][q XOR pair] layout (vh_hq8_index): the 8 lanes of a cell fill one 128-byte line per store instruction.
+// The q-sums of the cell vectors (rhs, cell diagonal) go through a per-warp shared buffer: the lane then plays node
+// a = lane % 8 and accumulates its 18 components over the 8 points; only __syncwarp() is needed.
+#define VH_PT_WARPS 4
+#define VH_PT_USTRIDE 146            /* 8 x 18 doubles per cell + 2: the 4 cells of a warp start in different banks */
+#define VH_PT_BSTRIDE (8 * 54 + 4)   /* per cell: 8 points x 54 doubles (+4: bank offset between the cells) */
+#define VH_PT_SMEM ((size_t)(64 + 192 + VH_PT_WARPS * 4 * (VH_PT_USTRIDE + VH_PT_BSTRIDE)) * sizeof(double))
+
+template <bool WANT_H, bool WANT_E>
+__global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
+  k_points_q1(int n_cells, const int32_t *__restrict__ cell_nodes, const double *__restrict__ cell_h,
+              const uint32_t *__restrict__ cell_faces, const uint8_t *__restrict__ cell_owned, const double *__restrict__ x,
+              VhTables tab, VhCoef cf, vh_hweights hw, double *__restrict__ Hq, double *__restrict__ Rc, double *__restrict__ Dc,
+              double *__restrict__ avgD, double *__restrict__ Ec)
+{
+  extern __shared__ __align__(16) double sm[];
+  double   *sNT  = sm;       // [q][a]
+  double   *sdNT = sm + 64;  // [q][x][a]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 3, q = lane & 7;
+  double   *sU = sm + 256 + warp * 4 * (VH_PT_USTRIDE + VH_PT_BSTRIDE); // [4][VH_PT_USTRIDE]
+  double   *sB = sU + 4 * VH_PT_USTRIDE;                                // [4][VH_PT_BSTRIDE]
+  if (t < 64)
+    sNT[(t & 7) * 8 + (t >> 3)] = tab.N[t];
+  for (int i = t; i < 192; i += VH_PT_WARPS * 32)
+    {
+      const int a = i / 24, r = i - 24 * a, qq = r / 3, xx = r - 3 * qq;
+      sdNT[(qq * 3 + xx) * 8 + a] = tab.dN[i];
+    }
+  const int cell0 = (blockIdx.x * VH_PT_WARPS + warp) * 4;
+#pragma unroll
+  for (int kk = 0; kk < 9; ++kk)
+    { // coalesced gather of the warp's 4 x 8 x 18 DoF values (16-byte pieces of the node rows)
+      const int i = lane + 32 * kk, gg = i / 72, r = i - 72 * gg, a = r / 9, pp = r - 9 * a;
+      const int e = min(cell0 + gg, n_cells - 1);
+      const double2 v = *reinterpret_cast<const double2 *>(x + 18 * (int64_t)cell_nodes[(int64_t)e * 8 + a] + 2 * pp);
+      *reinterpret_cast<double2 *>(sU + gg * VH_PT_USTRIDE + a * 18 + 2 * pp) = v;
+    }
+  __syncthreads();
+
+  const bool    live = cell0 + g < n_cells;
+  const int64_t cell = min(cell0 + g, n_cells - 1);
+  const double2 h01 = *reinterpret_cast<const double2 *>(cell_h + 4 * cell), h23 = *reinterpret_cast<const double2 *>(cell_h + 4 * cell + 2);
+  const double  vol = h23.y;
+  const double  hh[3] = {h01.x, h01.y, h23.x};
+  const double  ih[3] = {1.0 / h01.x, 1.0 / h01.y, 1.0 / h23.x};
+  const double  JxW = tab.wq[q] * vol;
+  const double *sUg = sU + g * VH_PT_USTRIDE;
+  double       *gB  = sB + g * VH_PT_BSTRIDE;
+
+  // ---- FE interpolation of the state and its gradient at this thread's point (s_vector2matrix.cc:154-162, 203-213) ----
+  double a18[18];
+  double eg = 0.0; // gradient energy density
+  {
+    double Nq[8], dNq[3][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+      {
+        Nq[a] = sNT[q * 8 + a];
+#pragma unroll
+        for (int xx = 0; xx < 3; ++xx)
+          dNq[xx][a] = sdNT[(q * 3 + xx) * 8 + a] * ih[xx];
+      }
+    double gt[54];
+    double dprev[3][3]; // gradients of the three components of the current row of A (c = 3*pm + xc)
+#pragma unroll
+    for (int cp = 0; cp < 9; ++cp)
+      {
+        double A0 = 0, A1 = 0, d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+          {
+            const double2 u = *reinterpret_cast<const double2 *>(sUg + a * 18 + 2 * cp);
+            A0 = fma(Nq[a], u.x, A0);
+            A1 = fma(Nq[a], u.y, A1);
+#pragma unroll
+            for (int xx = 0; xx < 3; ++xx)
+              {
+                d0[xx] = fma(dNq[xx][a], u.x, d0[xx]);
+                d1[xx] = fma(dNq[xx][a], u.y, d1[xx]);
+              }
+          }
+        a18[2 * cp]     = A0;
+        a18[2 * cp + 1] = A1;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          {
+            const int c = 2 * cp + h, xc = c % 3;
+#pragma unroll
+            for (int xx = 0; xx < 3; ++xx)
+              {
+                const double dv = h ? d1[xx] : d0[xx];
+                dprev[xc][xx]   = dv;
+                gt[3 * c + xx]  = cf.K1 * dv;
+                if (WANT_E)
+                  eg = fma(cf.K1 * dv, dv, eg);
+              }
+            if (xc == 2)
+              { // row pm = c/3 complete: divergence couples the three components (K2+K3 term)
+                const double div = dprev[0][0] + dprev[1][1] + dprev[2][2];
+#pragma unroll
+                for (int y = 0; y < 3; ++y)
+                  gt[3 * (c - 2 + y) + y] = fma(cf.K23, div, gt[3 * (c - 2 + y) + y]);
+                if (WANT_E)
+                  eg = fma(cf.K23 * div, div, eg);
+              }
+          }
+      }
+    // Gt[c][x] = JxW (K1 dA[c][x] + delta_{x,xc} K23 div): what the test gradient of node a is contracted with
+    double *myB = gB + q * 54;
+#pragma unroll
+    for (int i = 0; i < 27; ++i)
+      *reinterpret_cast<double2 *>(myB + 2 * i) = make_double2(JxW * gt[2 * i], JxW * gt[2 * i + 1]);
+  }
+  __syncwarp();
+  // ---- round 1: lane = node a of its cell;  rc[c] = sum_q grad N_a(q) . Gt_q[c]  (assemble.cc:257-276) ----
+  const int a_node = q;
+  double    rc[18];
+#pragma unroll
+  for (int c = 0; c < 18; ++c)
+    rc[c] = 0.0;
+#pragma unroll
+  for (int qq = 0; qq < 8; ++qq)
+    {
+      double wx[3];
+#pragma unroll
+      for (int xx = 0; xx < 3; ++xx)
+        wx[xx] = sdNT[(qq * 3 + xx) * 8 + a_node] * ih[xx];
+#pragma unroll
+      for (int i = 0; i < 27; ++i)
+        {
+          const double2 v = *reinterpret_cast<const double2 *>(gB + qq * 54 + 2 * i);
+          rc[(2 * i) / 3]     = fma(wx[(2 * i) % 3], v.x, rc[(2 * i) / 3]);
+          rc[(2 * i + 1) / 3] = fma(wx[(2 * i + 1) % 3], v.y, rc[(2 * i + 1) / 3]);
+        }
+    }
+  __syncwarp();
+
+  // ---- bulk terms at this thread's point ----
+  vh_prods pr;
+  vh_prods_compute(a18, pr);
+  {
+    double gv[18];
+    vh_g_all(a18, pr, hw, gv);
+    double *myB = gB + q * 18;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+      *reinterpret_cast<double2 *>(myB + 2 * i) = make_double2(JxW * gv[2 * i], JxW * gv[2 * i + 1]);
+  }
+  __syncwarp();
+  // ---- round 2: rc[c] += sum_q N_a(q) JxW g_q[c] ----
+#pragma unroll
+  for (int qq = 0; qq < 8; ++qq)
+    {
+      const double n = sNT[qq * 8 + a_node];
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+        {
+          const double2 v = *reinterpret_cast<const double2 *>(gB + qq * 18 + 2 * i);
+          rc[2 * i]       = fma(n, v.x, rc[2 * i]);
+          rc[2 * i + 1]   = fma(n, v.y, rc[2 * i + 1]);
+        }
+    }
+  __syncwarp();
+  const uint32_t faces = cell_faces[cell];
+  const bool     robin = (cf.bt < 1e10) && faces != 0u;
+  if (robin)
+    for (int f = 0; f < 6; ++f)
+      { // Robin (AdGR diffuse) wall faces: K1/bt * unit-face mass, components whose row index is the wall normal are skipped
+        const int bid = (faces >> (4 * f)) & 15u;
+        if (bid < 2 || bid > 4)
+          continue;
+        const double  s = cf.K1 / cf.bt * (vol / (f / 2 == 0 ? hh[0] : (f / 2 == 1 ? hh[1] : hh[2])));
+        const double *M = tab.Mf + (size_t)(f * 8 + a_node) * 8;
+        for (int b = 0; b < 8; ++b)
+          {
+            const double m = s * M[b];
+#pragma unroll
+            for (int c = 0; c < 18; ++c)
+              if (c % 3 != bid - 2)
+                rc[c] = fma(m, sUg[b * 18 + c], rc[c]);
+          }
+      }
+  if (live)
+    {
+      double *dst = Rc + cell * 144 + a_node * 18;
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+        *reinterpret_cast<double2 *>(dst + 2 * i) = make_double2(-rc[2 * i], -rc[2 * i + 1]);
+    }
+
+  if (WANT_H)
+    { // ---- the packed H_q, pre-multiplied by the cell volume, and the cell-matrix diagonal ----
+      const vh_hdiag hd    = vh_make_hdiag(pr, hw);
+      double        *hbase = Hq + cell * (int64_t)(8 * VH_SYMP);
+      double        *myB   = gB + q * 18;
+#pragma unroll
+      for (int cc = 0; cc < 18; ++cc)
+        { // rows in the order 0, 9, 1, 10, ...: Re and Im rows of one matrix position share their complex products
+          const int c = (cc >> 1) + 9 * (cc & 1);
+#pragma unroll
+          for (int d = 2 * (c >> 1); d < 18; d += 2)
+            {
+              const int    pp = vh_sym_index(c, d) >> 1;
+              const double v0 = d >= c ? vh_h_entry(a18, pr, hw, hd, c, d) : 0.0; // (c, c-1) is the zero dummy of odd rows
+              const double v1 = vh_h_entry(a18, pr, hw, hd, c, d + 1);
+              if (d == c)
+                myB[c] = JxW * v0;
+              if (d + 1 == c)
+                myB[c] = JxW * v1;
+              if (live)
+                *reinterpret_cast<double2 *>(hbase + ((pp << 3) + (q ^ (pp & 7))) * 2) = make_double2(v0 * vol, v1 * vol);
+            }
+        }
+      __syncwarp();
+      // round 3: diagonal of the cell matrix, dg[c] = sum_q N_a(q)^2 JxW H_q[c][c] + geometry (+ Robin)
+      double dg[18];
+      {
+        const double *G  = tab.Gref + (size_t)(a_node * 8 + a_node) * 9;
+        const double  g0 = G[0] * ih[0] * ih[0], g1 = G[4] * ih[1] * ih[1], g2 = G[8] * ih[2] * ih[2];
+        const double  k1 = vol * cf.K1 * (g0 + g1 + g2);
+#pragma unroll
+        for (int c = 0; c < 18; ++c)
+          dg[c] = k1 + vol * cf.K23 * (c % 3 == 0 ? g0 : (c % 3 == 1 ? g1 : g2));
+      }
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq)
+        {
+          const double n = sNT[qq * 8 + a_node], n2 = n * n;
+#pragma unroll
+          for (int i = 0; i < 9; ++i)
+            {
+              const double2 v = *reinterpret_cast<const double2 *>(gB + qq * 18 + 2 * i);
+              dg[2 * i]       = fma(n2, v.x, dg[2 * i]);
+              dg[2 * i + 1]   = fma(n2, v.y, dg[2 * i + 1]);
+            }
+        }
+      if (robin)
+        for (int f = 0; f < 6; ++f)
+          {
+            const int bid = (faces >> (4 * f)) & 15u;
+            if (bid < 2 || bid > 4)
+              continue;
+            const double s = cf.K1 / cf.bt * (vol / (f / 2 == 0 ? hh[0] : (f / 2 == 1 ? hh[1] : hh[2])));
+            const double m = s * tab.Mf[(size_t)(f * 8 + a_node) * 8 + a_node];
+#pragma unroll
+            for (int c = 0; c < 18; ++c)
+              if (c % 3 != bid - 2)
+                dg[c] += m;
+          }
+      double absd = 0.0;
+#pragma unroll
+      for (int c = 0; c < 18; ++c)
+        absd += fabs(dg[c]);
+      absd += __shfl_xor_sync(0xffffffffu, absd, 1);
+      absd += __shfl_xor_sync(0xffffffffu, absd, 2);
+      absd += __shfl_xor_sync(0xffffffffu, absd, 4);
+      if (live)
+        {
+          double *dst = Dc + cell * 144 + a_node * 18;
+#pragma unroll
+          for (int i = 0; i < 9; ++i)
+            *reinterpret_cast<double2 *>(dst + 2 * i) = make_double2(dg[2 * i], dg[2 * i + 1]);
+          if (a_node == 0)
+            avgD[cell] = absd / 144.0;
+        }
+    }
+  if (WANT_E)
+    { // GL functional, SURVEY.md A.1 (only locally owned cells count; ghost cells are assembled redundantly)
+      double e = JxW * (eg + vh_bulk_energy_u(pr, cf.alpha, cf.beta));
+      if (robin)
+        for (int f = 0; f < 6; ++f)
+          { // lane = node a: its share  s * sum_c U[a][c] sum_b M[a][b] U[b][c]
+            const int bid = (faces >> (4 * f)) & 15u;
+            if (bid < 2 || bid > 4)
+              continue;
+            const double  s = cf.K1 / cf.bt * (vol / (f / 2 == 0 ? hh[0] : (f / 2 == 1 ? hh[1] : hh[2])));
+            const double *M = tab.Mf + (size_t)(f * 8 + a_node) * 8;
+            double        ef = 0.0;
+            for (int c = 0; c < 18; ++c)
+              {
+                if (c % 3 == bid - 2)
+                  continue;
+                double m = 0.0;
+                for (int b = 0; b < 8; ++b)
+                  m += M[b] * sUg[b * 18 + c];
+                ef += sUg[a_node * 18 + c] * m;
+              }
+            e += s * ef;
+          }
+      e += __shfl_xor_sync(0xffffffffu, e, 1);
+      e += __shfl_xor_sync(0xffffffffu, e, 2);
+      e += __shfl_xor_sync(0xffffffffu, e, 4);
+      if (live && a_node == 0)
+        Ec[cell] = cell_owned[cell] ? e : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 2. row-owner Jacobian kernel for Q1 rows whose neighbourhood is a piece of a structured lattice
 // ------------------------------------------------------------------------------------------------
 #define VH_FAST_STAGES 4
@@ -384,18 +688,18 @@ __global__ void __launch_bounds__(192 / EPT, 4)
           uses ^= 1u << st;
           if (t < ACT)
             {
-              const double *Hs = s_H + (size_t)st * (8 * VH_SYMP) + EPT * t;
+              // cell table layout [pair][q XOR (pair & 7)] (vh_hq8_index): the stage base is 128-byte aligned, so the
+              // address of point q is the address of point 0 with bits 4..6 flipped by q
+              const int      pr0 = (EPT * t) >> 1;
+              const uint32_t Hs0 = smem_u32(s_H + (size_t)st * (8 * VH_SYMP)) + (uint32_t)((pr0 << 7) + ((pr0 & 7) << 4) + ((EPT * t) & 1) * 8);
 #pragma unroll
               for (int q = 0; q < 8; ++q)
                 {
                   double hv[EPT];
                   if constexpr (EPT == 2)
-                    {
-                      const double2 h2 = *reinterpret_cast<const double2 *>(Hs + q * VH_SYMP);
-                      hv[0] = h2.x, hv[1] = h2.y;
-                    }
+                    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(hv[0]), "=d"(hv[1]) : "r"(Hs0 ^ (uint32_t)(q << 4)));
                   else
-                    hv[0] = Hs[q * VH_SYMP];
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(hv[0]) : "r"(Hs0 ^ (uint32_t)(q << 4)));
 #pragma unroll
                   for (int b = 0; b < 8; ++b)
                     {
@@ -593,13 +897,15 @@ __global__ void __launch_bounds__(VH_MMA_THREADS, 2)
   __syncthreads();
 
   // B-fragment offsets of this lane inside a cell table: row q = 4*kstep + lane%4, column = packed entry of tile + lane/4
-  int boff[4];
+  int boff[2][4];
 #pragma unroll
-  for (int tl = 0; tl < 4; ++tl)
-    {
-      const int e = 8 * (4 * warp + tl) + (lane >> 2);
-      boff[tl]    = (lane & 3) * VH_SYMP + (e < VH_SYMP ? e : 18); // out-of-range columns read the zero dummy entry (1,0)
-    }
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int tl = 0; tl < 4; ++tl)
+      {
+        const int e  = 8 * (4 * warp + tl) + (lane >> 2);
+        boff[ks][tl] = vh_hq8_index(4 * ks + (lane & 3), e < VH_SYMP ? e : 18); // out-of-range columns read the zero dummy (1,0)
+      }
   double acc[8][4][2];
 #pragma unroll
   for (int o = 0; o < 8; ++o)
@@ -622,7 +928,7 @@ __global__ void __launch_bounds__(VH_MMA_THREADS, 2)
 #pragma unroll
               for (int tl = 0; tl < 4; ++tl)
                 {
-                  const double b = Hs[ks * 4 * VH_SYMP + boff[tl]];
+                  const double b = Hs[boff[ks][tl]];
                   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                                : "+d"(acc[o][tl][0]), "+d"(acc[o][tl][1])
                                : "d"(a), "d"(b));
@@ -906,7 +1212,7 @@ __global__ void k_cells_slow(SlowArgs A, VhTables tab, VhCoef cf, int want_matri
             const int sidx = c <= d ? vh_sym_index(c, d) : vh_sym_index(d, c);
             double    v = 0.0;
             for (int q = 0; q < NQ; ++q)
-              v += swq[q] * sN[a * NQ + q] * sN[b * NQ + q] * sH[q * VH_SYMP + sidx]; // H_q is stored pre-scaled by vol
+              v += swq[q] * sN[a * NQ + q] * sN[b * NQ + q] * sH[NQ == 8 ? vh_hq8_index(q, sidx) : q * VH_SYMP + sidx]; // pre-scaled by vol
             if (c == d)
               v += vol * cf.K1 * (G[0] * ih[0] * ih[0] + G[4] * ih[1] * ih[1] + G[8] * ih[2] * ih[2]);
             if (c / 3 == d / 3)
@@ -1002,10 +1308,30 @@ int vhk_pointwise(vh_ctx *ctx, const double *x_local, bool want_h, bool want_e)
     return VH_OK;
   if (ctx->degree == 1)
     {
-      const size_t smem = pointwise_smem<8, 8>(want_h);
-      k_pointwise<8, 8><<<ctx->n_cells, 192, smem, ctx->stream>>>(ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned,
-                                                                 x_local, ctx->tab, ctx->coef, want_h, want_e, ctx->Hq, ctx->Rc,
-                                                                 ctx->Dc, ctx->avgD, ctx->Ec);
+      static bool attr_set = false;
+      if (!attr_set)
+        {
+          VH_CUDA(cudaFuncSetAttribute(k_points_q1<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VH_PT_SMEM));
+          VH_CUDA(cudaFuncSetAttribute(k_points_q1<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VH_PT_SMEM));
+          VH_CUDA(cudaFuncSetAttribute(k_points_q1<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VH_PT_SMEM));
+          VH_CUDA(cudaFuncSetAttribute(k_points_q1<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VH_PT_SMEM));
+          attr_set = true;
+        }
+      const vh_hweights hw   = vh_make_hweights(ctx->coef.alpha, ctx->coef.beta);
+      const int         grid = (ctx->n_cells + 4 * VH_PT_WARPS - 1) / (4 * VH_PT_WARPS);
+#define VH_LAUNCH_POINTS(H, E)                                                                                                    \
+  k_points_q1<H, E><<<grid, VH_PT_WARPS * 32, VH_PT_SMEM, ctx->stream>>>(ctx->n_cells, ctx->cell_nodes, ctx->cell_h,              \
+                                                                        ctx->cell_faces, ctx->cell_owned, x_local, ctx->tab,      \
+                                                                        ctx->coef, hw, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec)
+      if (want_h && want_e)
+        VH_LAUNCH_POINTS(true, true);
+      else if (want_h)
+        VH_LAUNCH_POINTS(true, false);
+      else if (want_e)
+        VH_LAUNCH_POINTS(false, true);
+      else
+        VH_LAUNCH_POINTS(false, false);
+#undef VH_LAUNCH_POINTS
     }
   else
     {

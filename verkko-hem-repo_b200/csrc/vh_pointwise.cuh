@@ -356,6 +356,169 @@ VH_HD double vh_entry_eval(const double *tab, const vh_terms &T)
   return v;
 }
 
+// ---- register-resident evaluation (what k_points_q1 uses): one thread owns one quadrature point ---------------------
+// The thread keeps A (18 doubles) and the UNIQUE entries of the four products (R, S complex symmetric: 6 complex each;
+// Q, P Hermitian: 6 real parts + 3 imaginary parts each; 42 doubles instead of 72) in registers and evaluates the packed
+// entries (c,d) with c, d compile-time constants after unrolling, so only the terms that are not structurally zero are
+// executed (7.7 on average instead of the 17 table terms of vh_entry_eval) and there is no index arithmetic at all.
+struct vh_prods
+{
+  double Rr[6], Ri[6]; // R = A A^T
+  double Qr[6], Qi[3]; // Q = A A^+   (Q_ji = conj Q_ij)
+  double Pr[6], Pi[3]; // P = A^+ A   (P_ji = conj P_ij)
+  double Sr[6], Si[6]; // S = A^T A
+};
+// (0,0)=0 (0,1)=1 (0,2)=2 (1,1)=3 (1,2)=4 (2,2)=5
+VH_HD int vh_sym6(int i, int j) { return i <= j ? (i == 0 ? j : (i == 1 ? 2 + j : 5)) : (j == 0 ? i : (j == 1 ? 2 + i : 5)); }
+VH_HD void vh_prods_compute(const double *a, vh_prods &p)
+{
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j)
+      {
+        double rr = 0, ri = 0, qr = 0, qi = 0, pr = 0, pi = 0, sr = 0, si = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          {
+            const double ux = a[3 * i + k], vx = a[9 + 3 * i + k], uy = a[3 * j + k], vy = a[9 + 3 * j + k]; // A_ik, A_jk
+            rr += ux * uy - vx * vy;
+            ri += ux * vy + vx * uy;
+            qr += ux * uy + vx * vy;
+            qi += vx * uy - ux * vy;
+            const double us = a[3 * k + i], vs = a[9 + 3 * k + i], ut = a[3 * k + j], vt = a[9 + 3 * k + j]; // A_ki, A_kj
+            pr += us * ut + vs * vt;
+            pi += us * vt - vs * ut;
+            sr += us * ut - vs * vt;
+            si += us * vt + vs * ut;
+          }
+        const int e = vh_sym6(i, j);
+        p.Rr[e] = rr, p.Ri[e] = ri, p.Qr[e] = qr, p.Pr[e] = pr, p.Sr[e] = sr, p.Si[e] = si;
+        if (i < j)
+          p.Qi[i + j - 1] = qi, p.Pi[i + j - 1] = pi;
+      }
+}
+VH_HD vh_cx vh_getR(const vh_prods &p, int i, int j) { return vh_cx{p.Rr[vh_sym6(i, j)], p.Ri[vh_sym6(i, j)]}; }
+VH_HD vh_cx vh_getS(const vh_prods &p, int i, int j) { return vh_cx{p.Sr[vh_sym6(i, j)], p.Si[vh_sym6(i, j)]}; }
+VH_HD vh_cx vh_getQ(const vh_prods &p, int i, int j)
+{
+  return vh_cx{p.Qr[vh_sym6(i, j)], i == j ? 0.0 : (i < j ? p.Qi[i + j - 1] : -p.Qi[i + j - 1])};
+}
+VH_HD vh_cx vh_getP(const vh_prods &p, int i, int j)
+{
+  return vh_cx{p.Pr[vh_sym6(i, j)], i == j ? 0.0 : (i < j ? p.Pi[i + j - 1] : -p.Pi[i + j - 1])};
+}
+
+// weights of the Hessian terms; b_k = 2 beta_k
+struct vh_hweights
+{
+  double alpha, b1x2, b2x2, b3, b4, b5, b35p, b35m, b34p, b43m, b45p, b45m, b1, b2;
+};
+VH_HD vh_hweights vh_make_hweights(double alpha, const double *beta)
+{
+  const double b1 = 2.0 * beta[0], b2 = 2.0 * beta[1], b3 = 2.0 * beta[2], b4 = 2.0 * beta[3], b5 = 2.0 * beta[4];
+  return vh_hweights{alpha, 2.0 * b1, 2.0 * b2, b3, b4, b5, b3 + b5, b3 - b5, b3 + b4, b4 - b3, b4 + b5, b4 - b5, b1, b2};
+}
+// acc + component pc of  (s or conj s) * (wr zr + i wi zi),  s = 1 (pd = 0) or i (pd = 1)
+VH_HD double vh_acc_s(double acc, bool pd, bool pc, bool sbar, double wr, double wi, double zr, double zi)
+{
+  if (!pd)
+    return pc ? fma(wi, zi, acc) : fma(wr, zr, acc);
+  if (!sbar)
+    return pc ? fma(wr, zr, acc) : fma(-wi, zi, acc);
+  return pc ? fma(-wr, zr, acc) : fma(wi, zi, acc);
+}
+// per-point scalars of the "row == column" terms: c0 = alpha + 2 beta2 tr Q, (tr, ti) = 2 beta1 tr R
+struct vh_hdiag
+{
+  double c0, tr, ti;
+};
+VH_HD vh_hdiag vh_make_hdiag(const vh_prods &p, const vh_hweights &w)
+{
+  return vh_hdiag{fma(w.b2, p.Qr[0] + p.Qr[3] + p.Qr[5], w.alpha), w.b1 * (p.Rr[0] + p.Rr[3] + p.Rr[5]),
+                  w.b1 * (p.Ri[0] + p.Ri[3] + p.Ri[5])};
+}
+// H[c][d]; same terms as vh_hessian_entry.  Meant to be called with c, d known at compile time.
+VH_HD double vh_h_entry(const double *a, const vh_prods &p, const vh_hweights &w, const vh_hdiag &hd, int c, int d)
+{
+  const bool pc = c >= 9, pd = d >= 9;
+  const int  mu = (c % 9) / 3, j = c % 3, nu = (d % 9) / 3, k = d % 3;
+  const int  X = 3 * nu + k, Y = 3 * mu + j, M = 3 * mu + k, N = 3 * nu + j;
+  // z1a = A_X conj(A_Y), z1b = A_M conj(A_N), z2b = A_M A_N : only the component that lands in pc is live
+  double v = vh_acc_s(0.0, pd, pc, false, w.b1x2, w.b1x2, fma(a[X], a[Y], a[9 + X] * a[9 + Y]), fma(a[9 + X], a[Y], -(a[X] * a[9 + Y])));
+  v        = fma(w.b2x2 * a[c], a[d], v);
+  v = vh_acc_s(v, pd, pc, false, w.b35p, w.b35m, fma(a[M], a[N], a[9 + M] * a[9 + N]), fma(a[9 + M], a[N], -(a[M] * a[9 + N])));
+  v = vh_acc_s(v, pd, pc, true, w.b4, w.b4, fma(a[M], a[N], -(a[9 + M] * a[9 + N])), fma(a[M], a[9 + N], a[9 + M] * a[N]));
+  if (mu == nu)
+    { // row nu only: s (b3 conj P + b4 P)_kj + b5 conj(s) S_kj
+      const vh_cx P = vh_getP(p, k, j), S = vh_getS(p, k, j);
+      v = vh_acc_s(v, pd, pc, false, w.b34p, w.b43m, P.re, P.im);
+      v = vh_acc_s(v, pd, pc, true, w.b5, w.b5, S.re, S.im);
+    }
+  if (j == k)
+    { // column k only: b3 conj(s) R + s (b4 Q + b5 conj Q), entry (mu,nu)
+      const vh_cx R = vh_getR(p, mu, nu), Q = vh_getQ(p, mu, nu);
+      v = vh_acc_s(v, pd, pc, true, w.b3, w.b3, R.re, R.im);
+      v = vh_acc_s(v, pd, pc, false, w.b45p, w.b45m, Q.re, Q.im);
+      if (mu == nu)
+        { // s (alpha + 2 beta2 tr Q) + 2 beta1 conj(s) tr R
+          if (pc == pd)
+            v += pd ? hd.c0 - hd.tr : hd.c0 + hd.tr;
+          else
+            v += hd.ti;
+        }
+    }
+  return v;
+}
+// all 18 components of g = alpha A + 2 sum_k beta_k G_k from the unique products
+VH_HD void vh_g_all(const double *a, const vh_prods &p, const vh_hweights &w, double *g)
+{
+  const double Tr = p.Rr[0] + p.Rr[3] + p.Rr[5], Ti = p.Ri[0] + p.Ri[3] + p.Ri[5], Sq = p.Qr[0] + p.Qr[3] + p.Qr[5];
+  const double c0 = fma(w.b2, Sq, w.alpha);
+#pragma unroll
+  for (int mu = 0; mu < 3; ++mu)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      {
+        const double u = a[3 * mu + j], v = a[9 + 3 * mu + j];
+        // alpha a + b2 trQ a + b1 T conj(a)
+        double re = fma(w.b1, Tr * u + Ti * v, c0 * u), im = fma(w.b1, Ti * u - Tr * v, c0 * v);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          {
+            const vh_cx akj = vh_ld(a, k, j), amk = vh_ld(a, mu, k);
+            const vh_cx t3 = vh_cmul(vh_getR(p, mu, k), vh_conj(akj)), t4 = vh_cmul(vh_getQ(p, mu, k), akj),
+                        t5 = vh_cmul(vh_conj(amk), vh_getS(p, k, j));
+            re += w.b3 * t3.re + w.b4 * t4.re + w.b5 * t5.re;
+            im += w.b3 * t3.im + w.b4 * t4.im + w.b5 * t5.im;
+          }
+        g[3 * mu + j]     = re;
+        g[9 + 3 * mu + j] = im;
+      }
+}
+VH_HD double vh_bulk_energy_u(const vh_prods &p, double alpha, const double *beta)
+{
+  const double Tr = p.Rr[0] + p.Rr[3] + p.Rr[5], Ti = p.Ri[0] + p.Ri[3] + p.Ri[5], Sq = p.Qr[0] + p.Qr[3] + p.Qr[5];
+  double       I3 = 0, I4 = 0, I5 = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j)
+      {
+        const int    e = vh_sym6(i, j);
+        const double m = i == j ? 1.0 : 2.0, qi = i == j ? 0.0 : p.Qi[i + j - 1];
+        I3 += m * (p.Rr[e] * p.Rr[e] + p.Ri[e] * p.Ri[e]);
+        I4 += m * (p.Qr[e] * p.Qr[e] + qi * qi);
+        I5 += m * (p.Qr[e] * p.Qr[e] - qi * qi);
+      }
+  return alpha * Sq + beta[0] * (Tr * Tr + Ti * Ti) + beta[1] * Sq * Sq + beta[2] * I3 + beta[3] * I4 + beta[4] * I5;
+}
+
+// Storage of a Q1 cell's eight packed H_q (k_points_q1 -> row-owner kernels): [pair p = e/2][slot] double2 with
+// slot = q XOR (p & 7).  The eight quadrature points of one pair fill one 128-byte line (the producer's 8 lanes of a
+// cell write it with one 16-byte store each); the XOR keeps the consumer's per-entry reads free of bank conflicts.
+VH_HD int vh_hq8_index(int q, int e) { return (((e >> 1) << 3) + (q ^ ((e >> 1) & 7))) * 2 + (e & 1); }
+
 // Packed layout of a symmetric 18x18 ("P180"): row c stores the entries (c,d) for d = 2*(c/2) .. 17, so every row
 // starts at an EVEN column and every 16-byte pair (d, d+1) of the packed array belongs to one row and pairs with an
 // aligned 16-byte pair of the vector in the SpMV.  For odd c the first stored entry (c, c-1) is a dummy that is always 0.
