@@ -355,8 +355,19 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   // ---- classify rows: lattice rows go to the write-once row kernel ----
   std::vector<uint8_t> row_slow(n_owned, 1);
   std::vector<int32_t> fast_rows, fast_cells;
-  std::vector<int8_t>  fast_slot;
+  std::vector<int8_t>  fast_slot, fast_a;
   std::vector<uint8_t> fast_posslot;
+  // stencil slots: offsets (t(b) - t(a)) in [-p, p] per direction, slot = sum_d (off_d + p) (2p+1)^d
+  const int p1 = ctx->degree, sw = 2 * p1 + 1, nslots = sw * sw * sw, sstride = ctx->degree == 1 ? 32 : 128;
+  ctx->n_slots     = nslots;
+  ctx->slot_stride = sstride;
+  ctx->diag_slot   = (nslots - 1) / 2;
+  auto slot_of = [&](int a, int b) {
+    int ta[3], tb[3];
+    node_t(ctx->degree, a, ta);
+    node_t(ctx->degree, b, tb);
+    return (tb[0] - ta[0] + p1) + sw * ((tb[1] - ta[1] + p1) + sw * (tb[2] - ta[2] + p1));
+  };
   if (ctx->degree == 1)
     for (int I = 0; I < n_owned; ++I)
       {
@@ -415,6 +426,8 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
         row_slow[I] = 0;
         fast_rows.push_back(I);
         fast_cells.insert(fast_cells.end(), cells8, cells8 + 8);
+        for (int o = 0; o < 8; ++o)
+          fast_a.push_back((int8_t)(7 - o));
         fast_slot.insert(fast_slot.end(), pos27, pos27 + 32);
         uint8_t ps[32];
         std::fill(ps, ps + 32, (uint8_t)13);
@@ -423,6 +436,72 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
             ps[pos27[sl]] = (uint8_t)sl;
         fast_posslot.insert(fast_posslot.end(), ps, ps + 32);
       }
+  if (ctx->degree == 2 && !(getenv("VH_Q2_SCATTER") && getenv("VH_Q2_SCATTER")[0] == '1'))
+    { // Q2 lattice rows: vertex / edge / face / interior nodes with 8 / 4 / 2 / 1 incident cells and 125 / 75 / 45 / 27 blocks
+      std::vector<std::pair<int32_t, int32_t>> order; // (first incident cell, row): rows of one cell are launched together
+      for (int I = 0; I < n_owned; ++I)
+        if (!is_master[I] && !has_masters[I] && inc_ptr[I + 1] > inc_ptr[I] && inc_ptr[I + 1] - inc_ptr[I] <= 8)
+          order.push_back({inc_cell[inc_ptr[I]], I});
+      std::sort(order.begin(), order.end());
+      std::vector<int32_t> slot_node(nslots);
+      for (const auto &pr : order)
+        {
+          const int I = pr.second;
+          std::fill(slot_node.begin(), slot_node.end(), -1);
+          bool ok = true;
+          for (int k = inc_ptr[I]; k < inc_ptr[I + 1] && ok; ++k)
+            {
+              const int e = inc_cell[k], a = inc_a[k];
+              if (d->cell_nodes[(size_t)e * nn + a] != I)
+                ok = false;
+              for (int b = 0; b < nn && ok; ++b)
+                {
+                  const int J = d->cell_nodes[(size_t)e * nn + b], sl = slot_of(a, b);
+                  if (has_masters[J] || (slot_node[sl] >= 0 && slot_node[sl] != J))
+                    ok = false;
+                  slot_node[sl] = J;
+                }
+            }
+          if (!ok)
+            continue;
+          int8_t  pos[128];
+          uint8_t ps[128];
+          std::fill(pos, pos + 128, (int8_t)-1);
+          std::fill(ps, ps + 128, (uint8_t)ctx->diag_slot);
+          int        n_present = 0;
+          const auto b = col.begin() + row_ptr[I], en = col.begin() + row_ptr[I + 1];
+          for (int sl = 0; sl < nslots && ok; ++sl)
+            {
+              if (slot_node[sl] < 0)
+                continue;
+              const auto it = std::lower_bound(b, en, slot_node[sl]);
+              if (it == en || *it != slot_node[sl] || it - b > 127)
+                ok = false;
+              else
+                {
+                  pos[sl]    = (int8_t)(it - b);
+                  ps[it - b] = (uint8_t)sl;
+                }
+              ++n_present;
+            }
+          // two slots on one node would both have claimed ps[]: detect through the round trip
+          for (int sl = 0; sl < nslots && ok; ++sl)
+            if (pos[sl] >= 0 && ps[pos[sl]] != (uint8_t)sl)
+              ok = false;
+          if (!ok || n_present != row_ptr[I + 1] - row_ptr[I])
+            continue;
+          row_slow[I] = 0;
+          fast_rows.push_back(I);
+          for (int k = 0; k < 8; ++k)
+            {
+              const bool have = inc_ptr[I] + k < inc_ptr[I + 1];
+              fast_cells.push_back(have ? inc_cell[inc_ptr[I] + k] : -1);
+              fast_a.push_back(have ? (int8_t)inc_a[inc_ptr[I] + k] : (int8_t)0);
+            }
+          fast_slot.insert(fast_slot.end(), pos, pos + 128);
+          fast_posslot.insert(fast_posslot.end(), ps, ps + 128);
+        }
+    }
   // geometry classes of the fast rows: the gradient (K1, K2+K3) and Robin-face forms depend only on the shapes of
   // the incident cells, so rows with identical stencils share one 27 x 12 table (a uniform mesh has a few dozen).
   std::vector<int32_t> fast_class(fast_rows.size());
@@ -432,6 +511,7 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
     for (size_t r = 0; r < fast_rows.size(); ++r)
       {
         const int32_t *c8 = &fast_cells[8 * r];
+        const int8_t  *a8 = &fast_a[8 * r];
         std::string    sig;
         for (int o = 0; o < 8; ++o)
           {
@@ -441,6 +521,7 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
                 continue;
               }
             sig.push_back('+');
+            sig.push_back((char)a8[o]);
             sig.append(reinterpret_cast<const char *>(&h4[4 * (size_t)c8[o]]), 3 * sizeof(double));
             sig.append(reinterpret_cast<const char *>(&faces[c8[o]]), sizeof(uint32_t));
           }
@@ -449,21 +530,21 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
           {
             const int32_t id = (int32_t)class_of.size();
             class_of[sig]    = id;
-            class_tab.resize((size_t)(id + 1) * VH_BLK, 0.0);
-            double *tab = &class_tab[(size_t)id * VH_BLK];
+            class_tab.resize((size_t)(id + 1) * nslots * 12, 0.0);
+            double *tab = &class_tab[(size_t)id * nslots * 12];
             for (int o = 0; o < 8; ++o)
               {
                 const int e = c8[o];
                 if (e < 0)
                   continue;
                 const double *h = &h4[4 * (size_t)e];
-                const int     a = 7 - o;
-                for (int b = 0; b < 8; ++b)
+                const int     a = a8[o];
+                for (int b = 0; b < nn; ++b)
                   {
-                    const int sl = ((o & 1) + (b & 1)) + 3 * (((o >> 1) & 1) + ((b >> 1) & 1)) + 9 * ((o >> 2) + (b >> 2));
+                    const int sl = slot_of(a, b);
                     for (int x = 0; x < 3; ++x)
                       for (int y = 0; y < 3; ++y)
-                        tab[sl * 12 + 3 * x + y] += h[3] / (h[x] * h[y]) * T.Gref[((size_t)a * 8 + b) * 9 + 3 * x + y];
+                        tab[sl * 12 + 3 * x + y] += h[3] / (h[x] * h[y]) * T.Gref[((size_t)a * nn + b) * 9 + 3 * x + y];
                     for (int f = 0; f < 6; ++f)
                       {
                         const int bid = (faces[e] >> (4 * f)) & 15u;
@@ -471,7 +552,7 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
                           continue;
                         for (int x = 0; x < 3; ++x)
                           if (x != bid - 2)
-                            tab[sl * 12 + 9 + x] += (h[3] / h[f / 2]) * T.Mf[((size_t)f * 8 + a) * 8 + b];
+                            tab[sl * 12 + 9 + x] += (h[3] / h[f / 2]) * T.Mf[((size_t)f * nn + a) * nn + b];
                       }
                   }
               }
@@ -515,7 +596,8 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   }
   VH_TRY(vh_dev_upload(ctx, &ctx->fast_class, fast_class.data(), fast_class.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->class_tab, class_tab.data(), class_tab.size()));
-  VH_TRY(vh_dev_alloc(ctx, &ctx->class_M, (size_t)ctx->n_classes * 270));
+  VH_TRY(vh_dev_alloc(ctx, &ctx->class_M, (size_t)ctx->n_classes * nslots * 10));
+  VH_TRY(vh_dev_upload(ctx, &ctx->fast_a, fast_a.data(), fast_a.size()));
   ctx->h_class_tab = class_tab;
   VH_TRY(vh_dev_upload(ctx, &ctx->slow_rows, slow_rows.data(), slow_rows.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->slow_cells, slow_cells.data(), slow_cells.size()));
@@ -570,7 +652,7 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
 
   // ---- matrix, scratch, vectors ----
   // storage format: packed symmetric blocks for the lattice rows unless VH_FULL_BSR=1 (A/B switch, full 18x18 blocks)
-  ctx->packed = ctx->degree == 1 && ctx->n_fast > 0 && !(getenv("VH_FULL_BSR") && getenv("VH_FULL_BSR")[0] == '1');
+  ctx->packed = ctx->n_fast > 0 && (ctx->degree == 2 || !(getenv("VH_FULL_BSR") && getenv("VH_FULL_BSR")[0] == '1'));
   if (ctx->packed)
     {
       VH_TRY(vh_dev_alloc(ctx, &ctx->pvals, (size_t)ctx->nnzb * VH_SYMP));
@@ -717,7 +799,7 @@ int vh_destroy(vh_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
   vh_comm_destroy(ctx);
   void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
-                  ctx->diag_pos, ctx->minv, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->row_slow,
+                  ctx->diag_pos, ctx->minv, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->row_slow,
                   ctx->slow_cells, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
                   ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
                   ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,
@@ -767,15 +849,16 @@ int vh_set_coefficients(vh_ctx *ctx, double K1, double K2, double K3, double alp
     {
       VH_CUDA(cudaSetDevice(ctx->device));
       const double        kf = bt < 1e10 ? K1 / bt : 0.0;
-      std::vector<double> M((size_t)ctx->n_classes * 270, 0.0);
+      const int           ns = ctx->n_slots;
+      std::vector<double> M((size_t)ctx->n_classes * ns * 10, 0.0);
       for (int cl = 0; cl < ctx->n_classes; ++cl)
-        for (int s = 0; s < 27; ++s)
+        for (int s = 0; s < ns; ++s)
           {
-            const double *G  = &ctx->h_class_tab[(size_t)cl * VH_BLK + s * 12];
+            const double *G  = &ctx->h_class_tab[((size_t)cl * ns + s) * 12];
             const double  tr = G[0] + G[4] + G[8];
             for (int x = 0; x < 3; ++x)
               for (int y = 0; y < 3; ++y)
-                M[(size_t)cl * 270 + s * 10 + 3 * x + y] = (K2 + K3) * G[3 * x + y] + (x == y ? K1 * tr + kf * G[9 + x] : 0.0);
+                M[((size_t)cl * ns + s) * 10 + 3 * x + y] = (K2 + K3) * G[3 * x + y] + (x == y ? K1 * tr + kf * G[9 + x] : 0.0);
           }
       VH_CUDA(cudaMemcpy(ctx->class_M, M.data(), M.size() * sizeof(double), cudaMemcpyHostToDevice));
     }

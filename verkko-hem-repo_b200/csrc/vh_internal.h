@@ -85,9 +85,11 @@ struct vh_ctx
   // row classification
   int32_t  n_fast = 0, n_slow_rows = 0, n_slow_cells = 0;
   int32_t *fast_rows  = nullptr; // [n_fast]
-  int32_t *fast_cells = nullptr; // [n_fast][8]   cell in octant o (row node is local vertex 7-o), -1 = absent
-  int8_t  *fast_slot  = nullptr; // [n_fast][32]  stencil slot (dx+1)+3(dy+1)+9(dz+1) -> position in the row, -1 = absent
-  uint8_t *fast_posslot = nullptr; // [n_fast][32] position in the row -> stencil slot
+  int32_t *fast_cells = nullptr; // [n_fast][8]   incident cells, -1 = absent (Q1: octant order, row node is local vertex 7-o)
+  int8_t  *fast_a     = nullptr; // [n_fast][8]   local index of the row node in each incident cell
+  int32_t  n_slots = 27, slot_stride = 32, diag_slot = 13; // stencil slots (2p+1)^3, row stride of fast_slot/fast_posslot
+  int8_t  *fast_slot  = nullptr; // [n_fast][slot_stride]  stencil slot -> position in the row, -1 = absent
+  uint8_t *fast_posslot = nullptr; // [n_fast][slot_stride] position in the row -> stencil slot
   int32_t *fast_index = nullptr; // [n_owned]     index into fast_rows or -1
   int32_t *fast_class = nullptr; // [n_fast]      geometry class of the row's stencil
   double  *class_tab  = nullptr; // [n_classes][27][12] per slot: GS[3][3] = sum vol/(h_x h_y) Gref, FS[3] = sum area Mf (x != normal)
