@@ -23,6 +23,8 @@
 
 __constant__ double  c_W1[512];   // Q1: w_q N_a(q) N_b(q), index (a*8+b)*8+q
 __constant__ uint8_t c_symc[VH_SYMP], c_symd[VH_SYMP];
+__constant__ double  c_T2[27];    // Q2, one direction: w_q l_a(q) l_b(q), index (t_a*3 + t_b)*3 + q  (t = 0 low, 1 mid, 2 high)
+__constant__ uint8_t c_q2t[27 * 3]; // Q2: tensor index (t_x, t_y, t_z) of local node a (deal.II hierarchical order)
 
 namespace
 {
@@ -825,6 +827,94 @@ __global__ void __launch_bounds__(192 / EPT, 4)
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2q. row-owner Jacobian kernel for Q2 lattice rows (packed storage), sum-factorised
+// ------------------------------------------------------------------------------------------------
+// Row node I is local node a_k (tensor index (ax,ay,az)) of its 1/2/4/8 incident cells; its stencil has up to 5x5x5
+// slots.  For one incident cell and one packed Hessian entry e the 27 contributions
+//     out[bx][by][bz] = sum_q w_q N_a(q) N_b(q) (vol H_q)[e],   N_a(q) = l_ax(qx) l_ay(qy) l_az(qz)
+// factorise over the directions:  W[a][b][q] = T[ax][bx][qx] T[ay][by][qy] T[az][bz][qz]  with the 27-entry 1-D table T.
+// Thread e keeps its 27 H values in registers and contracts qx, qy, qz in turn: 3 x 81 = 243 FMAs instead of 27 x 27 =
+// 729 (the full Q2 cell matrix costs 2.36 MFLOP instead of SURVEY's 13.2 MFLOP).  Slots fed by several cells are
+// accumulated by the SAME thread with plain load-add-store on its own entry (first-writer mask from the host): no
+// atomics, no memset, and the row (<= 180 KB) stays in L2 between the visits.
+__global__ void __launch_bounds__(192, 2)
+  k_rows_fast_q2(const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells, const int8_t *__restrict__ fast_a,
+                 const int8_t *__restrict__ fast_slot, const uint32_t *__restrict__ fast_first, const int32_t *__restrict__ row_ptr,
+                 const double *__restrict__ Hq, double *__restrict__ vals)
+{
+  __shared__ int8_t   s_pos[128];
+  __shared__ int      s_cells[8], s_a[8];
+  __shared__ uint32_t s_first[8];
+  const int t = threadIdx.x, r = blockIdx.x;
+  if (t < 128)
+    s_pos[t] = fast_slot[(size_t)r * 128 + t];
+  if (t >= 128 && t < 136)
+    {
+      s_cells[t - 128] = fast_cells[(size_t)r * 8 + (t - 128)];
+      s_a[t - 128]     = fast_a[(size_t)r * 8 + (t - 128)];
+      s_first[t - 128] = fast_first[(size_t)r * 8 + (t - 128)];
+    }
+  __syncthreads();
+  if (t >= VH_SYMP)
+    return;
+  double *row = vals + (size_t)row_ptr[fast_rows[r]] * VH_SYMP + t;
+  for (int k = 0; k < 8; ++k)
+    {
+      const int e = s_cells[k];
+      if (e < 0)
+        break;
+      const int      a = s_a[k], ax = c_q2t[3 * a], ay = c_q2t[3 * a + 1], az = c_q2t[3 * a + 2];
+      const uint32_t first = s_first[k];
+      const double  *H = Hq + (size_t)e * (27 * VH_SYMP) + t;
+      double         h[27];
+#pragma unroll
+      for (int q = 0; q < 27; ++q)
+        h[q] = __ldg(H + q * VH_SYMP);
+      double T[9];
+      // contract qx:  t1[bx][qy,qz]
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+        T[i] = c_T2[ax * 9 + i];
+      double t1[3][9];
+#pragma unroll
+      for (int bx = 0; bx < 3; ++bx)
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+          t1[bx][j] = fma(T[3 * bx + 2], h[3 * j + 2], fma(T[3 * bx + 1], h[3 * j + 1], T[3 * bx] * h[3 * j]));
+      // contract qy:  t2[bx][by][qz]
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+        T[i] = c_T2[ay * 9 + i];
+      double t2[3][3][3];
+#pragma unroll
+      for (int bx = 0; bx < 3; ++bx)
+#pragma unroll
+        for (int by = 0; by < 3; ++by)
+#pragma unroll
+          for (int qz = 0; qz < 3; ++qz)
+            t2[bx][by][qz] = fma(T[3 * by + 2], t1[bx][3 * qz + 2], fma(T[3 * by + 1], t1[bx][3 * qz + 1], T[3 * by] * t1[bx][3 * qz]));
+      // contract qz and add into the row
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+        T[i] = c_T2[az * 9 + i];
+      const int base = (2 - ax) + 5 * (2 - ay) + 25 * (2 - az);
+#pragma unroll
+      for (int bz = 0; bz < 3; ++bz)
+#pragma unroll
+        for (int by = 0; by < 3; ++by)
+#pragma unroll
+          for (int bx = 0; bx < 3; ++bx)
+            {
+              double  v   = fma(T[3 * bz + 2], t2[bx][by][2], fma(T[3 * bz + 1], t2[bx][by][1], T[3 * bz] * t2[bx][by][0]));
+              double *dst = row + (size_t)s_pos[base + bx + 5 * by + 25 * bz] * VH_SYMP;
+              if (!((first >> (bx + 3 * by + 9 * bz)) & 1u))
+                v += *dst;
+              *dst = v;
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 2c. row-owner kernel with the contraction on the FP64 tensor cores (mma.sync m8n8k4 -> SASS DMMA.8x8x4).
 //     For one incident cell o the row's contribution is the GEMM  out[b][entry] = sum_q W_o[b][q] * H_o[q][entry]
 //     with M = 8 column nodes b, K = 8 quadrature points (two k-steps of 4), N = 172 packed entries (22 tiles of 8).
@@ -1058,9 +1148,10 @@ __global__ void __launch_bounds__(192) k_store_probe(int n_rows, const int32_t *
 }
 
 // rhs of fast rows: deterministic gather of the cell rhs over the incident cells (no atomics)
-__global__ void k_rhs_fast_q1(int n_fast, const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells,
-                              const uint32_t *__restrict__ dirmask, const double *__restrict__ Rc, double *__restrict__ rhs,
-                              const double *__restrict__ Dc, const double *__restrict__ avgD, double *__restrict__ cdiag)
+__global__ void k_rhs_fast(int n_fast, int dpc, const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells,
+                           const int8_t *__restrict__ fast_a, const uint32_t *__restrict__ dirmask, const double *__restrict__ Rc,
+                           double *__restrict__ rhs, const double *__restrict__ Dc, const double *__restrict__ avgD,
+                           double *__restrict__ cdiag)
 {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (int64_t)n_fast * 18)
@@ -1073,7 +1164,7 @@ __global__ void k_rhs_fast_q1(int n_fast, const int32_t *__restrict__ fast_rows,
     {
       const int e = fast_cells[(size_t)r * 8 + o];
       if (e >= 0)
-        s += Rc[(size_t)e * 144 + (7 - o) * 18 + c];
+        s += Rc[(size_t)e * dpc + fast_a[(size_t)r * 8 + o] * 18 + c];
     }
   const bool masked = (dirmask[I] >> c) & 1u;
   if (masked)
@@ -1088,7 +1179,7 @@ __global__ void k_rhs_fast_q1(int n_fast, const int32_t *__restrict__ fast_rows,
             const int e = fast_cells[(size_t)r * 8 + o];
             if (e < 0)
               continue;
-            double dv = fabs(Dc[(size_t)e * 144 + (7 - o) * 18 + c]);
+            double dv = fabs(Dc[(size_t)e * dpc + fast_a[(size_t)r * 8 + o] * 18 + c]);
             if (dv == 0.0)
               dv = avgD[e];
             dsum += dv;
@@ -1099,7 +1190,8 @@ __global__ void k_rhs_fast_q1(int n_fast, const int32_t *__restrict__ fast_rows,
 
 // Expansion of the packed rows into full 18x18 blocks (export / diagnostics): block = Sym(P) + kron(I_6, M_slot), Dirichlet
 // rows and columns zeroed, constrained diagonal from cdiag.
-__global__ void k_expand_packed(int n_fast, const int32_t *__restrict__ fast_rows, const uint8_t *__restrict__ fast_posslot,
+__global__ void k_expand_packed(int n_fast, int ps_stride, int cm_stride, const int32_t *__restrict__ fast_rows,
+                                const uint8_t *__restrict__ fast_posslot,
                                 const int32_t *__restrict__ fast_class, const double *__restrict__ class_M,
                                 const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                                 const uint32_t *__restrict__ dirmask, const double *__restrict__ pvals,
@@ -1110,7 +1202,7 @@ __global__ void k_expand_packed(int n_fast, const int32_t *__restrict__ fast_row
     return;
   const int      I = fast_rows[r], rp = row_ptr[I], nb = row_ptr[I + 1] - rp;
   const uint32_t maskI = dirmask[I];
-  const double  *M0 = class_M + (size_t)fast_class[r] * 270;
+  const double  *M0 = class_M + (size_t)fast_class[r] * cm_stride;
   for (int i = threadIdx.x; i < nb * VH_BLK; i += blockDim.x)
     {
       const int      pos = i / VH_BLK, e = i - VH_BLK * pos, c = e / 18, d = e - 18 * c;
@@ -1119,7 +1211,7 @@ __global__ void k_expand_packed(int n_fast, const int32_t *__restrict__ fast_row
       const double  *P = pvals + (size_t)(rp + pos) * VH_SYMP;
       double         v = P[c <= d ? vh_sym_index(c, d) : vh_sym_index(d, c)];
       if (c / 3 == d / 3)
-        v += M0[fast_posslot[(size_t)r * 32 + pos] * 10 + (c % 3) * 3 + d % 3];
+        v += M0[fast_posslot[(size_t)r * ps_stride + pos] * 10 + (c % 3) * 3 + d % 3];
       if (((maskI >> c) & 1u) || ((maskJ >> d) & 1u))
         v = 0.0;
       if (J == I && c == d && ((maskI >> c) & 1u))
@@ -1296,6 +1388,13 @@ int vhk_upload_constants(vh_ctx *ctx)
   return VH_OK;
 }
 
+int vhk_upload_q2(vh_ctx *ctx, const double *T2, const uint8_t *q2t)
+{
+  VH_CUDA(cudaMemcpyToSymbol(c_T2, T2, 27 * sizeof(double)));
+  VH_CUDA(cudaMemcpyToSymbol(c_q2t, q2t, 81));
+  return VH_OK;
+}
+
 int vhk_upload_w1(vh_ctx *ctx, const double *W1)
 {
   VH_CUDA(cudaMemcpyToSymbol(c_W1, W1, 512 * sizeof(double)));
@@ -1355,6 +1454,13 @@ int vhk_rows_fast(vh_ctx *ctx)
 {
   if (ctx->n_fast == 0)
     return VH_OK;
+  if (ctx->degree == 2)
+    {
+      k_rows_fast_q2<<<ctx->n_fast, 192, 0, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_slot, ctx->fast_first,
+                                                          ctx->row_ptr, ctx->Hq, ctx->pvals);
+      VH_LAUNCH_CHECK();
+      return VH_OK;
+    }
   static int ept = 0;
   if (!ept)
     {
@@ -1406,7 +1512,7 @@ int vhk_expand_packed(vh_ctx *ctx, double *full_vals)
 {
   if (!ctx->packed || ctx->n_fast == 0)
     return VH_OK;
-  k_expand_packed<<<ctx->n_fast, 256, 0, ctx->stream>>>(ctx->n_fast, ctx->fast_rows, ctx->fast_posslot, ctx->fast_class, ctx->class_M,
+  k_expand_packed<<<ctx->n_fast, 256, 0, ctx->stream>>>(ctx->n_fast, ctx->slot_stride, ctx->n_slots * 10, ctx->fast_rows, ctx->fast_posslot, ctx->fast_class, ctx->class_M,
                                                        ctx->row_ptr, ctx->col, ctx->dirmask, ctx->pvals, ctx->cdiag, full_vals);
   VH_LAUNCH_CHECK();
   return VH_OK;
@@ -1425,9 +1531,9 @@ int vhk_rhs_fast(vh_ctx *ctx, double *rhs_out, bool with_cdiag)
     return VH_OK;
   const int64_t n = (int64_t)ctx->n_fast * 18;
   // the constrained-diagonal values are (re)computed whenever the Jacobian was (the cell diagonals Dc are fresh then)
-  k_rhs_fast_q1<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n_fast, ctx->fast_rows, ctx->fast_cells, ctx->dirmask,
-                                                                     ctx->Rc, rhs_out, ctx->Dc, ctx->avgD,
-                                                                     (ctx->packed && with_cdiag) ? ctx->cdiag : nullptr);
+  k_rhs_fast<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n_fast, ctx->dpc, ctx->fast_rows, ctx->fast_cells, ctx->fast_a,
+                                                                  ctx->dirmask, ctx->Rc, rhs_out, ctx->Dc, ctx->avgD,
+                                                                  (ctx->packed && with_cdiag) ? ctx->cdiag : nullptr);
   VH_LAUNCH_CHECK();
   return VH_OK;
 }

@@ -598,6 +598,44 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   VH_TRY(vh_dev_upload(ctx, &ctx->class_tab, class_tab.data(), class_tab.size()));
   VH_TRY(vh_dev_alloc(ctx, &ctx->class_M, (size_t)ctx->n_classes * nslots * 10));
   VH_TRY(vh_dev_upload(ctx, &ctx->fast_a, fast_a.data(), fast_a.size()));
+  if (ctx->degree == 2)
+    { // first-writer masks of the Q2 row kernel and its 1-D weight table
+      std::vector<uint32_t> first(fast_rows.size() * 8, 0u);
+      std::vector<uint8_t>  seen(nslots);
+      for (size_t r = 0; r < fast_rows.size(); ++r)
+        {
+          std::fill(seen.begin(), seen.end(), 0);
+          for (int k = 0; k < 8 && fast_cells[8 * r + k] >= 0; ++k)
+            {
+              int ta[3];
+              node_t(2, fast_a[8 * r + k], ta);
+              for (int j = 0; j < 27; ++j)
+                {
+                  const int sl = (j % 3 - ta[0] + 2) + 5 * ((j / 3) % 3 - ta[1] + 2) + 25 * (j / 9 - ta[2] + 2);
+                  if (!seen[sl])
+                    first[8 * r + k] |= 1u << j;
+                  seen[sl] = 1;
+                }
+            }
+        }
+      VH_TRY(vh_dev_upload(ctx, &ctx->fast_first, first.data(), first.size()));
+      double gx[3], gw[3], T2[27];
+      gauss01(3, gx, gw);
+      for (int ta = 0; ta < 3; ++ta)
+        for (int tb = 0; tb < 3; ++tb)
+          for (int q = 0; q < 3; ++q)
+            {
+              double va, vb, dd;
+              lag(2, ta, gx[q], va, dd);
+              lag(2, tb, gx[q], vb, dd);
+              T2[(ta * 3 + tb) * 3 + q] = gw[q] * va * vb;
+            }
+      uint8_t q2t[81];
+      for (int a = 0; a < 27; ++a)
+        for (int k = 0; k < 3; ++k)
+          q2t[3 * a + k] = (uint8_t)Q2_T[a][k];
+      VH_TRY(vhk_upload_q2(ctx, T2, q2t));
+    }
   ctx->h_class_tab = class_tab;
   VH_TRY(vh_dev_upload(ctx, &ctx->slow_rows, slow_rows.data(), slow_rows.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->slow_cells, slow_cells.data(), slow_cells.size()));
@@ -799,7 +837,7 @@ int vh_destroy(vh_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
   vh_comm_destroy(ctx);
   void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
-                  ctx->diag_pos, ctx->minv, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->row_slow,
+                  ctx->diag_pos, ctx->minv, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_first, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->row_slow,
                   ctx->slow_cells, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
                   ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
                   ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,

@@ -86,6 +86,7 @@ struct vh_ctx
   int32_t  n_fast = 0, n_slow_rows = 0, n_slow_cells = 0;
   int32_t *fast_rows  = nullptr; // [n_fast]
   int32_t *fast_cells = nullptr; // [n_fast][8]   incident cells, -1 = absent (Q1: octant order, row node is local vertex 7-o)
+  uint32_t *fast_first = nullptr; // [n_fast][8]  Q2: bit j = bx+3by+9bz set if cell k is the first one to write that slot
   int8_t  *fast_a     = nullptr; // [n_fast][8]   local index of the row node in each incident cell
   int32_t  n_slots = 27, slot_stride = 32, diag_slot = 13; // stencil slots (2p+1)^3, row stride of fast_slot/fast_posslot
   int8_t  *fast_slot  = nullptr; // [n_fast][slot_stride]  stencil slot -> position in the row, -1 = absent
@@ -186,6 +187,7 @@ int vhk_rhs_fast(vh_ctx *ctx, double *rhs_out, bool with_cdiag);
 int vhk_store_probe(vh_ctx *ctx, int mode);
 int vhk_upload_constants(vh_ctx *ctx);
 int vhk_upload_w1(vh_ctx *ctx, const double *W1);
+int vhk_upload_q2(vh_ctx *ctx, const double *T2, const uint8_t *q2t);
 
 // ---- linear algebra (vh_linalg.cu) ----
 // x_is_masked: the caller guarantees zeros at the homogeneous-Dirichlet DoFs of x (all Krylov vectors satisfy this)

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(VH_SPMV_WARPS * 32)
 // lane_tab[3][32]: per (slot k, lane) packed  c | d_even<<8 | m0<<16 | m1<<17;  gather_tab[26][18]: partial-sum indices.
 template <int NB, int MINB> // NB blocks in flight per warp, MINB resident CTAs per SM
 __global__ void __launch_bounds__(VH_PSPMV_WARPS * 32, MINB)
-  k_spmv_sym18(int n_fast, const int32_t *__restrict__ fast_rows, const uint8_t *__restrict__ fast_posslot,
+  k_spmv_sym18(int n_fast, int ps_stride, int cm_stride, const int32_t *__restrict__ fast_rows, const uint8_t *__restrict__ fast_posslot,
                const int32_t *__restrict__ fast_class, const double *__restrict__ class_M, const int32_t *__restrict__ row_ptr,
                const int32_t *__restrict__ col, const uint32_t *__restrict__ dirmask, const double *__restrict__ pvals,
                const double *__restrict__ cdiag, const uint32_t *__restrict__ lane_tab, const uint16_t *__restrict__ gather_tab,
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(VH_PSPMV_WARPS * 32, MINB)
   if (r >= n_fast)
     return;
   const int     I = fast_rows[r], b0 = row_ptr[I], b1 = row_ptr[I + 1];
-  const double *M0 = class_M + (size_t)fast_class[r] * 270;
+  const double *M0 = class_M + (size_t)fast_class[r] * cm_stride;
   const bool    third = lane < (VH_SYMP / 2 - 64); // double2 #(lane+64) exists for lanes 0..25
   int           pc[3], pd[3];
   double        m0[3], m1[3];
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(VH_PSPMV_WARPS * 32, MINB)
     {
       const int nchunk = min(32, b1 - base);
       const int mycol  = lane < nchunk ? __ldg(col + base + lane) : 0;
-      const int myslot = lane < nchunk ? (int)fast_posslot[(size_t)r * 32 + (base - b0) + lane] : 13;
+      const int myslot = lane < nchunk ? (int)fast_posslot[(size_t)r * ps_stride + (base - b0) + lane] : 0;
       int       j      = 0;
       for (; j + NB <= nchunk; j += NB)
         { // NB blocks (NB x 3 x 16 B per lane) in flight, no tail logic here
@@ -234,7 +234,7 @@ __global__ void k_mask_dirichlet(int64_t n, const uint32_t *__restrict__ dirmask
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
   k_block_invert(int n_rows, const int32_t *__restrict__ diag_pos, const double *__restrict__ vals, double *__restrict__ minv,
-                 int *__restrict__ n_singular, const double *__restrict__ pvals, const int32_t *__restrict__ fast_index,
+                 int *__restrict__ n_singular, const double *__restrict__ pvals, int cm_stride, int diag_slot, const int32_t *__restrict__ fast_index,
                  const int32_t *__restrict__ fast_class, const double *__restrict__ class_M, const uint32_t *__restrict__ dirmask,
                  const double *__restrict__ cdiag)
 {
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(128)
   if (fi >= 0)
     { // packed row: diagonal block = Sym(P) + kron(I_6, M_13), Dirichlet rows/columns -> sum_cells |a_ii| on the diagonal
       const double  *P  = pvals + (size_t)diag_pos[row] * VH_SYMP;
-      const double  *M  = class_M + (size_t)fast_class[fi] * 270 + 13 * 10;
+      const double  *M  = class_M + (size_t)fast_class[fi] * cm_stride + diag_slot * 10;
       const uint32_t mI = dirmask[row];
 #pragma unroll
       for (int c = 0; c < 18; ++c)
@@ -745,7 +745,7 @@ int vhk_spmv(vh_ctx *ctx, const double *x_local, double *y_owned, bool x_is_mask
           variant       = e ? atoi(e) : 0;
         }
 #define VH_LAUNCH_PSPMV(NB, MINB)                                                                                                  \
-  k_spmv_sym18<NB, MINB><<<grid, VH_PSPMV_WARPS * 32, 0, ctx->stream>>>(ctx->n_fast, ctx->fast_rows, ctx->fast_posslot,            \
+  k_spmv_sym18<NB, MINB><<<grid, VH_PSPMV_WARPS * 32, 0, ctx->stream>>>(ctx->n_fast, ctx->slot_stride, ctx->n_slots * 10, ctx->fast_rows, ctx->fast_posslot, \
                                                                        ctx->fast_class, ctx->class_M, ctx->row_ptr, ctx->col,      \
                                                                        ctx->dirmask, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab,   \
                                                                        ctx->spmv_gather_tab, xg, x_local, y_owned)
@@ -782,7 +782,7 @@ int vhk_block_jacobi_setup(vh_ctx *ctx)
   int *d_sing = reinterpret_cast<int *>(ctx->scal + VH_SCAL_MISC);
   VH_CUDA(cudaMemsetAsync(d_sing, 0, sizeof(int), ctx->stream));
   k_block_invert<<<(ctx->n_owned + 3) / 4, 128, 0, ctx->stream>>>(ctx->n_owned, ctx->diag_pos, ctx->vals, ctx->minv, d_sing,
-                                                                  ctx->packed ? ctx->pvals : nullptr, ctx->fast_index, ctx->fast_class,
+                                                                  ctx->packed ? ctx->pvals : nullptr, ctx->n_slots * 10, ctx->diag_slot, ctx->fast_index, ctx->fast_class,
                                                                   ctx->class_M, ctx->dirmask, ctx->cdiag);
   VH_LAUNCH_CHECK();
   int h_sing = 0;
