@@ -60,9 +60,17 @@ def test_q1_hanging_nodes_general_scatter():
     assert info["n_slow_cells"] > 0 and info["n_fast_rows"] > 0
 
 
-def test_q2_assembly_matches_oracle():
-    T = vh.unit_cube(2, 1, half=2.0).tables(0)
-    _check_assembly(T, coef_vector(MATEP_SCC_ON, 2.0), b_phase_state(T))
+@pytest.mark.parametrize("refine", [1, 2])
+def test_q2_assembly_matches_oracle(refine):
+    """Q2 lattice rows (vertex / edge / face / interior nodes): sum-factorised row-owner kernel, packed storage."""
+    T = vh.unit_cube(2, refine, half=2.0).tables(0)
+    _check_assembly(T, coef_vector(MATEP_SCC_ON, 2.0), b_phase_state(T), expect_fast=True)
+
+
+def test_q2_all_walls_and_anisotropic_box():
+    m = vh.Mesh(2, [-1.0, -2.0, -0.5], [1.5, 1.0, 0.75], base=(2, 1, 1), face_bid=(2, 2, 3, 1, 4, 4), n_global_refine=1).finalize(1)
+    T = m.tables(0)
+    _check_assembly(T, coef_vector(MATEP_SCC_ON, 0.7), b_phase_state(T), expect_fast=True)
 
 
 def test_q2_hanging_nodes():
@@ -73,7 +81,8 @@ def test_q2_hanging_nodes():
     m.finalize(1)
     assert m.n_hanging_nodes > 0
     T = m.tables(0)
-    _check_assembly(T, coef_vector(MATEP_SCC_ON, 2.0), b_phase_state(T))
+    info = _check_assembly(T, coef_vector(MATEP_SCC_ON, 2.0), b_phase_state(T))
+    assert info["n_slow_cells"] > 0 and info["n_fast_rows"] > 0
 
 
 def test_residual_and_energy_match_oracle():
@@ -99,8 +108,9 @@ def test_residual_and_energy_match_oracle():
     ctx.close()
 
 
-def test_spmv_and_block_jacobi_match_oracle():
-    T = vh.unit_cube(1, 3, half=2.0).tables(0)
+@pytest.mark.parametrize("degree,refine", [(1, 3), (2, 2)])
+def test_spmv_and_block_jacobi_match_oracle(degree, refine):
+    T = vh.unit_cube(degree, refine, half=2.0).tables(0)
     coef = coef_vector(MATEP_SCC_ON, 2.0)
     x = b_phase_state(T)
     ctx = _ctx(T, coef)
@@ -119,9 +129,9 @@ def test_spmv_and_block_jacobi_match_oracle():
     ctx.close()
 
 
-@pytest.mark.parametrize("tol", [1e-1, 1e-8])
-def test_gmres_history_matches_oracle(tol):
-    T = vh.unit_cube(1, 3, half=2.0).tables(0)
+@pytest.mark.parametrize("degree,refine,tol", [(1, 3, 1e-1), (1, 3, 1e-8), (2, 2, 1e-6)])
+def test_gmres_history_matches_oracle(degree, refine, tol):
+    T = vh.unit_cube(degree, refine, half=2.0).tables(0)
     coef = coef_vector(MATEP_SCC_ON, 2.0)
     x = b_phase_state(T)
     ctx = _ctx(T, coef)

@@ -257,124 +257,172 @@ __global__ void __launch_bounds__(NQ == 8 ? 192 : 512)
 }
 
 // ------------------------------------------------------------------------------------------------
-// 1b. pointwise kernel for Q1, one THREAD per quadrature point
+// 1b. pointwise kernel, one THREAD per quadrature point (Q1: 8 points per cell, Q2: 27)
 // ------------------------------------------------------------------------------------------------
-// A warp owns 4 cells x 8 quadrature points (lane = 8*g + q).  The thread interpolates A and grad A at its point, keeps A
-// and the 42 unique product entries in registers and evaluates g (18) and the packed H_q (171 entries) with fully
-// unrolled, compile-time specialised formulas (vh_h_entry): ~12 FP64 instructions per entry and no index arithmetic,
-// against ~75 instructions per entry of the table-driven k_pointwise.  H_q leaves the registers with 16-byte stores in the
-// [pair][q XOR pair] layout (vh_hq8_index): the 8 lanes of a cell fill one 128-byte line per store instruction.
+// Q1: a warp owns 4 cells x 8 quadrature points (lane = 8*g + q); Q2: a warp owns one cell (lanes 0..26 = q, 5 idle).
+// The thread interpolates A and grad A at its point, keeps A and the 42 unique product entries in registers and
+// evaluates g (18) and the packed H_q (171 entries) with fully unrolled, compile-time specialised formulas (vh_h_entry):
+// ~12 FP64 instructions per entry and no index arithmetic, against ~75 instructions per entry of the table-driven
+// k_pointwise.  Q1: H_q leaves the registers with 16-byte stores in the [pair][q XOR pair] layout (vh_hq8_index): the 8
+// lanes of a cell fill one 128-byte line per store instruction.  Q2: [q][180], each lane streams its own 1440-byte row.
 // The q-sums of the cell vectors (rhs, cell diagonal) go through a per-warp shared buffer: the lane then plays node
-// a = lane % 8 and accumulates its 18 components over the 8 points; only __syncwarp() is needed.
+// a = lane % G and accumulates its 18 components over the NQ points; only __syncwarp() is needed.
 #define VH_PT_WARPS 4
-#define VH_PT_USTRIDE 146            /* 8 x 18 doubles per cell + 2: the 4 cells of a warp start in different banks */
-#define VH_PT_BSTRIDE (8 * 54 + 4)   /* per cell: 8 points x 54 doubles (+4: bank offset between the cells) */
-#define VH_PT_SMEM ((size_t)(64 + 192 + VH_PT_WARPS * 4 * (VH_PT_USTRIDE + VH_PT_BSTRIDE)) * sizeof(double))
-
-template <bool WANT_H, bool WANT_E>
-__global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
-  k_points_q1(int n_cells, const int32_t *__restrict__ cell_nodes, const double *__restrict__ cell_h,
-              const uint32_t *__restrict__ cell_faces, const uint8_t *__restrict__ cell_owned, const double *__restrict__ x,
-              VhTables tab, VhCoef cf, vh_hweights hw, double *__restrict__ Hq, double *__restrict__ Rc, double *__restrict__ Dc,
-              double *__restrict__ avgD, double *__restrict__ Ec)
+template <int NN>
+struct VhPt
 {
+  static constexpr int G       = NN == 8 ? 8 : 32;          // lanes per cell
+  static constexpr int CPW     = 32 / G;                    // cells per warp
+  static constexpr int USTRIDE = NN * 18 + 2;               // +2: the cells of a warp start in different banks
+  static constexpr int BSTRIDE = NN * 54 + 4;               // per cell: NQ points x 54 doubles (+4: bank offset)
+  static constexpr int TAB     = 4 * NN * NN;               // sNT [q][a] | sdNT [q][x][a]
+  static constexpr size_t SMEM = (size_t)(TAB + VH_PT_WARPS * CPW * (USTRIDE + BSTRIDE)) * sizeof(double);
+};
+
+template <int NN, bool WANT_H, bool WANT_E>
+__global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
+  k_points(int n_cells, const int32_t *__restrict__ cell_nodes, const double *__restrict__ cell_h,
+           const uint32_t *__restrict__ cell_faces, const uint8_t *__restrict__ cell_owned, const double *__restrict__ x,
+           VhTables tab, VhCoef cf, vh_hweights hw, double *__restrict__ Hq, double *__restrict__ Rc, double *__restrict__ Dc,
+           double *__restrict__ avgD, double *__restrict__ Ec)
+{
+  using P = VhPt<NN>;
+  constexpr int NQ = NN, G = P::G, CPW = P::CPW, DPC = 18 * NN;
   extern __shared__ __align__(16) double sm[];
-  double   *sNT  = sm;       // [q][a]
-  double   *sdNT = sm + 64;  // [q][x][a]
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 3, q = lane & 7;
-  double   *sU = sm + 256 + warp * 4 * (VH_PT_USTRIDE + VH_PT_BSTRIDE); // [4][VH_PT_USTRIDE]
-  double   *sB = sU + 4 * VH_PT_USTRIDE;                                // [4][VH_PT_BSTRIDE]
-  if (t < 64)
-    sNT[(t & 7) * 8 + (t >> 3)] = tab.N[t];
-  for (int i = t; i < 192; i += VH_PT_WARPS * 32)
+  double   *sNT  = sm;            // [q][a]
+  double   *sdNT = sm + NN * NN;  // [q][x][a]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane / G, ql = lane % G;
+  const bool pt = ql < NQ;                 // Q2: lanes 27..31 carry no point / node
+  const int  q  = pt ? ql : NQ - 1;
+  double    *sU = sm + P::TAB + warp * CPW * (P::USTRIDE + P::BSTRIDE); // [CPW][USTRIDE]
+  double    *sB = sU + CPW * P::USTRIDE;                                // [CPW][BSTRIDE]
+  for (int i = t; i < NN * NQ; i += VH_PT_WARPS * 32)
+    sNT[(i % NQ) * NN + i / NQ] = tab.N[i];
+  for (int i = t; i < NN * NQ * 3; i += VH_PT_WARPS * 32)
     {
-      const int a = i / 24, r = i - 24 * a, qq = r / 3, xx = r - 3 * qq;
-      sdNT[(qq * 3 + xx) * 8 + a] = tab.dN[i];
+      const int a = i / (3 * NQ), r = i - 3 * NQ * a, qq = r / 3, xx = r - 3 * qq;
+      sdNT[(qq * 3 + xx) * NN + a] = tab.dN[i];
     }
-  const int cell0 = (blockIdx.x * VH_PT_WARPS + warp) * 4;
-#pragma unroll
-  for (int kk = 0; kk < 9; ++kk)
-    { // coalesced gather of the warp's 4 x 8 x 18 DoF values (16-byte pieces of the node rows)
-      const int i = lane + 32 * kk, gg = i / 72, r = i - 72 * gg, a = r / 9, pp = r - 9 * a;
-      const int e = min(cell0 + gg, n_cells - 1);
-      const double2 v = *reinterpret_cast<const double2 *>(x + 18 * (int64_t)cell_nodes[(int64_t)e * 8 + a] + 2 * pp);
-      *reinterpret_cast<double2 *>(sU + gg * VH_PT_USTRIDE + a * 18 + 2 * pp) = v;
+  const int cell0 = (blockIdx.x * VH_PT_WARPS + warp) * CPW;
+  for (int i = lane; i < CPW * NN * 9; i += 32)
+    { // coalesced gather of the warp's DoF values (16-byte pieces of the node rows)
+      const int gg = i / (NN * 9), r = i - NN * 9 * gg, a = r / 9, pp = r - 9 * a;
+      const int e  = min(cell0 + gg, n_cells - 1);
+      const double2 v = *reinterpret_cast<const double2 *>(x + 18 * (int64_t)cell_nodes[(int64_t)e * NN + a] + 2 * pp);
+      *reinterpret_cast<double2 *>(sU + gg * P::USTRIDE + a * 18 + 2 * pp) = v;
     }
   __syncthreads();
 
-  const bool    live = cell0 + g < n_cells;
+  const bool    live = pt && cell0 + g < n_cells;
   const int64_t cell = min(cell0 + g, n_cells - 1);
   const double2 h01 = *reinterpret_cast<const double2 *>(cell_h + 4 * cell), h23 = *reinterpret_cast<const double2 *>(cell_h + 4 * cell + 2);
   const double  vol = h23.y;
   const double  hh[3] = {h01.x, h01.y, h23.x};
   const double  ih[3] = {1.0 / h01.x, 1.0 / h01.y, 1.0 / h23.x};
   const double  JxW = tab.wq[q] * vol;
-  const double *sUg = sU + g * VH_PT_USTRIDE;
-  double       *gB  = sB + g * VH_PT_BSTRIDE;
+  const double *sUg = sU + g * P::USTRIDE;
+  double       *gB  = sB + g * P::BSTRIDE;
 
   // ---- FE interpolation of the state and its gradient at this thread's point (s_vector2matrix.cc:154-162, 203-213) ----
   double a18[18];
   double eg = 0.0; // gradient energy density
   {
-    double Nq[8], dNq[3][8];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-      {
-        Nq[a] = sNT[q * 8 + a];
-#pragma unroll
-        for (int xx = 0; xx < 3; ++xx)
-          dNq[xx][a] = sdNT[(q * 3 + xx) * 8 + a] * ih[xx];
-      }
     double gt[54];
-    double dprev[3][3]; // gradients of the three components of the current row of A (c = 3*pm + xc)
-#pragma unroll
-    for (int cp = 0; cp < 9; ++cp)
+    if constexpr (NN == 8)
       {
-        double A0 = 0, A1 = 0, d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
+        double Nq[8], dNq[3][8];
 #pragma unroll
         for (int a = 0; a < 8; ++a)
           {
-            const double2 u = *reinterpret_cast<const double2 *>(sUg + a * 18 + 2 * cp);
-            A0 = fma(Nq[a], u.x, A0);
-            A1 = fma(Nq[a], u.y, A1);
+            Nq[a] = sNT[q * 8 + a];
 #pragma unroll
             for (int xx = 0; xx < 3; ++xx)
-              {
-                d0[xx] = fma(dNq[xx][a], u.x, d0[xx]);
-                d1[xx] = fma(dNq[xx][a], u.y, d1[xx]);
-              }
+              dNq[xx][a] = sdNT[(q * 3 + xx) * 8 + a] * ih[xx];
           }
-        a18[2 * cp]     = A0;
-        a18[2 * cp + 1] = A1;
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int cp = 0; cp < 9; ++cp)
           {
-            const int c = 2 * cp + h, xc = c % 3;
+            double A0 = 0, A1 = 0, d0[3] = {0, 0, 0}, d1[3] = {0, 0, 0};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+              {
+                const double2 u = *reinterpret_cast<const double2 *>(sUg + a * 18 + 2 * cp);
+                A0 = fma(Nq[a], u.x, A0);
+                A1 = fma(Nq[a], u.y, A1);
+#pragma unroll
+                for (int xx = 0; xx < 3; ++xx)
+                  {
+                    d0[xx] = fma(dNq[xx][a], u.x, d0[xx]);
+                    d1[xx] = fma(dNq[xx][a], u.y, d1[xx]);
+                  }
+              }
+            a18[2 * cp]     = A0;
+            a18[2 * cp + 1] = A1;
 #pragma unroll
             for (int xx = 0; xx < 3; ++xx)
               {
-                const double dv = h ? d1[xx] : d0[xx];
-                dprev[xc][xx]   = dv;
-                gt[3 * c + xx]  = cf.K1 * dv;
-                if (WANT_E)
-                  eg = fma(cf.K1 * dv, dv, eg);
-              }
-            if (xc == 2)
-              { // row pm = c/3 complete: divergence couples the three components (K2+K3 term)
-                const double div = dprev[0][0] + dprev[1][1] + dprev[2][2];
-#pragma unroll
-                for (int y = 0; y < 3; ++y)
-                  gt[3 * (c - 2 + y) + y] = fma(cf.K23, div, gt[3 * (c - 2 + y) + y]);
-                if (WANT_E)
-                  eg = fma(cf.K23 * div, div, eg);
+                gt[6 * cp + xx]     = d0[xx];
+                gt[6 * cp + 3 + xx] = d1[xx];
               }
           }
       }
-    // Gt[c][x] = JxW (K1 dA[c][x] + delta_{x,xc} K23 div): what the test gradient of node a is contracted with
-    double *myB = gB + q * 54;
+    else
+      { // Q2: the 27 x 4 shape values of this point stay in shared memory ([q][a]: conflict-free for lane = q)
 #pragma unroll
-    for (int i = 0; i < 27; ++i)
-      *reinterpret_cast<double2 *>(myB + 2 * i) = make_double2(JxW * gt[2 * i], JxW * gt[2 * i + 1]);
+        for (int c = 0; c < 18; ++c)
+          a18[c] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 54; ++i)
+          gt[i] = 0.0;
+#pragma unroll 1
+        for (int a = 0; a < NN; ++a)
+          {
+            const double n = sNT[q * NN + a], n0 = sdNT[(q * 3 + 0) * NN + a] * ih[0], n1 = sdNT[(q * 3 + 1) * NN + a] * ih[1],
+                         n2 = sdNT[(q * 3 + 2) * NN + a] * ih[2];
+#pragma unroll
+            for (int cp = 0; cp < 9; ++cp)
+              {
+                const double2 u = *reinterpret_cast<const double2 *>(sUg + a * 18 + 2 * cp);
+                a18[2 * cp]     = fma(n, u.x, a18[2 * cp]);
+                a18[2 * cp + 1] = fma(n, u.y, a18[2 * cp + 1]);
+                gt[6 * cp + 0]  = fma(n0, u.x, gt[6 * cp + 0]);
+                gt[6 * cp + 1]  = fma(n1, u.x, gt[6 * cp + 1]);
+                gt[6 * cp + 2]  = fma(n2, u.x, gt[6 * cp + 2]);
+                gt[6 * cp + 3]  = fma(n0, u.y, gt[6 * cp + 3]);
+                gt[6 * cp + 4]  = fma(n1, u.y, gt[6 * cp + 4]);
+                gt[6 * cp + 5]  = fma(n2, u.y, gt[6 * cp + 5]);
+              }
+          }
+      }
+    // gt[3c+x] = d_x A_c -> Gt[c][x] = JxW (K1 dA[c][x] + delta_{x,xc} K23 div): what the test gradient of
+    // node a is contracted with
+#pragma unroll
+    for (int pm = 0; pm < 6; ++pm)
+      {
+        double dv[3][3];
+#pragma unroll
+        for (int y = 0; y < 3; ++y)
+#pragma unroll
+          for (int xx = 0; xx < 3; ++xx)
+            {
+              dv[y][xx] = gt[3 * (3 * pm + y) + xx];
+              if (WANT_E)
+                eg = fma(cf.K1 * dv[y][xx], dv[y][xx], eg);
+            }
+        const double div = dv[0][0] + dv[1][1] + dv[2][2]; // the divergence couples the three components of a row of A
+        if (WANT_E)
+          eg = fma(cf.K23 * div, div, eg);
+#pragma unroll
+        for (int y = 0; y < 3; ++y)
+#pragma unroll
+          for (int xx = 0; xx < 3; ++xx)
+            gt[3 * (3 * pm + y) + xx] = JxW * (xx == y ? fma(cf.K23, div, cf.K1 * dv[y][xx]) : cf.K1 * dv[y][xx]);
+      }
+    double *myB = gB + q * 54;
+    if (pt)
+#pragma unroll
+      for (int i = 0; i < 27; ++i)
+        *reinterpret_cast<double2 *>(myB + 2 * i) = make_double2(gt[2 * i], gt[2 * i + 1]);
   }
   __syncwarp();
   // ---- round 1: lane = node a of its cell;  rc[c] = sum_q grad N_a(q) . Gt_q[c]  (assemble.cc:257-276) ----
@@ -383,13 +431,13 @@ __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
 #pragma unroll
   for (int c = 0; c < 18; ++c)
     rc[c] = 0.0;
-#pragma unroll
-  for (int qq = 0; qq < 8; ++qq)
+#pragma unroll(NN == 8 ? 8 : 1)
+  for (int qq = 0; qq < NQ; ++qq)
     {
       double wx[3];
 #pragma unroll
       for (int xx = 0; xx < 3; ++xx)
-        wx[xx] = sdNT[(qq * 3 + xx) * 8 + a_node] * ih[xx];
+        wx[xx] = sdNT[(qq * 3 + xx) * NN + a_node] * ih[xx];
 #pragma unroll
       for (int i = 0; i < 27; ++i)
         {
@@ -407,16 +455,17 @@ __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
     double gv[18];
     vh_g_all(a18, pr, hw, gv);
     double *myB = gB + q * 18;
+    if (pt)
 #pragma unroll
-    for (int i = 0; i < 9; ++i)
-      *reinterpret_cast<double2 *>(myB + 2 * i) = make_double2(JxW * gv[2 * i], JxW * gv[2 * i + 1]);
+      for (int i = 0; i < 9; ++i)
+        *reinterpret_cast<double2 *>(myB + 2 * i) = make_double2(JxW * gv[2 * i], JxW * gv[2 * i + 1]);
   }
   __syncwarp();
   // ---- round 2: rc[c] += sum_q N_a(q) JxW g_q[c] ----
-#pragma unroll
-  for (int qq = 0; qq < 8; ++qq)
+#pragma unroll(NN == 8 ? 8 : 1)
+  for (int qq = 0; qq < NQ; ++qq)
     {
-      const double n = sNT[qq * 8 + a_node];
+      const double n = sNT[qq * NN + a_node];
 #pragma unroll
       for (int i = 0; i < 9; ++i)
         {
@@ -435,8 +484,8 @@ __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
         if (bid < 2 || bid > 4)
           continue;
         const double  s = cf.K1 / cf.bt * (vol / (f / 2 == 0 ? hh[0] : (f / 2 == 1 ? hh[1] : hh[2])));
-        const double *M = tab.Mf + (size_t)(f * 8 + a_node) * 8;
-        for (int b = 0; b < 8; ++b)
+        const double *M = tab.Mf + (size_t)(f * NN + a_node) * NN;
+        for (int b = 0; b < NN; ++b)
           {
             const double m = s * M[b];
 #pragma unroll
@@ -447,7 +496,7 @@ __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
       }
   if (live)
     {
-      double *dst = Rc + cell * 144 + a_node * 18;
+      double *dst = Rc + cell * DPC + a_node * 18;
 #pragma unroll
       for (int i = 0; i < 9; ++i)
         *reinterpret_cast<double2 *>(dst + 2 * i) = make_double2(-rc[2 * i], -rc[2 * i + 1]);
@@ -456,7 +505,7 @@ __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
   if (WANT_H)
     { // ---- the packed H_q, pre-multiplied by the cell volume, and the cell-matrix diagonal ----
       const vh_hdiag hd    = vh_make_hdiag(pr, hw);
-      double        *hbase = Hq + cell * (int64_t)(8 * VH_SYMP);
+      double        *hbase = Hq + cell * (int64_t)(NQ * VH_SYMP) + (NN == 8 ? 0 : q * VH_SYMP);
       double        *myB   = gB + q * 18;
 #pragma unroll
       for (int cc = 0; cc < 18; ++cc)
@@ -468,29 +517,34 @@ __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
               const int    pp = vh_sym_index(c, d) >> 1;
               const double v0 = d >= c ? vh_h_entry(a18, pr, hw, hd, c, d) : 0.0; // (c, c-1) is the zero dummy of odd rows
               const double v1 = vh_h_entry(a18, pr, hw, hd, c, d + 1);
-              if (d == c)
+              if (d == c && pt)
                 myB[c] = JxW * v0;
-              if (d + 1 == c)
+              if (d + 1 == c && pt)
                 myB[c] = JxW * v1;
               if (live)
-                *reinterpret_cast<double2 *>(hbase + ((pp << 3) + (q ^ (pp & 7))) * 2) = make_double2(v0 * vol, v1 * vol);
+                {
+                  if constexpr (NN == 8)
+                    *reinterpret_cast<double2 *>(hbase + ((pp << 3) + (q ^ (pp & 7))) * 2) = make_double2(v0 * vol, v1 * vol);
+                  else
+                    *reinterpret_cast<double2 *>(hbase + 2 * pp) = make_double2(v0 * vol, v1 * vol);
+                }
             }
         }
       __syncwarp();
       // round 3: diagonal of the cell matrix, dg[c] = sum_q N_a(q)^2 JxW H_q[c][c] + geometry (+ Robin)
       double dg[18];
       {
-        const double *G  = tab.Gref + (size_t)(a_node * 8 + a_node) * 9;
-        const double  g0 = G[0] * ih[0] * ih[0], g1 = G[4] * ih[1] * ih[1], g2 = G[8] * ih[2] * ih[2];
+        const double *Gd = tab.Gref + (size_t)(a_node * NN + a_node) * 9;
+        const double  g0 = Gd[0] * ih[0] * ih[0], g1 = Gd[4] * ih[1] * ih[1], g2 = Gd[8] * ih[2] * ih[2];
         const double  k1 = vol * cf.K1 * (g0 + g1 + g2);
 #pragma unroll
         for (int c = 0; c < 18; ++c)
           dg[c] = k1 + vol * cf.K23 * (c % 3 == 0 ? g0 : (c % 3 == 1 ? g1 : g2));
       }
-#pragma unroll
-      for (int qq = 0; qq < 8; ++qq)
+#pragma unroll(NN == 8 ? 8 : 1)
+      for (int qq = 0; qq < NQ; ++qq)
         {
-          const double n = sNT[qq * 8 + a_node], n2 = n * n;
+          const double n = sNT[qq * NN + a_node], n2 = n * n;
 #pragma unroll
           for (int i = 0; i < 9; ++i)
             {
@@ -506,7 +560,7 @@ __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
             if (bid < 2 || bid > 4)
               continue;
             const double s = cf.K1 / cf.bt * (vol / (f / 2 == 0 ? hh[0] : (f / 2 == 1 ? hh[1] : hh[2])));
-            const double m = s * tab.Mf[(size_t)(f * 8 + a_node) * 8 + a_node];
+            const double m = s * tab.Mf[(size_t)(f * NN + a_node) * NN + a_node];
 #pragma unroll
             for (int c = 0; c < 18; ++c)
               if (c % 3 != bid - 2)
@@ -516,17 +570,19 @@ __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
 #pragma unroll
       for (int c = 0; c < 18; ++c)
         absd += fabs(dg[c]);
-      absd += __shfl_xor_sync(0xffffffffu, absd, 1);
-      absd += __shfl_xor_sync(0xffffffffu, absd, 2);
-      absd += __shfl_xor_sync(0xffffffffu, absd, 4);
+      if (!pt)
+        absd = 0.0;
+#pragma unroll
+      for (int o = 1; o < G; o <<= 1)
+        absd += __shfl_xor_sync(0xffffffffu, absd, o);
       if (live)
         {
-          double *dst = Dc + cell * 144 + a_node * 18;
+          double *dst = Dc + cell * DPC + a_node * 18;
 #pragma unroll
           for (int i = 0; i < 9; ++i)
             *reinterpret_cast<double2 *>(dst + 2 * i) = make_double2(dg[2 * i], dg[2 * i + 1]);
           if (a_node == 0)
-            avgD[cell] = absd / 144.0;
+            avgD[cell] = absd / (double)DPC;
         }
     }
   if (WANT_E)
@@ -539,22 +595,24 @@ __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
             if (bid < 2 || bid > 4)
               continue;
             const double  s = cf.K1 / cf.bt * (vol / (f / 2 == 0 ? hh[0] : (f / 2 == 1 ? hh[1] : hh[2])));
-            const double *M = tab.Mf + (size_t)(f * 8 + a_node) * 8;
+            const double *M = tab.Mf + (size_t)(f * NN + a_node) * NN;
             double        ef = 0.0;
             for (int c = 0; c < 18; ++c)
               {
                 if (c % 3 == bid - 2)
                   continue;
                 double m = 0.0;
-                for (int b = 0; b < 8; ++b)
+                for (int b = 0; b < NN; ++b)
                   m += M[b] * sUg[b * 18 + c];
                 ef += sUg[a_node * 18 + c] * m;
               }
             e += s * ef;
           }
-      e += __shfl_xor_sync(0xffffffffu, e, 1);
-      e += __shfl_xor_sync(0xffffffffu, e, 2);
-      e += __shfl_xor_sync(0xffffffffu, e, 4);
+      if (!pt)
+        e = 0.0;
+#pragma unroll
+      for (int o = 1; o < G; o <<= 1)
+        e += __shfl_xor_sync(0xffffffffu, e, o);
       if (live && a_node == 0)
         Ec[cell] = cell_owned[cell] ? e : 0.0;
     }
@@ -1405,42 +1463,56 @@ int vhk_pointwise(vh_ctx *ctx, const double *x_local, bool want_h, bool want_e)
 {
   if (ctx->n_cells == 0)
     return VH_OK;
+  const bool legacy_q2 = getenv("VH_Q2_POINTWISE_LEGACY") && getenv("VH_Q2_POINTWISE_LEGACY")[0] == '1';
+  const vh_hweights hw = vh_make_hweights(ctx->coef.alpha, ctx->coef.beta);
+#define VH_LAUNCH_POINTS(NN, H, E)                                                                                                \
+  k_points<NN, H, E><<<grid, VH_PT_WARPS * 32, VhPt<NN>::SMEM, ctx->stream>>>(ctx->n_cells, ctx->cell_nodes, ctx->cell_h,         \
+                                                                             ctx->cell_faces, ctx->cell_owned, x_local, ctx->tab, \
+                                                                             ctx->coef, hw, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, \
+                                                                             ctx->Ec)
+#define VH_LAUNCH_POINTS_MODE(NN)      \
+  if (want_h && want_e)                \
+    VH_LAUNCH_POINTS(NN, true, true);  \
+  else if (want_h)                     \
+    VH_LAUNCH_POINTS(NN, true, false); \
+  else if (want_e)                     \
+    VH_LAUNCH_POINTS(NN, false, true); \
+  else                                 \
+    VH_LAUNCH_POINTS(NN, false, false)
+#define VH_POINTS_ATTR(NN)                                                                                                        \
+  VH_CUDA(cudaFuncSetAttribute(k_points<NN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VhPt<NN>::SMEM));     \
+  VH_CUDA(cudaFuncSetAttribute(k_points<NN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VhPt<NN>::SMEM));      \
+  VH_CUDA(cudaFuncSetAttribute(k_points<NN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VhPt<NN>::SMEM));    \
+  VH_CUDA(cudaFuncSetAttribute(k_points<NN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VhPt<NN>::SMEM))
+  static bool attr_set = false;
+  if (!attr_set)
+    {
+      VH_POINTS_ATTR(8);
+      VH_POINTS_ATTR(27);
+      attr_set = true;
+    }
   if (ctx->degree == 1)
     {
-      static bool attr_set = false;
-      if (!attr_set)
-        {
-          VH_CUDA(cudaFuncSetAttribute(k_points_q1<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VH_PT_SMEM));
-          VH_CUDA(cudaFuncSetAttribute(k_points_q1<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VH_PT_SMEM));
-          VH_CUDA(cudaFuncSetAttribute(k_points_q1<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VH_PT_SMEM));
-          VH_CUDA(cudaFuncSetAttribute(k_points_q1<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VH_PT_SMEM));
-          attr_set = true;
-        }
-      const vh_hweights hw   = vh_make_hweights(ctx->coef.alpha, ctx->coef.beta);
-      const int         grid = (ctx->n_cells + 4 * VH_PT_WARPS - 1) / (4 * VH_PT_WARPS);
-#define VH_LAUNCH_POINTS(H, E)                                                                                                    \
-  k_points_q1<H, E><<<grid, VH_PT_WARPS * 32, VH_PT_SMEM, ctx->stream>>>(ctx->n_cells, ctx->cell_nodes, ctx->cell_h,              \
-                                                                        ctx->cell_faces, ctx->cell_owned, x_local, ctx->tab,      \
-                                                                        ctx->coef, hw, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec)
-      if (want_h && want_e)
-        VH_LAUNCH_POINTS(true, true);
-      else if (want_h)
-        VH_LAUNCH_POINTS(true, false);
-      else if (want_e)
-        VH_LAUNCH_POINTS(false, true);
-      else
-        VH_LAUNCH_POINTS(false, false);
-#undef VH_LAUNCH_POINTS
+      const int grid = (ctx->n_cells + 4 * VH_PT_WARPS - 1) / (4 * VH_PT_WARPS);
+      VH_LAUNCH_POINTS_MODE(8);
     }
+  else if (!legacy_q2)
+    {
+      const int grid = (ctx->n_cells + VH_PT_WARPS - 1) / VH_PT_WARPS;
+      VH_LAUNCH_POINTS_MODE(27);
+    }
+#undef VH_LAUNCH_POINTS
+#undef VH_LAUNCH_POINTS_MODE
+#undef VH_POINTS_ATTR
   else
     {
       const size_t smem = pointwise_smem<27, 27>(want_h);
-      static bool  attr_set = false;
-      if (!attr_set)
+      static bool  attr_set2 = false;
+      if (!attr_set2)
         {
           VH_CUDA(cudaFuncSetAttribute(k_pointwise<27, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)pointwise_smem<27, 27>(true)));
-          attr_set = true;
+          attr_set2 = true;
         }
       k_pointwise<27, 27><<<ctx->n_cells, 512, smem, ctx->stream>>>(ctx->cell_nodes, ctx->cell_h, ctx->cell_faces,
                                                                    ctx->cell_owned, x_local, ctx->tab, ctx->coef, want_h, want_e,
