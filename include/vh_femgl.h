@@ -133,6 +133,7 @@ typedef struct vh_info
   int64_t n_fast_rows;   /* rows assembled by the write-once row kernel  */
   int64_t n_slow_cells;  /* cells routed through the constrained scatter */
   int64_t device_bytes;  /* device memory held by the context            */
+  int64_t n_packed_blocks; /* blocks stored as packed symmetric 18x18 (180 doubles) instead of 324 doubles */
 } vh_info;
 int vh_get_info(vh_ctx *ctx, vh_info *info);
 /* BSR(18) copy of the owned rows: row_ptr[n_owned+1], col[nnzb] (local node ids), vals[nnzb][18][18] row-major */

@@ -6,7 +6,7 @@ sys.path[:0] = [R, R + "/tests", R + "/oracle"]
 import verkko_hem_repo_b200 as vh  # noqa: E402
 from helpers import b_phase_state, coef_vector  # noqa: E402
 
-for refine in (3, 4):
+for refine in ([int(a) for a in sys.argv[1:]] or [3, 4]):
     m = vh.unit_cube(2, refine, half=20.0)
     T = m.tables(0)
     ctx = vh.Context(T)
@@ -20,6 +20,11 @@ for refine in (3, 4):
     its, res = ctx.solve(1e-1)
     nnzb = info["nnzb"]
     bytes_spmv = 8 * 324 * nnzb + 4 * nnzb + 16 * 18 * T.n_owned_nodes
-    print("Q2 r%d: dofs %d nnzb %d slow_cells %d | assembly %.2f ms (pointwise %.2f) | spmv %.3f ms = %.0f GB/s | gmres its %d"
-          % (refine, 18 * m.n_nodes, nnzb, info["n_slow_cells"], t_asm, t_pw, t_spmv, bytes_spmv / t_spmv / 1e6, its))
+    npk = info["n_packed_blocks"]
+    moved = 8 * (180 * npk + 324 * (nnzb - npk)) + 4 * nnzb + 16 * 18 * T.n_owned_nodes
+    t_rows = ctx.time_kernel(6, reps=3, flush_l2=True)
+    print("Q2 r%d: dofs %d nnzb %d slow_cells %d | assembly %.2f ms (pointwise %.2f, rows %.2f = %.0f GB/s stored) | spmv %.3f ms = %.0f GB/s "
+          "algorithmic, %.0f GB/s moved | gmres its %d | device %.2f GB"
+          % (refine, 18 * m.n_nodes, nnzb, info["n_slow_cells"], t_asm, t_pw, t_rows, 8 * 180 * npk / t_rows / 1e6, t_spmv,
+             bytes_spmv / t_spmv / 1e6, moved / t_spmv / 1e6, its, info["device_bytes"] / 1e9))
     ctx.close()

@@ -18,7 +18,8 @@ VH_ERR_NOT_CONVERGED = -4
 
 class _Info(ctypes.Structure):
     _fields_ = [("n_owned_dofs", ctypes.c_int64), ("n_local_dofs", ctypes.c_int64), ("nnzb", ctypes.c_int64),
-                ("n_fast_rows", ctypes.c_int64), ("n_slow_cells", ctypes.c_int64), ("device_bytes", ctypes.c_int64)]
+                ("n_fast_rows", ctypes.c_int64), ("n_slow_cells", ctypes.c_int64), ("device_bytes", ctypes.c_int64),
+                ("n_packed_blocks", ctypes.c_int64)]
 
 
 _lib = None

@@ -304,8 +304,12 @@ __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
       sdNT[(qq * 3 + xx) * NN + a] = tab.dN[i];
     }
   const int cell0 = (blockIdx.x * VH_PT_WARPS + warp) * CPW;
-  for (int i = lane; i < CPW * NN * 9; i += 32)
-    { // coalesced gather of the warp's DoF values (16-byte pieces of the node rows)
+#pragma unroll
+  for (int kk = 0; kk < (CPW * NN * 9 + 31) / 32; ++kk)
+    { // coalesced gather of the warp's DoF values (16-byte pieces of the node rows), all loads in flight at once
+      const int i = lane + 32 * kk;
+      if (i >= CPW * NN * 9)
+        break;
       const int gg = i / (NN * 9), r = i - NN * 9 * gg, a = r / 9, pp = r - 9 * a;
       const int e  = min(cell0 + gg, n_cells - 1);
       const double2 v = *reinterpret_cast<const double2 *>(x + 18 * (int64_t)cell_nodes[(int64_t)e * NN + a] + 2 * pp);
@@ -895,7 +899,8 @@ __global__ void __launch_bounds__(192 / EPT, 4)
 // 729 (the full Q2 cell matrix costs 2.36 MFLOP instead of SURVEY's 13.2 MFLOP).  Slots fed by several cells are
 // accumulated by the SAME thread with plain load-add-store on its own entry (first-writer mask from the host): no
 // atomics, no memset, and the row (<= 180 KB) stays in L2 between the visits.
-__global__ void __launch_bounds__(192, 2)
+template <int MINB>
+__global__ void __launch_bounds__(192, MINB)
   k_rows_fast_q2(const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells, const int8_t *__restrict__ fast_a,
                  const int8_t *__restrict__ fast_slot, const uint32_t *__restrict__ fast_first, const int32_t *__restrict__ row_ptr,
                  const double *__restrict__ Hq, double *__restrict__ vals)
@@ -1528,8 +1533,21 @@ int vhk_rows_fast(vh_ctx *ctx)
     return VH_OK;
   if (ctx->degree == 2)
     {
-      k_rows_fast_q2<<<ctx->n_fast, 192, 0, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_slot, ctx->fast_first,
-                                                          ctx->row_ptr, ctx->Hq, ctx->pvals);
+      static int minb = 0;
+      if (!minb)
+        {
+          const char *e = getenv("VH_Q2_ROWS_MINB"); // tuning knob: resident CTAs per SM the kernel is compiled for (2, 3 or 4)
+          minb          = e ? atoi(e) : 4;
+        }
+      if (minb == 2)
+        k_rows_fast_q2<2><<<ctx->n_fast, 192, 0, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_slot,
+                                                               ctx->fast_first, ctx->row_ptr, ctx->Hq, ctx->pvals);
+      else if (minb == 4)
+        k_rows_fast_q2<4><<<ctx->n_fast, 192, 0, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_slot,
+                                                               ctx->fast_first, ctx->row_ptr, ctx->Hq, ctx->pvals);
+      else
+        k_rows_fast_q2<3><<<ctx->n_fast, 192, 0, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_slot,
+                                                               ctx->fast_first, ctx->row_ptr, ctx->Hq, ctx->pvals);
       VH_LAUNCH_CHECK();
       return VH_OK;
     }

@@ -593,6 +593,18 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
     for (size_t r = 0; r < fast_rows.size(); ++r)
       fidx[fast_rows[r]] = (int32_t)r;
     VH_TRY(vh_dev_upload(ctx, &ctx->fast_index, fidx.data(), fidx.size()));
+    ctx->h_fast_index = fidx;
+  }
+  {
+    // SpMV schedule: one warp per row, eight rows per CTA -> rows of equal length share a CTA and the longest rows are
+    // launched first (vertex rows of a Q2 mesh have 125 blocks, interior rows 27), ties keep the spatial order
+    std::vector<int32_t> order(fast_rows.size());
+    for (size_t r = 0; r < order.size(); ++r)
+      order[r] = (int32_t)r;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+      return row_ptr[fast_rows[a] + 1] - row_ptr[fast_rows[a]] > row_ptr[fast_rows[b] + 1] - row_ptr[fast_rows[b]];
+    });
+    VH_TRY(vh_dev_upload(ctx, &ctx->spmv_order, order.data(), order.size()));
   }
   VH_TRY(vh_dev_upload(ctx, &ctx->fast_class, fast_class.data(), fast_class.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->class_tab, class_tab.data(), class_tab.size()));
@@ -837,7 +849,7 @@ int vh_destroy(vh_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
   vh_comm_destroy(ctx);
   void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
-                  ctx->diag_pos, ctx->minv, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_first, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->row_slow,
+                  ctx->diag_pos, ctx->minv, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_first, ctx->spmv_order, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->row_slow,
                   ctx->slow_cells, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
                   ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
                   ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,
@@ -1100,6 +1112,11 @@ int vh_get_info(vh_ctx *ctx, vh_info *info)
   info->n_fast_rows  = ctx->n_fast;
   info->n_slow_cells = ctx->n_slow_cells;
   info->device_bytes = ctx->device_bytes;
+  info->n_packed_blocks = 0;
+  if (ctx->packed)
+    for (int32_t I = 0; I < ctx->n_owned; ++I)
+      if (ctx->h_fast_index.size() && ctx->h_fast_index[I] >= 0)
+        info->n_packed_blocks += ctx->h_row_ptr[I + 1] - ctx->h_row_ptr[I];
   return VH_OK;
 }
 

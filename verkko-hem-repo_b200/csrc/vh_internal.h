@@ -80,13 +80,14 @@ struct vh_ctx
   double  *cdiag    = nullptr; // [n_owned][18] constrained-diagonal values sum_cells |a_ii| (0 for unconstrained DoFs)
   int32_t *diag_pos = nullptr; // [n_owned] block index of (I,I)
   double  *minv     = nullptr; // [n_owned][18][18] inverse diagonal blocks (block-Jacobi)
-  std::vector<int32_t> h_row_ptr, h_col;
+  std::vector<int32_t> h_row_ptr, h_col, h_fast_index;
 
   // row classification
   int32_t  n_fast = 0, n_slow_rows = 0, n_slow_cells = 0;
   int32_t *fast_rows  = nullptr; // [n_fast]
   int32_t *fast_cells = nullptr; // [n_fast][8]   incident cells, -1 = absent (Q1: octant order, row node is local vertex 7-o)
   uint32_t *fast_first = nullptr; // [n_fast][8]  Q2: bit j = bx+3by+9bz set if cell k is the first one to write that slot
+  int32_t *spmv_order = nullptr; // [n_fast]      permutation of the fast rows for the SpMV: longest rows first
   int8_t  *fast_a     = nullptr; // [n_fast][8]   local index of the row node in each incident cell
   int32_t  n_slots = 27, slot_stride = 32, diag_slot = 13; // stencil slots (2p+1)^3, row stride of fast_slot/fast_posslot
   int8_t  *fast_slot  = nullptr; // [n_fast][slot_stride]  stencil slot -> position in the row, -1 = absent

@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(VH_SPMV_WARPS * 32)
 // lane_tab[3][32]: per (slot k, lane) packed  c | d_even<<8 | m0<<16 | m1<<17;  gather_tab[26][18]: partial-sum indices.
 template <int NB, int MINB> // NB blocks in flight per warp, MINB resident CTAs per SM
 __global__ void __launch_bounds__(VH_PSPMV_WARPS * 32, MINB)
-  k_spmv_sym18(int n_fast, int ps_stride, int cm_stride, const int32_t *__restrict__ fast_rows, const uint8_t *__restrict__ fast_posslot,
+  k_spmv_sym18(int n_fast, int ps_stride, int cm_stride, const int32_t *__restrict__ order, const int32_t *__restrict__ fast_rows,
+               const uint8_t *__restrict__ fast_posslot,
                const int32_t *__restrict__ fast_class, const double *__restrict__ class_M, const int32_t *__restrict__ row_ptr,
                const int32_t *__restrict__ col, const uint32_t *__restrict__ dirmask, const double *__restrict__ pvals,
                const double *__restrict__ cdiag, const uint32_t *__restrict__ lane_tab, const uint16_t *__restrict__ gather_tab,
@@ -119,9 +120,10 @@ __global__ void __launch_bounds__(VH_PSPMV_WARPS * 32, MINB)
 {
   __shared__ double s_part[VH_PSPMV_WARPS][VH_PSPMV_NPART * 32 + 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int r    = blockIdx.x * VH_PSPMV_WARPS + wid;
-  if (r >= n_fast)
+  const int r0   = blockIdx.x * VH_PSPMV_WARPS + wid;
+  if (r0 >= n_fast)
     return;
+  const int     r = order[r0];
   const int     I = fast_rows[r], b0 = row_ptr[I], b1 = row_ptr[I + 1];
   const double *M0 = class_M + (size_t)fast_class[r] * cm_stride;
   const bool    third = lane < (VH_SYMP / 2 - 64); // double2 #(lane+64) exists for lanes 0..25
@@ -745,7 +747,7 @@ int vhk_spmv(vh_ctx *ctx, const double *x_local, double *y_owned, bool x_is_mask
           variant       = e ? atoi(e) : 0;
         }
 #define VH_LAUNCH_PSPMV(NB, MINB)                                                                                                  \
-  k_spmv_sym18<NB, MINB><<<grid, VH_PSPMV_WARPS * 32, 0, ctx->stream>>>(ctx->n_fast, ctx->slot_stride, ctx->n_slots * 10, ctx->fast_rows, ctx->fast_posslot, \
+  k_spmv_sym18<NB, MINB><<<grid, VH_PSPMV_WARPS * 32, 0, ctx->stream>>>(ctx->n_fast, ctx->slot_stride, ctx->n_slots * 10, ctx->spmv_order, ctx->fast_rows, ctx->fast_posslot, \
                                                                        ctx->fast_class, ctx->class_M, ctx->row_ptr, ctx->col,      \
                                                                        ctx->dirmask, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab,   \
                                                                        ctx->spmv_gather_tab, xg, x_local, y_owned)
