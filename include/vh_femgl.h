@@ -144,7 +144,8 @@ int vh_spmv(vh_ctx *ctx, const double *x_owned, double *y_owned);
 int vh_precondition(vh_ctx *ctx, const double *x_owned, double *y_owned);
 /* Device-timed kernels (CUDA events on the launching stream; average ms per launch over `reps`):
  *   what: 0 SpMV, 1 Jacobian+rhs assembly, 2 residual assembly, 3 block-Jacobi apply, 4 fused add_and_dot,
- *         5 pointwise kernel only, 6 row-owner Jacobian kernel only */
+ *         5 pointwise kernel only, 6 row-owner Jacobian kernel only;
+ *         collective (every rank must call): 9 = 20 ghost refreshes, 10 = 20 inner products with their all-reduce */
 int vh_time_kernel(vh_ctx *ctx, int what, int reps, int flush_l2, float *ms_avg);
 /* Cumulative device time (ms) and launch counts since the last reset:
  *   [0] assemble [1] residual [2] solve [3] line search vector ops [4] halo; n_launches = kernels launched */

@@ -121,13 +121,16 @@ class Context:
         assert x.size == self.n_owned
         self._chk(self.L.vh_set_solution(self._h, x.ctypes.data_as(_dp)))
 
-    def _get(self, fn):
-        out = np.zeros(self.n_owned)
+    def _get(self, fn, out=None):
+        if out is None:
+            out = np.zeros(self.n_owned)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == self.n_owned
         self._chk(fn(self._h, out.ctypes.data_as(_dp)))
         return out
 
-    def get_solution(self):
-        return self._get(self.L.vh_get_solution)
+    def get_solution(self, out=None):
+        """Owned part of local_solution; pass a (pinned) float64 array as `out` to receive it without a staging copy."""
+        return self._get(self.L.vh_get_solution, out)
 
     def get_newton_update(self):
         return self._get(self.L.vh_get_newton_update)

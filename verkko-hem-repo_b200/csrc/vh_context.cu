@@ -736,6 +736,7 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   VH_CUDA(cudaMemset(ctx->ticket, 0, 4 * sizeof(unsigned int)));
   VH_CUDA(cudaMemset(ctx->scal, 0, VH_SCAL_COUNT * sizeof(double)));
   VH_CUDA(cudaMallocHost((void **)&ctx->h_pinned, VH_SCAL_COUNT * sizeof(double)));
+  VH_TRY(vh_p2p_alloc_local(ctx, 1)); // mailbox of the fused Gram-Schmidt kernel (one-rank communicator until vh_comm_init)
   return VH_OK;
 }
 
@@ -1222,6 +1223,14 @@ int vh_time_kernel(vh_ctx *ctx, int what, int reps, int do_flush, float *ms_avg)
             return vh_fail(ctx, VH_ERR_STATE, "store probe needs full-format storage (VH_FULL_BSR=1)");
           VH_TRY(vhk_store_probe(ctx, what - 7));
           ctx->have_matrix = false;
+          break;
+        case 9: // collective: 20 ghost refreshes back to back (ms_avg is per batch of 20)
+          for (int k = 0; k < 20; ++k)
+            VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
+          break;
+        case 10: // collective: 20 inner products (kernel + all-reduce) back to back
+          for (int k = 0; k < 20; ++k)
+            VH_TRY(vhk_dot(ctx, ctx->rhs, ctx->rhs, ctx->scal + VH_SCAL_MISC + 2));
           break;
         default:
           return vh_fail(ctx, VH_ERR_ARG, "vh_time_kernel: unknown kernel id");

@@ -196,6 +196,14 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
 
   *iterations = accumulated;
   *final_res  = res;
+  if (ctx->p2p)
+    { // a peer that never posted its partial sum makes the mailbox wait give up after ~10 s and raise this flag
+      int h_err = 0;
+      VH_CUDA(cudaMemcpyAsync(&h_err, ctx->p2p_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      VH_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (h_err)
+        return vh_fail(ctx, VH_ERR_NCCL, "peer-memory all-reduce: a rank did not arrive (mailbox wait timed out)");
+    }
   if (state != SUCCESS)
     return vh_fail(ctx, VH_ERR_NOT_CONVERGED,
                    "GMRES: no convergence after " + std::to_string(accumulated) + " iterations, residual " + std::to_string(res));

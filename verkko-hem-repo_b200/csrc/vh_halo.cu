@@ -9,6 +9,7 @@
 // NCCL is bound with dlopen so the library has no link-time NCCL dependency: inside a torchrun worker the
 // already-loaded torch-bundled libnccl.so.2 is reused, in a plain C++ host the system one is loaded.
 #include "vh_internal.h"
+#include "vh_p2p.cuh"
 
 #include <dlfcn.h>
 
@@ -35,6 +36,7 @@ struct NcclApi
   int (*CommInitRank)(nccl_comm *, int, nccl_uid, int);
   int (*CommDestroy)(nccl_comm);
   int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t);
+  int (*AllGather)(const void *, void *, size_t, int, nccl_comm, cudaStream_t);
   int (*Send)(const void *, size_t, int, int, nccl_comm, cudaStream_t);
   int (*Recv)(void *, size_t, int, int, nccl_comm, cudaStream_t);
   int (*GroupStart)();
@@ -80,6 +82,7 @@ bool load_nccl()
   SYM(CommInitRank, "ncclCommInitRank")
   SYM(CommDestroy, "ncclCommDestroy")
   SYM(AllReduce, "ncclAllReduce")
+  SYM(AllGather, "ncclAllGather")
   SYM(Send, "ncclSend")
   SYM(Recv, "ncclRecv")
   SYM(GroupStart, "ncclGroupStart")
@@ -100,6 +103,16 @@ __global__ void k_unpack(int64_t n, const int32_t *__restrict__ nodes, const dou
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n)
     x[18 * (int64_t)nodes[i / 18] + i % 18] = buf[i];
+}
+// all-reduce of n scalars in place, one block of 32 threads per rank
+__global__ void k_p2p_allreduce(VhP2P P, unsigned long long seq0, double *__restrict__ v, int n)
+{
+  for (int i = 0; i < n; ++i)
+    {
+      const double s = vh_p2p_allreduce_warp(P, seq0 + i, v[i]);
+      if (threadIdx.x == 0)
+        v[i] = s;
+    }
 }
 } // namespace
 
@@ -146,11 +159,121 @@ extern "C" int vh_comm_init(vh_ctx *ctx, int rank, int n_ranks, const void *uniq
   nccl_comm comm = nullptr;
   VH_NCCL(api().CommInitRank(&comm, n_ranks, id, rank));
   ctx->nccl_comm = comm;
+
+  // ---- peer-memory mailboxes for the scalar all-reduces (VH_P2P=0 keeps ncclAllReduce) ----
+  const char *e = getenv("VH_P2P");
+  if (n_ranks <= VH_P2P_MAX_RANKS && !(e && e[0] == '0'))
+    {
+      int                ok = vh_p2p_alloc_local(ctx, n_ranks) == VH_OK;
+      cudaIpcMemHandle_t mine;
+      std::memset(&mine, 0, sizeof(mine));
+      if (ok && cudaIpcGetMemHandle(&mine, ctx->p2p_mbox) != cudaSuccess)
+        ok = 0;
+      cudaGetLastError();
+      // exchange the IPC handles (and the per-rank status) with one ncclAllGather of bytes
+      const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+      char        *d_all = nullptr;
+      VH_CUDA(cudaMalloc((void **)&d_all, rec * n_ranks));
+      std::vector<char> h_all(rec * n_ranks, 0);
+      std::memcpy(&h_all[rec * rank], &mine, sizeof(mine));
+      h_all[rec * rank + sizeof(mine)] = (char)ok;
+      VH_CUDA(cudaMemcpy(d_all + rec * rank, &h_all[rec * rank], rec, cudaMemcpyHostToDevice));
+      VH_NCCL(api().AllGather(d_all + rec * rank, d_all, rec, /*ncclChar*/ 0, comm, ctx->stream));
+      VH_CUDA(cudaStreamSynchronize(ctx->stream));
+      VH_CUDA(cudaMemcpy(h_all.data(), d_all, rec * n_ranks, cudaMemcpyDeviceToHost));
+      for (int r = 0; r < n_ranks; ++r)
+        ok = ok && h_all[rec * r + sizeof(mine)];
+      int opened = ok;
+      if (ok)
+        for (int r = 0; r < n_ranks && opened; ++r)
+          {
+            if (r == rank)
+              continue;
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, &h_all[rec * r], sizeof(h));
+            if (cudaIpcOpenMemHandle(&ctx->p2p_open[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+              {
+                cudaGetLastError();
+                ctx->p2p_open[r] = nullptr;
+                opened           = 0;
+              }
+          }
+      // every rank must take the same path: agree on the minimum
+      double *d_flag = reinterpret_cast<double *>(d_all); // reuse (rec * n_ranks >= 8 bytes, 256-byte aligned)
+      double  h_flag = opened ? 1.0 : 0.0;
+      VH_CUDA(cudaMemcpy(d_flag, &h_flag, sizeof(double), cudaMemcpyHostToDevice));
+      VH_NCCL(api().AllReduce(d_flag, d_flag, 1, NCCL_FLOAT64, /*ncclMin*/ 3, comm, ctx->stream));
+      VH_CUDA(cudaStreamSynchronize(ctx->stream));
+      VH_CUDA(cudaMemcpy(&h_flag, d_flag, sizeof(double), cudaMemcpyDeviceToHost));
+      cudaFree(d_all);
+      if (h_flag == 1.0)
+        {
+          // the fused Gram-Schmidt kernel must be chosen identically on every rank: agree on the largest requirement
+          double *d_mode = nullptr, h_mode = (double)vhk_mgs_mode_local(ctx);
+          VH_CUDA(cudaMalloc((void **)&d_mode, sizeof(double)));
+          VH_CUDA(cudaMemcpy(d_mode, &h_mode, sizeof(double), cudaMemcpyHostToDevice));
+          VH_NCCL(api().AllReduce(d_mode, d_mode, 1, NCCL_FLOAT64, /*ncclMax*/ 2, comm, ctx->stream));
+          VH_CUDA(cudaStreamSynchronize(ctx->stream));
+          VH_CUDA(cudaMemcpy(&h_mode, d_mode, sizeof(double), cudaMemcpyDeviceToHost));
+          cudaFree(d_mode);
+          ctx->mgs_mode    = (int)h_mode;
+          ctx->p2p         = true;
+          ctx->p2p_dev.me  = rank;
+          ctx->p2p_dev.n   = n_ranks;
+          ctx->p2p_dev.err = ctx->p2p_err;
+          for (int r = 0; r < n_ranks; ++r)
+            ctx->p2p_dev.peer[r] = static_cast<VhP2PCell *>(r == rank ? ctx->p2p_mbox : ctx->p2p_open[r]);
+        }
+    }
+  return VH_OK;
+}
+
+// (Re)allocates this rank's mailbox for n_ranks senders and points p2p_dev at it as a one-rank communicator; vh_comm_init
+// then replaces the peer pointers by the IPC-mapped mailboxes of the other ranks.
+int vh_p2p_alloc_local(vh_ctx *ctx, int n_ranks)
+{
+  VH_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->p2p_mbox)
+    {
+      VH_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->p2p_mbox);
+      ctx->p2p_mbox = nullptr;
+    }
+  const size_t bytes = sizeof(VhP2PCell) * VH_P2P_SLOTS * n_ranks;
+  VH_CUDA(cudaMalloc(&ctx->p2p_mbox, bytes));
+  VH_CUDA(cudaMemset(ctx->p2p_mbox, 0, bytes));
+  if (!ctx->p2p_err)
+    {
+      VH_CUDA(cudaMalloc((void **)&ctx->p2p_err, sizeof(int)));
+      VH_CUDA(cudaMemset(ctx->p2p_err, 0, sizeof(int)));
+      VH_CUDA(cudaMalloc((void **)&ctx->mgs_tickets, sizeof(unsigned int) * (VH_MAX_RESTART + 2)));
+      VH_CUDA(cudaMemset(ctx->mgs_tickets, 0, sizeof(unsigned int) * (VH_MAX_RESTART + 2)));
+    }
+  ctx->p2p_seq = 0;
+  ctx->p2p_dev = VhP2P();
+  ctx->p2p_dev.peer[0] = static_cast<VhP2PCell *>(ctx->p2p_mbox);
+  ctx->p2p_dev.me      = 0;
+  ctx->p2p_dev.n       = 1;
+  ctx->p2p_dev.err     = ctx->p2p_err;
   return VH_OK;
 }
 
 void vh_comm_destroy(vh_ctx *ctx)
 {
+  if (ctx->p2p_mbox)
+    { // nobody may still be spinning on / writing to a mailbox that is about to go away
+      cudaStreamSynchronize(ctx->stream);
+      for (int r = 0; r < VH_P2P_MAX_RANKS; ++r)
+        if (ctx->p2p_open[r])
+          cudaIpcCloseMemHandle(ctx->p2p_open[r]);
+      cudaFree(ctx->p2p_mbox);
+      cudaFree(ctx->p2p_err);
+      cudaFree(ctx->mgs_tickets);
+      ctx->p2p_mbox    = nullptr;
+      ctx->p2p_err     = nullptr;
+      ctx->mgs_tickets = nullptr;
+      ctx->p2p         = false;
+    }
   if (ctx->nccl_comm && api().handle)
     api().CommDestroy((nccl_comm)ctx->nccl_comm);
   ctx->nccl_comm = nullptr;
@@ -162,6 +285,13 @@ int vhk_allreduce_sum(vh_ctx *ctx, double *dev, int n)
     return VH_OK;
   if (!ctx->nccl_comm)
     return vh_fail(ctx, VH_ERR_STATE, "multi-rank context without vh_comm_init");
+  if (ctx->p2p)
+    { // latency path: one 32-thread kernel that posts to / polls the peer mailboxes over NVLink
+      k_p2p_allreduce<<<1, 32, 0, ctx->stream>>>(ctx->p2p_dev, ctx->p2p_seq + 1, dev, n);
+      ctx->p2p_seq += n;
+      VH_LAUNCH_CHECK();
+      return VH_OK;
+    }
   VH_NCCL(api().AllReduce(dev, dev, (size_t)n, NCCL_FLOAT64, NCCL_SUM, (nccl_comm)ctx->nccl_comm, ctx->stream));
   return VH_OK;
 }

@@ -27,6 +27,24 @@ struct VhTables
   double *Mf;   // [6][nn][nn]        unit-face mass  sum_qf wf Nf_a Nf_b  for face_no 0..5
 };
 
+// Mailbox all-reduce over peer memory.  Rank r owns mbox[VH_P2P_SLOTS][n_ranks] cells of {value, sequence}; an
+// all-reduce number `seq` writes this rank's partial into cell [seq % SLOTS][me] of EVERY rank (release store of the
+// sequence number after the value), then waits until its own cells [seq % SLOTS][0..n) carry `seq` and adds the values in
+// rank order, so every rank gets the bit-identical sum.
+#define VH_P2P_MAX_RANKS 8
+#define VH_P2P_SLOTS 8
+struct VhP2PCell
+{
+  double             val;
+  unsigned long long seq;
+};
+struct VhP2P
+{
+  VhP2PCell *peer[VH_P2P_MAX_RANKS]; // peer[r] = mailbox of rank r (peer[me] is local memory)
+  int        me, n;
+  int       *err;
+};
+
 struct VhCoef
 {
   double K1, K23, alpha, beta[5], bt;
@@ -126,6 +144,15 @@ struct vh_ctx
   // halo
   int                  rank = 0, n_ranks = 1;
   void                *nccl_comm = nullptr;
+  // peer-memory mailboxes (NVLink P2P through CUDA IPC) for latency-bound scalar all-reduces; see vh_halo.cu
+  int                  mgs_mode = -1;      // fused Gram-Schmidt: elements per thread (8 / 32), 1000 = kernel chain, -1 = undecided
+  bool                 p2p = false;
+  VhP2P                p2p_dev;            // by-value kernel argument
+  void                *p2p_mbox = nullptr; // this rank's mailbox (device)
+  void                *p2p_open[VH_P2P_MAX_RANKS] = {}; // peers' mailboxes opened with cudaIpcOpenMemHandle
+  unsigned long long   p2p_seq = 0;        // number of all-reduces issued so far (identical on every rank)
+  int                 *p2p_err = nullptr;  // device flag: a wait timed out
+  unsigned int        *mgs_tickets = nullptr; // [VH_MAX_RESTART + 2] arrival counters of the fused Gram-Schmidt kernel
   std::vector<int32_t> peer_rank, send_ptr, recv_ptr;
   int32_t             *send_nodes = nullptr, *recv_nodes = nullptr; // device lists
   double              *send_buf = nullptr, *recv_buf = nullptr;
@@ -213,7 +240,10 @@ int vh_read_scalars(vh_ctx *ctx, const double *dev, int n, double *host);       
 // ---- halo (vh_halo.cu) ----
 int vhk_halo_exchange(vh_ctx *ctx, double *x_local);
 int vhk_allreduce_sum(vh_ctx *ctx, double *dev, int n);
+int vhk_mgs_mode_local(vh_ctx *ctx);
+
 void vh_comm_destroy(vh_ctx *ctx);
+int  vh_p2p_alloc_local(vh_ctx *ctx, int n_ranks);
 
 // ---- GMRES (vh_gmres.cu) ----
 int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iterations, double *final_res);

@@ -7,6 +7,7 @@
 // 16-byte coalesced streaming of the 2592-byte blocks, x gathered through L1/L2, and deterministic
 // two-stage reductions whose results stay on the device (no host round trip inside the Gram-Schmidt loop).
 #include "vh_internal.h"
+#include "vh_p2p.cuh"
 
 #include <cstdlib>
 
@@ -434,20 +435,22 @@ __global__ void __launch_bounds__(256)
 // are summed in the same fixed order by every block.
 // ------------------------------------------------------------------------------------------------
 #define VH_MGS_THREADS 256
-#define VH_MGS_EPT 8 /* elements of w per thread held in registers (as double2 x 4) */
+// EPT = elements of w per thread held in registers (as double2): 8 covers 1.2 M DoFs per GPU, 32 covers 4.8 M (C5 on 8 GPUs)
+template <int EPT>
 __global__ void __launch_bounds__(VH_MGS_THREADS)
   k_mgs_fused(int64_t n, double *__restrict__ w, const double *__restrict__ V, int64_t ld, int j, double *__restrict__ hcol,
-              double *__restrict__ partials)
+              double *__restrict__ partials, unsigned int *__restrict__ tickets, VhP2P P, unsigned long long seq0)
 {
-  cg::grid_group    grid = cg::this_grid();
+  // Launched cooperatively (all blocks co-resident): one GPU uses cg grid barriers, several GPUs wait through the mailboxes.
   __shared__ double s_w[VH_MGS_THREADS / 32];
   __shared__ double s_tot;
+  __shared__ bool   s_last;
   const int         lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t     base = ((int64_t)blockIdx.x * VH_MGS_THREADS + threadIdx.x) * 2;
   const int64_t     stride = (int64_t)gridDim.x * VH_MGS_THREADS * 2;
-  double2           wr[VH_MGS_EPT / 2];
+  double2           wr[EPT / 2];
 #pragma unroll
-  for (int k = 0; k < VH_MGS_EPT / 2; ++k)
+  for (int k = 0; k < EPT / 2; ++k)
     {
       const int64_t i = base + k * stride;
       wr[k]           = make_double2(0.0, 0.0);
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(VH_MGS_THREADS)
       const double *vu = step <= j ? V + (size_t)step * ld : nullptr;      // dot with v_step (or with w itself)
       double        s  = 0.0;
 #pragma unroll
-      for (int k = 0; k < VH_MGS_EPT / 2; ++k)
+      for (int k = 0; k < EPT / 2; ++k)
         {
           const int64_t i = base + k * stride;
           if (i >= n)
@@ -492,27 +495,90 @@ __global__ void __launch_bounds__(VH_MGS_THREADS)
           for (int k = 0; k < VH_MGS_THREADS / 32; ++k)
             b += s_w[k];
           partials[(size_t)step * gridDim.x + blockIdx.x] = b;
+          if (P.n > 1)
+            {
+              __threadfence();
+              s_last = atomicAdd(tickets + step, 1u) == gridDim.x - 1;
+            }
         }
-      grid.sync();
-      if (wid == 0)
-        { // every block sums all partials of this step in the same order
-          double t = 0.0;
-          for (int b = lane; b < (int)gridDim.x; b += 32)
-            t += partials[(size_t)step * gridDim.x + b];
+      if (P.n == 1)
+        { // one GPU: a grid-wide barrier, then every block sums all partials of this step in the same order
+          cg::this_grid().sync();
+          if (wid == 0)
+            {
+              double t = 0.0;
+              for (int b = lane; b < (int)gridDim.x; b += 32)
+                t += partials[(size_t)step * gridDim.x + b];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
-            t += __shfl_xor_sync(0xffffffffu, t, o);
+              for (int o = 16; o > 0; o >>= 1)
+                t += __shfl_xor_sync(0xffffffffu, t, o);
+              if (lane == 0)
+                s_tot = t;
+            }
+          __syncthreads();
+          hprev = s_tot;
+          if (blockIdx.x == 0 && threadIdx.x == 0)
+            hcol[step] = hprev;
+          __syncthreads();
+          continue;
+        }
+      // several GPUs: no grid barrier at all - the blocks of all ranks meet in the peer-memory mailboxes
+      __syncthreads();
+      const unsigned long long seq  = seq0 + step;
+      const int                slot = (int)(seq % VH_P2P_SLOTS);
+      if (wid == 0)
+        {
+          if (s_last)
+            { // the last block of this rank adds the partials in index order and posts the rank's total into the mailbox of
+              // every rank (its own included): one NVLink store per peer, released by the sequence number
+              __threadfence();
+              double t = 0.0;
+              for (int b = lane; b < (int)gridDim.x; b += 32)
+                t += __ldcg(partials + (size_t)step * gridDim.x + b);
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1)
+                t += __shfl_xor_sync(0xffffffffu, t, o);
+              if (lane < P.n)
+                {
+                  VhP2PCell *dst = P.peer[lane] + slot * P.n + P.me;
+                  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(&dst->val), "d"(t) : "memory");
+                  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->seq), "l"(seq) : "memory");
+                }
+              if (lane == 0)
+                tickets[step] = 0u; // ready for the next launch (nobody touches it again in this one)
+            }
+          // every block polls its own rank's mailbox and adds the ranks' totals in rank order (bit-identical everywhere)
+          double got = 0.0;
+          if (lane < P.n)
+            {
+              const VhP2PCell   *src = P.peer[P.me] + slot * P.n + lane;
+              unsigned long long sq  = 0;
+              const long long    t0  = clock64();
+              do
+                {
+                  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(sq) : "l"(&src->seq) : "memory");
+                  if (sq != seq && clock64() - t0 > 20000000000ll)
+                    {
+                      *P.err = 1;
+                      break;
+                    }
+                }
+              while (sq != seq);
+              asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(got) : "l"(&src->val) : "memory");
+            }
+          double sum = 0.0;
+          for (int r = 0; r < P.n; ++r)
+            sum += __shfl_sync(0xffffffffu, got, r);
           if (lane == 0)
-            s_tot = t;
+            s_tot = sum;
         }
       __syncthreads();
       hprev = s_tot;
       if (blockIdx.x == 0 && threadIdx.x == 0)
         hcol[step] = hprev;
-      __syncthreads();
     }
 #pragma unroll
-  for (int k = 0; k < VH_MGS_EPT / 2; ++k)
+  for (int k = 0; k < EPT / 2; ++k)
     {
       const int64_t i = base + k * stride;
       if (i + 1 < n)
@@ -815,31 +881,51 @@ int vhk_block_jacobi_apply_scaled(vh_ctx *ctx, const double *x_owned, const doub
 
 // Returns VH_OK and sets *used = true when the fused cooperative kernel ran; *used = false means "not applicable here"
 // (multi-rank context, vector too long for the register-resident slice, or no cooperative launch): use the kernel chain.
+// Largest vector the fused kernel can hold in registers with EPT elements per thread (0: no cooperative launch).
+static int64_t mgs_capacity(vh_ctx *ctx, int ept)
+{
+  int coop = 0, sms = 0, per_sm = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  if (ept == 8)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mgs_fused<8>, VH_MGS_THREADS, 0);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mgs_fused<32>, VH_MGS_THREADS, 0);
+  if (!coop)
+    return 0;
+  return (int64_t)sms * (per_sm < 4 ? per_sm : 4) * VH_MGS_THREADS * ept;
+}
+// 8 or 32 = elements per thread this rank needs for its owned vector, 1000 = cannot fuse
+int vhk_mgs_mode_local(vh_ctx *ctx)
+{
+  if (ctx->NO == 0)
+    return 8;
+  for (int ept : {8, 32})
+    if (ctx->NO <= mgs_capacity(ctx, ept) && (int64_t)(VH_MAX_RESTART + 2) * ((ctx->NO + VH_MGS_THREADS * ept - 1) / (VH_MGS_THREADS * ept)) <= (int64_t)VH_MAX_RED_BLOCKS * 32)
+      return ept;
+  return 1000;
+}
+
 int vhk_mgs_fused(vh_ctx *ctx, double *w, const double *V, int64_t ld, int j, double *hcol_dev, bool *used)
 {
   *used = false;
-  if (ctx->n_ranks != 1 || ctx->NO == 0)
+  if (ctx->mgs_mode < 0) // single rank: decided here; multi-rank: agreed over all ranks in vh_comm_init
+    ctx->mgs_mode = ctx->n_ranks == 1 ? vhk_mgs_mode_local(ctx) : 1000;
+  if (ctx->mgs_mode > 32 || (ctx->n_ranks > 1 && !ctx->p2p) || (ctx->n_ranks == 1 && ctx->NO == 0))
     return VH_OK;
-  static int coop = -1, max_blocks = 0;
-  if (coop < 0)
-    {
-      int dev = ctx->device, sms = 0, per_sm = 0;
-      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mgs_fused, VH_MGS_THREADS, 0);
-      max_blocks = sms * (per_sm < 4 ? per_sm : 4);
-    }
-  if (!coop || max_blocks < 1)
-    return VH_OK;
-  const int64_t per_block = (int64_t)VH_MGS_THREADS * VH_MGS_EPT;
-  int64_t       grid      = (ctx->NO + per_block - 1) / per_block;
-  if (grid > max_blocks || (int64_t)(j + 2) * grid > VH_MAX_RED_BLOCKS * 32)
-    return VH_OK;
-  int64_t n     = ctx->NO;
-  void   *args[] = {&n, &w, (void *)&V, &ld, &j, &hcol_dev, &ctx->partials};
-  cudaError_t e = cudaLaunchCooperativeKernel((void *)k_mgs_fused, dim3((unsigned)grid), dim3(VH_MGS_THREADS), args, 0, ctx->stream);
+  const int     ept       = ctx->mgs_mode;
+  const int64_t per_block = (int64_t)VH_MGS_THREADS * ept;
+  int64_t       grid      = std::max<int64_t>(1, (ctx->NO + per_block - 1) / per_block);
+  int64_t       n         = ctx->NO;
+  VhP2P         P         = ctx->p2p_dev; // single rank: the mailbox is this context's own buffer (set up in vh_create)
+  unsigned long long seq0 = ctx->p2p_seq + 1;
+  void       *args[] = {&n, &w, (void *)&V, &ld, &j, &hcol_dev, &ctx->partials, &ctx->mgs_tickets, &P, &seq0};
+  cudaError_t e = cudaLaunchCooperativeKernel(ept == 8 ? (void *)k_mgs_fused<8> : (void *)k_mgs_fused<32>, dim3((unsigned)grid),
+                                              dim3(VH_MGS_THREADS), args, 0, ctx->stream);
   if (e != cudaSuccess)
     return vh_fail(ctx, VH_ERR_CUDA, std::string("cooperative launch: ") + cudaGetErrorString(e));
+  if (ctx->n_ranks > 1)
+    ctx->p2p_seq += j + 2;
   ctx->n_launches++;
   *used = true;
   return VH_OK;
