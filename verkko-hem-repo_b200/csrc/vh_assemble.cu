@@ -1432,6 +1432,266 @@ __global__ void k_cells_slow(SlowArgs A, VhTables tab, VhCoef cf, int want_matri
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3b. row-owner assembly of the constrained rows (hanging-node neighbourhoods, constraint masters)
+// ------------------------------------------------------------------------------------------------
+// One CTA per owned row node I that the lattice kernels do not take.  The host lists the (cell, local node a) pairs that
+// feed the row: a is I itself or a hanging node whose constraint line names I as a master (weight w).  Thread (c,d) owns
+// entry (c,d) of every block of the row: for each pair it contracts the cell's packed H_q table (staged in shared memory)
+// with the weights of all column nodes b, adds the gradient / Robin terms and applies deal.II's
+// distribute_local_to_global rule: row weight of (a,c) -> (I,c), column b either direct or spread over
+// the masters of its line, constrained rows reduced to  sum_cells |a_ii|  on the diagonal.  The row belongs to this CTA
+// alone and entry (c,d) to one thread, so the accumulation is a plain read-modify-write on pre-zeroed blocks: no atomics.
+// (Constraint lines that couple different components - none are generated by the hosts in this repository - would let
+// two threads meet in one entry; such contexts keep the atomic cell scatter k_cells_slow.)
+struct SlowRowArgs
+{
+  const int32_t *slow_rows, *srow_ptr, *srow_cell;
+  const int8_t  *srow_a;       // local node of the pair | 64 if that node is the row node itself
+  const int16_t *srow_posb;    // [pairs][nn] position of the cell's node b in the row (-1: not a column)
+  const double  *srow_wr;      // [pairs][18] weight of local row (a,c) in global row (I,c)
+  const uint32_t *srow_bcons;  // [pairs]     bit b: node b of the cell has constrained DoFs
+  const int32_t *srow_mnode;   // [pairs][nn][MAXM] master nodes of the constrained column node b (-1 padded), MAXM = 4 (Q1) / 9 (Q2)
+  const int16_t *srow_mpos;    // [pairs][nn][MAXM] their positions in the row
+  const int32_t *srow_posI;    // [rows]      position of the diagonal block
+  const uint32_t *srow_cons;   // [rows]      constrained components of the row node
+  const int32_t *cell_nodes, *row_ptr, *col;
+  const double  *cell_h;
+  const uint32_t *cell_faces;
+  const int32_t *line_of, *cptr, *cmaster;
+  const double  *cweight;
+  const double  *Hq, *Rc, *Dc, *avgD;
+};
+
+// rhs / residual of the constrained rows: one thread per (row, component), deterministic gather (constrained DoFs stay 0)
+__global__ void k_rhs_slow(int n_slow_rows, int nn, SlowRowArgs A, double *__restrict__ rhs)
+{
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_slow_rows * 18)
+    return;
+  const int r = gid / 18, c = gid - 18 * r, I = A.slow_rows[r];
+  double    s = 0.0;
+  for (int k = A.srow_ptr[r]; k < A.srow_ptr[r + 1]; ++k)
+    {
+      const int64_t e = A.srow_cell[k];
+      const int     a = A.srow_a[k] & 63;
+      const double  w = A.srow_wr[(size_t)k * 18 + c];
+      if (w != 0.0)
+        s += w * A.Rc[e * (18 * nn) + a * 18 + c];
+    }
+  rhs[(size_t)I * 18 + c] = s;
+}
+
+// Per (row, pair) metadata is resolved on the host (positions of the cell's nodes in the row, row weights, which column
+// nodes carry constrained DoFs), so the device code has no dependent index loads; the next pair's H_q table and
+// metadata are fetched into registers while the current pair is being contracted.
+template <int NN, int NQ>
+__global__ void __launch_bounds__(352, NN == 8 ? 2 : 1)
+  k_rows_slow(SlowRowArgs A, VhTables tab, VhCoef cf, double *__restrict__ vals)
+{
+  constexpr int NT = 352, HPT = (NQ * VH_SYMP + NT - 1) / NT; // table doubles per thread
+  extern __shared__ double sm[];
+  double *sH = sm;                 // [NQ * 180] packed H_q table of the current cell
+  double *sN = sH + NQ * VH_SYMP;  // [NN][NQ]   shape values
+  double *sW = sN + NN * NQ;       // [NQ]       quadrature weights
+  __shared__ int    s_posb[NN], s_nodes[NN];
+  __shared__ double s_wr[18];
+  constexpr int MAXM = NN == 8 ? 4 : 9;
+  __shared__ int   s_mnode[NN * MAXM];
+  __shared__ short s_mpos[NN * MAXM];
+  __shared__ double s_geo[NN * 12]; // per column node b: M[3][3] = vol K23 G_xy/(h_x h_y), then D[3] = K1 trace part + Robin
+  const int      t = threadIdx.x, r = blockIdx.x;
+  const int      I = A.slow_rows[r], rp = A.row_ptr[I];
+  const int      c = t / 18, d = t - 18 * c;
+  const bool     ent = t < VH_BLK;
+  const int      sidx = ent ? (c <= d ? vh_sym_index(c, d) : vh_sym_index(d, c)) : 0;
+  const int      gsel = (ent && c / 3 == d / 3) ? (c % 3) * 3 + d % 3 : -1;
+  const int      posI = A.srow_posI[r];
+  const uint32_t consI = A.srow_cons[r]; // components of node I that are constrained
+  for (int i = t; i < NN * NQ; i += NT)
+    sN[i] = tab.N[i];
+  if (t < NQ)
+    sW[t] = tab.wq[t];
+  const int k0 = A.srow_ptr[r], k1 = A.srow_ptr[r + 1];
+  // prefetch registers: table slice, per-node metadata, and the pair's scalars (every thread keeps its own copy)
+  double   pH[HPT];
+  int      p_posb = -1, p_node = 0, p_a = 0;
+  int64_t  p_e = 0;
+  double   p_wr = 0.0, p_h0 = 1.0, p_h1 = 1.0, p_h2 = 1.0, p_vol = 0.0;
+  uint32_t p_bcons = 0u, p_faces = 0u;
+  auto fetch = [&](int k) {
+    p_e = A.srow_cell[k];
+#pragma unroll
+    for (int i = 0; i < HPT; ++i)
+      pH[i] = (t + i * NT < NQ * VH_SYMP) ? __ldg(A.Hq + p_e * (NQ * VH_SYMP) + t + i * NT) : 0.0;
+    if (t < NN)
+      {
+        p_posb = A.srow_posb[(size_t)k * NN + t];
+        p_node = A.cell_nodes[p_e * NN + t];
+      }
+    if (t >= 32 && t < 50)
+      p_wr = A.srow_wr[(size_t)k * 18 + (t - 32)];
+    p_a     = A.srow_a[k];
+    p_bcons = A.srow_bcons[k];
+    p_faces = A.cell_faces[p_e];
+    p_h0 = A.cell_h[4 * p_e], p_h1 = A.cell_h[4 * p_e + 1], p_h2 = A.cell_h[4 * p_e + 2], p_vol = A.cell_h[4 * p_e + 3];
+  };
+  if (k0 < k1)
+    fetch(k0);
+  for (int k = k0; k < k1; ++k)
+    {
+      const int64_t  e = p_e;
+      const int      a = p_a & 63;
+      const bool     self = p_a & 64;   // the pair's node is I itself
+      const uint32_t bcons = p_bcons;   // column nodes with constrained DoFs
+      const uint32_t faces = p_faces;
+      const double   h[3] = {p_h0, p_h1, p_h2}, vol = p_vol;
+      __syncthreads(); // everybody is done with the previous pair's shared data
+#pragma unroll
+      for (int i = 0; i < HPT; ++i)
+        if (t + i * NT < NQ * VH_SYMP)
+          sH[t + i * NT] = pH[i];
+      if (t < NN)
+        {
+          s_posb[t]  = p_posb;
+          s_nodes[t] = p_node;
+        }
+      if (t >= 32 && t < 50)
+        s_wr[t - 32] = p_wr;
+      if (bcons)
+        for (int i = t; i < NN * MAXM; i += NT)
+          {
+            s_mnode[i] = A.srow_mnode[(size_t)k * (NN * MAXM) + i];
+            s_mpos[i]  = A.srow_mpos[(size_t)k * (NN * MAXM) + i];
+          }
+      for (int i = t; i < NN * 12; i += NT)
+        { // geometry-only part of the cell matrix for row node a and every column node b (gradient forms + Robin faces)
+          const int     b = i / 12, j = i - 12 * b;
+          const double *G = tab.Gref + (size_t)(a * NN + b) * 9;
+          double        v;
+          if (j < 9)
+            v = vol * cf.K23 * G[j] / (h[j / 3] * h[j % 3]);
+          else
+            {
+              const int x = j - 9;
+              v = vol * cf.K1 * (G[0] / (h[0] * h[0]) + G[4] / (h[1] * h[1]) + G[8] / (h[2] * h[2]));
+              if ((cf.bt < 1e10) && faces != 0u)
+                for (int f = 0; f < 6; ++f)
+                  {
+                    const int bid = (faces >> (4 * f)) & 15u;
+                    if (bid < 2 || bid > 4 || x == bid - 2)
+                      continue;
+                    v += cf.K1 / cf.bt * (vol / h[f / 2]) * tab.Mf[(size_t)(f * NN + a) * NN + b];
+                  }
+            }
+          s_geo[i] = v;
+        }
+      __syncthreads();
+      if (k + 1 < k1)
+        fetch(k + 1);
+      if (!ent)
+        continue;
+      if (c == d && self && ((consI >> c) & 1u) && posI >= 0)
+        { // constrained DoF: its row keeps only  sum_cells |a_ii|  (the cell mean |diag| if a_ii == 0)
+          double dv = fabs(A.Dc[e * (18 * NN) + a * 18 + c]);
+          if (dv == 0.0)
+            dv = A.avgD[e];
+          vals[(size_t)(rp + posI) * VH_BLK + t] += dv;
+        }
+      const double wr = s_wr[c];
+      if (wr == 0.0)
+        continue;
+      double       hq[NQ]; // w_q N_a(q) (vol H_q)[c][d]
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        hq[q] = sW[q] * sN[a * NQ + q] * sH[NQ == 8 ? vh_hq8_index(q, sidx) : q * VH_SYMP + sidx];
+      // the old values of this thread's entry in the blocks of the unconstrained column nodes: all loads in flight at once
+      // (the row belongs to this CTA, the entry to this thread: plain read-modify-write)
+      double old[NN == 8 ? 8 : 1];
+      if constexpr (NN == 8)
+        {
+#pragma unroll
+          for (int b = 0; b < 8; ++b)
+            {
+              const int pos = s_posb[b];
+              old[b] = (pos >= 0 && !((bcons >> b) & 1u)) ? vals[(size_t)(rp + pos) * VH_BLK + t] : 0.0;
+            }
+        }
+#pragma unroll(NN == 8 ? 8 : 1)
+      for (int b = 0; b < NN; ++b)
+        {
+          double v = 0.0;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+            v = fma(sN[b * NQ + q], hq[q], v);
+          v += gsel >= 0 ? s_geo[b * 12 + gsel] : 0.0;
+          if (c == d)
+            v += s_geo[b * 12 + 9 + c % 3];
+          v *= wr;
+          if constexpr (NN == 8)
+            {
+              if (!((bcons >> b) & 1u))
+                { // all 18 DoFs of node b unconstrained: its block takes the preloaded value (first pass)
+                  const int pos = s_posb[b];
+                  if (pos >= 0)
+                    vals[(size_t)(rp + pos) * VH_BLK + t] = old[b] + v;
+                }
+              else
+                old[b] = v; // second pass below: masters may share a block with a first-pass node
+            }
+          else
+            {
+              const int lj = ((bcons >> b) & 1u) ? A.line_of[18 * s_nodes[b] + d] : -1;
+              if (lj < 0)
+                {
+                  const int pos = s_posb[b];
+                  if (pos >= 0)
+                    vals[(size_t)(rp + pos) * VH_BLK + t] += v;
+                }
+              else
+                for (int p = A.cptr[lj]; p < A.cptr[lj + 1]; ++p)
+                  { // constrained column: spread over its masters (same component: checked on the host)
+                    const int md = A.cmaster[p], J = md / 18;
+                    int       pos = -1;
+#pragma unroll
+                    for (int m = 0; m < MAXM; ++m)
+                      if (s_mnode[b * MAXM + m] == J)
+                        pos = s_mpos[b * MAXM + m];
+                    if (pos >= 0)
+                      vals[(size_t)(rp + pos) * VH_BLK + c * 18 + md % 18] += A.cweight[p] * v;
+                  }
+            }
+        }
+      if constexpr (NN == 8)
+        if (bcons)
+#pragma unroll
+          for (int b = 0; b < 8; ++b)
+            if ((bcons >> b) & 1u)
+              {
+                const double v  = old[b];
+                const int    lj = A.line_of[18 * s_nodes[b] + d];
+                if (lj < 0)
+                  {
+                    const int pos = s_posb[b];
+                    if (pos >= 0)
+                      vals[(size_t)(rp + pos) * VH_BLK + t] += v;
+                  }
+                else
+                  for (int p = A.cptr[lj]; p < A.cptr[lj + 1]; ++p)
+                    {
+                      const int md = A.cmaster[p], J = md / 18;
+                      int       pos = -1;
+#pragma unroll
+                      for (int m = 0; m < MAXM; ++m)
+                        if (s_mnode[b * MAXM + m] == J)
+                          pos = s_mpos[b * MAXM + m];
+                      if (pos >= 0)
+                        vals[(size_t)(rp + pos) * VH_BLK + c * 18 + md % 18] += A.cweight[p] * v;
+                    }
+              }
+    }
+}
+
 template <int NN, int NQ>
 size_t pointwise_smem(bool want_h)
 {
@@ -1637,6 +1897,54 @@ int vhk_rows_slow(vh_ctx *ctx, bool want_matrix, double *rhs_out)
   VH_LAUNCH_CHECK();
   if (ctx->n_slow_cells == 0)
     return VH_OK;
+  if (ctx->slow_row_owner)
+    { // row-owner kernel: no atomics (constraint lines stay within one component)
+      SlowRowArgs R;
+      R.slow_rows  = ctx->slow_rows;
+      R.srow_ptr   = ctx->srow_ptr;
+      R.srow_cell  = ctx->srow_cell;
+      R.srow_a     = ctx->srow_a;
+      R.srow_posb  = ctx->srow_posb;
+      R.srow_wr    = ctx->srow_wr;
+      R.srow_bcons = ctx->srow_bcons;
+      R.srow_mnode = ctx->srow_mnode;
+      R.srow_mpos  = ctx->srow_mpos;
+      R.srow_posI  = ctx->srow_posI;
+      R.srow_cons  = ctx->srow_cons;
+      R.cell_nodes = ctx->cell_nodes;
+      R.row_ptr    = ctx->row_ptr;
+      R.col        = ctx->col;
+      R.cell_h     = ctx->cell_h;
+      R.cell_faces = ctx->cell_faces;
+      R.line_of    = ctx->cons[0].line_of;
+      R.cptr       = ctx->cons[0].ptr;
+      R.cmaster    = ctx->cons[0].master;
+      R.cweight    = ctx->cons[0].weight;
+      R.Hq         = ctx->Hq;
+      R.Rc         = ctx->Rc;
+      R.Dc         = ctx->Dc;
+      R.avgD       = ctx->avgD;
+      k_rhs_slow<<<(ctx->n_slow_rows * 18 + 127) / 128, 128, 0, ctx->stream>>>(ctx->n_slow_rows, ctx->nn, R, rhs_out);
+      VH_LAUNCH_CHECK();
+      if (!want_matrix)
+        return VH_OK;
+      if (ctx->degree == 1)
+        k_rows_slow<8, 8><<<ctx->n_slow_rows, 352, (8 * VH_SYMP + 64 + 8) * sizeof(double), ctx->stream>>>(R, ctx->tab, ctx->coef, ctx->vals);
+      else
+        {
+          static bool attr = false;
+          if (!attr)
+            {
+              VH_CUDA(cudaFuncSetAttribute(k_rows_slow<27, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)((27 * VH_SYMP + 729 + 27) * sizeof(double))));
+              attr = true;
+            }
+          k_rows_slow<27, 27><<<ctx->n_slow_rows, 352, (27 * VH_SYMP + 729 + 27) * sizeof(double), ctx->stream>>>(R, ctx->tab, ctx->coef,
+                                                                                                                 ctx->vals);
+        }
+      VH_LAUNCH_CHECK();
+      return VH_OK;
+    }
   SlowArgs A;
   A.slow_cells = ctx->slow_cells;
   A.cell_nodes = ctx->cell_nodes;

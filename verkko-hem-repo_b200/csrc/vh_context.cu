@@ -650,6 +650,82 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
     }
   ctx->h_class_tab = class_tab;
   VH_TRY(vh_dev_upload(ctx, &ctx->slow_rows, slow_rows.data(), slow_rows.size()));
+  {
+    std::vector<int32_t>  sp(slow_rows.size() + 1, 0), sc, posI(slow_rows.size(), -1);
+    std::vector<int8_t>   sa;
+    std::vector<int16_t>  posb, mpos;
+    std::vector<int32_t>  mnode;
+    const int             maxm = ctx->degree == 1 ? 4 : 9;
+    bool                  too_many_masters = false;
+    std::vector<double>   wr;
+    std::vector<uint32_t> bcons, consI(slow_rows.size(), 0u);
+    for (size_t r = 0; r < slow_rows.size(); ++r)
+      {
+        const int  I = slow_rows[r];
+        const auto cb = col.begin() + row_ptr[I], ce = col.begin() + row_ptr[I + 1];
+        auto       find = [&](int J) {
+          const auto it = std::lower_bound(cb, ce, J);
+          return (it != ce && *it == J) ? (int)(it - cb) : -1;
+        };
+        posI[r] = find(I);
+        for (int c = 0; c < 18; ++c)
+          if (line0[18 * (size_t)I + c] >= 0)
+            consI[r] |= 1u << c;
+        for (int k = inc_ptr[I]; k < inc_ptr[I + 1]; ++k)
+          {
+            const int e = inc_cell[k], a = inc_a[k], node_a = d->cell_nodes[(size_t)e * nn + a];
+            sc.push_back(e);
+            sa.push_back((int8_t)(a | (node_a == I ? 64 : 0)));
+            uint32_t bc = 0;
+            for (int b = 0; b < nn; ++b)
+              {
+                const int J = d->cell_nodes[(size_t)e * nn + b];
+                posb.push_back((int16_t)find(J));
+                for (int c = 0; c < 18; ++c)
+                  if (line0[18 * (size_t)J + c] >= 0)
+                    bc |= 1u << b;
+                if ((int)masters_of[J].size() > maxm)
+                  too_many_masters = true;
+                for (int m = 0; m < maxm; ++m)
+                  {
+                    const int M = m < (int)masters_of[J].size() ? masters_of[J][m] : -1;
+                    mnode.push_back(M);
+                    mpos.push_back((int16_t)(M >= 0 ? find(M) : -1));
+                  }
+              }
+            bcons.push_back(bc);
+            for (int c = 0; c < 18; ++c)
+              { // weight of local row (node_a, c) in global row (I, c)
+                const int li = line0[18 * (size_t)node_a + c];
+                double    w  = 0.0;
+                if (node_a == I)
+                  w = li < 0 ? 1.0 : 0.0;
+                else if (li >= 0)
+                  for (int p = C.ptr[li]; p < C.ptr[li + 1]; ++p)
+                    if (C.master[p] == 18 * I + c)
+                      w = C.weight[p];
+                wr.push_back(w);
+              }
+          }
+        sp[r + 1] = (int32_t)sc.size();
+      }
+    VH_TRY(vh_dev_upload(ctx, &ctx->srow_ptr, sp.data(), sp.size()));
+    VH_TRY(vh_dev_upload(ctx, &ctx->srow_cell, sc.data(), sc.size()));
+    VH_TRY(vh_dev_upload(ctx, &ctx->srow_a, sa.data(), sa.size()));
+    VH_TRY(vh_dev_upload(ctx, &ctx->srow_posb, posb.data(), posb.size()));
+    VH_TRY(vh_dev_upload(ctx, &ctx->srow_wr, wr.data(), wr.size()));
+    VH_TRY(vh_dev_upload(ctx, &ctx->srow_bcons, bcons.data(), bcons.size()));
+    VH_TRY(vh_dev_upload(ctx, &ctx->srow_posI, posI.data(), posI.size()));
+    VH_TRY(vh_dev_upload(ctx, &ctx->srow_mnode, mnode.data(), mnode.size()));
+    VH_TRY(vh_dev_upload(ctx, &ctx->srow_mpos, mpos.data(), mpos.size()));
+    VH_TRY(vh_dev_upload(ctx, &ctx->srow_cons, consI.data(), consI.size()));
+    bool mixes = false; // a line whose master sits in another component than the constrained DoF
+    for (int l = 0; l < C.n_lines && !mixes; ++l)
+      for (int p = C.ptr[l]; p < C.ptr[l + 1]; ++p)
+        if (C.master[p] % 18 != C.dof[l] % 18)
+          mixes = true;
+    ctx->slow_row_owner = !mixes && !too_many_masters && !(getenv("VH_SLOW_SCATTER") && getenv("VH_SLOW_SCATTER")[0] == '1');
+  }
   VH_TRY(vh_dev_upload(ctx, &ctx->slow_cells, slow_cells.data(), slow_cells.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->row_slow, row_slow.data(), row_slow.size()));
 
@@ -850,7 +926,7 @@ int vh_destroy(vh_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
   vh_comm_destroy(ctx);
   void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
-                  ctx->diag_pos, ctx->minv, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_first, ctx->spmv_order, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->row_slow,
+                  ctx->diag_pos, ctx->minv, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_first, ctx->spmv_order, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->srow_ptr, ctx->srow_cell, ctx->srow_a, ctx->srow_posb, ctx->srow_wr, ctx->srow_bcons, ctx->srow_posI, ctx->srow_mnode, ctx->srow_mpos, ctx->srow_cons, ctx->row_slow,
                   ctx->slow_cells, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
                   ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
                   ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,

@@ -120,6 +120,16 @@ struct vh_ctx
   int32_t *slow_rows  = nullptr; // [n_slow_rows]
   uint8_t *row_slow   = nullptr; // [n_owned]
   int32_t *slow_cells = nullptr; // [n_slow_cells]
+  // row-owner lists of the constrained rows: (cell, local node) pairs feeding slow row r (the node itself or a hanging
+  // node that names it as a master)
+  int32_t *srow_ptr = nullptr, *srow_cell = nullptr; // [n_slow_rows + 1], [srow_ptr[n_slow_rows]]
+  int8_t  *srow_a = nullptr;
+  int16_t *srow_posb = nullptr;
+  double  *srow_wr = nullptr;
+  uint32_t *srow_bcons = nullptr, *srow_cons = nullptr;
+  int32_t *srow_posI = nullptr, *srow_mnode = nullptr;
+  int16_t *srow_mpos = nullptr;
+  bool     slow_row_owner = false; // false: constraint lines couple components (or VH_SLOW_SCATTER=1) -> atomic cell scatter
   // node -> incident (cell, local node) lists for the deterministic rhs gather of fast rows
   // (fast rows use fast_cells; kept for Q2 later)
 
