@@ -187,16 +187,26 @@ __global__ void __launch_bounds__(VH_PSPMV_WARPS * 32, MINB)
               VH_PSPMV_BLOCK(v[u], J, sl)
             }
         }
-      for (; j < nchunk; ++j)
-        {
-          double2        v[3];
-          const double2 *B = reinterpret_cast<const double2 *>(pvals + (size_t)(base + j) * VH_SYMP);
-          v[0]             = __ldcs(B + lane);
-          v[1]             = __ldcs(B + lane + 32);
-          v[2]             = third ? __ldcs(B + lane + 64) : make_double2(0.0, 0.0);
-          const int J      = __shfl_sync(0xffffffffu, mycol, j);
-          const int sl     = __shfl_sync(0xffffffffu, myslot, j);
-          VH_PSPMV_BLOCK(v, J, sl)
+      if (j < nchunk)
+        { // tail (< NB blocks): one masked batch, so its loads are in flight together like in the main loop
+          double2 v[NB][3];
+#pragma unroll
+          for (int u = 0; u < NB; ++u)
+            {
+              const bool     on = j + u < nchunk;
+              const double2 *B  = reinterpret_cast<const double2 *>(pvals + (size_t)(base + (on ? j + u : j)) * VH_SYMP);
+              v[u][0]           = on ? __ldcs(B + lane) : make_double2(0.0, 0.0);
+              v[u][1]           = on ? __ldcs(B + lane + 32) : make_double2(0.0, 0.0);
+              v[u][2]           = (on && third) ? __ldcs(B + lane + 64) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+          for (int u = 0; u < NB; ++u)
+            if (j + u < nchunk)
+              {
+                const int J  = __shfl_sync(0xffffffffu, mycol, j + u);
+                const int sl = __shfl_sync(0xffffffffu, myslot, j + u);
+                VH_PSPMV_BLOCK(v[u], J, sl)
+              }
         }
     }
 #undef VH_PSPMV_BLOCK
@@ -241,16 +251,15 @@ __global__ void __launch_bounds__(128)
                  const int32_t *__restrict__ fast_class, const double *__restrict__ class_M, const uint32_t *__restrict__ dirmask,
                  const double *__restrict__ cdiag)
 {
-  // Register-resident Gauss-Jordan: lane r < 18 keeps row r of [A | I] in registers; the scaled pivot row is broadcast
-  // through shared memory (shuffles would be the bottleneck: ~1000 per block), and rows are never swapped physically:
-  // the lane that pivots on column k ends up holding row k of A^-1.
-  __shared__ __align__(16) double s_row[4][36];
+  // Register-resident Gauss-Jordan, one warp per block; the scaled pivot row is broadcast through shared memory
+  // (shuffles would be the bottleneck: ~650 per block).
+  __shared__ __align__(16) double s_row[4][18];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int row  = blockIdx.x * 4 + wid;
   if (row >= n_rows)
     return;
   const int rr = lane < 18 ? lane : 17;
-  double    a[36];
+  double    a[18];
   const int fi = pvals ? fast_index[row] : -1;
   if (fi >= 0)
     { // packed row: diagonal block = Sym(P) + kron(I_6, M_13), Dirichlet rows/columns -> sum_cells |a_ii| on the diagonal
@@ -265,8 +274,7 @@ __global__ void __launch_bounds__(128)
             v += M[(rr % 3) * 3 + c % 3];
           if (((mI >> rr) & 1u) || ((mI >> c) & 1u))
             v = (rr == c) ? cdiag[(size_t)row * 18 + c] : 0.0;
-          a[c]      = v;
-          a[18 + c] = (c == rr) ? 1.0 : 0.0;
+          a[c] = v;
         }
     }
   else
@@ -275,60 +283,58 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
       for (int c = 0; c < 18; ++c)
         {
-          a[c]      = __ldg(B + rr * 18 + c);
-          a[18 + c] = (c == rr) ? 1.0 : 0.0;
+          a[c] = __ldg(B + rr * 18 + c);
         }
     }
+  // In-place Gauss-Jordan: lane r keeps row r of the working matrix (18 doubles).  Step k picks the not yet used row with
+  // the largest |a[r][k]| (one redux.sync on the float-truncated magnitudes + a ballot; ties go to the lowest lane),
+  // scales it, and eliminates column k from every other row; the freed column k then stores the column of the inverse that
+  // became non-trivial in this step (the one of the pivot row pl_k).  Rows are never swapped: at the end the lane that
+  // pivoted on column k holds row k of A^-1 with its columns in the order pl_0 .. pl_17.
   bool used     = lane >= 18;
   int  mycol    = -1;
   bool singular = false;
+  int  piv[18];
 #pragma unroll
   for (int k = 0; k < 18; ++k)
     {
-      double pv = used ? -1.0 : fabs(a[k]);
-      int    pl = lane;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-        {
-          const double ov = __shfl_xor_sync(0xffffffffu, pv, o);
-          const int    ol = __shfl_xor_sync(0xffffffffu, pl, o);
-          if (ov > pv || (ov == pv && ol < pl))
-            {
-              pv = ov;
-              pl = ol;
-            }
-        }
-      if (!(pv > 0.0))
+      const unsigned key  = used ? 0u : __float_as_uint(fabsf(__double2float_ru(fabs(a[k]))));
+      const unsigned best = __reduce_max_sync(0xffffffffu, key);
+      if (best == 0u)
         {
           singular = true;
           break;
         }
-      const double inv = 1.0 / __shfl_sync(0xffffffffu, a[k], pl);
+      const int    pl  = __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;
       const bool   me  = lane == pl;
       const double f   = a[k];
+      const double inv = 1.0 / __shfl_sync(0xffffffffu, f, pl);
+      piv[k]           = pl;
       if (me)
         {
+          a[k] = 1.0;
 #pragma unroll
-          for (int c = k + 1; c < 36; ++c)
-            {
-              a[c] *= inv;
-              s_row[wid][c] = a[c];
-            }
+          for (int c = 0; c < 18; ++c)
+            a[c] *= inv;
+#pragma unroll
+          for (int c = 0; c < 9; ++c)
+            *reinterpret_cast<double2 *>(&s_row[wid][2 * c]) = make_double2(a[2 * c], a[2 * c + 1]);
+          used  = true;
+          mycol = k;
         }
       __syncwarp();
       if (!me)
         {
+          a[k] = 0.0;
 #pragma unroll
-          for (int c = k + 1; c < 36; ++c)
-            a[c] = fma(-f, s_row[wid][c], a[c]);
+          for (int c = 0; c < 9; ++c)
+            {
+              const double2 p = *reinterpret_cast<const double2 *>(&s_row[wid][2 * c]);
+              a[2 * c]        = fma(-f, p.x, a[2 * c]);
+              a[2 * c + 1]    = fma(-f, p.y, a[2 * c + 1]);
+            }
         }
       __syncwarp();
-      a[k] = me ? 1.0 : 0.0;
-      if (me)
-        {
-          used  = true;
-          mycol = k;
-        }
     }
   if (singular)
     {
@@ -342,8 +348,8 @@ __global__ void __launch_bounds__(128)
     {
       double *out = minv + (size_t)row * VH_BLK + mycol * 18;
 #pragma unroll
-      for (int c = 0; c < 18; ++c)
-        out[c] = a[18 + c];
+      for (int m = 0; m < 18; ++m)
+        out[piv[m]] = a[m];
     }
 }
 
