@@ -812,6 +812,8 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   VH_CUDA(cudaMemset(ctx->ticket, 0, 4 * sizeof(unsigned int)));
   VH_CUDA(cudaMemset(ctx->scal, 0, VH_SCAL_COUNT * sizeof(double)));
   VH_CUDA(cudaMallocHost((void **)&ctx->h_pinned, VH_SCAL_COUNT * sizeof(double)));
+  VH_CUDA(cudaHostAlloc((void **)&ctx->h_mgs, VH_SCAL_COUNT * sizeof(double), cudaHostAllocMapped));
+  std::memset(ctx->h_mgs, 0, VH_SCAL_COUNT * sizeof(double));
   VH_TRY(vh_p2p_alloc_local(ctx, 1)); // mailbox of the fused Gram-Schmidt kernel (one-rank communicator until vh_comm_init)
   return VH_OK;
 }
@@ -903,7 +905,7 @@ int vh_create(const vh_mesh_desc *d, int cuda_device, vh_ctx **out)
   int rc       = VH_OK;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
       cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreate(&ctx->ev2) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev3) != cudaSuccess)
+      cudaEventCreate(&ctx->ev3) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_scal, cudaEventDisableTiming) != cudaSuccess)
     rc = vh_fail(ctx, VH_ERR_CUDA, "stream/event creation failed");
   if (rc == VH_OK)
     rc = build(ctx, d);
@@ -943,6 +945,8 @@ int vh_destroy(vh_ctx *ctx)
     }
   if (ctx->h_pinned)
     cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_mgs)
+    cudaFreeHost(ctx->h_mgs);
   if (ctx->ev0)
     cudaEventDestroy(ctx->ev0);
   if (ctx->ev1)
@@ -951,6 +955,8 @@ int vh_destroy(vh_ctx *ctx)
     cudaEventDestroy(ctx->ev2);
   if (ctx->ev3)
     cudaEventDestroy(ctx->ev3);
+  if (ctx->ev_scal)
+    cudaEventDestroy(ctx->ev_scal);
   if (ctx->stream)
     cudaStreamDestroy(ctx->stream);
   delete ctx;

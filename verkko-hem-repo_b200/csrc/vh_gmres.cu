@@ -17,6 +17,10 @@
 // one Hessenberg column per inner step (a single small D2H) to run the tiny QR and the stopping test.
 #include "vh_internal.h"
 
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+
 #include <cmath>
 #include <vector>
 
@@ -103,6 +107,20 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
     return (int)ITERATE;
   };
 
+  // VH_GMRES_TRACE=1: CUDA events around every kernel group of the inner loop, printed to stderr after the solve (diagnostic)
+  static const bool   trace = getenv("VH_GMRES_TRACE") && getenv("VH_GMRES_TRACE")[0] == '1';
+  std::vector<cudaEvent_t> tev;
+  std::vector<const char *> tname;
+  auto mark = [&](const char *name) {
+    if (!trace)
+      return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, ctx->stream);
+    tev.push_back(e);
+    tname.push_back(name);
+  };
+  static const bool   speculate = !(getenv("VH_GMRES_SPECULATE") && getenv("VH_GMRES_SPECULATE")[0] == '0');
   int                 accumulated = 0;
   double              res = 0.0;
   int                 state = ITERATE;
@@ -131,19 +149,34 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
       y.clear();
       double        a    = beta;
       const double *a2_d = nrm2; // device location of a^2
+      // Inner loop.  The host needs H(:,j) only to decide whether to stop, so the next step's basis-vector scaling,
+      // preconditioner application, ghost refresh and SpMV - which depend on device data only - are enqueued BEFORE the
+      // host waits for the coefficients: the GPU never idles during the host round trip.  No speculation right before an
+      // expected stop (residual within 4x of the tolerance) or at the end of a restart cycle; a wrongly speculated step
+      // only overwrites scratch vectors.  The decision depends on replicated scalars, so all ranks take the same path.
+      bool have_next = false; // v_j, z = M^-1 v_j and aux = A z of the coming step are already enqueued
       for (int j = 0; j < m; ++j)
         {
           double *vj = ctx->V + (size_t)j * NO;
-          // v_j = aux / a and z = M^-1 v_j (owned part of zbuf) in one pass; ghosts refreshed; aux = A z
-          if (a != 0.0)
-            VH_TRY(vhk_block_jacobi_apply_scaled(ctx, aux, a2_d, vj, ctx->zbuf));
-          else
+          if (!have_next)
             {
-              VH_CUDA(cudaMemsetAsync(vj, 0, sizeof(double) * NO, ctx->stream));
-              VH_CUDA(cudaMemsetAsync(ctx->zbuf, 0, sizeof(double) * NO, ctx->stream));
+              mark("step");
+              // v_j = aux / a and z = M^-1 v_j (owned part of zbuf) in one pass; ghosts refreshed; aux = A z
+              if (a != 0.0)
+                VH_TRY(vhk_block_jacobi_apply_scaled(ctx, aux, a2_d, vj, ctx->zbuf));
+              else
+                {
+                  VH_CUDA(cudaMemsetAsync(vj, 0, sizeof(double) * NO, ctx->stream));
+                  VH_CUDA(cudaMemsetAsync(ctx->zbuf, 0, sizeof(double) * NO, ctx->stream));
+                }
+              mark("apply");
+              VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
+              mark("halo");
+              VH_TRY(vhk_spmv(ctx, ctx->zbuf, aux, true)); // z = M^-1 v_j: zero at Dirichlet DoFs because v_j is
+              mark("spmv");
             }
-          VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
-          VH_TRY(vhk_spmv(ctx, ctx->zbuf, aux, true)); // z = M^-1 v_j: zero at Dirichlet DoFs because v_j is
+          have_next = false;
+          mark("pre-mgs");
           // modified Gram-Schmidt; the coefficients never leave the device between the fused steps
           bool fused = false;
           VH_TRY(vhk_mgs_fused(ctx, aux, ctx->V, NO, j, hcol, &fused));
@@ -154,16 +187,56 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
                 VH_TRY(vhk_add_and_dot(ctx, aux, hcol + (i - 1), ctx->V + (size_t)(i - 1) * NO, ctx->V + (size_t)i * NO, hcol + i));
               VH_TRY(vhk_add_and_dot(ctx, aux, hcol + j, vj, aux, hcol + j + 1));
             }
+          mark("mgs");
+          if (!fused)
+            {
+              VH_CUDA(cudaMemcpyAsync(ctx->h_pinned, hcol, (j + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+              VH_CUDA(cudaEventRecord(ctx->ev_scal, ctx->stream));
+              // keep a^2 where the next inner step's scaling kernel reads it, before hcol is overwritten
+              VH_CUDA(cudaMemcpyAsync(nrm2, hcol + j + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            } // fused: the kernel itself wrote a^2 to nrm2 and the column to mapped host memory (no copy in the stream)
+          a2_d = nrm2;
+          if (speculate && j + 1 < m && accumulated + 2 <= max_it && !(j > 0 && res <= 4.0 * tol_abs))
+            {
+              mark("step");
+              VH_TRY(vhk_block_jacobi_apply_scaled(ctx, aux, a2_d, ctx->V + (size_t)(j + 1) * NO, ctx->zbuf));
+              mark("apply");
+              VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
+              mark("halo");
+              VH_TRY(vhk_spmv(ctx, ctx->zbuf, aux, true));
+              mark("spmv");
+              have_next = true;
+            }
           std::vector<double> hc(j + 2);
-          VH_TRY(vh_read_scalars(ctx, hcol, j + 2, hc.data()));
+          if (fused)
+            { // poll the sequence flag the kernel writes after the column (system-scope fence in between)
+              volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(ctx->h_mgs + VH_SCAL_COUNT - 1);
+              long                         spins = 0;
+              while (*flag != ctx->h_mgs_seq)
+                if ((++spins & 0xfff) == 0)
+                  { // a failed launch / sticky error would leave us spinning: look at the stream now and then
+                    const cudaError_t q = cudaStreamQuery(ctx->stream);
+                    if (q != cudaSuccess && q != cudaErrorNotReady)
+                      return vh_fail(ctx, VH_ERR_CUDA, std::string("GMRES: ") + cudaGetErrorString(q));
+                    if (q == cudaSuccess && *flag != ctx->h_mgs_seq)
+                      return vh_fail(ctx, VH_ERR_CUDA, "GMRES: the Gram-Schmidt kernel finished without publishing its column");
+                  }
+              std::atomic_thread_fence(std::memory_order_acquire);
+              for (int i = 0; i < j + 2; ++i)
+                hc[i] = reinterpret_cast<volatile double *>(ctx->h_mgs)[i];
+            }
+          else
+            {
+              VH_CUDA(cudaEventSynchronize(ctx->ev_scal));
+              for (int i = 0; i < j + 2; ++i)
+                hc[i] = ctx->h_pinned[i];
+            }
           for (int i = 0; i <= j; ++i)
             H[(size_t)i * m + j] = hc[i];
           a                          = std::sqrt(hc[j + 1]);
           H[(size_t)(j + 1) * m + j] = a;
-          a2_d                       = hcol + j + 1;
-          // keep a^2 where the next inner step's scaling kernel reads it, before hcol is overwritten
-          VH_CUDA(cudaMemcpyAsync(nrm2, hcol + j + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-          a2_d = nrm2;
+          if (a == 0.0)
+            have_next = false; // breakdown: the speculated step divided by zero; it is redone through the memset path
           if (j > 0)
             {
               const int           rows = j + 1, cols = j;
@@ -194,6 +267,20 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
     }
   while (state == ITERATE);
 
+  if (trace && !tev.empty())
+    {
+      cudaStreamSynchronize(ctx->stream);
+      fprintf(stderr, "[gmres trace] %d iterations:", accumulated);
+      for (size_t i = 1; i < tev.size(); ++i)
+        {
+          float ms = 0;
+          cudaEventElapsedTime(&ms, tev[i - 1], tev[i]);
+          fprintf(stderr, " %s %.1f", tname[i], ms * 1e3f);
+        }
+      fprintf(stderr, " (us)\n");
+      for (cudaEvent_t e : tev)
+        cudaEventDestroy(e);
+    }
   *iterations = accumulated;
   *final_res  = res;
   if (ctx->p2p)

@@ -150,6 +150,8 @@ struct vh_ctx
   double *scal     = nullptr; // device scalars [VH_SCAL_COUNT]
   unsigned int *ticket = nullptr;
   double *h_pinned = nullptr; // pinned host scratch [VH_SCAL_COUNT]
+  double *h_mgs = nullptr;    // pinned + mapped: the fused Gram-Schmidt kernel writes H(:,j) here, flag in the last slot
+  unsigned long long h_mgs_seq = 0;
 
   // halo
   int                  rank = 0, n_ranks = 1;
@@ -174,7 +176,7 @@ struct vh_ctx
   // accounting
   int64_t     n_launches = 0;
   double      t_ms[5]    = {0, 0, 0, 0, 0};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_scal = nullptr;
   int64_t     device_bytes = 0;
   void       *flush_buf   = nullptr;
   size_t      flush_bytes = 0;

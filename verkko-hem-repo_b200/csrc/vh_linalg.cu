@@ -443,9 +443,10 @@ __global__ void __launch_bounds__(256)
 #define VH_MGS_THREADS 256
 // EPT = elements of w per thread held in registers (as double2): 8 covers 1.2 M DoFs per GPU, 32 covers 4.8 M (C5 on 8 GPUs)
 template <int EPT>
-__global__ void __launch_bounds__(VH_MGS_THREADS)
+__global__ void __launch_bounds__(VH_MGS_THREADS, EPT == 8 ? 3 : 1)
   k_mgs_fused(int64_t n, double *__restrict__ w, const double *__restrict__ V, int64_t ld, int j, double *__restrict__ hcol,
-              double *__restrict__ partials, unsigned int *__restrict__ tickets, VhP2P P, unsigned long long seq0)
+              double *__restrict__ partials, unsigned int *__restrict__ tickets, VhP2P P, unsigned long long seq0,
+              double *__restrict__ nrm2_out, volatile double *host_out, unsigned long long host_seq)
 {
   // Launched cooperatively (all blocks co-resident): one GPU uses cg grid barriers, several GPUs wait through the mailboxes.
   __shared__ double s_w[VH_MGS_THREADS / 32];
@@ -465,29 +466,79 @@ __global__ void __launch_bounds__(VH_MGS_THREADS)
       else if (i < n)
         wr[k].x = w[i];
     }
+  // Every basis vector is read ONCE: V[step] is the dot partner of step `step` and the subtracted vector of step + 1, and
+  // (EPT = 8) the next one is requested before this step's reduction so that its latency hides behind the barrier.
+  constexpr bool PF = EPT == 8;
+#define VH_MGS_LOAD(vptr, dst)                                              \
+  _Pragma("unroll") for (int k = 0; k < EPT / 2; ++k)                       \
+  {                                                                         \
+    const int64_t i = base + k * stride;                                    \
+    (dst)[k]        = make_double2(0.0, 0.0);                               \
+    if (i + 1 < n)                                                          \
+      (dst)[k] = *reinterpret_cast<const double2 *>((vptr) + i);            \
+    else if (i < n)                                                         \
+      (dst)[k].x = (vptr)[i];                                               \
+  }
+  double2 cu[PF ? EPT / 2 : 1], nu[PF ? EPT / 2 : 1];
+  if constexpr (PF)
+    {
+      VH_MGS_LOAD(V, nu)
+    }
   double hprev = 0.0;
   for (int step = 0; step <= j + 1; ++step)
     {
-      const double *vp = step > 0 ? V + (size_t)(step - 1) * ld : nullptr; // subtract hprev * v_{step-1}
-      const double *vu = step <= j ? V + (size_t)step * ld : nullptr;      // dot with v_step (or with w itself)
-      double        s  = 0.0;
-#pragma unroll
-      for (int k = 0; k < EPT / 2; ++k)
+      double s = 0.0;
+      if constexpr (PF)
         {
-          const int64_t i = base + k * stride;
-          if (i >= n)
-            continue;
-          const bool two = i + 1 < n;
-          if (vp)
+          // w -= hprev * V[step-1]  (cu still holds V[step-1] from the previous step)
+          if (step > 0)
+#pragma unroll
+            for (int k = 0; k < EPT / 2; ++k)
+              {
+                wr[k].x = fma(-hprev, cu[k].x, wr[k].x);
+                wr[k].y = fma(-hprev, cu[k].y, wr[k].y);
+              }
+          if (step <= j)
             {
-              const double2 pv = two ? *reinterpret_cast<const double2 *>(vp + i) : make_double2(vp[i], 0.0);
-              wr[k].x          = fma(-hprev, pv.x, wr[k].x);
-              wr[k].y          = fma(-hprev, pv.y, wr[k].y);
+#pragma unroll
+              for (int k = 0; k < EPT / 2; ++k)
+                cu[k] = nu[k];
+              if (step + 1 <= j)
+                {
+                  const double *vn = V + (size_t)(step + 1) * ld;
+                  VH_MGS_LOAD(vn, nu)
+                }
+#pragma unroll
+              for (int k = 0; k < EPT / 2; ++k)
+                s = fma(wr[k].x, cu[k].x, fma(wr[k].y, cu[k].y, s));
             }
-          double2 uv = wr[k];
-          if (vu)
-            uv = two ? *reinterpret_cast<const double2 *>(vu + i) : make_double2(vu[i], 0.0);
-          s = fma(wr[k].x, uv.x, fma(wr[k].y, uv.y, s));
+          else
+#pragma unroll
+            for (int k = 0; k < EPT / 2; ++k)
+              s = fma(wr[k].x, wr[k].x, fma(wr[k].y, wr[k].y, s));
+        }
+      else
+        { // long vectors: w fills the registers, the basis vectors are read where they are used
+          const double *vp = step > 0 ? V + (size_t)(step - 1) * ld : nullptr; // subtract hprev * v_{step-1}
+          const double *vu = step <= j ? V + (size_t)step * ld : nullptr;      // dot with v_step (or with w itself)
+#pragma unroll
+          for (int k = 0; k < EPT / 2; ++k)
+            {
+              const int64_t i = base + k * stride;
+              if (i >= n)
+                continue;
+              const bool two = i + 1 < n;
+              if (vp)
+                {
+                  const double2 pv = two ? *reinterpret_cast<const double2 *>(vp + i) : make_double2(vp[i], 0.0);
+                  wr[k].x          = fma(-hprev, pv.x, wr[k].x);
+                  wr[k].y          = fma(-hprev, pv.y, wr[k].y);
+                }
+              double2 uv = wr[k];
+              if (vu)
+                uv = two ? *reinterpret_cast<const double2 *>(vu + i) : make_double2(vu[i], 0.0);
+              s = fma(wr[k].x, uv.x, fma(wr[k].y, uv.y, s));
+            }
         }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1)
@@ -524,7 +575,10 @@ __global__ void __launch_bounds__(VH_MGS_THREADS)
           __syncthreads();
           hprev = s_tot;
           if (blockIdx.x == 0 && threadIdx.x == 0)
-            hcol[step] = hprev;
+            {
+              hcol[step]     = hprev;
+              host_out[step] = hprev; // mapped pinned host memory: the host polls instead of copying (see below)
+            }
           __syncthreads();
           continue;
         }
@@ -581,7 +635,16 @@ __global__ void __launch_bounds__(VH_MGS_THREADS)
       __syncthreads();
       hprev = s_tot;
       if (blockIdx.x == 0 && threadIdx.x == 0)
-        hcol[step] = hprev;
+        {
+          hcol[step]     = hprev;
+          host_out[step] = hprev;
+        }
+    }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    { // hand the column to the host without a copy operation in the stream: values first, then the sequence flag
+      *nrm2_out = hprev; // a^2 for the scaling kernel of the next inner step
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long *>(host_out + VH_SCAL_COUNT - 1) = host_seq;
     }
 #pragma unroll
   for (int k = 0; k < EPT / 2; ++k)
@@ -925,7 +988,10 @@ int vhk_mgs_fused(vh_ctx *ctx, double *w, const double *V, int64_t ld, int j, do
   int64_t       n         = ctx->NO;
   VhP2P         P         = ctx->p2p_dev; // single rank: the mailbox is this context's own buffer (set up in vh_create)
   unsigned long long seq0 = ctx->p2p_seq + 1;
-  void       *args[] = {&n, &w, (void *)&V, &ld, &j, &hcol_dev, &ctx->partials, &ctx->mgs_tickets, &P, &seq0};
+  double            *nrm2_out = ctx->scal + VH_SCAL_NRM2;
+  double            *host_out = ctx->h_mgs;
+  unsigned long long host_seq = ++ctx->h_mgs_seq;
+  void *args[] = {&n, &w, (void *)&V, &ld, &j, &hcol_dev, &ctx->partials, &ctx->mgs_tickets, &P, &seq0, &nrm2_out, &host_out, &host_seq};
   cudaError_t e = cudaLaunchCooperativeKernel(ept == 8 ? (void *)k_mgs_fused<8> : (void *)k_mgs_fused<32>, dim3((unsigned)grid),
                                               dim3(VH_MGS_THREADS), args, 0, ctx->stream);
   if (e != cudaSuccess)
