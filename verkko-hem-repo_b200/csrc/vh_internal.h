@@ -28,15 +28,13 @@ struct VhTables
 };
 
 // Mailbox all-reduce over peer memory.  Rank r owns mbox[VH_P2P_SLOTS][n_ranks] cells of {value, sequence}; an
-// all-reduce number `seq` writes this rank's partial into cell [seq % SLOTS][me] of EVERY rank (release store of the
-// sequence number after the value), then waits until its own cells [seq % SLOTS][0..n) carry `seq` and adds the values in
-// rank order, so every rank gets the bit-identical sum.
+// all-reduce number `seq` writes this rank's partial into cell [seq % SLOTS][me] of EVERY rank, then waits until its own
+// cells [seq % SLOTS][0..n) carry `seq` and adds the values in rank order, so every rank gets the bit-identical sum.
 #define VH_P2P_MAX_RANKS 8
 #define VH_P2P_SLOTS 8
-struct VhP2PCell
-{
-  double             val;
-  unsigned long long seq;
+struct VhP2PCell // two 8-byte words {half of the value, 32-bit sequence}: each word is written and read atomically, so no
+{                // fences are needed (the flag travels with the data, like NCCL's LL protocol)
+  unsigned long long lo, hi;
 };
 struct VhP2P
 {

@@ -599,33 +599,14 @@ __global__ void __launch_bounds__(VH_MGS_THREADS, EPT == 8 ? 3 : 1)
               for (int o = 16; o > 0; o >>= 1)
                 t += __shfl_xor_sync(0xffffffffu, t, o);
               if (lane < P.n)
-                {
-                  VhP2PCell *dst = P.peer[lane] + slot * P.n + P.me;
-                  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(&dst->val), "d"(t) : "memory");
-                  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->seq), "l"(seq) : "memory");
-                }
+                vh_p2p_post(P.peer[lane] + slot * P.n + P.me, seq, t);
               if (lane == 0)
                 tickets[step] = 0u; // ready for the next launch (nobody touches it again in this one)
             }
           // every block polls its own rank's mailbox and adds the ranks' totals in rank order (bit-identical everywhere)
           double got = 0.0;
           if (lane < P.n)
-            {
-              const VhP2PCell   *src = P.peer[P.me] + slot * P.n + lane;
-              unsigned long long sq  = 0;
-              const long long    t0  = clock64();
-              do
-                {
-                  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(sq) : "l"(&src->seq) : "memory");
-                  if (sq != seq && clock64() - t0 > 20000000000ll)
-                    {
-                      *P.err = 1;
-                      break;
-                    }
-                }
-              while (sq != seq);
-              asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(got) : "l"(&src->val) : "memory");
-            }
+            got = vh_p2p_wait(P.peer[P.me] + slot * P.n + lane, seq, P.err);
           double sum = 0.0;
           for (int r = 0; r < P.n; ++r)
             sum += __shfl_sync(0xffffffffu, got, r);
