@@ -768,6 +768,8 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
       for (int64_t i = 0; i < ctx->n_recv; ++i)
         if (d->recv_nodes[i] < n_owned || d->recv_nodes[i] >= n_local)
           return vh_fail(ctx, VH_ERR_ARG, "recv_nodes must be ghost nodes");
+      ctx->h_send_nodes.assign(d->send_nodes, d->send_nodes + ctx->n_send);
+      ctx->h_recv_nodes.assign(d->recv_nodes, d->recv_nodes + ctx->n_recv);
       VH_TRY(vh_dev_upload(ctx, &ctx->send_nodes, d->send_nodes, (size_t)ctx->n_send));
       VH_TRY(vh_dev_upload(ctx, &ctx->recv_nodes, d->recv_nodes, (size_t)ctx->n_recv));
       VH_TRY(vh_dev_alloc(ctx, &ctx->send_buf, (size_t)ctx->n_send * 18));
@@ -928,7 +930,7 @@ int vh_destroy(vh_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
   vh_comm_destroy(ctx);
   void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
-                  ctx->diag_pos, ctx->minv, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_first, ctx->spmv_order, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->srow_ptr, ctx->srow_cell, ctx->srow_a, ctx->srow_posb, ctx->srow_wr, ctx->srow_bcons, ctx->srow_posI, ctx->srow_mnode, ctx->srow_mpos, ctx->srow_cons, ctx->row_slow,
+                  ctx->diag_pos, ctx->minv, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_first, ctx->spmv_order, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->srow_ptr, ctx->srow_cell, ctx->srow_a, ctx->srow_posb, ctx->srow_wr, ctx->srow_bcons, ctx->srow_posI, ctx->srow_mnode, ctx->srow_mpos, ctx->srow_cons, ctx->push_ptr, ctx->push_dst, ctx->push_peer, ctx->push_ticket, ctx->row_slow,
                   ctx->slow_cells, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
                   ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
                   ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,

@@ -163,14 +163,17 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
               mark("step");
               // v_j = aux / a and z = M^-1 v_j (owned part of zbuf) in one pass; ghosts refreshed; aux = A z
               if (a != 0.0)
-                VH_TRY(vhk_block_jacobi_apply_scaled(ctx, aux, a2_d, vj, ctx->zbuf));
+                VH_TRY(vhk_block_jacobi_apply_scaled(ctx, aux, a2_d, vj, ctx->zbuf, ctx->zpush));
               else
                 {
                   VH_CUDA(cudaMemsetAsync(vj, 0, sizeof(double) * NO, ctx->stream));
                   VH_CUDA(cudaMemsetAsync(ctx->zbuf, 0, sizeof(double) * NO, ctx->stream));
                 }
               mark("apply");
-              VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
+              if (ctx->zpush && a != 0.0)
+                VH_TRY(vhk_halo_wait(ctx)); // the neighbours pushed their interface values into our ghost slots
+              else
+                VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
               mark("halo");
               VH_TRY(vhk_spmv(ctx, ctx->zbuf, aux, true)); // z = M^-1 v_j: zero at Dirichlet DoFs because v_j is
               mark("spmv");
@@ -199,9 +202,12 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
           if (speculate && j + 1 < m && accumulated + 2 <= max_it && !(j > 0 && res <= 4.0 * tol_abs))
             {
               mark("step");
-              VH_TRY(vhk_block_jacobi_apply_scaled(ctx, aux, a2_d, ctx->V + (size_t)(j + 1) * NO, ctx->zbuf));
+              VH_TRY(vhk_block_jacobi_apply_scaled(ctx, aux, a2_d, ctx->V + (size_t)(j + 1) * NO, ctx->zbuf, ctx->zpush));
               mark("apply");
-              VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
+              if (ctx->zpush)
+                VH_TRY(vhk_halo_wait(ctx));
+              else
+                VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
               mark("halo");
               VH_TRY(vhk_spmv(ctx, ctx->zbuf, aux, true));
               mark("spmv");

@@ -138,6 +138,117 @@ extern "C" int vh_nccl_unique_id(void *id_out)
   return VH_OK;
 }
 
+// Fused ghost push (GMRES): map every neighbour's zbuf through CUDA IPC and learn, for each of our send nodes, the ghost
+// slot it occupies in that neighbour's numbering (the neighbour's recv list, exchanged once with ncclSend/ncclRecv).
+static int setup_ghost_push(vh_ctx *ctx, nccl_comm comm)
+{
+  const char *e = getenv("VH_HALO_PUSH");
+  const int   n_ranks = ctx->n_ranks, rank = ctx->rank, np = (int)ctx->peer_rank.size();
+  int         ok = !(e && e[0] == '0') && np > 0 && np <= VH_P2P_MAX_RANKS && ctx->n_owned > 0;
+  // IPC handles of zbuf, all-gathered
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok && cudaIpcGetMemHandle(&mine, ctx->zbuf) != cudaSuccess)
+    {
+      cudaGetLastError();
+      ok = 0;
+    }
+  const size_t      rec = sizeof(cudaIpcMemHandle_t) + 8;
+  char             *d_all = nullptr;
+  std::vector<char> h_all(rec * n_ranks, 0);
+  VH_CUDA(cudaMalloc((void **)&d_all, rec * n_ranks));
+  std::memcpy(&h_all[rec * rank], &mine, sizeof(mine));
+  h_all[rec * rank + sizeof(mine)] = (char)ok;
+  VH_CUDA(cudaMemcpy(d_all + rec * rank, &h_all[rec * rank], rec, cudaMemcpyHostToDevice));
+  VH_NCCL(api().AllGather(d_all + rec * rank, d_all, rec, /*ncclChar*/ 0, comm, ctx->stream));
+  VH_CUDA(cudaStreamSynchronize(ctx->stream));
+  VH_CUDA(cudaMemcpy(h_all.data(), d_all, rec * n_ranks, cudaMemcpyDeviceToHost));
+  cudaFree(d_all);
+  for (int r = 0; r < n_ranks; ++r)
+    ok = ok && h_all[rec * r + sizeof(mine)];
+  // every rank now has the same `ok` (all flags were gathered); the exchanges below are collective only if ok
+  if (!ok)
+    return VH_OK;
+  int opened = 1;
+  for (int p = 0; p < np && opened; ++p)
+    {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, &h_all[rec * ctx->peer_rank[p]], sizeof(h));
+      if (cudaIpcOpenMemHandle(&ctx->zpush_open[p], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        {
+          cudaGetLastError();
+          ctx->zpush_open[p] = nullptr;
+          opened             = 0;
+        }
+    }
+  // destination slots: the neighbour's recv list for us, in the order of our send list
+  int32_t *d_dst = nullptr;
+  VH_CUDA(cudaMalloc((void **)&d_dst, sizeof(int32_t) * (size_t)std::max<int64_t>(ctx->n_send, 1)));
+  VH_NCCL(api().GroupStart());
+  for (int p = 0; p < np; ++p)
+    {
+      const size_t cs = (size_t)(ctx->send_ptr[p + 1] - ctx->send_ptr[p]), cr = (size_t)(ctx->recv_ptr[p + 1] - ctx->recv_ptr[p]);
+      if (cr)
+        VH_NCCL(api().Send(ctx->recv_nodes + ctx->recv_ptr[p], cr, /*ncclInt32*/ 2, ctx->peer_rank[p], comm, ctx->stream));
+      if (cs)
+        VH_NCCL(api().Recv(d_dst + ctx->send_ptr[p], cs, /*ncclInt32*/ 2, ctx->peer_rank[p], comm, ctx->stream));
+    }
+  VH_NCCL(api().GroupEnd());
+  VH_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<int32_t> h_dst((size_t)ctx->n_send);
+  if (ctx->n_send)
+    VH_CUDA(cudaMemcpy(h_dst.data(), d_dst, sizeof(int32_t) * (size_t)ctx->n_send, cudaMemcpyDeviceToHost));
+  cudaFree(d_dst);
+  // agree on success of the mappings
+  double *d_flag = nullptr, h_flag = opened ? 1.0 : 0.0;
+  VH_CUDA(cudaMalloc((void **)&d_flag, sizeof(double)));
+  VH_CUDA(cudaMemcpy(d_flag, &h_flag, sizeof(double), cudaMemcpyHostToDevice));
+  VH_NCCL(api().AllReduce(d_flag, d_flag, 1, NCCL_FLOAT64, /*ncclMin*/ 3, comm, ctx->stream));
+  VH_CUDA(cudaStreamSynchronize(ctx->stream));
+  VH_CUDA(cudaMemcpy(&h_flag, d_flag, sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(d_flag);
+  if (h_flag != 1.0)
+    return VH_OK;
+  // CSR over the owned nodes: (peer slot, destination ghost node)
+  std::vector<int32_t> pptr(ctx->n_owned + 1, 0), pdst((size_t)ctx->n_send);
+  std::vector<int8_t>  ppeer((size_t)ctx->n_send);
+  for (int64_t i = 0; i < ctx->n_send; ++i)
+    pptr[ctx->h_send_nodes[i] + 1]++;
+  for (int i = 0; i < ctx->n_owned; ++i)
+    pptr[i + 1] += pptr[i];
+  std::vector<int32_t> fill(pptr.begin(), pptr.end() - 1);
+  for (int p = 0; p < np; ++p)
+    for (int i = ctx->send_ptr[p]; i < ctx->send_ptr[p + 1]; ++i)
+      {
+        const int k = fill[ctx->h_send_nodes[i]]++;
+        pdst[k]     = h_dst[i];
+        ppeer[k]    = (int8_t)p;
+      }
+  VH_TRY(vh_dev_upload(ctx, &ctx->push_ptr, pptr.data(), pptr.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->push_dst, pdst.data(), pdst.size()));
+  VH_TRY(vh_dev_upload(ctx, &ctx->push_peer, ppeer.data(), ppeer.size()));
+  VH_CUDA(cudaMalloc((void **)&ctx->push_ticket, sizeof(unsigned int)));
+  VH_CUDA(cudaMemset(ctx->push_ticket, 0, sizeof(unsigned int)));
+  VhPush &H = ctx->zpush_dev;
+  H         = VhPush();
+  for (int p = 0; p < np; ++p)
+    {
+      const int r  = ctx->peer_rank[p];
+      H.zpeer[p]    = static_cast<double *>(ctx->zpush_open[p]);
+      H.flag_dst[p] = ctx->p2p_dev.peer[r] + VH_P2P_SLOTS * n_ranks + rank; // my cell in the neighbour's mailbox
+      H.flag_src[p] = ctx->p2p_dev.peer[rank] + VH_P2P_SLOTS * n_ranks + r; // the neighbour's cell in mine
+    }
+  H.push_ptr  = ctx->push_ptr;
+  H.push_dst  = ctx->push_dst;
+  H.push_peer = ctx->push_peer;
+  H.ticket    = ctx->push_ticket;
+  H.n_peers   = np;
+  H.err       = ctx->p2p_err;
+  ctx->zpush_seq = 0;
+  ctx->zpush     = true;
+  return VH_OK;
+}
+
 extern "C" int vh_comm_init(vh_ctx *ctx, int rank, int n_ranks, const void *unique_id)
 {
   if (!ctx || n_ranks < 1 || rank < 0 || rank >= n_ranks)
@@ -223,6 +334,7 @@ extern "C" int vh_comm_init(vh_ctx *ctx, int rank, int n_ranks, const void *uniq
           ctx->p2p_dev.err = ctx->p2p_err;
           for (int r = 0; r < n_ranks; ++r)
             ctx->p2p_dev.peer[r] = static_cast<VhP2PCell *>(r == rank ? ctx->p2p_mbox : ctx->p2p_open[r]);
+          VH_TRY(setup_ghost_push(ctx, comm));
         }
     }
   return VH_OK;
@@ -239,7 +351,7 @@ int vh_p2p_alloc_local(vh_ctx *ctx, int n_ranks)
       cudaFree(ctx->p2p_mbox);
       ctx->p2p_mbox = nullptr;
     }
-  const size_t bytes = sizeof(VhP2PCell) * VH_P2P_SLOTS * n_ranks;
+  const size_t bytes = sizeof(VhP2PCell) * (VH_P2P_SLOTS + 1) * n_ranks; // all-reduce slots, then one ghost-push flag per sender
   VH_CUDA(cudaMalloc(&ctx->p2p_mbox, bytes));
   VH_CUDA(cudaMemset(ctx->p2p_mbox, 0, bytes));
   if (!ctx->p2p_err)
@@ -261,11 +373,24 @@ int vh_p2p_alloc_local(vh_ctx *ctx, int n_ranks)
 void vh_comm_destroy(vh_ctx *ctx)
 {
   if (ctx->p2p_mbox)
-    { // nobody may still be spinning on / writing to a mailbox that is about to go away
+    { // nobody may still be spinning on / writing to a mailbox (or pushing into a vector) that is about to go away:
+      // finish our own work, then meet the other ranks (vh_destroy is collective like every other call)
       cudaStreamSynchronize(ctx->stream);
+      if (ctx->p2p && ctx->n_ranks > 1)
+        {
+          k_p2p_allreduce<<<1, 32, 0, ctx->stream>>>(ctx->p2p_dev, ctx->p2p_seq + 1, ctx->scal + VH_SCAL_MISC, 1);
+          ctx->p2p_seq += 1;
+          cudaStreamSynchronize(ctx->stream);
+        }
       for (int r = 0; r < VH_P2P_MAX_RANKS; ++r)
-        if (ctx->p2p_open[r])
-          cudaIpcCloseMemHandle(ctx->p2p_open[r]);
+        {
+          if (ctx->p2p_open[r])
+            cudaIpcCloseMemHandle(ctx->p2p_open[r]);
+          if (ctx->zpush_open[r])
+            cudaIpcCloseMemHandle(ctx->zpush_open[r]);
+          ctx->p2p_open[r] = ctx->zpush_open[r] = nullptr;
+        }
+      ctx->zpush = false;
       cudaFree(ctx->p2p_mbox);
       cudaFree(ctx->p2p_err);
       cudaFree(ctx->mgs_tickets);

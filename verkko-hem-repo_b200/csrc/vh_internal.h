@@ -43,6 +43,18 @@ struct VhP2P
   int       *err;
 };
 
+struct VhPush
+{
+  double    *zpeer[VH_P2P_MAX_RANKS];   // [peer slot] neighbour's zbuf
+  VhP2PCell *flag_dst[VH_P2P_MAX_RANKS]; // [peer slot] my flag cell in the neighbour's mailbox
+  VhP2PCell *flag_src[VH_P2P_MAX_RANKS]; // [peer slot] the neighbour's flag cell in my mailbox
+  const int32_t *push_ptr, *push_dst;
+  const int8_t  *push_peer;
+  unsigned int  *ticket;
+  int            n_peers;
+  int           *err;
+};
+
 struct VhCoef
 {
   double K1, K23, alpha, beta[5], bt;
@@ -167,6 +179,16 @@ struct vh_ctx
   int32_t             *send_nodes = nullptr, *recv_nodes = nullptr; // device lists
   double              *send_buf = nullptr, *recv_buf = nullptr;
   int64_t              n_send = 0, n_recv = 0;
+  std::vector<int32_t> h_send_nodes, h_recv_nodes;
+  // fused ghost push of the GMRES preconditioner kernel: z = M^-1 v of an interface node goes straight into the ghost slots of
+  // the neighbours' zbuf over NVLink (peer memory through CUDA IPC), completion flags in the mailboxes; see vh_halo.cu
+  bool      zpush = false;
+  VhPush    zpush_dev;                         // by-value kernel argument
+  void     *zpush_open[VH_P2P_MAX_RANKS] = {}; // peers' zbuf mapped with cudaIpcOpenMemHandle (indexed by peer slot)
+  int32_t  *push_ptr = nullptr, *push_dst = nullptr; // CSR over owned nodes: destination ghost node index in the peer ...
+  int8_t   *push_peer = nullptr;                      // ... and the peer slot
+  unsigned int *push_ticket = nullptr;
+  unsigned long long zpush_seq = 0;
 
   // state flags
   bool have_matrix = false, have_update = false, have_trial = false;
@@ -234,7 +256,9 @@ int vhk_upload_linalg_constants(vh_ctx *ctx);
 int vhk_expand_packed(vh_ctx *ctx, double *full_vals);
 int vhk_block_jacobi_setup(vh_ctx *ctx);
 int vhk_block_jacobi_apply(vh_ctx *ctx, const double *x_owned, double *y_owned);
-int vhk_block_jacobi_apply_scaled(vh_ctx *ctx, const double *x_owned, const double *nsq_dev, double *v_out, double *y_owned);
+// push = true (only with ctx->zpush and y_owned == ctx->zbuf): also store the interface values into the neighbours' ghost slots
+int vhk_block_jacobi_apply_scaled(vh_ctx *ctx, const double *x_owned, const double *nsq_dev, double *v_out, double *y_owned,
+                                  bool push = false);
 int vhk_mgs_fused(vh_ctx *ctx, double *w, const double *V, int64_t ld, int j, double *hcol_dev, bool *used);
 // out_scalar[0] = sum_i a[i]*b[i] over owned DoFs (all-reduced over ranks); stream-ordered, result on device
 int vhk_dot(vh_ctx *ctx, const double *a, const double *b, double *out_scalar);
@@ -250,6 +274,7 @@ int vh_read_scalars(vh_ctx *ctx, const double *dev, int n, double *host);       
 // ---- halo (vh_halo.cu) ----
 int vhk_halo_exchange(vh_ctx *ctx, double *x_local);
 int vhk_allreduce_sum(vh_ctx *ctx, double *dev, int n);
+int vhk_halo_wait(vh_ctx *ctx); // after a pushing vhk_block_jacobi_apply_scaled: wait for the neighbours' pushes
 int vhk_mgs_mode_local(vh_ctx *ctx);
 
 void vh_comm_destroy(vh_ctx *ctx);

@@ -391,13 +391,22 @@ __global__ void __launch_bounds__(256)
 // v = x / sqrt(*nsq) (written out: it is the next Krylov basis vector) and y = blockdiag(minv) v, in one pass
 __global__ void __launch_bounds__(256)
   k_block_apply_scaled(int n_rows, const double *__restrict__ minv, const double *__restrict__ x, const double *__restrict__ nsq,
-                       double *__restrict__ v_out, double *__restrict__ y)
+                       double *__restrict__ v_out, double *__restrict__ y, VhPush H, unsigned long long push_seq)
 {
+  // H.n_peers > 0: fused ghost push.  The 18 values of an interface node are also stored into the ghost slot of every
+  // neighbour's vector over NVLink; the last block to finish (ticket) posts this rank's completion flag to the neighbours.
   __shared__ double s_part[8][6 * 32];
+  __shared__ int    s_pushed;
+  if (H.n_peers > 0)
+    {
+      if (threadIdx.x == 0)
+        s_pushed = 0;
+      __syncthreads();
+    }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int row  = blockIdx.x * 8 + wid;
-  if (row >= n_rows)
-    return;
+  if (row < n_rows)
+  {
   const double   nrm = sqrt(*nsq);
   const double   inv = nrm != 0.0 ? 1.0 / nrm : 0.0;
   const double2 *B   = reinterpret_cast<const double2 *>(minv + (size_t)row * VH_BLK);
@@ -430,7 +439,46 @@ __global__ void __launch_bounds__(256)
       for (int k = 0; k < 9; ++k)
         s += s_part[wid][9 * lane + k];
       y[(size_t)row * 18 + lane] = s;
+      if (H.n_peers > 0)
+        for (int e = H.push_ptr[row]; e < H.push_ptr[row + 1]; ++e)
+          {
+            H.zpeer[H.push_peer[e]][18 * (size_t)H.push_dst[e] + lane] = s;
+            s_pushed = 1;
+          }
     }
+  }
+  if (H.n_peers > 0)
+    {
+      __syncthreads();
+      if (threadIdx.x < 32)
+        {
+          bool last = false;
+          if (threadIdx.x == 0)
+            {
+              if (s_pushed)
+                __threadfence_system(); // the remote stores of this block before the ticket
+              else
+                __threadfence();
+              last = atomicAdd(H.ticket, 1u) == gridDim.x - 1;
+            }
+          last = __shfl_sync(0xffffffffu, (int)last, 0);
+          if (last)
+            {
+              __threadfence_system();
+              if (lane < H.n_peers)
+                vh_p2p_post(H.flag_dst[lane], push_seq, 0.0);
+              if (lane == 0)
+                *H.ticket = 0u;
+            }
+        }
+    }
+}
+
+// waits until every neighbour has posted its completion flag for push number `seq`
+__global__ void k_halo_wait(VhPush H, unsigned long long seq)
+{
+  if ((int)threadIdx.x < H.n_peers)
+    (void)vh_p2p_wait(H.flag_src[threadIdx.x], seq, H.err);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -920,11 +968,24 @@ int vhk_block_jacobi_apply(vh_ctx *ctx, const double *x_owned, double *y_owned)
   return VH_OK;
 }
 
-int vhk_block_jacobi_apply_scaled(vh_ctx *ctx, const double *x_owned, const double *nsq_dev, double *v_out, double *y_owned)
+int vhk_halo_wait(vh_ctx *ctx)
+{
+  k_halo_wait<<<1, 32, 0, ctx->stream>>>(ctx->zpush_dev, ctx->zpush_seq);
+  VH_LAUNCH_CHECK();
+  return VH_OK;
+}
+
+int vhk_block_jacobi_apply_scaled(vh_ctx *ctx, const double *x_owned, const double *nsq_dev, double *v_out, double *y_owned, bool push)
 {
   if (ctx->n_owned == 0)
     return VH_OK;
-  k_block_apply_scaled<<<(ctx->n_owned + 7) / 8, 256, 0, ctx->stream>>>(ctx->n_owned, ctx->minv, x_owned, nsq_dev, v_out, y_owned);
+  VhPush H = ctx->zpush_dev;
+  if (!push)
+    H.n_peers = 0;
+  else
+    ++ctx->zpush_seq;
+  k_block_apply_scaled<<<(ctx->n_owned + 7) / 8, 256, 0, ctx->stream>>>(ctx->n_owned, ctx->minv, x_owned, nsq_dev, v_out, y_owned, H,
+                                                                        ctx->zpush_seq);
   VH_LAUNCH_CHECK();
   return VH_OK;
 }
