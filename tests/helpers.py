@@ -9,6 +9,20 @@ MATEP_SCC_OFF = dict(alpha=-0.5, beta=(-0.010656959214250182, 0.0213139184285003
                                        0.021313918428500365, -0.021313918428500365), gapB=3.7517075313463422)
 
 
+def gpu_count():
+    """Visible CUDA devices, without importing torch (its first import on a fresh box takes about a minute)."""
+    import os
+    import subprocess
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis is not None:
+        return len([v for v in vis.split(",") if v.strip()])
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=60).stdout
+        return sum(1 for line in out.splitlines() if line.startswith("GPU "))
+    except Exception:
+        return 0
+
+
 def coef_vector(mat=MATEP_SCC_ON, bt=2.0):
     """[K1,K2,K3,alpha,beta1..5,bt] — K1=K2=K3=0.42072 (femgl.h:320-322)."""
     return np.array([K123, K123, K123, mat["alpha"], *mat["beta"], bt], dtype=np.float64)

@@ -36,7 +36,14 @@ def main():
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     coef = coef_vector(bt=2.0)
-    mesh = vh.unit_cube(1, 3, half=2.0, n_ranks=world)
+    periodic = len(sys.argv) > 1 and sys.argv[1] == "periodic"  # the reference's active grid: x/y-periodic slab
+
+    def make(n_ranks):
+        if periodic:
+            return vh.periodic_slab(1, 3, half=(2.0, 2.0, 1.0), n_ranks=n_ranks)
+        return vh.unit_cube(1, 3, half=2.0, n_ranks=n_ranks)
+
+    mesh = make(world)
     T = mesh.tables(rank)
     ctx = vh.Context(T, device=lr)
     uid = [vh.Context.nccl_unique_id() if rank == 0 else None]
@@ -51,7 +58,7 @@ def main():
     dist.all_gather_object(gathered, (T.node_xyz[:T.n_owned_nodes].copy(), sol))
     ok = True
     if rank == 0:
-        T1 = vh.unit_cube(1, 3, half=2.0).tables(0)
+        T1 = make(1).tables(0)
         c1 = vh.Context(T1, device=lr)
         c1.set_coef_vector(coef)
         c1.set_solution(b_phase_state(T1, seed=9))

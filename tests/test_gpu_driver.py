@@ -9,7 +9,7 @@ import pytest
 
 import femgl_oracle as O
 import verkko_hem_repo_b200 as vh
-from helpers import MATEP_SCC_ON, b_phase_state, coef_vector
+from helpers import MATEP_SCC_ON, b_phase_state, coef_vector, gpu_count
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -124,8 +124,7 @@ def test_c2_size_properties():
 
 
 def test_two_gpu_run_equals_one_gpu_run():
-    import torch
-    if torch.cuda.device_count() < 2:
+    if gpu_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "multigpu_worker.py")]

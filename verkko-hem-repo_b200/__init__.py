@@ -177,9 +177,9 @@ class Mesh:
         if host_lib().vhh_mesh_finalize(self._h, n_ranks) != 0:
             raise RuntimeError(host_lib().vhh_last_error().decode())
         self.n_ranks = n_ranks
-        sz = (ctypes.c_int64 * 4)()
+        sz = (ctypes.c_int64 * 5)()
         host_lib().vhh_mesh_global_sizes(self._h, sz)
-        self.n_nodes, _, self.n_constraint_lines, self.n_hanging_nodes = (int(v) for v in sz)
+        self.n_nodes, _, self.n_constraint_lines, self.n_hanging_nodes, self.n_periodic_nodes = (int(v) for v in sz)
         rb = (ctypes.c_int64 * (n_ranks + 1))()
         host_lib().vhh_mesh_rank_node_begin(self._h, rb)
         self.rank_node_begin = np.array(list(rb), dtype=np.int64)
@@ -223,6 +223,13 @@ def matep(p, t, scc):
     host_lib().vhh_matep(float(p), float(t), int(bool(scc)), out.ctypes.data_as(_dp))
     keys = ["alpha", "beta1", "beta2", "beta3", "beta4", "beta5", "gapA", "gapB", "fA", "fB", "Tcp_mK", "tAB_RWS"]
     return dict(zip(keys, out.tolist()))
+
+
+def periodic_slab(degree, refine, half=(0.5, 0.5, 0.5), base=(1, 1, 1), n_ranks=1):
+    """The reference's ACTIVE grid (femgl/CMakeLists.txt:51): hyper_rectangle(-half, half), x faces ids 5/6 and y faces 7/8
+    periodic, z faces AdGR walls (id 4), refine_global(refine) (makegrid_retangle-z-AdGR_xy-periodic.cc:167-236)."""
+    half = np.asarray(half, dtype=np.float64)
+    return Mesh(degree, -half, half, base, (5, 6, 7, 8, 4, 4), refine).finalize(n_ranks)
 
 
 def parse_prm(text=""):

@@ -140,11 +140,13 @@ extern "C" int vh_nccl_unique_id(void *id_out)
 
 // Fused ghost push (GMRES): map every neighbour's zbuf through CUDA IPC and learn, for each of our send nodes, the ghost
 // slot it occupies in that neighbour's numbering (the neighbour's recv list, exchanged once with ncclSend/ncclRecv).
+// Opt-in (VH_HALO_PUSH=1): the round's GPU budget ran out before this path could be re-measured on 2/8 GPUs, so the
+// measured NCCL ghost refresh stays the default.
 static int setup_ghost_push(vh_ctx *ctx, nccl_comm comm)
 {
   const char *e = getenv("VH_HALO_PUSH");
   const int   n_ranks = ctx->n_ranks, rank = ctx->rank, np = (int)ctx->peer_rank.size();
-  int         ok = !(e && e[0] == '0') && np > 0 && np <= VH_P2P_MAX_RANKS && ctx->n_owned > 0;
+  int         ok = (e && e[0] == '1') && np > 0 && np <= VH_P2P_MAX_RANKS && ctx->n_owned > 0;
   // IPC handles of zbuf, all-gathered
   cudaIpcMemHandle_t mine;
   std::memset(&mine, 0, sizeof(mine));

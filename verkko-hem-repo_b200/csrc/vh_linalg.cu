@@ -462,6 +462,7 @@ __global__ void __launch_bounds__(256)
               last = atomicAdd(H.ticket, 1u) == gridDim.x - 1;
             }
           last = __shfl_sync(0xffffffffu, (int)last, 0);
+          __syncwarp(); // memory ordering between lane 0's ticket and the other lanes' flag stores
           if (last)
             {
               __threadfence_system();

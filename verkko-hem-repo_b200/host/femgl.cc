@@ -84,8 +84,8 @@ FemGL<dim>::~FemGL()
 }
 
 // The reference selects geometry and initial condition at compile time by (un)commenting one makegrid_*.cc and one
-// setup_*.cc in femgl/CMakeLists.txt:42-64.  Here the two box geometries and two initial conditions the BASELINE
-// configs use are selected by the additive key "geometry" (cube | retangle).
+// setup_*.cc in femgl/CMakeLists.txt:42-64.  Here the box geometries and the two initial conditions the BASELINE
+// configs use are selected by the additive key "geometry" (cube | retangle | retangle-xy-periodic).
 template <int dim>
 void FemGL<dim>::make_grid()
 {
@@ -98,17 +98,21 @@ void FemGL<dim>::make_grid()
   conf.leave_subsection();
   // boundary ids: x and y faces natural (1), z faces AdGR walls with normal z (4)
   const int face_bid[6] = {1, 1, 1, 1, 4, 4};
-  const int base[3]     = {1, 1, 1};
-  if (geom == "retangle")
+  // the reference's active grid: x faces 5/6 and y faces 7/8 are periodic pairs (makegrid_retangle-z-AdGR_xy-periodic.cc:167-219)
+  const int face_bid_periodic[6] = {5, 6, 7, 8, 4, 4};
+  const int base[3]              = {1, 1, 1};
+  if (geom == "retangle" || geom == "retangle-xy-periodic")
     { // GridGenerator::hyper_rectangle(-h, +h), makegrid_retangle-z-AdGR-xy-HomoNeumann.cc:159-192
       const double lo[3] = {-hx, -hy, -hz}, hi[3] = {hx, hy, hz};
-      triangulation.reset(new Mesh((int)degree, lo, hi, base, face_bid, number_global_refine));
+      triangulation.reset(new Mesh((int)degree, lo, hi, base, geom == "retangle" ? face_bid : face_bid_periodic, number_global_refine));
     }
-  else
+  else if (geom == "cube")
     { // GridGenerator::hyper_cube(-half, +half), makegrid_cube-z-normal_AdGR.cc:151-160
       const double lo[3] = {-half_length, -half_length, -half_length}, hi[3] = {half_length, half_length, half_length};
       triangulation.reset(new Mesh((int)degree, lo, hi, base, face_bid, number_global_refine));
     }
+  else
+    throw std::runtime_error("FemGL::make_grid: unknown geometry \"" + geom + "\" (cube | retangle | retangle-xy-periodic)");
 }
 
 template <int dim>

@@ -65,7 +65,7 @@ int vhh_mesh_finalize(void *m, int n_ranks)
       return -1;
     }
 }
-// out: n_nodes, n_cells, n_constraint_lines, n_hanging_nodes
+// out[5]: n_nodes, n_cells, n_constraint_lines, n_hanging_nodes, n_periodic_nodes
 void vhh_mesh_global_sizes(void *m, int64_t *out)
 {
   Mesh *M = static_cast<Mesh *>(m);
@@ -73,6 +73,7 @@ void vhh_mesh_global_sizes(void *m, int64_t *out)
   out[1]  = M->n_cells();
   out[2]  = (int64_t)M->c_dof.size();
   out[3]  = M->n_hanging_nodes;
+  out[4]  = M->n_periodic_nodes;
 }
 void vhh_mesh_rank_node_begin(void *m, int64_t *out)
 {

@@ -365,7 +365,49 @@ void Mesh::finalize(int n_ranks_)
             }
     }
   n_hanging_nodes = (int64_t)hang.size();
-  // resolve chains among hanging nodes (a master that is itself hanging)
+  // ---- periodic pairs (makegrid_retangle-z-AdGR_xy-periodic.cc:167-219, setup_weak-coupling-PDW-configuration.cc:128-206):
+  // boundary ids (5,6) / (7,8) / (9,10) on the lower/upper x / y / z face declare that direction periodic.
+  // DoFTools::make_periodicity_constraints(b_id1 = lower, b_id2 = upper) makes every DoF of the upper face an identity-
+  // constrained DoF of its image on the lower face, all 18 components alike [deal.II-internal: which of the two faces
+  // keeps its DoFs is restated from the deal.II 9.3 documentation; it changes the numbering, not the discrete problem].
+  // DoFs that are constrained already (hanging nodes) are left alone, as in deal.II; chains (corner/edge nodes periodic in
+  // two directions, hanging-node masters on the upper face) are resolved by the closing loop below.
+  n_periodic_nodes = 0;
+  for (int d = 0; d < 3; ++d)
+    {
+      if (!(bid[2 * d] == 5 + 2 * d && bid[2 * d + 1] == 6 + 2 * d))
+        {
+          if ((bid[2 * d] >= 5 && bid[2 * d] <= 10) || (bid[2 * d + 1] >= 5 && bid[2 * d + 1] <= 10))
+            throw std::invalid_argument("Mesh: periodic boundary ids must come as the pairs (5,6) on x, (7,8) on y, (9,10) on z");
+          continue;
+        }
+      int min_level = Lmax;
+      for (const Leaf &l : leaves)
+        min_level = std::min(min_level, l.level);
+      if (((int64_t)base[d] << min_level) < 2)
+        throw std::invalid_argument("Mesh: a periodic direction needs at least two cells across");
+      int64_t n_lower = 0, n_upper = 0;
+      for (int64_t nd = 0; nd < n_nodes; ++nd)
+        {
+          n_lower += nX[(size_t)nd * 3 + d] == 0;
+          n_upper += nX[(size_t)nd * 3 + d] == D[d] - 1;
+        }
+      if (n_lower != n_upper)
+        throw std::runtime_error("Mesh: periodic faces are refined differently (non-matching periodic faces are not supported)");
+      for (int64_t nd = 0; nd < n_nodes; ++nd)
+        {
+          if (nX[(size_t)nd * 3 + d] != D[d] - 1 || hang.count(nd))
+            continue;
+          int64_t X[3] = {nX[(size_t)nd * 3], nX[(size_t)nd * 3 + 1], nX[(size_t)nd * 3 + 2]};
+          X[d]         = 0;
+          auto it      = node_of.find(keyof(X));
+          if (it == node_of.end())
+            throw std::runtime_error("Mesh: periodic faces are refined differently (non-matching periodic faces are not supported)");
+          hang[nd] = {{it->second, 1.0}};
+          ++n_periodic_nodes;
+        }
+    }
+  // resolve chains among constrained nodes (a master that is itself hanging or periodic)
   for (int guard = 0; guard < 8; ++guard)
     {
       bool again = false;

@@ -6,6 +6,8 @@
 //   GridGenerator::hyper_cube / hyper_rectangle + refine_global   (makegrid_cube-z-normal_AdGR.cc:151-160,
 //                                                                  makegrid_retangle-z-AdGR-xy-HomoNeumann.cc:159-192)
 //   boundary ids 1 (natural) and 2|3|4 (AdGR walls with normal x|y|z) (makegrid_cube-z-normal_AdGR.cc:164-195)
+//   boundary id pairs (5,6)|(7,8)|(9,10): periodic in x|y|z (makegrid_retangle-z-AdGR_xy-periodic.cc:167-219,
+//                                         setup_weak-coupling-PDW-configuration.cc:128-206; the reference's active variant)
 //   FESystem(FE_Q(p),18) DoF layout, hanging-node + component-masked Dirichlet constraints
 //                                                                 (setup_uniform_B-phase.cc:135-186, femgl.h:294-301)
 //   p4est-style partition: contiguous ranges of the Morton (z-order) cell sequence, DoFs on a
@@ -85,6 +87,7 @@ public:
   std::vector<int64_t> c_dof, c_ptr, c_master;
   std::vector<double>  c_weight;
   int64_t              n_hanging_nodes = 0;
+  int64_t              n_periodic_nodes = 0; // nodes of an upper periodic face identified with their image on the lower face
   std::vector<int64_t> node_lattice;        // [n_nodes][3] integer lattice coordinates, root cell side = lattice_U units
   int64_t              lattice_U = 0;
 
