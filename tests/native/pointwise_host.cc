@@ -65,3 +65,24 @@ extern "C" void vht_points_q1(const double *A, const double *coef, double *g18, 
   *f = vh_bulk_energy_u(p, coef[3], coef + 4);
 }
 extern "C" int vht_hq8_index(int q, int e) { return vh_hq8_index(q, e); }
+// the packed symmetric mat-vec of the matrix-free operator apply (k_apply_cells), on a block stored in the Q1 cell layout
+// (hq: one cell's 1440 doubles, vh_hq8_index) or in the plain packed layout (q < 0: hq is 180 doubles)
+extern "C" void vht_sym_matvec(const double *hq, int q, const double *z, double *t)
+{
+  for (int c = 0; c < 18; ++c)
+    t[c] = 0.0;
+  vh_sym_matvec(
+    [&](int p, double &v0, double &v1) {
+      if (q < 0)
+        {
+          v0 = hq[2 * p];
+          v1 = hq[2 * p + 1];
+        }
+      else
+        {
+          v0 = hq[((p << 3) + (q ^ (p & 7))) * 2];
+          v1 = hq[((p << 3) + (q ^ (p & 7))) * 2 + 1];
+        }
+    },
+    z, t);
+}

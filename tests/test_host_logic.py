@@ -244,3 +244,33 @@ def test_hq8_layout_is_a_bijection():
     assert seen == set(range(1440))
     for p in range(90):  # the eight quadrature points of one pair share one 128-byte line
         assert {L.vht_hq8_index(q, 2 * p) // 16 for q in range(8)} == {p}
+
+
+def test_packed_symmetric_matvec_of_the_matrix_free_apply():
+    """vh_sym_matvec (the H_q z product of k_apply_cells) on both storage layouts of the packed H_q tables equals the dense
+    symmetric product; the zero dummies of the odd rows never contribute."""
+    L = _native_pointwise_lib()
+    P = ctypes.POINTER(ctypes.c_double)
+    L.vht_sym_matvec.argtypes = [P, ctypes.c_int, P, P]
+    rng = np.random.default_rng(5)
+    H = rng.standard_normal((8, 18, 18))
+    H = H + H.transpose(0, 2, 1)
+    cell = np.full(1440, np.nan)
+    plain = np.full((8, 180), 7.5)  # dummies deliberately non-zero in the plain layout: they must be ignored
+    for q in range(8):
+        for c in range(18):
+            for d in range(c, 18):
+                e = L.vht_sym_index(c, d)
+                cell[L.vht_hq8_index(q, e)] = H[q, c, d]
+                plain[q, e] = H[q, c, d]
+        for c in range(1, 18, 2):
+            cell[L.vht_hq8_index(q, L.vht_sym_index(c, c) - 1)] = 7.5
+    assert not np.isnan(cell).any()
+    for q in range(8):
+        z = rng.standard_normal(18)
+        t = np.zeros(18)
+        L.vht_sym_matvec(cell.ctypes.data_as(P), q, z.ctypes.data_as(P), t.ctypes.data_as(P))
+        assert np.abs(t - H[q] @ z).max() <= 1e-13 * np.abs(H[q] @ z).max()
+        row = np.ascontiguousarray(plain[q])
+        L.vht_sym_matvec(row.ctypes.data_as(P), -1, z.ctypes.data_as(P), t.ctypes.data_as(P))
+        assert np.abs(t - H[q] @ z).max() <= 1e-13 * np.abs(H[q] @ z).max()

@@ -19,7 +19,7 @@ VH_ERR_NOT_CONVERGED = -4
 class _Info(ctypes.Structure):
     _fields_ = [("n_owned_dofs", ctypes.c_int64), ("n_local_dofs", ctypes.c_int64), ("nnzb", ctypes.c_int64),
                 ("n_fast_rows", ctypes.c_int64), ("n_slow_cells", ctypes.c_int64), ("device_bytes", ctypes.c_int64),
-                ("n_packed_blocks", ctypes.c_int64)]
+                ("n_packed_blocks", ctypes.c_int64), ("spmv_matrix_free", ctypes.c_int64)]
 
 
 _lib = None
@@ -61,6 +61,7 @@ def cuda_lib():
         L.vh_timer_start.argtypes = [_vp]
         L.vh_timer_stop.argtypes = [_vp, ctypes.POINTER(ctypes.c_float)]
         L.vh_measure_fp64_peak.argtypes = [_vp, _dp]
+        L.vh_set_spmv_matrix_free.argtypes = [_vp, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -209,6 +210,9 @@ class Context:
         ms = ctypes.c_float()
         self._chk(self.L.vh_timer_stop(self._h, ctypes.byref(ms)))
         return ms.value
+
+    def set_spmv_matrix_free(self, on=True):
+        self._chk(self.L.vh_set_spmv_matrix_free(self._h, int(bool(on))))
 
     def measure_fp64_peak(self):
         v = ctypes.c_double()

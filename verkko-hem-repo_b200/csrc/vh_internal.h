@@ -190,6 +190,10 @@ struct vh_ctx
   unsigned int *push_ticket = nullptr;
   unsigned long long zpush_seq = 0;
 
+  // operator apply of the lattice rows inside vhk_spmv: false = packed SpMV over the assembled blocks (default),
+  // true = matrix-free from the H_q tables (VH_SPMV_MF=1; opt-in until measured on hardware)
+  bool spmv_mf = false;
+
   // state flags
   bool have_matrix = false, have_update = false, have_trial = false;
 
@@ -254,6 +258,8 @@ int vhk_upload_q2(vh_ctx *ctx, const double *T2, const uint8_t *q2t);
 int vhk_spmv(vh_ctx *ctx, const double *x_local, double *y_owned, bool x_is_masked);
 int vhk_upload_linalg_constants(vh_ctx *ctx);
 int vhk_expand_packed(vh_ctx *ctx, double *full_vals);
+// matrix-free apply of the lattice rows from the stored H_q tables (ctx->spmv_mf, VH_SPMV_MF=1); see k_points<APPLY>
+int vhk_apply_fast(vh_ctx *ctx, const double *z_masked, const double *x_orig, double *y_owned);
 int vhk_block_jacobi_setup(vh_ctx *ctx);
 int vhk_block_jacobi_apply(vh_ctx *ctx, const double *x_owned, double *y_owned);
 // push = true (only with ctx->zpush and y_owned == ctx->zbuf): also store the interface values into the neighbours' ghost slots

@@ -905,6 +905,18 @@ int vhk_spmv(vh_ctx *ctx, const double *x_local, double *y_owned, bool x_is_mask
           VH_LAUNCH_CHECK();
           xg = ctx->xmask;
         }
+      if (ctx->spmv_mf)
+        { // matrix-free: K_cell z_cell from the H_q tables, gathered per lattice row; constrained rows below as usual
+          VH_TRY(vhk_apply_fast(ctx, xg, x_local, y_owned));
+          if (ctx->n_slow_rows > 0)
+            {
+              const unsigned gs = (ctx->n_slow_rows + VH_SPMV_WARPS - 1) / VH_SPMV_WARPS;
+              k_spmv_bsr18<<<gs, VH_SPMV_WARPS * 32, 0, ctx->stream>>>(ctx->n_slow_rows, ctx->slow_rows, ctx->row_ptr, ctx->col, ctx->vals,
+                                                                      x_local, y_owned);
+              VH_LAUNCH_CHECK();
+            }
+          return VH_OK;
+        }
       static int variant = -1;
       if (variant < 0)
         {

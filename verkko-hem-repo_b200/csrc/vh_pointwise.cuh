@@ -531,6 +531,37 @@ VH_HD int vh_sym_rowstart(int c)
 }
 // index of (c,d), c <= d
 VH_HD int vh_sym_index(int c, int d) { return vh_sym_rowstart(c) + d - 2 * (c >> 1); }
+// t += Sym(P) z for one packed block whose 90 16-byte pieces are fetched by ld(piece, v0, v1): piece p of row c holds
+// the entries (c,d), (c,d+1) with d = 2*(c/2) + 2k.  Fully unrolled: every index is a compile-time constant, so z and t
+// stay in registers (matrix-free operator apply, k_apply_cells).
+template <class LD>
+VH_HD void vh_sym_matvec(LD ld, const double *z, double *t)
+{
+#pragma unroll
+  for (int c = 0; c < 18; ++c)
+#pragma unroll
+    for (int d = 2 * (c >> 1); d < 18; d += 2)
+      {
+        double v0, v1;
+        ld(vh_sym_index(c, d) >> 1, v0, v1);
+        if (d > c)
+          { // off-diagonal entry (c,d): feeds rows c and d
+            t[c] += v0 * z[d];
+            t[d] += v0 * z[c];
+          }
+        else if (d == c)
+          t[c] += v0 * z[c];
+        // d == c - 1: the zero dummy of an odd row
+        if (d + 1 > c)
+          {
+            t[c] += v1 * z[d + 1];
+            t[d + 1] += v1 * z[c];
+          }
+        else
+          t[c] += v1 * z[c]; // d + 1 == c: the diagonal entry of an odd row
+      }
+}
+
 // fills c[e], d[e] for e in [0,180); dummies have d[e] = c[e] - 1 (i.e. d < c)
 inline void vh_sym_tables(unsigned char *tc, unsigned char *td)
 {
