@@ -256,6 +256,8 @@ def run_ours(args):
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
     ctx.set_coef_vector(coef_vector())
+    if args.spmv_mf:  # whole run with the matrix-free operator apply inside GMRES (opt-in this round)
+        ctx.set_spmv_matrix_free(True)
     x0 = initial_state(T)[:18 * T.n_owned_nodes]
     n_dofs = 18 * mesh.n_nodes
     info = ctx.info()
@@ -322,6 +324,7 @@ def run_ours(args):
     n_fast_blocks = info["n_packed_blocks"]
     packed = n_fast_blocks > 0
     spmv_moved = 8 * (180 * n_fast_blocks + 324 * (nnzb - n_fast_blocks)) + 4 * nnzb + 4 * (nb + 1) + 16 * 18 * nb
+    spmv_moved_packed = spmv_moved
     t_spmv = ctx.time_kernel(0, reps=20, flush_l2=True)
     t_asm = ctx.time_kernel(1, reps=5, flush_l2=True)
     t_pw = ctx.time_kernel(5, reps=5, flush_l2=True)
@@ -345,8 +348,13 @@ def run_ours(args):
             traffic = tj[key][kname]["read_bytes"] + tj[key][kname]["write_bytes"]
     except Exception:
         traffic = None
+    # matrix-free apply: the H_q tables (8*180*n_q bytes per cell) + the per-cell products written and gathered once
+    mf_moved = 8 * 180 * n * T.n_cells + 2 * 8 * 18 * n * T.n_cells + 8 * 324 * (nnzb - n_fast_blocks) + 16 * 18 * nb
+    if args.spmv_mf:
+        spmv_moved, traffic = mf_moved, None
     moved_gbs = spmv_moved / (t_spmv * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_spmv_sym18" if n_fast_blocks else "k_spmv_bsr18", "achieved": spmv_gbs, "peak": hbm_peak,
+    kernel_name = ("k_points<APPLY>+k_gather_apply" if args.spmv_mf else "k_spmv_sym18") if n_fast_blocks else "k_spmv_bsr18"
+    roof = {"bound": "hbm", "kernel": kernel_name, "achieved": spmv_gbs, "peak": hbm_peak,
             "unit": "GB/s", "frac": spmv_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src, "ms_per_launch": t_spmv,
             "algorithmic_bytes_per_launch": spmv_bytes, "moved_bytes_per_launch": spmv_moved, "moved_gbs": moved_gbs,
             "hbm_utilization": moved_gbs / hbm_peak,
@@ -361,6 +369,23 @@ def run_ours(args):
            # flops the row-owner kernels really execute: packed symmetric entries (180 of 324) and, at Q2, the
            # sum-factorised contraction (3 x 81 FMAs per entry and row node instead of 27 x 27)
            "executed_flops": 2.0 * 180 * T.n_cells * (8 * 64 if args.degree == 1 else 27 * 243)}
+
+    # the other operator-apply mode, kernel-only (the timed Newton steps above used the mode of this run)
+    other = None
+    if packed:
+        try:
+            ctx.set_spmv_matrix_free(not args.spmv_mf)
+            t_other = ctx.time_kernel(0, reps=20, flush_l2=True)
+            om = spmv_moved_packed if args.spmv_mf else mf_moved
+            other = {"mode": "packed-spmv" if args.spmv_mf else "matrix-free", "ms": t_other, "moved_bytes": om,
+                     "moved_gbs": om / (t_other * 1e-3) / 1e9, "hbm_utilization": om / (t_other * 1e-3) / 1e9 / hbm_peak}
+        except Exception as exc:  # never let the side measurement take the bench line down
+            other = {"error": str(exc)}
+        finally:
+            try:
+                ctx.set_spmv_matrix_free(args.spmv_mf)
+            except Exception:
+                pass
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -388,7 +413,8 @@ def run_ours(args):
                "newton_history": [{"gmres_its": h[0], "line_search_trials": h[1], "residual": h[2]} for h in hist],
                "phase_ms_per_step": {k: tm[k] / args.steps for k in ("assemble", "residual", "solve", "vector")},
                "roofline": roof, "assembly": asm,
-               "kernels": {"spmv_ms": t_spmv, "spmv_gbs": spmv_gbs, "residual_ms": t_res, "block_jacobi_apply_ms": t_bj},
+               "kernels": {"spmv_ms": t_spmv, "spmv_gbs": spmv_gbs, "residual_ms": t_res, "block_jacobi_apply_ms": t_bj,
+                           "operator_apply_mode": "matrix-free" if args.spmv_mf else "packed-spmv", "other_apply_mode": other},
                "e2e": {"value": e2e_val, "unit": "DoF/s", "h2d_bytes_per_step": int(8 * 18 * T.n_owned_nodes),
                        "d2h_bytes_per_step": int(8 * 18 * T.n_owned_nodes), "ms_per_step": ms_e2e / args.steps,
                        "wall_ms_per_step": wall_e2e / args.steps * 1e3},
@@ -413,6 +439,8 @@ def main():
     ap.add_argument("--refine", type=int, default=5)
     ap.add_argument("--degree", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spmv-mf", action="store_true",
+                    help="run GMRES with the matrix-free operator apply (vh_set_spmv_matrix_free) instead of the packed SpMV")
     ap.add_argument("--global-refine", type=int, default=None,
                     help="strong scaling: one cube with this many global refinements split over the GPUs (7 = BASELINE C5, 38.6M DoFs)")
     args = ap.parse_args()
