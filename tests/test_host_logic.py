@@ -274,3 +274,42 @@ def test_packed_symmetric_matvec_of_the_matrix_free_apply():
         row = np.ascontiguousarray(plain[q])
         L.vht_sym_matvec(row.ctypes.data_as(P), -1, z.ctypes.data_as(P), t.ctypes.data_as(P))
         assert np.abs(t - H[q] @ z).max() <= 1e-13 * np.abs(H[q] @ z).max()
+
+
+GRID_VARIANTS = {  # stem of /root/reference/femgl/src/makegrid_<stem>.cc -> (n DoFs at 2 global refinements, has periodic pairs)
+    "cube-z-normal_AdGR": (18 * 125, False), "cube-xyz-Homo-Neumann": (18 * 125, False), "cube-xyz-periodic": (18 * 125, True),
+    "cube-z-normal_AdGR-xy-periodic": (18 * 125, True), "retangle-z-AdGR-xy-HomoNeumann": (18 * 125, False),
+    "retangle-xyz-homogenous-Neumann": (18 * 125, False), "retangle-xyz-periodic": (18 * 125, True),
+    "retangle-z-AdGR_x-periodic-y-HomoNeumann": (18 * 125, True), "retangle-z-AdGR_xy-periodic": (18 * 125, True),
+    "xz-normal_AdGR": (18 * 125, False), "cube": (18 * 125, False), "retangle": (18 * 125, False),
+    "retangle-xy-periodic": (18 * 125, True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GRID_VARIANTS))
+def test_driver_mirror_selects_every_box_grid_variant(name):
+    """FemGL::make_grid() + setup_system() of the C++ driver mirror accept the stem of every box makegrid_*.cc variant that
+    femgl/CMakeLists.txt:42-53 lists: the run gets as far as printing the DoF count and then needs the GPU (vh_create) —
+    on this CPU-only container that is a loud error, never a fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by tests/test_gpu_driver.py and tests/test_gpu_periodic.py")
+    prm = """
+subsection control parameters
+  set geometry = %s
+  set Number of initial global refinments = 2
+  set Number of refinements = 0
+  set Number of interations = 0
+end
+""" % name
+    with pytest.raises(RuntimeError) as e:
+        vh.run_prm(prm)
+    msg = str(e.value)
+    assert "unknown geometry" not in msg and "vh_create" in msg, msg
+    assert "Number of degrees of freedom: %d" % GRID_VARIANTS[name][0] in msg, msg
+
+
+def test_driver_mirror_rejects_unknown_names():
+    with pytest.raises(RuntimeError) as e:
+        vh.run_prm("subsection control parameters\n  set geometry = cube_cylider_hole\nend\n")
+    assert "unknown geometry" in str(e.value) and "retangle-z-AdGR_xy-periodic" in str(e.value)

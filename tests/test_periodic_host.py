@@ -143,3 +143,38 @@ def test_periodic_partition_independence():
         assert np.abs(rhs - r1[dof_perm[:18 * T.n_owned_nodes]]).max() <= 1e-13 * np.abs(r1).max()
         n_owned += T.n_owned_nodes
     assert n_owned == T1.n_owned_nodes
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_hanging_node_partition_independence(degree):
+    """C4-shaped tables (locally refined slab, hanging nodes) split over 3 ranks: every rank's owned rows, assembled from its
+    owned + ghost-layer cells with the constraint lines it sees, equal the 1-rank rows — also for the rows of masters whose
+    hanging nodes live in another rank's cells."""
+    coef = coef_vector(bt=2.0)
+
+    def make(n_ranks):
+        m = vh.Mesh(degree, [-2, -2, -2], [2, 2, 2], n_global_refine=2 if degree == 1 else 1)
+        c = m.cell_centers()
+        m.refine((np.abs(c[:, 2]) < 1.1) & (c[:, 0] < 0.1))
+        return m.finalize(n_ranks)
+
+    m1 = make(1)
+    assert m1.n_hanging_nodes > 0
+    T1 = m1.tables(0)
+    mP = make(3)
+    key1 = {tuple(np.round(p, 9)): i for i, p in enumerate(T1.node_xyz)}
+    x1 = b_phase_state(T1, seed=5)
+    A1, r1 = O.assemble_global(T1, x1, coef, True)
+    A1 = A1.tocsr()
+    n_owned = 0
+    for r in range(3):
+        T = mP.tables(r)
+        perm = np.array([key1[tuple(np.round(p, 9))] for p in T.node_xyz])
+        x = x1.reshape(-1, 18)[perm].ravel()
+        A, rhs = O.assemble_global(T, x, coef, True)
+        dof_perm = (18 * perm[:, None] + np.arange(18)[None, :]).ravel()
+        want = A1[dof_perm[:18 * T.n_owned_nodes]][:, dof_perm]
+        assert abs(A - want).max() <= 1e-13 * abs(A1).max()
+        assert np.abs(rhs - r1[dof_perm[:18 * T.n_owned_nodes]]).max() <= 1e-13 * np.abs(r1).max()
+        n_owned += T.n_owned_nodes
+    assert n_owned == T1.n_owned_nodes

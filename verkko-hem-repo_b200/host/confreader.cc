@@ -60,8 +60,8 @@ void confreader::declare_parameters()
     prm.declare_entry("GMRES restart length", "30");      // SolverFGMRES default max_basis_size
     prm.declare_entry("polynomial degree", "1");          // main.cc:116 hard-codes FemGL<3>(1, prm)
     // the reference picks geometry / initial condition by (un)commenting sources in femgl/CMakeLists.txt:42-64
-    prm.declare_entry("geometry", "cube");                // cube: makegrid_cube-z-normal_AdGR.cc | retangle: makegrid_retangle-z-AdGR-xy-HomoNeumann.cc | retangle-xy-periodic: makegrid_retangle-z-AdGR_xy-periodic.cc
-    prm.declare_entry("initial condition", "B-phase");    // B-phase: setup_uniform_B-phase.cc | BnA: setup_uniform_BnA-flatwall-configuration.cc
+    prm.declare_entry("geometry", "cube");                // stem of a reference makegrid_<stem>.cc box variant (list: host/femgl.cc grid_variants); aliases cube, retangle, retangle-xy-periodic
+    prm.declare_entry("initial condition", "B-phase");    // B-phase: setup_uniform_B-phase.cc | A-phase: setup_uniform_A-phase.cc | BnA: setup_uniform_BnA-flatwall-configuration.cc
   }
   prm.leave_subsection();
 }

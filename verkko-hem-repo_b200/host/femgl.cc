@@ -84,8 +84,44 @@ FemGL<dim>::~FemGL()
 }
 
 // The reference selects geometry and initial condition at compile time by (un)commenting one makegrid_*.cc and one
-// setup_*.cc in femgl/CMakeLists.txt:42-64.  Here the box geometries and the two initial conditions the BASELINE
-// configs use are selected by the additive key "geometry" (cube | retangle | retangle-xy-periodic).
+// setup_*.cc in femgl/CMakeLists.txt:42-64.  Here the additive key "geometry" selects among the box variants that list
+// names, by the stem of the reference file (short aliases: cube, retangle, retangle-xy-periodic).
+namespace
+{
+struct GridVariant
+{
+  const char *name;
+  int         box;         // 0: hyper_cube(-half, half)   1: hyper_rectangle(-h, +h) from the .prm   2: hard-wired box of the file
+  int         face_bid[6]; // x0 x1 y0 y1 z0 z1; 1 natural, 2|3|4 AdGR wall with normal x|y|z, (5,6)|(7,8)|(9,10) periodic pairs
+  double      lo[3], hi[3];
+};
+const GridVariant grid_variants[] = {
+  // makegrid_cube-z-normal_AdGR.cc:157-195
+  {"cube", 0, {1, 1, 1, 1, 4, 4}, {}, {}},
+  {"cube-z-normal_AdGR", 0, {1, 1, 1, 1, 4, 4}, {}, {}},
+  // makegrid_cube-xyz-Homo-Neumann.cc:158-196
+  {"cube-xyz-Homo-Neumann", 0, {1, 1, 1, 1, 1, 1}, {}, {}},
+  // makegrid_cube-xyz-periodic.cc:159-226
+  {"cube-xyz-periodic", 0, {5, 6, 7, 8, 9, 10}, {}, {}},
+  // makegrid_cube-z-normal_AdGR-xy-periodic.cc:157-214
+  {"cube-z-normal_AdGR-xy-periodic", 0, {5, 6, 7, 8, 4, 4}, {}, {}},
+  // makegrid_retangle-z-AdGR-xy-HomoNeumann.cc:159-192
+  {"retangle", 1, {1, 1, 1, 1, 4, 4}, {}, {}},
+  {"retangle-z-AdGR-xy-HomoNeumann", 1, {1, 1, 1, 1, 4, 4}, {}, {}},
+  // makegrid_retangle-xyz-homogenous-Neumann.cc:163-200
+  {"retangle-xyz-homogenous-Neumann", 1, {1, 1, 1, 1, 1, 1}, {}, {}},
+  // makegrid_retangle-xyz-periodic.cc:164-230
+  {"retangle-xyz-periodic", 1, {5, 6, 7, 8, 9, 10}, {}, {}},
+  // makegrid_retangle-z-AdGR_x-periodic-y-HomoNeumann.cc:164-209
+  {"retangle-z-AdGR_x-periodic-y-HomoNeumann", 1, {5, 6, 1, 1, 4, 4}, {}, {}},
+  // makegrid_retangle-z-AdGR_xy-periodic.cc:164-219 (the variant femgl/CMakeLists.txt:51 compiles)
+  {"retangle-xy-periodic", 1, {5, 6, 7, 8, 4, 4}, {}, {}},
+  {"retangle-z-AdGR_xy-periodic", 1, {5, 6, 7, 8, 4, 4}, {}, {}},
+  // makegrid_xz-normal_AdGR.cc:156-197: box (-l,0,0)-(l,Ex,D) with l = 15, Ex = 8, D = 6; x and z faces are AdGR walls
+  {"xz-normal_AdGR", 2, {2, 2, 1, 1, 4, 4}, {-15.0, 0.0, 0.0}, {15.0, 8.0, 6.0}},
+};
+} // namespace
+
 template <int dim>
 void FemGL<dim>::make_grid()
 {
@@ -96,23 +132,24 @@ void FemGL<dim>::make_grid()
                hz        = conf.get_double("half z length of retangle");
   const std::string geom = conf.get("geometry");
   conf.leave_subsection();
-  // boundary ids: x and y faces natural (1), z faces AdGR walls with normal z (4)
-  const int face_bid[6] = {1, 1, 1, 1, 4, 4};
-  // the reference's active grid: x faces 5/6 and y faces 7/8 are periodic pairs (makegrid_retangle-z-AdGR_xy-periodic.cc:167-219)
-  const int face_bid_periodic[6] = {5, 6, 7, 8, 4, 4};
-  const int base[3]              = {1, 1, 1};
-  if (geom == "retangle" || geom == "retangle-xy-periodic")
-    { // GridGenerator::hyper_rectangle(-h, +h), makegrid_retangle-z-AdGR-xy-HomoNeumann.cc:159-192
-      const double lo[3] = {-hx, -hy, -hz}, hi[3] = {hx, hy, hz};
-      triangulation.reset(new Mesh((int)degree, lo, hi, base, geom == "retangle" ? face_bid : face_bid_periodic, number_global_refine));
-    }
-  else if (geom == "cube")
-    { // GridGenerator::hyper_cube(-half, +half), makegrid_cube-z-normal_AdGR.cc:151-160
-      const double lo[3] = {-half_length, -half_length, -half_length}, hi[3] = {half_length, half_length, half_length};
-      triangulation.reset(new Mesh((int)degree, lo, hi, base, face_bid, number_global_refine));
-    }
-  else
-    throw std::runtime_error("FemGL::make_grid: unknown geometry \"" + geom + "\" (cube | retangle | retangle-xy-periodic)");
+  const int base[3] = {1, 1, 1};
+  for (const GridVariant &v : grid_variants)
+    if (geom == v.name)
+      {
+        double lo[3], hi[3];
+        for (int d = 0; d < 3; ++d)
+          {
+            const double h = d == 0 ? hx : (d == 1 ? hy : hz);
+            lo[d]          = v.box == 0 ? -half_length : (v.box == 1 ? -h : v.lo[d]);
+            hi[d]          = v.box == 0 ? half_length : (v.box == 1 ? h : v.hi[d]);
+          }
+        triangulation.reset(new Mesh((int)degree, lo, hi, base, v.face_bid, number_global_refine));
+        return;
+      }
+  std::string known;
+  for (const GridVariant &v : grid_variants)
+    known += std::string(known.empty() ? "" : " | ") + v.name;
+  throw std::runtime_error("FemGL::make_grid: unknown geometry \"" + geom + "\" (" + known + ")");
 }
 
 template <int dim>
@@ -180,6 +217,17 @@ void FemGL<dim>::setup_system()
                 v[0] = v[10] = matelem_A;
             }
         }
+      else if (ic == "A-phase")
+        { // uniform A phase: u11 = v12 = gap_A * 0.707107f, setup_uniform_A-phase.cc:235-251
+          const double amp = mat.gap_A_td(p, reduced_t) * 0.707107f;
+          for (int n = 0; n < T.n_owned_nodes; ++n)
+            {
+              double *v = &host_solution[(size_t)18 * n];
+              v[0] = v[10] = amp;
+            }
+        }
+      else if (ic != "B-phase")
+        throw std::runtime_error("FemGL::setup_system: unknown initial condition \"" + ic + "\" (B-phase | A-phase | BnA)");
       else
         { // uniform B phase, setup_uniform_B-phase.cc:245-259
           const double amp = mat.gap_B_td(p, reduced_t) * 0.577350269f;
