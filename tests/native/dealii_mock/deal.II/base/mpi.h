@@ -1,0 +1,2 @@
+// mock: see tests/native/dealii_mock/dealii_mock.h
+#include "../../dealii_mock.h"
