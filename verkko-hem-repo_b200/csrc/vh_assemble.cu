@@ -1781,12 +1781,11 @@ int vhk_pointwise(vh_ctx *ctx, const double *x_local, bool want_h, bool want_e)
   VH_CUDA(cudaFuncSetAttribute(k_points<NN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VhPt<NN>::SMEM));      \
   VH_CUDA(cudaFuncSetAttribute(k_points<NN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VhPt<NN>::SMEM));    \
   VH_CUDA(cudaFuncSetAttribute(k_points<NN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VhPt<NN>::SMEM))
-  static bool attr_set = false;
-  if (!attr_set)
+  static unsigned long long attr_mask = 0;
+  if (vh_first_time_on_device(attr_mask, ctx->device))
     {
       VH_POINTS_ATTR(8);
       VH_POINTS_ATTR(27);
-      attr_set = true;
     }
   if (ctx->degree == 1)
     {
@@ -1804,13 +1803,10 @@ int vhk_pointwise(vh_ctx *ctx, const double *x_local, bool want_h, bool want_e)
   else
     {
       const size_t smem = pointwise_smem<27, 27>(want_h);
-      static bool  attr_set2 = false;
-      if (!attr_set2)
-        {
-          VH_CUDA(cudaFuncSetAttribute(k_pointwise<27, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)pointwise_smem<27, 27>(true)));
-          attr_set2 = true;
-        }
+      static unsigned long long attr_mask2 = 0;
+      if (vh_first_time_on_device(attr_mask2, ctx->device))
+        VH_CUDA(cudaFuncSetAttribute(k_pointwise<27, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)pointwise_smem<27, 27>(true)));
       k_pointwise<27, 27><<<ctx->n_cells, 512, smem, ctx->stream>>>(ctx->cell_nodes, ctx->cell_h, ctx->cell_faces,
                                                                    ctx->cell_owned, x_local, ctx->tab, ctx->coef, want_h, want_e,
                                                                    ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec);
@@ -1851,12 +1847,11 @@ int vhk_apply_fast(vh_ctx *ctx, const double *z_masked, const double *x_orig, do
   if (ctx->n_fast == 0 || ctx->n_cells == 0)
     return VH_OK;
   const vh_hweights hw = vh_make_hweights(ctx->coef.alpha, ctx->coef.beta); // unused by the apply
-  static bool       attr_set = false;
-  if (!attr_set)
+  static unsigned long long attr_mask = 0;
+  if (vh_first_time_on_device(attr_mask, ctx->device))
     {
       VH_CUDA(cudaFuncSetAttribute(k_points<8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VhPt<8>::SMEM));
       VH_CUDA(cudaFuncSetAttribute(k_points<27, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VhPt<27>::SMEM));
-      attr_set = true;
     }
   if (ctx->degree == 1)
     {
@@ -1904,11 +1899,15 @@ int vhk_rows_fast(vh_ctx *ctx)
       VH_LAUNCH_CHECK();
       return VH_OK;
     }
-  static int ept = 0;
+  static int                ept = 0;
+  static unsigned long long rows_attr_mask = 0;
   if (!ept)
     {
       const char *e = getenv("VH_ROWS_EPT"); // tuning knob: packed entries per thread (1 or 2)
       ept           = (e && e[0] == '2') ? 2 : 1;
+    }
+  if (vh_first_time_on_device(rows_attr_mask, ctx->device))
+    {
       VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
       VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
       VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
@@ -1919,8 +1918,10 @@ int vhk_rows_fast(vh_ctx *ctx)
     {
       const char *e = getenv("VH_ROWS_MMA"); // tuning knob (full-format storage only): 1 = FP64 tensor-core kernel, 0 = scalar DFMA kernel (default, faster)
       use_mma       = (e && e[0] == '1') ? 1 : 0;
-      VH_CUDA(cudaFuncSetAttribute(k_rows_mma_q1, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_MMA_SMEM));
     }
+  static unsigned long long mma_attr_mask = 0;
+  if (use_mma && vh_first_time_on_device(mma_attr_mask, ctx->device))
+    VH_CUDA(cudaFuncSetAttribute(k_rows_mma_q1, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_MMA_SMEM));
   if (ctx->packed)
     { // packed symmetric storage: no expansion stage, half the bytes
       if (ept == 2)
@@ -2025,13 +2026,10 @@ int vhk_rows_slow(vh_ctx *ctx, bool want_matrix, double *rhs_out)
         k_rows_slow<8, 8><<<ctx->n_slow_rows, 352, (8 * VH_SYMP + 64 + 8) * sizeof(double), ctx->stream>>>(R, ctx->tab, ctx->coef, ctx->vals);
       else
         {
-          static bool attr = false;
-          if (!attr)
-            {
-              VH_CUDA(cudaFuncSetAttribute(k_rows_slow<27, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)((27 * VH_SYMP + 729 + 27) * sizeof(double))));
-              attr = true;
-            }
+          static unsigned long long attr_mask = 0;
+          if (vh_first_time_on_device(attr_mask, ctx->device))
+            VH_CUDA(cudaFuncSetAttribute(k_rows_slow<27, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((27 * VH_SYMP + 729 + 27) * sizeof(double))));
           k_rows_slow<27, 27><<<ctx->n_slow_rows, 352, (27 * VH_SYMP + 729 + 27) * sizeof(double), ctx->stream>>>(R, ctx->tab, ctx->coef,
                                                                                                                  ctx->vals);
         }

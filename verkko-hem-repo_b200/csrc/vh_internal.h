@@ -55,6 +55,17 @@ struct VhPush
   int           *err;
 };
 
+// Once-per-device guard for cudaFuncSetAttribute: function attributes belong to the device's context, and a process may
+// hold contexts on several devices (one bit per device ordinal in a function-local static mask).
+inline bool vh_first_time_on_device(unsigned long long &mask, int device)
+{
+  const unsigned long long bit = 1ull << (device & 63);
+  if (mask & bit)
+    return false;
+  mask |= bit;
+  return true;
+}
+
 struct VhCoef
 {
   double K1, K23, alpha, beta[5], bt;
