@@ -90,6 +90,11 @@ typedef struct vh_mesh_desc
   const int32_t *recv_nodes; /* ghost local node ids filled from each peer        */
 } vh_mesh_desc;
 
+/* Host-only consistency check of a descriptor (no CUDA call, works on a machine without a GPU): sizes, null arrays,
+ * index ranges, sorted and closed constraint tables, masters that stay in their component's node range, wall-face and
+ * halo-plan entries.  Returns VH_OK or VH_ERR_ARG with the first finding in msg (may be NULL).  vh_create runs it first. */
+int vh_validate_mesh_desc(const vh_mesh_desc *desc, char *msg, int msg_len);
+
 /* ---- lifetime (one context per mesh; destroy and re-create after refine_grid, refine.cc:109-181) ---- */
 int         vh_create(const vh_mesh_desc *desc, int cuda_device, vh_ctx **out);
 int         vh_destroy(vh_ctx *ctx);

@@ -313,3 +313,74 @@ def test_driver_mirror_rejects_unknown_names():
     with pytest.raises(RuntimeError) as e:
         vh.run_prm("subsection control parameters\n  set geometry = cube_cylider_hole\nend\n")
     assert "unknown geometry" in str(e.value) and "retangle-z-AdGR_xy-periodic" in str(e.value)
+
+
+def _all_kinds_of_tables():
+    yield vh.unit_cube(1, 2, half=2.0).tables(0)
+    yield vh.unit_cube(2, 1, half=2.0).tables(0)
+    for r in range(3):
+        yield vh.unit_cube(1, 2, half=2.0, n_ranks=3).tables(r)
+        yield vh.periodic_slab(1, 2, n_ranks=3).tables(r)
+    m = vh.Mesh(1, [-2, -2, -2], [2, 2, 2], n_global_refine=2)
+    c = m.cell_centers()
+    m.refine((np.abs(c[:, 2]) < 1.1) & (c[:, 0] < 0.1))
+    m.finalize(2)
+    yield m.tables(0)
+    yield m.tables(1)
+
+
+def test_descriptor_validation_accepts_every_table_the_host_builds():
+    """vh_validate_mesh_desc (host-only part of vh_create) on uniform / periodic / hanging-node tables, 1-3 ranks."""
+    n = 0
+    for T in _all_kinds_of_tables():
+        assert vh.validate_tables(T) == ""
+        n += 1
+    assert n == 10
+
+
+@pytest.mark.parametrize("field,index,value,expect", [
+    ("cell_nodes", (0, 0), -1, "cell_nodes entry out of range"),
+    ("cell_nodes", (3, 1), 10 ** 6, "cell_nodes entry out of range"),
+    ("cell_nodes", (2, 5), "dup", "same node twice"),
+    ("cell_h", (1, 2), 0.0, "cell_h must be positive"),
+    ("cell_h", (1, 0), float("nan"), "cell_h must be positive"),
+    ("wall_face_bid", 0, 7, "wall face table entry out of range"),
+    ("wall_face_no", 1, 6, "wall face table entry out of range"),
+    ("wall_face_cell", 0, 10 ** 6, "wall face table entry out of range"),
+    ("c_dof", 1, "swap", "strictly ascending"),
+    ("c_dof", 0, -5, "constrained DoF out of range"),
+    ("c_master", 0, 10 ** 8, "master out of range"),
+    ("c_master", 0, "constrained", "not closed"),
+    ("c_weight", 0, float("inf"), "weight is not finite"),
+    ("send_nodes", 0, "ghost", "send_nodes must be owned"),
+    ("recv_nodes", 0, 0, "recv_nodes must be ghost"),
+    ("recv_nodes", 1, "dup", "received twice"),
+    ("peer_rank", 0, -1, "negative peer rank"),
+])
+def test_descriptor_validation_names_the_defect(field, index, value, expect):
+    """Corrupt one entry of an otherwise valid two-rank table with hanging nodes and Dirichlet walls: the host-only
+    validator (and therefore vh_create, before it touches CUDA) must name the defect."""
+    m = vh.Mesh(1, [-2, -2, -2], [2, 2, 2], n_global_refine=2)
+    c = m.cell_centers()
+    m.refine((np.abs(c[:, 2]) < 1.1) & (c[:, 0] < 0.1))
+    m.finalize(2)
+    T = m.tables(0)
+    assert vh.validate_tables(T) == ""
+    arr = getattr(T, field)
+    arr.flags.writeable = True
+    old = arr[index]
+    if value == "dup":
+        value = arr[(index[0], index[1] - 1)] if isinstance(index, tuple) else arr[index - 1]
+    elif value == "swap":
+        value = arr[index - 1]
+    elif value == "constrained":
+        value = T.c_dof[-1]
+    elif value == "ghost":
+        value = T.n_owned_nodes
+    arr[index] = value
+    try:
+        msg = vh.validate_tables(T)
+    finally:
+        arr[index] = old
+    assert expect in msg, msg
+    assert vh.validate_tables(T) == ""

@@ -246,4 +246,4 @@ def unit_cube(degree, refine, half=0.5, face_bid=(1, 1, 1, 1, 4, 4), n_ranks=1):
     return Mesh(degree, [-half] * 3, [half] * 3, (1, 1, 1), face_bid, refine).finalize(n_ranks)
 
 
-from ._capi import Context, cuda_lib, have_cuda_lib, run_prm  # noqa: E402,F401
+from ._capi import Context, cuda_lib, have_cuda_lib, run_prm, validate_tables  # noqa: E402,F401

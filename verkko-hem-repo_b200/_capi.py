@@ -62,8 +62,16 @@ def cuda_lib():
         L.vh_timer_stop.argtypes = [_vp, ctypes.POINTER(ctypes.c_float)]
         L.vh_measure_fp64_peak.argtypes = [_vp, _dp]
         L.vh_set_spmv_matrix_free.argtypes = [_vp, ctypes.c_int]
+        L.vh_validate_mesh_desc.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int]
         _lib = L
     return _lib
+
+
+def validate_tables(tables):
+    """Host-only consistency check of a RankTables descriptor (vh_validate_mesh_desc; needs no GPU).  Returns "" or the finding."""
+    msg = ctypes.create_string_buffer(512)
+    rc = cuda_lib().vh_validate_mesh_desc(tables.desc_ptr(), msg, 512)
+    return "" if rc == VH_OK else (msg.value.decode() or "invalid")
 
 
 class Context:

@@ -867,11 +867,132 @@ const char *vh_last_error(const vh_ctx *ctx)
   return copy.c_str();
 }
 
+int vh_validate_mesh_desc(const vh_mesh_desc *d, char *msg, int msg_len)
+{
+  std::string why;
+  auto        bad = [&](const std::string &m) {
+    why = m;
+    return false;
+  };
+  auto check_constraints = [&](const vh_constraints &c, const char *name, int64_t NL) {
+    const std::string nm(name);
+    if (c.n_lines < 0)
+      return bad(nm + ": n_lines < 0");
+    if (c.n_lines == 0)
+      return true;
+    if (!c.dof || !c.ptr)
+      return bad(nm + ": null dof / ptr array");
+    if (c.ptr[0] != 0)
+      return bad(nm + ": ptr[0] != 0");
+    for (int l = 0; l < c.n_lines; ++l)
+      {
+        if (c.dof[l] < 0 || c.dof[l] >= NL)
+          return bad(nm + ": constrained DoF out of range");
+        if (l > 0 && c.dof[l] <= c.dof[l - 1])
+          return bad(nm + ": dof[] must be strictly ascending");
+        if (c.ptr[l + 1] < c.ptr[l])
+          return bad(nm + ": ptr not monotone");
+      }
+    const int nent = c.ptr[c.n_lines];
+    if (nent > 0 && (!c.master || !c.weight))
+      return bad(nm + ": null master / weight array");
+    for (int p = 0; p < nent; ++p)
+      {
+        if (c.master[p] < 0 || c.master[p] >= NL)
+          return bad(nm + ": master out of range");
+        if (std::binary_search(c.dof, c.dof + c.n_lines, c.master[p]))
+          return bad(nm + ": object is not closed (a master is itself constrained)");
+        if (!(c.weight[p] == c.weight[p]) || std::fabs(c.weight[p]) > 1e300)
+          return bad(nm + ": weight is not finite");
+      }
+    return true;
+  };
+  const bool ok = [&]() {
+    if (!d)
+      return bad("null descriptor");
+    if (d->degree != 1 && d->degree != 2)
+      return bad("degree must be 1 or 2");
+    if (d->n_owned_nodes < 0 || d->n_ghost_nodes < 0 || d->n_cells < 0 || d->n_wall_faces < 0 || d->n_peers < 0)
+      return bad("negative size");
+    const int64_t n_local = (int64_t)d->n_owned_nodes + d->n_ghost_nodes;
+    if (18 * n_local > (int64_t)INT32_MAX)
+      return bad("more than 2^31 local DoFs on one rank");
+    const int nn = d->degree == 1 ? 8 : 27;
+    if (d->n_cells > 0 && (!d->cell_nodes || !d->cell_h))
+      return bad("cell tables are null");
+    for (int64_t i = 0; i < (int64_t)d->n_cells * nn; ++i)
+      if (d->cell_nodes[i] < 0 || d->cell_nodes[i] >= n_local)
+        return bad("cell_nodes entry out of range");
+    for (int64_t e = 0; e < d->n_cells; ++e)
+      {
+        for (int a = 0; a < nn; ++a)
+          for (int b = a + 1; b < nn; ++b)
+            if (d->cell_nodes[e * nn + a] == d->cell_nodes[e * nn + b])
+              return bad("a cell names the same node twice");
+        for (int k = 0; k < 3; ++k)
+          if (!(d->cell_h[3 * e + k] > 0.0) || !(d->cell_h[3 * e + k] < 1e300))
+            return bad("cell_h must be positive and finite");
+      }
+    if (d->n_wall_faces > 0 && (!d->wall_face_cell || !d->wall_face_no || !d->wall_face_bid))
+      return bad("wall face tables are null");
+    for (int f = 0; f < d->n_wall_faces; ++f)
+      if (d->wall_face_cell[f] < 0 || d->wall_face_cell[f] >= d->n_cells || d->wall_face_no[f] < 0 || d->wall_face_no[f] > 5 ||
+          d->wall_face_bid[f] < 2 || d->wall_face_bid[f] > 4)
+        return bad("wall face table entry out of range (boundary id must be 2, 3 or 4)");
+    if (!check_constraints(d->constraints_newton_update, "constraints_newton_update", 18 * n_local) ||
+        !check_constraints(d->constraints_solution, "constraints_solution", 18 * n_local))
+      return false;
+    if (d->n_peers > 0)
+      {
+        if (!d->peer_rank || !d->send_ptr || !d->recv_ptr)
+          return bad("halo plan arrays are null");
+        if (d->send_ptr[0] != 0 || d->recv_ptr[0] != 0)
+          return bad("halo plan: ptr[0] != 0");
+        for (int p = 0; p < d->n_peers; ++p)
+          {
+            if (d->peer_rank[p] < 0)
+              return bad("halo plan: negative peer rank");
+            for (int q = 0; q < p; ++q)
+              if (d->peer_rank[q] == d->peer_rank[p])
+                return bad("halo plan: a peer is listed twice");
+            if (d->send_ptr[p + 1] < d->send_ptr[p] || d->recv_ptr[p + 1] < d->recv_ptr[p])
+              return bad("halo plan: ptr not monotone");
+          }
+        const int ns = d->send_ptr[d->n_peers], nr = d->recv_ptr[d->n_peers];
+        if ((ns > 0 && !d->send_nodes) || (nr > 0 && !d->recv_nodes))
+          return bad("halo plan: null node list");
+        for (int i = 0; i < ns; ++i)
+          if (d->send_nodes[i] < 0 || d->send_nodes[i] >= d->n_owned_nodes)
+            return bad("send_nodes must be owned nodes");
+        std::vector<uint8_t> seen((size_t)d->n_ghost_nodes, 0);
+        for (int i = 0; i < nr; ++i)
+          {
+            if (d->recv_nodes[i] < d->n_owned_nodes || d->recv_nodes[i] >= n_local)
+              return bad("recv_nodes must be ghost nodes");
+            if (seen[d->recv_nodes[i] - d->n_owned_nodes]++)
+              return bad("a ghost node is received twice");
+          }
+      }
+    return true;
+  }();
+  if (msg && msg_len > 0)
+    {
+      std::strncpy(msg, why.c_str(), (size_t)msg_len - 1);
+      msg[msg_len - 1] = 0;
+    }
+  return ok ? VH_OK : VH_ERR_ARG;
+}
+
 int vh_create(const vh_mesh_desc *d, int cuda_device, vh_ctx **out)
 {
   if (!d || !out)
     return vh_fail(nullptr, VH_ERR_ARG, "vh_create: null argument");
   *out = nullptr;
+  {
+    char why[256];
+    if (vh_validate_mesh_desc(d, why, (int)sizeof why) != VH_OK)
+      return vh_fail(nullptr, VH_ERR_ARG, std::string("vh_create: ") + why);
+  }
   if (d->degree != 1 && d->degree != 2)
     return vh_fail(nullptr, VH_ERR_ARG, "vh_create: degree must be 1 or 2");
   if (d->n_owned_nodes < 0 || d->n_ghost_nodes < 0 || d->n_cells < 0 || d->n_wall_faces < 0)
