@@ -397,36 +397,6 @@ HostTables build_tables(const dealii::DoFHandler<dim> &dof_handler, const dealii
           }
     }
 
-  // ---- step 5: constraint tables over local DoFs (lines whose masters are all local; the others belong to ghost DoFs
-  //      whose value simply arrives through the halo) ----
-  auto fill = [&](const internal::Lines &c, ConstraintTable &out) {
-    out.ptr.push_back(0);
-    const int32_t n_local = T.n_owned_nodes + T.n_ghost_nodes;
-    Entries       scratch;
-    for (int32_t ln = 0; ln < n_local; ++ln)
-      for (unsigned int comp = 0; comp < 18; ++comp)
-        {
-          const Entries *entries = c.find(18 * (gdi)T.node_global[ln] + comp, scratch);
-          if (!entries)
-            continue;
-          bool all_local = true;
-          for (const auto &e : *entries)
-            if (local_of(e.first / 18) < 0)
-              all_local = false;
-          if (!all_local)
-            continue;
-          out.dof.push_back(18 * ln + (int32_t)comp);
-          for (const auto &e : *entries)
-            {
-              out.master.push_back(18 * local_of(e.first / 18) + (int32_t)(e.first % 18));
-              out.weight.push_back(e.second);
-            }
-          out.ptr.push_back((int32_t)out.master.size());
-        }
-  };
-  fill(L[0], T.newton_update);
-  fill(L[1], T.solution);
-
   // ---- step 6: halo plan: tell every owner which of its nodes we ghost (in our ghost order = its send order) ----
   std::map<unsigned int, std::vector<gdi>>     wanted; // owner -> global nodes
   std::map<unsigned int, std::vector<int32_t>> recv_local;
@@ -461,6 +431,86 @@ HostTables build_tables(const dealii::DoFHandler<dim> &dof_handler, const dealii
       T.send_ptr.push_back((int32_t)T.send_nodes.size());
       T.recv_ptr.push_back((int32_t)T.recv_nodes.size());
     }
+
+  // ---- step 6b: a ghost node that is local only as somebody's master (or sits in a shipped cell) may carry constraint
+  //      lines this rank's AffineConstraints objects do not hold (they know the locally relevant lines only), e.g. the
+  //      Dirichlet-masked components of a wall node.  Its owner knows them: it answers the halo request with the lines. ----
+  {
+    std::map<unsigned int, std::vector<double>> reply;
+    Entries                                     scratch;
+    for (const auto &kv : requested)
+      {
+        std::vector<double> &out = reply[kv.first];
+        for (const gdi node : kv.second)
+          for (int o = 0; o < 2; ++o)
+            for (unsigned int comp = 0; comp < 18; ++comp)
+              {
+                const Entries *e = L[o].find(18 * node + comp, scratch);
+                out.push_back(e ? (double)e->size() : -1.0);
+                if (e)
+                  for (const auto &en : *e)
+                    {
+                      out.push_back((double)en.first);
+                      out.push_back(en.second);
+                    }
+              }
+      }
+    const std::map<unsigned int, std::vector<double>> answers = dealii::Utilities::MPI::some_to_some(mpi_communicator, reply);
+    for (const auto &kv : answers)
+      {
+        const std::vector<double> &in    = kv.second;
+        const std::vector<gdi>    &nodes = wanted[kv.first];
+        size_t                     k     = 0;
+        for (const gdi node : nodes)
+          for (int o = 0; o < 2; ++o)
+            for (unsigned int comp = 0; comp < 18; ++comp)
+              {
+                const double cnt = in.at(k++);
+                if (cnt < 0)
+                  continue;
+                Entries e((size_t)cnt);
+                for (auto &en : e)
+                  {
+                    en.first  = (gdi)in.at(k++);
+                    en.second = in.at(k++);
+                  }
+                const gdi dof = 18 * node + comp;
+                if (!L[o].object->is_constrained(dof) && !L[o].shipped.count(dof))
+                  L[o].shipped[dof] = std::move(e);
+              }
+      }
+  }
+
+  // ---- step 7: constraint tables over local DoFs (lines whose masters are all local; the others belong to ghost DoFs
+  //      whose value simply arrives through the halo) ----
+  auto fill = [&](const internal::Lines &c, ConstraintTable &out) {
+    out.ptr.push_back(0);
+    const int32_t n_local = T.n_owned_nodes + T.n_ghost_nodes;
+    Entries       scratch;
+    for (int32_t ln = 0; ln < n_local; ++ln)
+      for (unsigned int comp = 0; comp < 18; ++comp)
+        {
+          const Entries *entries = c.find(18 * (gdi)T.node_global[ln] + comp, scratch);
+          if (!entries)
+            continue;
+          bool all_local = true;
+          for (const auto &e : *entries)
+            if (local_of(e.first / 18) < 0)
+              all_local = false;
+          if (!all_local)
+            continue;
+          out.dof.push_back(18 * ln + (int32_t)comp);
+          for (const auto &e : *entries)
+            {
+              out.master.push_back(18 * local_of(e.first / 18) + (int32_t)(e.first % 18));
+              out.weight.push_back(e.second);
+            }
+          out.ptr.push_back((int32_t)out.master.size());
+        }
+  };
+  fill(L[0], T.newton_update);
+  fill(L[1], T.solution);
+
   return T;
 }
 

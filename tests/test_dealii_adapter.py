@@ -71,6 +71,14 @@ def test_adapter_ships_cells_from_beyond_the_ghost_layer(degree, refine, n_ranks
     assert rc == 0, msg
 
 
+@pytest.mark.parametrize("degree,refine", [(1, 2), (2, 1)])
+@pytest.mark.parametrize("n_ranks", [1, 2, 4])
+def test_adapter_on_the_active_grid_with_differently_refined_periodic_faces(degree, refine, n_ranks):
+    """Periodic pairs + local refinement reaching one periodic face only (hanging nodes across the seam)."""
+    rc, msg = _check(degree, refine, (2, 1, 1), ACTIVE, True, n_ranks)
+    assert rc == 0, msg
+
+
 def test_the_mock_ghost_layer_really_misses_cells():
     """Guard of the test above: switch the shipping off (VH_ADAPTER_TEST_NO_SHIPPING) and the tables must differ."""
     os.environ["VH_ADAPTER_TEST_NO_SHIPPING"] = "1"

@@ -62,12 +62,75 @@ def test_bad_periodic_ids_are_rejected():
         vh.Mesh(1, [-1] * 3, [1] * 3, face_bid=(7, 8, 1, 1, 4, 4), n_global_refine=2).finalize(1)
     with pytest.raises(RuntimeError):  # one cell across: a cell would hold a node and its own image
         vh.Mesh(1, [-1] * 3, [1] * 3, face_bid=(5, 6, 1, 1, 4, 4), n_global_refine=0).finalize(1)
-    m = vh.Mesh(1, [-1] * 3, [1] * 3, face_bid=(5, 6, 1, 1, 4, 4), n_global_refine=2)
-    fl = np.zeros(m.n_cells, dtype=np.uint8)
-    fl[0] = 1  # refines the lower x face only -> the two periodic faces no longer match
+
+
+def _lagrange(degree, t, xi):
+    if degree == 1:
+        return xi if t else 1.0 - xi
+    return [(2 * xi - 1) * (xi - 1), 4 * xi * (1 - xi), xi * (2 * xi - 1)][t]
+
+
+def _fe_value(T, x, cell, point):
+    """FE function of the local vector x in cell `cell` at the physical point `point` (18 components)."""
+    _, _, _, support = O.fe_tables(T.degree)
+    xi = (np.asarray(point) - T.cell_origin[cell]) / T.cell_h[cell]
+    assert (xi > -1e-12).all() and (xi < 1 + 1e-12).all()
+    val = np.zeros(18)
+    for a, node in enumerate(T.cell_nodes[cell]):
+        t = np.rint(support[a] * T.degree).astype(int)
+        w = np.prod([_lagrange(T.degree, t[d], xi[d]) for d in range(3)])
+        val += w * x.reshape(-1, 18)[node]
+    return val
+
+
+@pytest.mark.parametrize("degree,refine", [(1, 2), (2, 1)])
+def test_differently_refined_periodic_faces_stay_conforming(degree, refine):
+    """Local refinement that reaches one periodic face only: Mesh::refine balances 2:1 across the seam and the nodes of
+    the finer face without a counterpart hang on the coarse cell across the seam (what make_periodicity_constraints does
+    for refined faces).  After distribute() the FE function must be single-valued across both periodic pairs, at matching
+    and non-matching places alike, and the assembled system must still be the gradient of the energy."""
+    half = np.array([1.0, 1.5, 0.75])
+    m = vh.Mesh(degree, -half, half, face_bid=(5, 6, 7, 8, 4, 4), n_global_refine=refine)
+    c = m.cell_centers()
+    fl = (c[:, 0] < -half[0] + 0.6) & (c[:, 1] < -half[1] + 0.8) & (c[:, 2] < 0)  # touches the lower x and lower y faces only
     m.refine(fl)
-    with pytest.raises(RuntimeError):
-        m.finalize(1)
+    m.finalize(1)
+    assert m.n_hanging_nodes > 0 and m.n_periodic_nodes > 0
+    T = m.tables(0)
+    rng = np.random.default_rng(2)
+    x = O.distribute(T, rng.uniform(-1, 1, 18 * T.n_local_nodes))
+    assert np.abs(O.distribute(T, x) - x).max() == 0.0
+    lo, hi = T.cell_origin, T.cell_origin + T.cell_h
+    n_nonmatching = 0
+    for d in (0, 1):
+        lower = np.nonzero(np.abs(lo[:, d] + half[d]) < 1e-12)[0]
+        upper = np.nonzero(np.abs(hi[:, d] - half[d]) < 1e-12)[0]
+        for _ in range(200):
+            p = rng.uniform(-half, half)
+            p_lo, p_hi = p.copy(), p.copy()
+            p_lo[d], p_hi[d] = -half[d], half[d]
+            k_lo = next(k for k in lower if (lo[k] <= p_lo + 1e-12).all() and (hi[k] >= p_lo - 1e-12).all())
+            k_hi = next(k for k in upper if (lo[k] <= p_hi + 1e-12).all() and (hi[k] >= p_hi - 1e-12).all())
+            n_nonmatching += abs(T.cell_h[k_lo, 0] - T.cell_h[k_hi, 0]) > 1e-12
+            v_lo, v_hi = _fe_value(T, x, k_lo, p_lo), _fe_value(T, x, k_hi, p_hi)
+            assert np.abs(v_lo - v_hi).max() <= 1e-12, (d, p)
+    assert n_nonmatching > 10  # the samples really crossed differently refined places
+    # the constrained system is still the gradient of the energy: -2 rhs = dE/dx along free directions (SURVEY.md A.1)
+    coef = coef_vector(bt=2.0)
+    xs = b_phase_state(T, seed=4)
+    _, rhs = O.assemble_global(T, xs, coef, False)
+    con = np.zeros(18 * T.n_local_nodes, dtype=bool)
+    con[T.c_dof] = True
+    free = np.nonzero(~con)[0]
+    for i in rng.choice(free, size=6, replace=False):
+        eps = 1e-5
+        e = []
+        for sgn in (1, -1):
+            xp = xs.copy()
+            xp[i] += sgn * eps
+            e.append(O.energy_global(T, O.distribute(T, xp), coef))
+        fd = (e[0] - e[1]) / (2 * eps)
+        assert abs(fd + 2.0 * rhs[i]) <= 1e-6 * max(1.0, abs(fd)), (i, fd, rhs[i])
 
 
 def _shift_x(T, x, n_cells_x, hx, x_lo, x_hi):
@@ -178,3 +241,32 @@ def test_hanging_node_partition_independence(degree):
         assert np.abs(rhs - r1[dof_perm[:18 * T.n_owned_nodes]]).max() <= 1e-13 * np.abs(r1).max()
         n_owned += T.n_owned_nodes
     assert n_owned == T1.n_owned_nodes
+
+
+def test_differently_refined_periodic_faces_partition_independence():
+    """The same mesh type split over 3 ranks: owned rows from owned + ghost-layer cells equal the 1-rank rows."""
+    coef = coef_vector(bt=2.0)
+    half = np.array([1.0, 1.5, 0.75])
+
+    def make(n_ranks):
+        m = vh.Mesh(1, -half, half, face_bid=(5, 6, 7, 8, 4, 4), n_global_refine=2)
+        c = m.cell_centers()
+        m.refine((c[:, 0] < -half[0] + 0.6) & (c[:, 1] < -half[1] + 0.8) & (c[:, 2] < 0))
+        return m.finalize(n_ranks)
+
+    T1 = make(1).tables(0)
+    mP = make(3)
+    key1 = {tuple(np.round(p, 9)): i for i, p in enumerate(T1.node_xyz)}
+    x1 = b_phase_state(T1, seed=5)
+    A1, r1 = O.assemble_global(T1, x1, coef, True)
+    A1 = A1.tocsr()
+    for r in range(3):
+        T = mP.tables(r)
+        assert vh.validate_tables(T) == ""
+        perm = np.array([key1[tuple(np.round(p, 9))] for p in T.node_xyz])
+        x = x1.reshape(-1, 18)[perm].ravel()
+        A, rhs = O.assemble_global(T, x, coef, True)
+        dof_perm = (18 * perm[:, None] + np.arange(18)[None, :]).ravel()
+        want = A1[dof_perm[:18 * T.n_owned_nodes]][:, dof_perm]
+        assert abs(A - want).max() <= 1e-13 * abs(A1).max()
+        assert np.abs(rhs - r1[dof_perm[:18 * T.n_owned_nodes]]).max() <= 1e-13 * np.abs(r1).max()

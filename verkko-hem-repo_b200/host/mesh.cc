@@ -178,7 +178,14 @@ void Mesh::refine(const std::vector<uint8_t> &flags_in)
                   bool    out  = false;
                   for (int d = 0; d < 3; ++d)
                     if (g[d] < 0 || g[d] >= (base[d] << l.level))
-                      out = true;
+                      {
+                        // across a periodic pair the neighbour is the cell at the opposite face (p4est does the same
+                        // once add_periodicity has been called, makegrid_retangle-z-AdGR_xy-periodic.cc:204-219)
+                        if (bid[2 * d] == 5 + 2 * d && bid[2 * d + 1] == 6 + 2 * d)
+                          g[d] = g[d] < 0 ? (base[d] << l.level) - 1 : 0;
+                        else
+                          out = true;
+                      }
                   if (out)
                     continue;
                   // find the leaf covering that same-level position: it is at level <= l.level (or finer: then fine)
@@ -386,14 +393,54 @@ void Mesh::finalize(int n_ranks_)
         min_level = std::min(min_level, l.level);
       if (((int64_t)base[d] << min_level) < 2)
         throw std::invalid_argument("Mesh: a periodic direction needs at least two cells across");
-      int64_t n_lower = 0, n_upper = 0;
-      for (int64_t nd = 0; nd < n_nodes; ++nd)
+      // (a) the two faces are refined differently somewhere (2:1 after refine()): the nodes of the finer side that have no
+      //     counterpart hang on the coarse cell across the seam, exactly like hanging nodes on an interior face
+      //     (deal.II: make_periodicity_constraints recurses into the children of the refined face)
+      for (int64_t e = 0; e < nc; ++e)
         {
-          n_lower += nX[(size_t)nd * 3 + d] == 0;
-          n_upper += nX[(size_t)nd * 3 + d] == D[d] - 1;
+          const Leaf &l = leaves[e];
+          if (l.level == Lmax)
+            continue;
+          const int64_t cs = U >> l.level, half = cs / (2 * degree);
+          const int     m = 2 * degree;
+          for (int side = 0; side < 2; ++side)
+            {
+              if (l.g[d] != (side ? (base[d] << l.level) - 1 : 0))
+                continue;
+              const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+              for (int i2 = 0; i2 <= m; ++i2)
+                for (int i1 = 0; i1 <= m; ++i1)
+                  {
+                    if (!((i1 | i2) & 1))
+                      continue; // the image of one of this cell's own nodes: identity, see (b)
+                    int i3[3];
+                    i3[d]  = side ? m : 0;
+                    i3[d1] = i1;
+                    i3[d2] = i2;
+                    int64_t X[3];
+                    for (int k = 0; k < 3; ++k)
+                      X[k] = l.g[k] * cs + i3[k] * half;
+                    X[d]    = side ? 0 : D[d] - 1; // the same point seen from the other side of the seam
+                    auto it = node_of.find(keyof(X));
+                    if (it == node_of.end() || hang.count(it->second))
+                      continue;
+                    std::vector<std::pair<int64_t, double>> ent;
+                    for (int a = 0; a < n; ++a)
+                      {
+                        int t[3];
+                        node_t(degree, a, t);
+                        double w = 1.0;
+                        for (int k = 0; k < 3; ++k)
+                          w *= lagrange(degree, t[k], (double)i3[k] / (double)m);
+                        if (std::fabs(w) > 1e-14)
+                          ent.push_back({cell_nodes[(size_t)e * n + a], w});
+                      }
+                    hang[it->second] = ent;
+                    ++n_hanging_nodes;
+                  }
+            }
         }
-      if (n_lower != n_upper)
-        throw std::runtime_error("Mesh: periodic faces are refined differently (non-matching periodic faces are not supported)");
+      // (b) identities: a node of the upper face equals its image on the lower face
       for (int64_t nd = 0; nd < n_nodes; ++nd)
         {
           if (nX[(size_t)nd * 3 + d] != D[d] - 1 || hang.count(nd))
@@ -402,7 +449,8 @@ void Mesh::finalize(int n_ranks_)
           X[d]         = 0;
           auto it      = node_of.find(keyof(X));
           if (it == node_of.end())
-            throw std::runtime_error("Mesh: periodic faces are refined differently (non-matching periodic faces are not supported)");
+            throw std::runtime_error("Mesh: a node of a periodic face has neither an image nor a coarse cell across the seam "
+                                     "(the periodic faces are not 2:1 balanced; refine through Mesh::refine)");
           hang[nd] = {{it->second, 1.0}};
           ++n_periodic_nodes;
         }
