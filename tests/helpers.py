@@ -31,7 +31,6 @@ def coef_vector(mat=MATEP_SCC_ON, bt=2.0):
 def b_phase_state(T, mat=MATEP_SCC_ON, noise=0.05, seed=20250101):
     """Uniform B-phase u11=u22=u33=gapB*0.577350269f (setup_uniform_B-phase.cc:245-259) plus a seeded
     perturbation keyed on the GLOBAL node id (so every partition sees the same field), constraints distributed."""
-    import femgl_oracle as O
     amp = mat["gapB"] * float(np.float32(0.577350269))
     x = np.zeros((T.n_local_nodes, 18))
     x[:, [0, 4, 8]] = amp
@@ -45,7 +44,20 @@ def b_phase_state(T, mat=MATEP_SCC_ON, noise=0.05, seed=20250101):
             g = T.node_global.astype(np.uint64)[:, None] * np.uint64(18) + np.arange(18, dtype=np.uint64)[None, :]
             h = (g * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)) & np.uint64(0xFFFFFFFFFFFF)
             x += noise * mat["gapB"] * (h.astype(np.float64) / float(0xFFFFFFFFFFFF) * 2.0 - 1.0)
-    return O.distribute(T, x.ravel())
+    return distribute_constraints(T, x.ravel())
+
+
+def distribute_constraints(T, x_local):
+    """constraints_solution.distribute (setup_uniform_B-phase.cc:262): constrained entries from their masters, Dirichlet
+    entries zero.  Plain numpy on the host tables — input preparation for tests, tools and bench.py, independent of oracle/."""
+    x = np.array(x_local, dtype=np.float64, copy=True)
+    if T.c_dof.size:
+        cnt = np.diff(T.c_ptr)
+        vals = np.zeros(T.c_dof.size)
+        if T.c_master.size:
+            np.add.at(vals, np.repeat(np.arange(T.c_dof.size), cnt), T.c_weight * x_local[T.c_master])
+        x[T.c_dof] = vals
+    return x
 
 
 def bsr_to_csr(row_ptr, col, vals, n_local_nodes):

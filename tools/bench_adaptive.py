@@ -3,7 +3,7 @@ more -> two planes of hanging nodes; prints the split between lattice rows and g
 import os
 import sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [R, R + "/tests", R + "/oracle"]
+sys.path[:0] = [R, R + "/tests"]
 import numpy as np  # noqa: E402
 import verkko_hem_repo_b200 as vh  # noqa: E402
 from helpers import b_phase_state, coef_vector  # noqa: E402

@@ -2,7 +2,7 @@
 import os
 import sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [R, R + "/tests", R + "/oracle"]
+sys.path[:0] = [R, R + "/tests"]
 import verkko_hem_repo_b200 as vh  # noqa: E402
 from helpers import b_phase_state, coef_vector  # noqa: E402
 

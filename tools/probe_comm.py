@@ -3,7 +3,7 @@ import os
 import sys
 import time
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [R, R + "/tests", R + "/oracle"]
+sys.path[:0] = [R, R + "/tests"]
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 import verkko_hem_repo_b200 as vh  # noqa: E402

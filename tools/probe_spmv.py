@@ -1,7 +1,7 @@
 """SpMV timing probe at C2 (Q1 r5): ms per launch with and without L2 flush."""
 import os, sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [R, R + "/tests", R + "/oracle"]
+sys.path[:0] = [R, R + "/tests"]
 import verkko_hem_repo_b200 as vh
 from helpers import b_phase_state, coef_vector
 m = vh.unit_cube(1, 5, half=20.0); T = m.tables(0)

@@ -1,4 +1,4 @@
-import sys; import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0]=[R, R+'/tests', R+'/oracle']
+import sys; import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0]=[R, R+'/tests']
 import numpy as np, verkko_hem_repo_b200 as vh
 from helpers import b_phase_state, coef_vector
 m=vh.unit_cube(1,5,half=20.0); T=m.tables(0)

@@ -5,7 +5,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+for p in (ROOT,):
     sys.path.insert(0, p)
 import numpy as np  # noqa: E402
 import verkko_hem_repo_b200 as vh  # noqa: E402
