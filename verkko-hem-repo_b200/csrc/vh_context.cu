@@ -7,6 +7,8 @@
 // femgl.h:310-316.  Everything here runs once per mesh.
 #include "vh_internal.h"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -213,11 +215,21 @@ int upload_constraints(vh_ctx *ctx, const vh_constraints &c, VhConstraintsDev &D
   return VH_OK;
 }
 
+// Phase timer = the reference's TimerOutput scopes: CUDA events on the library's stream for
+// vh_get_timers, and an NVTX range of the same name as the reference's scope so that ncu / nsys can filter a phase
+// (`ncu --nvtx --nvtx-include "solve/"`).  NVTX3 is header-only and a no-op unless a tool is attached.
 struct PhaseTimer
 {
   vh_ctx *ctx;
   int     slot;
-  PhaseTimer(vh_ctx *c, int s) : ctx(c), slot(s) { cudaEventRecord(ctx->ev0, ctx->stream); }
+  bool    open;
+  PhaseTimer(vh_ctx *c, int s) : ctx(c), slot(s), open(true)
+  {
+    // slots of vh_get_timers: 0 assemble, 1 residual, 2 solve, 3 vector work of newton_iteration
+    static const char *const names[] = {"assembly", "compute_residual", "solve", "newton_iteration"}; // assemble.cc:111, residual.cc:112, solve.cc:111, iteration.cc:112
+    nvtxRangePushA(names[s & 3]);
+    cudaEventRecord(ctx->ev0, ctx->stream);
+  }
   void stop()
   {
     cudaEventRecord(ctx->ev1, ctx->stream);
@@ -225,6 +237,14 @@ struct PhaseTimer
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->t_ms[slot] += ms;
+    if (open)
+      nvtxRangePop();
+    open = false;
+  }
+  ~PhaseTimer()
+  { // an error return between construction and stop(): close the range, leave the timers alone
+    if (open)
+      nvtxRangePop();
   }
 };
 
