@@ -384,3 +384,15 @@ def test_descriptor_validation_names_the_defect(field, index, value, expect):
         arr[index] = old
     assert expect in msg, msg
     assert vh.validate_tables(T) == ""
+
+
+def test_abi_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 with -pedantic and a C program links against libvhfemgl.so."""
+    import subprocess
+    libdir = os.path.join(ROOT, "verkko-hem-repo_b200", "lib")
+    exe = str(tmp_path / "abi_from_c")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           "-o", exe, os.path.join(ROOT, "tests", "native", "abi_from_c.c"), "-L", libdir, "-lvhfemgl",
+                           "-Wl,-rpath," + libdir])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout, r.stderr)
