@@ -396,3 +396,14 @@ def test_abi_header_is_plain_c_and_links_from_c(tmp_path):
                            "-Wl,-rpath," + libdir])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout, r.stderr)
+
+
+def test_example_prm_files_parse_with_the_confreader_mirror():
+    """examples/*.prm (the reference ships no femgl .prm): every key is one the confreader mirror declares."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "examples", "*.prm")))
+    assert len(files) >= 5
+    for f in files:
+        d = vh.parse_prm(open(f).read())
+        assert d["control parameters/geometry"] in GRID_VARIANTS, f
+        assert d["control parameters/initial condition"] in ("B-phase", "A-phase", "BnA"), f
