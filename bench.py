@@ -295,6 +295,12 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     tm = ctx.timers()
+    # GL free energy of the state the timed steps ended in (outside the timed region; the reference never evaluates the
+    # functional, SURVEY.md section 0.6 — vh_energy integrates the functional whose half-gradient is the residual)
+    try:
+        final_energy = ctx.energy(0)
+    except Exception:
+        final_energy = None
     ms = max_over_ranks(ms)
     ms_per_step = ms / args.steps
     value = n_dofs / (ms_per_step * 1e-3)
@@ -431,6 +437,7 @@ def run_ours(args):
                                 % (8 * 324 * nnzb / 1e9),
                           "parallelism": "subdomain x%d (Morton partition, NCCL halo + all-reduce)" % world},
                "newton_history": [{"gmres_its": h[0], "line_search_trials": h[1], "residual": h[2]} for h in hist],
+               "final_energy": final_energy,
                "phase_ms_per_step": {k: tm[k] / args.steps for k in ("assemble", "residual", "solve", "vector")},
                "roofline": roof, "assembly": asm,
                "kernels": {"spmv_ms": t_spmv, "spmv_gbs": spmv_gbs, "residual_ms": t_res, "block_jacobi_apply_ms": t_bj,
