@@ -118,7 +118,21 @@ extern "C" int vht_adapter_check(int degree, int n_global_refine, const int *bas
     {
       const double lo[3] = {-2.0, -1.5, -1.0}, hi[3] = {2.0, 1.5, 1.0};
       Mesh         M(degree, lo, hi, base, face_bid, n_global_refine);
-      if (local_refine)
+      if (local_refine >= 2)
+        { // randomised multi-level refinement: three rounds, ~15 % of the cells each (seed = local_refine)
+          unsigned long long st = 0x9E3779B97F4A7C15ull * (unsigned long long)local_refine;
+          for (int round = 0; round < 3; ++round)
+            {
+              std::vector<uint8_t> fl(M.n_cells(), 0);
+              for (int64_t e = 0; e < M.n_cells(); ++e)
+                {
+                  st = st * 6364136223846793005ull + 1442695040888963407ull;
+                  fl[e] = ((st >> 33) % 100) < 15 ? 1 : 0;
+                }
+              M.refine(fl);
+            }
+        }
+      else if (local_refine)
         {
           std::vector<uint8_t> fl(M.n_cells(), 0);
           for (int64_t e = 0; e < M.n_cells(); ++e)

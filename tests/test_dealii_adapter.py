@@ -79,6 +79,15 @@ def test_adapter_on_the_active_grid_with_differently_refined_periodic_faces(degr
     assert rc == 0, msg
 
 
+@pytest.mark.parametrize("degree,refine,seed", [(1, 1, 2), (1, 1, 3), (2, 1, 4)])
+@pytest.mark.parametrize("bid", [WALLS, ACTIVE])
+@pytest.mark.parametrize("n_ranks", [1, 3, 8])
+def test_adapter_on_randomly_refined_multi_level_meshes(degree, refine, seed, bid, n_ranks):
+    """Three rounds of random refinement (several levels, chains of hanging nodes, periodic seams refined differently)."""
+    rc, msg = _check(degree, refine, (2, 1, 1), bid, seed, n_ranks)
+    assert rc == 0, msg
+
+
 def test_the_mock_ghost_layer_really_misses_cells():
     """Guard of the test above: switch the shipping off (VH_ADAPTER_TEST_NO_SHIPPING) and the tables must differ."""
     os.environ["VH_ADAPTER_TEST_NO_SHIPPING"] = "1"
