@@ -1,0 +1,56 @@
+"""GPU parity on randomly refined MULTI-LEVEL meshes (what several adaptive cycles of run.cc:182-195 produce): chains of
+hanging nodes resolved to more masters than one coarse face has, rows fed through several constrained nodes, masked
+walls.  Same checks and tolerances as tests/test_gpu_parity.py.  (Written after the round's GPU budget was spent: the
+kernels it exercises are the ones the single-level hanging-node tests cover; this input shape first runs on hardware in the
+driver's round-end test run.)"""
+import numpy as np
+import pytest
+
+import femgl_oracle as O
+import verkko_hem_repo_b200 as vh
+from helpers import MATEP_SCC_ON, b_phase_state, blockrow_rel_error, bsr_to_csr, coef_vector
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_mesh(degree, seed, rounds, frac=0.15):
+    rng = np.random.default_rng(seed)
+    m = vh.Mesh(degree, [-1.0, -0.5, 0.0], [1.0, 1.0, 1.5], base=(2, 1, 1), face_bid=(1, 1, 2, 1, 4, 4), n_global_refine=1)
+    for _ in range(rounds):
+        m.refine(rng.uniform(size=m.n_cells) < frac)
+    return m.finalize(1)
+
+
+@pytest.mark.parametrize("degree,seed,rounds,scatter", [(1, 11, 3, "0"), (1, 12, 4, "0"), (1, 11, 3, "1"), (2, 13, 2, "0")])
+def test_multilevel_assembly_spmv_and_solve_match_oracle(degree, seed, rounds, scatter, monkeypatch):
+    monkeypatch.setenv("VH_SLOW_SCATTER", scatter)
+    m = _random_mesh(degree, seed, rounds)
+    assert m.n_hanging_nodes > 0
+    T = m.tables(0)
+    coef = coef_vector(MATEP_SCC_ON, 2.0)
+    x = b_phase_state(T, seed=seed)
+    ctx = vh.Context(T)
+    ctx.set_coef_vector(coef)
+    ctx.set_solution(x)
+    rhs_norm = ctx.assemble()
+    assert ctx.info()["n_slow_cells"] > 0
+    A_ora, rhs_ora = O.assemble_global(T, x, coef, True)
+    A_gpu = bsr_to_csr(*ctx.export_matrix_bsr(), T.n_local_nodes)
+    err = blockrow_rel_error(A_gpu, A_ora)
+    assert err <= 1e-12, "matrix blockrow-relative error %.3e" % err
+    rhs = ctx.get_rhs()
+    assert np.abs(rhs - rhs_ora).max() <= 1e-12 * np.abs(rhs_ora).max()
+    assert abs(rhs_norm - np.linalg.norm(rhs_ora)) <= 1e-12 * np.linalg.norm(rhs_ora)
+    e_ora = O.energy_global(T, x, coef)
+    assert abs(ctx.energy(0) - e_ora) <= 1e-12 * abs(e_ora)
+    z = np.random.default_rng(3).uniform(-1, 1, A_ora.shape[1])
+    y, y_ora = ctx.spmv(z), A_ora @ z
+    assert np.abs(y - y_ora).max() <= 1e-13 * np.abs(y_ora).max()
+    # the linear solve and the distributed update (hanging DoFs interpolated from their resolved masters)
+    its, res = ctx.solve(1e-1)  # the production tolerance (declare.cc:203); the stopping decision has a >8 % margin here
+    Minv = O.block_jacobi_inverse(A_ora, T.n_owned_nodes)
+    d_ora, its_ora, _, ok = O.gmres_block_jacobi(A_ora, rhs_ora, Minv, 1e-1 * np.linalg.norm(rhs_ora))
+    assert ok and its == its_ora
+    d_ora = O.distribute(T, d_ora)
+    assert np.abs(ctx.get_newton_update() - d_ora).max() <= 1e-9 * np.abs(d_ora).max()
+    ctx.close()
