@@ -290,7 +290,7 @@ template <int NN, bool WANT_H, bool WANT_E, bool APPLY = false>
 __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
   k_points(int n_cells, const int32_t *__restrict__ cell_nodes, const double *__restrict__ cell_h,
            const uint32_t *__restrict__ cell_faces, const uint8_t *__restrict__ cell_owned, const double *__restrict__ x,
-           VhTables tab, VhCoef cf, vh_hweights hw, double *Hq, double *__restrict__ Rc, double *__restrict__ Dc,
+           VhTables tab, VhCoef cf, vh_hweights hw, double *__restrict__ Hq, double *__restrict__ Rc, double *__restrict__ Dc,
            double *__restrict__ avgD, double *__restrict__ Ec)
 {
   static_assert(!APPLY || (!WANT_H && !WANT_E), "the operator apply neither writes H_q nor integrates the energy");
