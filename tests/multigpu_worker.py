@@ -38,9 +38,17 @@ def main():
     coef = coef_vector(bt=2.0)
     periodic = len(sys.argv) > 1 and sys.argv[1] == "periodic"  # the reference's active grid: x/y-periodic slab
 
+    hanging = len(sys.argv) > 1 and sys.argv[1] == "hanging"    # C4-shaped: locally refined slab, several levels
+
     def make(n_ranks):
         if periodic:
             return vh.periodic_slab(1, 3, half=(2.0, 2.0, 1.0), n_ranks=n_ranks)
+        if hanging:
+            m = vh.Mesh(1, [-3, -2, -4], [3, 2, 4], n_global_refine=2)
+            for _ in range(2):  # two "adaptive cycles": the 30 % of the cells nearest the plane z = 0.4
+                d = np.abs(m.cell_centers()[:, 2] - 0.4)
+                m.refine(d <= np.sort(d)[int(0.3 * m.n_cells)])
+            return m.finalize(n_ranks)
         return vh.unit_cube(1, 3, half=2.0, n_ranks=n_ranks)
 
     mesh = make(world)

@@ -8,7 +8,7 @@ import pytest
 
 import femgl_oracle as O
 import verkko_hem_repo_b200 as vh
-from helpers import MATEP_SCC_ON, b_phase_state, blockrow_rel_error, bsr_to_csr, coef_vector
+from helpers import MATEP_SCC_ON, b_phase_state, blockrow_rel_error, bsr_to_csr, coef_vector, gpu_count
 
 pytestmark = pytest.mark.gpu
 
@@ -54,3 +54,19 @@ def test_multilevel_assembly_spmv_and_solve_match_oracle(degree, seed, rounds, s
     d_ora = O.distribute(T, d_ora)
     assert np.abs(ctx.get_newton_update() - d_ora).max() <= 1e-9 * np.abs(d_ora).max()
     ctx.close()
+
+
+def test_two_gpu_run_with_hanging_nodes_equals_one_gpu_run():
+    """C4-shaped mesh (two refinement cycles around a plane, several levels) split over two GPUs: Newton history and solution
+    equal the one-GPU run (constraint masters across the subdomain interface, rows fed by cells of the other rank)."""
+    import os
+    import subprocess
+    import sys
+    if gpu_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29539", os.path.join(root, "tests", "multigpu_worker.py"), "hanging"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MULTIGPU PARITY OK" in r.stdout
