@@ -3,6 +3,7 @@
 # bench command and one full capture of the dominant kernels.  Everything lands in gpurun_out/; turn the raw files into
 # the committed summaries with profiles/summarize.py (see its header).
 #   gpurun --timeout 900 -- 'bash tools/gpu_session.sh [tests|bench|ncu|all]'
+#   gpurun --gpus 2 --timeout 600 -- 'bash tools/gpu_session.sh multi 2'      (multi-rank checks; N = 2, 4 or 8; never under ncu)
 # ncu replays every profiled launch ~40x: the captures below use a SHORT bench command (2 steps) and are limited with -c.
 set -u
 what=${1:-all}
@@ -40,4 +41,25 @@ if [ "$what" = ncu ] || [ "$what" = all ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:k_points' -s 8 -c 6 \
     -o gpurun_out/prof_mf -f $B --spmv-mf > gpurun_out/ncu_full_mf.log 2>&1
   ls -la gpurun_out/*.ncu-rep gpurun_out/launches_*.csv 2>/dev/null
+fi
+if [ "$what" = multi ]; then
+  N=${2:-2}
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+  port=29600
+  for mode in cube periodic hanging; do   # parity of the N-rank run with the 1-rank run (tests/multigpu_worker.py)
+    for env in "" "VH_SPMV_MF=1" "VH_HALO_PUSH=1" "VH_SPMV_MF=1 VH_HALO_PUSH=1"; do
+      port=$((port + 1))
+      arg=$mode; [ "$mode" = cube ] && arg=""
+      ( env $env timeout 120 $TR --master-port $port tests/multigpu_worker.py $arg 2>&1 | grep -E "PARITY|Error|error" | tail -2 ) > gpurun_out/mg_${mode}_$(echo "$env" | tr ' =' '__').log
+      echo "$mode [$env]: $(tail -1 gpurun_out/mg_${mode}_$(echo "$env" | tr ' =' '__').log)"
+    done
+  done
+  for flags in "" "--spmv-mf"; do
+    for env in "" "VH_HALO_PUSH=1"; do
+      port=$((port + 1))
+      tag=$(echo "n${N}${flags}_${env}" | tr ' =-' '___')
+      ( env $env timeout 200 $TR --master-port $port bench.py --gpus $N --steps 5 --warmup 3 $flags 2> gpurun_out/bench_$tag.err | tail -1 ) > gpurun_out/bench_$tag.json
+      python -c "import json,sys; j=json.load(open('gpurun_out/bench_$tag.json')); print('$tag', 'ms/step %.3f' % j['ms_per_step'], j['phase_ms_per_step'], [h['gmres_its'] for h in j['newton_history']])" || echo "$tag ERR"
+    done
+  done
 fi
