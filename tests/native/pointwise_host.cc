@@ -86,3 +86,11 @@ extern "C" void vht_sym_matvec(const double *hq, int q, const double *z, double 
     },
     z, t);
 }
+// table-free H z: the directional derivative of g at A in the direction z (roadmap of the matrix-free apply)
+extern "C" void vht_hessian_apply(const double *A, const double *coef, const double *z, double *out18)
+{
+  double prod[72];
+  for (int e = 0; e < 36; ++e)
+    vh_product_entry(A, e, prod + 2 * e);
+  vh_hessian_apply(A, prod, z, coef[3], coef + 4, out18);
+}

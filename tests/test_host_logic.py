@@ -407,3 +407,27 @@ def test_example_prm_files_parse_with_the_confreader_mirror():
         d = vh.parse_prm(open(f).read())
         assert d["control parameters/geometry"] in GRID_VARIANTS, f
         assert d["control parameters/initial condition"] in ("B-phase", "A-phase", "BnA"), f
+
+
+def test_table_free_hessian_apply_equals_the_hessian_times_z():
+    """vh_hessian_apply (directional derivative of the bulk residual density, eight 3x3 complex products) = H z with the
+    oracle's H (restating cell_mat_lhs_alpha/beta1..5) for random states and directions, and is linear in z."""
+    L = _native_pointwise_lib()
+    P = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(23)
+    for trial in range(25):
+        coef = coef_vector()
+        if trial % 5 == 4:  # generic coefficients: every beta_k different, nothing cancels
+            coef = coef.copy()
+            coef[3:9] = rng.uniform(-1, 1, 6)
+        A = rng.standard_normal(18)
+        z = rng.standard_normal(18)
+        out = np.zeros(18)
+        L.vht_hessian_apply(A.ctypes.data_as(P), coef.ctypes.data_as(P), z.ctypes.data_as(P), out.ctypes.data_as(P))
+        _, H0, _ = O.pointwise(A, coef)
+        want = H0 @ z
+        assert np.abs(out - want).max() <= 1e-13 * max(1.0, np.abs(want).max()), trial
+        out2 = np.zeros(18)
+        z2 = -2.5 * z
+        L.vht_hessian_apply(A.ctypes.data_as(P), coef.ctypes.data_as(P), z2.ctypes.data_as(P), out2.ctypes.data_as(P))
+        assert np.abs(out2 + 2.5 * out).max() <= 1e-12 * max(1.0, np.abs(out).max())

@@ -562,6 +562,94 @@ VH_HD void vh_sym_matvec(LD ld, const double *z, double *t)
       }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Table-free H z (roadmap of the matrix-free operator apply): the directional derivative of
+// g = alpha A + 2 sum_k beta_k G_k at A in the direction Z (z[18] in the layout of A),
+//   dG1 = 2 tr(A Z^T) A* + tr(AA^T) Z*          dG2 = 2 Re tr(A Z^+) A + tr(AA^+) Z
+//   dG3 = Z (A^T A*) + (A Z^T) A* + (A A^T) Z*   dG4 = Z (A^+ A) + (A Z^+) A + (A A^+) Z
+//   dG5 = Z* (A^T A) + (A Z^+)* A + (A A^+)* Z
+// from A and the four products R = AA^T, Q = AA^+, P = A^+A, S = A^T A (prod[72], vh_product_entry): eight 3x3 complex
+// products, no 18x18 table.  Equals the symmetric H of vh_hessian_column / vh_h_entry applied to z (host-tested).
+VH_HD void vh_hessian_apply(const double *A, const double *prod, const double *z, double alpha, const double *beta, double *out)
+{
+  vh_cx a[3][3], zz[3][3], M1[3][3], M2[3][3], WL[3][3], WR[3][3];
+  vh_cx dT{0.0, 0.0};
+  double dS = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      {
+        a[i][j]  = vh_ld(A, i, j);
+        zz[i][j] = vh_ld(z, i, j);
+        const vh_cx t = vh_cmul(a[i][j], zz[i][j]);
+        dT.re += 2.0 * t.re;
+        dT.im += 2.0 * t.im;
+        dS += 2.0 * (a[i][j].re * zz[i][j].re + a[i][j].im * zz[i][j].im);
+      }
+  const vh_cx  T{prod[0] + prod[8] + prod[16], prod[1] + prod[9] + prod[17]}; // tr R
+  const double Sr = prod[18 + 0] + prod[18 + 8] + prod[18 + 16];             // tr Q (real)
+  // M1 = A Z^T, M2 = A Z^+
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      {
+        vh_cx m1{0.0, 0.0}, m2{0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          {
+            const vh_cx t1 = vh_cmul(a[i][j], zz[k][j]), t2 = vh_cmul(a[i][j], vh_conj(zz[k][j]));
+            m1.re += t1.re, m1.im += t1.im, m2.re += t2.re, m2.im += t2.im;
+          }
+        M1[i][k] = m1;
+        M2[i][k] = m2;
+      }
+  // z-independent combinations: WL = beta4 Q + beta5 Q* (multiplies Z from the left), WR = beta3 P* + beta4 P (from the right)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      {
+        const vh_cx q = vh_ldp(prod, 1, i, j), p = vh_ldp(prod, 2, i, j);
+        WL[i][j] = vh_cx{(beta[3] + beta[4]) * q.re, (beta[3] - beta[4]) * q.im};
+        WR[i][j] = vh_cx{(beta[2] + beta[3]) * p.re, (beta[3] - beta[2]) * p.im};
+      }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      {
+        // beta1 dG1 + beta2 dG2
+        vh_cx t = vh_cmul(dT, vh_conj(a[i][j]));
+        vh_cx u = vh_cmul(T, vh_conj(zz[i][j]));
+        double re = beta[0] * (t.re + u.re) + beta[1] * (dS * a[i][j].re + Sr * zz[i][j].re);
+        double im = beta[0] * (t.im + u.im) + beta[1] * (dS * a[i][j].im + Sr * zz[i][j].im);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          {
+            // left products: WL Z + beta3 R Z*
+            t = vh_cmul(WL[i][k], zz[k][j]);
+            u = vh_cmul(vh_ldp(prod, 0, i, k), vh_conj(zz[k][j]));
+            re += t.re + beta[2] * u.re;
+            im += t.im + beta[2] * u.im;
+            // right products: Z WR + beta5 Z* S
+            t = vh_cmul(zz[i][k], WR[k][j]);
+            u = vh_cmul(vh_conj(zz[i][k]), vh_ldp(prod, 3, k, j));
+            re += t.re + beta[4] * u.re;
+            im += t.im + beta[4] * u.im;
+            // middle products: beta3 M1 A* + (beta4 M2 + beta5 M2*) A
+            t = vh_cmul(M1[i][k], vh_conj(a[k][j]));
+            const vh_cx m{(beta[3] + beta[4]) * M2[i][k].re, (beta[3] - beta[4]) * M2[i][k].im};
+            u = vh_cmul(m, a[k][j]);
+            re += beta[2] * t.re + u.re;
+            im += beta[2] * t.im + u.im;
+          }
+        out[3 * i + j]     = alpha * zz[i][j].re + 2.0 * re;
+        out[9 + 3 * i + j] = alpha * zz[i][j].im + 2.0 * im;
+      }
+}
+
 // fills c[e], d[e] for e in [0,180); dummies have d[e] = c[e] - 1 (i.e. d < c)
 inline void vh_sym_tables(unsigned char *tc, unsigned char *td)
 {
