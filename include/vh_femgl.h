@@ -139,7 +139,7 @@ typedef struct vh_info
   int64_t n_slow_cells;  /* cells routed through the constrained scatter */
   int64_t device_bytes;  /* device memory held by the context            */
   int64_t n_packed_blocks; /* blocks stored as packed symmetric 18x18 (180 doubles) instead of 324 doubles */
-  int64_t spmv_matrix_free; /* 1: vh_solve / vh_spmv apply the lattice rows matrix-free from the H_q tables (VH_SPMV_MF=1) */
+  int64_t spmv_matrix_free; /* 1: vh_solve / vh_spmv apply the lattice rows matrix-free from the H_q tables (VH_SPMV_MF=1); 2: table-free */
 } vh_info;
 int vh_get_info(vh_ctx *ctx, vh_info *info);
 /* BSR(18) copy of the owned rows: row_ptr[n_owned+1], col[nnzb] (local node ids), vals[nnzb][18][18] row-major */
@@ -162,7 +162,8 @@ int vh_timer_stop(vh_ctx *ctx, float *ms);
 /* FP64 DFMA peak of the device this context lives on, measured by a register-resident FMA chain (TFLOP/s). */
 int vh_measure_fp64_peak(vh_ctx *ctx, double *tflops);
 /* Operator apply of the lattice rows inside vh_solve / vh_spmv (collective: same value on every rank):
- *   0 = packed SpMV over the assembled blocks (default), 1 = matrix-free from the H_q tables of the last vh_assemble.
+ *   0 = packed SpMV over the assembled blocks (default), 1 = matrix-free from the H_q tables of the last vh_assemble,
+ *   2 = matrix-free and table-free: H(A_q) z_q evaluated from the Newton state (unverified on hardware in round 1).
  * The initial value comes from the environment variable VH_SPMV_MF.  VH_ERR_UNSUPPORTED if the context has no packed
  * lattice rows (nothing to apply matrix-free). */
 int vh_set_spmv_matrix_free(vh_ctx *ctx, int on);

@@ -220,7 +220,8 @@ class Context:
         return ms.value
 
     def set_spmv_matrix_free(self, on=True):
-        self._chk(self.L.vh_set_spmv_matrix_free(self._h, int(bool(on))))
+        """0 / False: packed SpMV; 1 / True: matrix-free from the H_q tables; 2: matrix-free and table-free."""
+        self._chk(self.L.vh_set_spmv_matrix_free(self._h, int(on)))
 
     def measure_fp64_peak(self):
         v = ctypes.c_double()

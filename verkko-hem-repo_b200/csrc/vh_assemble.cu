@@ -277,6 +277,8 @@ struct VhPt
   static constexpr int BSTRIDE = NN * 54 + 4;               // per cell: NQ points x 54 doubles (+4: bank offset)
   static constexpr int TAB     = 4 * NN * NN;               // sNT [q][a] | sdNT [q][x][a]
   static constexpr size_t SMEM = (size_t)(TAB + VH_PT_WARPS * CPW * (USTRIDE + BSTRIDE)) * sizeof(double);
+  // table-free operator apply: a second gather buffer per cell (the Newton state next to the Krylov vector)
+  static constexpr size_t SMEM_TFREE = (size_t)(TAB + VH_PT_WARPS * CPW * (2 * USTRIDE + BSTRIDE)) * sizeof(double);
 };
 
 //
@@ -286,14 +288,19 @@ struct VhPt
 // gradient and Robin forms are linear in the field, so that code is shared verbatim with the residual.  Per apply the
 // kernel streams 8*180*NQ bytes per cell (the H_q tables) instead of the 8*180 bytes per matrix block of the packed SpMV:
 // 3.5x fewer bytes at Q1 (27 blocks per row vs 8 tables per cell) and 19x fewer at Q2 (C3: 1.27 GB of tables vs 24.4 GB).
-template <int NN, bool WANT_H, bool WANT_E, bool APPLY = false>
+//
+// APPLY + TFREE = the TABLE-FREE apply (VH_SPMV_MF=2, unverified on hardware in round 1): no H_q table is read; the thread
+// also interpolates the Newton state A_q from x_state and evaluates H(A_q) z_q as the directional derivative
+// vh_hessian_apply (eight 3x3 complex products).  18 doubles of state per node instead of 180 per point.
+template <int NN, bool WANT_H, bool WANT_E, bool APPLY = false, bool TFREE = false>
 __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
   k_points(int n_cells, const int32_t *__restrict__ cell_nodes, const double *__restrict__ cell_h,
            const uint32_t *__restrict__ cell_faces, const uint8_t *__restrict__ cell_owned, const double *__restrict__ x,
            VhTables tab, VhCoef cf, vh_hweights hw, double *__restrict__ Hq, double *__restrict__ Rc, double *__restrict__ Dc,
-           double *__restrict__ avgD, double *__restrict__ Ec)
+           double *__restrict__ avgD, double *__restrict__ Ec, const double *__restrict__ x_state = nullptr)
 {
   static_assert(!APPLY || (!WANT_H && !WANT_E), "the operator apply neither writes H_q nor integrates the energy");
+  static_assert(!TFREE || APPLY, "table-free is a mode of the operator apply");
   using P = VhPt<NN>;
   constexpr int NQ = NN, G = P::G, CPW = P::CPW, DPC = 18 * NN;
   extern __shared__ __align__(16) double sm[];
@@ -302,8 +309,9 @@ __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane / G, ql = lane % G;
   const bool pt = ql < NQ;                 // Q2: lanes 27..31 carry no point / node
   const int  q  = pt ? ql : NQ - 1;
-  double    *sU = sm + P::TAB + warp * CPW * (P::USTRIDE + P::BSTRIDE); // [CPW][USTRIDE]
-  double    *sB = sU + CPW * P::USTRIDE;                                // [CPW][BSTRIDE]
+  double    *sU = sm + P::TAB + warp * CPW * ((TFREE ? 2 : 1) * P::USTRIDE + P::BSTRIDE); // [CPW][USTRIDE]
+  double    *sB = sU + CPW * P::USTRIDE;                                                  // [CPW][BSTRIDE]
+  double    *sX = sB + CPW * P::BSTRIDE;                                                  // [CPW][USTRIDE] (TFREE only)
   for (int i = t; i < NN * NQ; i += VH_PT_WARPS * 32)
     sNT[(i % NQ) * NN + i / NQ] = tab.N[i];
   for (int i = t; i < NN * NQ * 3; i += VH_PT_WARPS * 32)
@@ -322,6 +330,9 @@ __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
       const int e  = min(cell0 + gg, n_cells - 1);
       const double2 v = *reinterpret_cast<const double2 *>(x + 18 * (int64_t)cell_nodes[(int64_t)e * NN + a] + 2 * pp);
       *reinterpret_cast<double2 *>(sU + gg * P::USTRIDE + a * 18 + 2 * pp) = v;
+      if constexpr (TFREE)
+        *reinterpret_cast<double2 *>(sX + gg * P::USTRIDE + a * 18 + 2 * pp) =
+          *reinterpret_cast<const double2 *>(x_state + 18 * (int64_t)cell_nodes[(int64_t)e * NN + a] + 2 * pp);
     }
   __syncthreads();
 
@@ -462,7 +473,38 @@ __global__ void __launch_bounds__(VH_PT_WARPS * 32, 2)
 
   // ---- bulk terms at this thread's point ----
   vh_prods pr;
-  if constexpr (APPLY)
+  if constexpr (APPLY && TFREE)
+    { // H(A_q) z_q without a table: A_q interpolated from the Newton state, then the directional derivative of g
+      double Aq[18];
+#pragma unroll
+      for (int c = 0; c < 18; ++c)
+        Aq[c] = 0.0;
+      const double *sXg = sX + g * P::USTRIDE;
+#pragma unroll(NN == 8 ? 8 : 1)
+      for (int a = 0; a < NN; ++a)
+        {
+          const double n = sNT[q * NN + a];
+#pragma unroll
+          for (int cp = 0; cp < 9; ++cp)
+            {
+              const double2 u = *reinterpret_cast<const double2 *>(sXg + a * 18 + 2 * cp);
+              Aq[2 * cp]      = fma(n, u.x, Aq[2 * cp]);
+              Aq[2 * cp + 1]  = fma(n, u.y, Aq[2 * cp + 1]);
+            }
+        }
+      double prod[72];
+#pragma unroll
+      for (int e = 0; e < 36; ++e)
+        vh_product_entry(Aq, e, prod + 2 * e);
+      double gv[18];
+      vh_hessian_apply(Aq, prod, a18, cf.alpha, cf.beta, gv);
+      double *myB = gB + q * 18;
+      if (pt)
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+          *reinterpret_cast<double2 *>(myB + 2 * i) = make_double2(JxW * gv[2 * i], JxW * gv[2 * i + 1]);
+    }
+  else if constexpr (APPLY)
     { // (vol H_q) z_q from the stored packed table of this (cell, point); the tables carry the cell volume already
       double        gv[18];
 #pragma unroll
@@ -1846,6 +1888,31 @@ int vhk_apply_fast(vh_ctx *ctx, const double *z_masked, const double *x_orig, do
 {
   if (ctx->n_fast == 0 || ctx->n_cells == 0)
     return VH_OK;
+  if (ctx->spmv_mf_table_free)
+    { // table-free variant: the Jacobian is the one of the state the last vh_assemble saw (ctx->x_sol until vh_accept_trial,
+      // which invalidates the matrix anyway)
+      const vh_hweights hw0 = vh_make_hweights(ctx->coef.alpha, ctx->coef.beta);
+      static unsigned long long tf_mask = 0;
+      if (vh_first_time_on_device(tf_mask, ctx->device))
+        {
+          VH_CUDA(cudaFuncSetAttribute(k_points<8, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VhPt<8>::SMEM_TFREE));
+          VH_CUDA(cudaFuncSetAttribute(k_points<27, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VhPt<27>::SMEM_TFREE));
+        }
+      if (ctx->degree == 1)
+        k_points<8, false, false, true, true><<<(ctx->n_cells + 4 * VH_PT_WARPS - 1) / (4 * VH_PT_WARPS), VH_PT_WARPS * 32, VhPt<8>::SMEM_TFREE, ctx->stream>>>(
+          ctx->n_cells, ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, z_masked, ctx->tab, ctx->coef, hw0, ctx->Hq, ctx->Rc,
+          ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol);
+      else
+        k_points<27, false, false, true, true><<<(ctx->n_cells + VH_PT_WARPS - 1) / VH_PT_WARPS, VH_PT_WARPS * 32, VhPt<27>::SMEM_TFREE, ctx->stream>>>(
+          ctx->n_cells, ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, z_masked, ctx->tab, ctx->coef, hw0, ctx->Hq, ctx->Rc,
+          ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol);
+      VH_LAUNCH_CHECK();
+      const int64_t n0 = (int64_t)ctx->n_fast * 18;
+      k_gather_apply<<<(unsigned)((n0 + 255) / 256), 256, 0, ctx->stream>>>(ctx->n_fast, ctx->dpc, ctx->fast_rows, ctx->fast_cells, ctx->fast_a,
+                                                                           ctx->dirmask, ctx->Rc, ctx->cdiag, x_orig, y_owned);
+      VH_LAUNCH_CHECK();
+      return VH_OK;
+    }
   const vh_hweights hw = vh_make_hweights(ctx->coef.alpha, ctx->coef.beta); // unused by the apply
   static unsigned long long attr_mask = 0;
   if (vh_first_time_on_device(attr_mask, ctx->device))

@@ -204,6 +204,9 @@ struct vh_ctx
   // operator apply of the lattice rows inside vhk_spmv: false = packed SpMV over the assembled blocks (default),
   // true = matrix-free from the H_q tables (VH_SPMV_MF=1; opt-in until measured on hardware)
   bool spmv_mf = false;
+  // with spmv_mf: evaluate H(A_q) z_q from the Newton state instead of reading the H_q tables (VH_SPMV_MF=2 or
+  // vh_set_spmv_matrix_free(ctx, 2); written after the round-1 GPU budget was spent: unverified on hardware)
+  bool spmv_mf_table_free = false;
 
   // state flags
   bool have_matrix = false, have_update = false, have_trial = false;
