@@ -280,6 +280,9 @@ def run_ours(args):
     ctx.set_coef_vector(coef_vector())
     if args.spmv_mf:  # whole run with the matrix-free operator apply inside GMRES (opt-in this round)
         ctx.set_spmv_matrix_free(True)
+    # the mode this run really uses (the library's default may come from VH_SPMV_MF): 0 packed SpMV, 1 matrix-free, 2 table-free
+    mf_mode = int(ctx.info().get("spmv_matrix_free", 0))
+    use_mf = mf_mode != 0
     x0 = initial_state(T)[:18 * T.n_owned_nodes]
     n_dofs = 18 * mesh.n_nodes
     info = ctx.info()
@@ -383,10 +386,10 @@ def run_ours(args):
         traffic = None
     # matrix-free apply: the H_q tables (8*180*n_q bytes per cell) + the per-cell products written and gathered once
     mf_moved = 8 * 180 * n * T.n_cells + 2 * 8 * 18 * n * T.n_cells + 8 * 324 * (nnzb - n_fast_blocks) + 16 * 18 * nb
-    if args.spmv_mf:
+    if use_mf:
         spmv_moved, traffic = mf_moved, None
     moved_gbs = spmv_moved / (t_spmv * 1e-3) / 1e9
-    kernel_name = ("k_points<APPLY>+k_gather_apply" if args.spmv_mf else "k_spmv_sym18") if n_fast_blocks else "k_spmv_bsr18"
+    kernel_name = ("k_points<APPLY>+k_gather_apply" if use_mf else "k_spmv_sym18") if n_fast_blocks else "k_spmv_bsr18"
     roof = {"bound": "hbm", "kernel": kernel_name, "achieved": spmv_gbs, "peak": hbm_peak,
             "unit": "GB/s", "frac": spmv_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src, "ms_per_launch": t_spmv,
             "algorithmic_bytes_per_launch": spmv_bytes, "moved_bytes_per_launch": spmv_moved, "moved_gbs": moved_gbs,
@@ -407,16 +410,16 @@ def run_ours(args):
     other = None
     if packed:
         try:
-            ctx.set_spmv_matrix_free(not args.spmv_mf)
+            ctx.set_spmv_matrix_free(0 if use_mf else 1)
             t_other = ctx.time_kernel(0, reps=20, flush_l2=True)
-            om = spmv_moved_packed if args.spmv_mf else mf_moved
-            other = {"mode": "packed-spmv" if args.spmv_mf else "matrix-free", "ms": t_other, "moved_bytes": om,
+            om = spmv_moved_packed if use_mf else mf_moved
+            other = {"mode": "packed-spmv" if use_mf else "matrix-free", "ms": t_other, "moved_bytes": om,
                      "moved_gbs": om / (t_other * 1e-3) / 1e9, "hbm_utilization": om / (t_other * 1e-3) / 1e9 / hbm_peak}
         except Exception as exc:  # never let the side measurement take the bench line down
             other = {"error": str(exc)}
         finally:
             try:
-                ctx.set_spmv_matrix_free(args.spmv_mf)
+                ctx.set_spmv_matrix_free(mf_mode)
             except Exception:
                 pass
 
@@ -465,7 +468,7 @@ def run_ours(args):
                "phase_ms_per_step": {k: tm[k] / args.steps for k in ("assemble", "residual", "solve", "vector")},
                "roofline": roof, "assembly": asm,
                "kernels": {"spmv_ms": t_spmv, "spmv_gbs": spmv_gbs, "residual_ms": t_res, "block_jacobi_apply_ms": t_bj,
-                           "operator_apply_mode": "matrix-free" if args.spmv_mf else "packed-spmv", "other_apply_mode": other},
+                           "operator_apply_mode": ("packed-spmv", "matrix-free", "table-free")[mf_mode], "other_apply_mode": other},
                "e2e": {"value": e2e_val, "unit": "DoF/s", "h2d_bytes_per_step": int(8 * 18 * T.n_owned_nodes),
                        "d2h_bytes_per_step": int(8 * 18 * T.n_owned_nodes), "ms_per_step": ms_e2e / args.steps,
                        "wall_ms_per_step": wall_e2e / args.steps * 1e3},
