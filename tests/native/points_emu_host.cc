@@ -1,0 +1,83 @@
+// TEST INFRASTRUCTURE: the product's pointwise kernel family (csrc/vh_points_kernel.cuh) compiled by g++ and executed
+// lane by lane under tests/native/cuda_emu.h, so that kernel logic written without GPU access (the matrix-free and
+// table-free operator apply) is checked against the oracle in the CPU-only container.  Never part of the product.
+#include <cuda_runtime.h> // vector types (double2) and the __global__ / __launch_bounds__ macros for a host compiler
+
+#include <algorithm>
+#include <cmath>
+using std::min;
+
+#include "../../verkko-hem-repo_b200/csrc/vh_internal.h"
+
+#include "cuda_emu.h"
+
+#include "../../verkko-hem-repo_b200/csrc/vh_points_kernel.cuh"
+
+// mode 0: assembly (WANT_H: writes Hq, Rc = -cell residual, Dc, avgD)      x = Newton state
+// mode 1: residual only (Rc)                                                x = trial state
+// mode 2: operator apply from the H_q tables (Rc = K_cell z_cell)           x = z (masked Krylov vector), Hq from mode 0
+// mode 3: table-free operator apply                                         x = z, x_state = Newton state
+// mode 4: energy (Ec)
+extern "C" int vht_points_emulated(int degree, int mode, int n_cells, const int32_t *cell_nodes, const double *cell_h4,
+                                   const uint32_t *cell_faces, const uint8_t *cell_owned, const double *x, const double *x_state,
+                                   const double *N, const double *dN, const double *wq, const double *Gref, const double *Mf,
+                                   const double *coef10, double *Hq, double *Rc, double *Dc, double *avgD, double *Ec)
+{
+  VhTables tab{};
+  tab.degree = degree;
+  tab.nn = tab.nq = degree == 1 ? 8 : 27;
+  tab.N    = const_cast<double *>(N);
+  tab.dN   = const_cast<double *>(dN);
+  tab.wq   = const_cast<double *>(wq);
+  tab.Gref = const_cast<double *>(Gref);
+  tab.Mf   = const_cast<double *>(Mf);
+  VhCoef cf{};
+  cf.K1    = coef10[0];
+  cf.K23   = coef10[1] + coef10[2];
+  cf.alpha = coef10[3];
+  for (int k = 0; k < 5; ++k)
+    cf.beta[k] = coef10[4 + k];
+  cf.bt = coef10[9];
+  const vh_hweights hw = vh_make_hweights(cf.alpha, cf.beta);
+  try
+    {
+      if (degree == 1)
+        {
+          const unsigned grid = (unsigned)((n_cells + 4 * VH_PT_WARPS - 1) / (4 * VH_PT_WARPS));
+          const size_t   sm = mode == 3 ? VhPt<8>::SMEM_TFREE : VhPt<8>::SMEM;
+          auto           go = [&](auto kernel) { emu::launch(grid, VH_PT_WARPS * 32, sm, kernel); };
+          if (mode == 0)
+            go([&] { k_points<8, true, false>(n_cells, cell_nodes, cell_h4, cell_faces, cell_owned, x, tab, cf, hw, Hq, Rc, Dc, avgD, Ec); });
+          else if (mode == 1)
+            go([&] { k_points<8, false, false>(n_cells, cell_nodes, cell_h4, cell_faces, cell_owned, x, tab, cf, hw, Hq, Rc, Dc, avgD, Ec); });
+          else if (mode == 2)
+            go([&] { k_points<8, false, false, true>(n_cells, cell_nodes, cell_h4, cell_faces, cell_owned, x, tab, cf, hw, Hq, Rc, Dc, avgD, Ec); });
+          else if (mode == 3)
+            go([&] { k_points<8, false, false, true, true>(n_cells, cell_nodes, cell_h4, cell_faces, cell_owned, x, tab, cf, hw, Hq, Rc, Dc, avgD, Ec, x_state); });
+          else
+            go([&] { k_points<8, false, true>(n_cells, cell_nodes, cell_h4, cell_faces, cell_owned, x, tab, cf, hw, Hq, Rc, Dc, avgD, Ec); });
+        }
+      else
+        {
+          const unsigned grid = (unsigned)((n_cells + VH_PT_WARPS - 1) / VH_PT_WARPS);
+          const size_t   sm = mode == 3 ? VhPt<27>::SMEM_TFREE : VhPt<27>::SMEM;
+          auto           go = [&](auto kernel) { emu::launch(grid, VH_PT_WARPS * 32, sm, kernel); };
+          if (mode == 0)
+            go([&] { k_points<27, true, false>(n_cells, cell_nodes, cell_h4, cell_faces, cell_owned, x, tab, cf, hw, Hq, Rc, Dc, avgD, Ec); });
+          else if (mode == 1)
+            go([&] { k_points<27, false, false>(n_cells, cell_nodes, cell_h4, cell_faces, cell_owned, x, tab, cf, hw, Hq, Rc, Dc, avgD, Ec); });
+          else if (mode == 2)
+            go([&] { k_points<27, false, false, true>(n_cells, cell_nodes, cell_h4, cell_faces, cell_owned, x, tab, cf, hw, Hq, Rc, Dc, avgD, Ec); });
+          else if (mode == 3)
+            go([&] { k_points<27, false, false, true, true>(n_cells, cell_nodes, cell_h4, cell_faces, cell_owned, x, tab, cf, hw, Hq, Rc, Dc, avgD, Ec, x_state); });
+          else
+            go([&] { k_points<27, false, true>(n_cells, cell_nodes, cell_h4, cell_faces, cell_owned, x, tab, cf, hw, Hq, Rc, Dc, avgD, Ec); });
+        }
+    }
+  catch (const std::exception &e)
+    {
+      std::fprintf(stderr, "vht_points_emulated: %s\n", e.what());
+      return -1;
+    }
+  return 0;
+}

@@ -1,0 +1,108 @@
+"""The product's pointwise kernel family k_points (csrc/vh_points_kernel.cuh: assembly tables + cell rhs, residual,
+energy, matrix-free operator apply from the H_q tables, table-free operator apply) compiled by g++ and executed lane by
+lane under a small CUDA emulation (tests/native/cuda_emu.h: one fibre per CUDA thread, __syncthreads / __syncwarp /
+__shfl_*_sync as cooperative yields, dynamic shared memory per block), checked against the oracle's cell matrices.
+This is how kernel LOGIC written without GPU access gets checked in the CPU-only container; parity on hardware is what
+tests/test_gpu_*.py assert."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import femgl_oracle as O
+import verkko_hem_repo_b200 as vh
+from helpers import MATEP_SCC_ON, b_phase_state, coef_vector
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    src = os.path.join(ROOT, "tests", "native", "points_emu_host.cc")
+    csrc = os.path.join(ROOT, "verkko-hem-repo_b200", "csrc")
+    deps = [src, os.path.join(ROOT, "tests", "native", "cuda_emu.h")] + [os.path.join(csrc, f) for f in
+                                                                          ("vh_points_kernel.cuh", "vh_pointwise.cuh", "vh_internal.h")]
+    out = os.path.join(ROOT, "tests", "native", "_build", "libvhpoints_emu.so")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-w", "-shared", "-fPIC", "-I", "/usr/local/cuda/include",
+                               "-I", os.path.join(ROOT, "include"), "-o", out, src])
+    return ctypes.CDLL(out)
+
+
+def _p(a, t=ctypes.c_double):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def _run(T, mode, x, coef, Hq=None, x_state=None):
+    L = _lib()
+    n = T.cell_nodes.shape[1]
+    nq = n
+    N, dN, w, _ = O.fe_tables(T.degree)
+    Gref = np.einsum("q,aqx,bqy->abxy", w, dN, dN).copy()
+    Mf = np.zeros((6, n, n))
+    for f in range(6):
+        Nf, wf = O.face_tables(T.degree, f)
+        Mf[f] = np.einsum("q,aq,bq->ab", wf, Nf, Nf)
+    h4 = np.concatenate([T.cell_h, T.cell_h.prod(axis=1, keepdims=True)], axis=1).copy()
+    faces = np.zeros(T.n_cells, dtype=np.uint32)
+    for c, f, b in zip(T.wall_face_cell, T.wall_face_no, T.wall_face_bid):
+        faces[c] |= np.uint32(int(b) << (4 * int(f)))
+    owned = np.ascontiguousarray(T.cell_owned, dtype=np.uint8)
+    nodes = np.ascontiguousarray(T.cell_nodes, dtype=np.int32)
+    if Hq is None:
+        Hq = np.zeros(T.n_cells * nq * 180)
+    Rc = np.full((T.n_cells, 18 * n), np.nan)
+    Dc = np.zeros((T.n_cells, 18 * n))
+    avgD = np.zeros(T.n_cells)
+    Ec = np.zeros(T.n_cells)
+    xs = x if x_state is None else x_state
+    rc = L.vht_points_emulated(T.degree, mode, T.n_cells, _p(nodes, ctypes.c_int32), _p(h4), _p(faces, ctypes.c_uint32),
+                               _p(owned, ctypes.c_uint8), _p(x), _p(xs), _p(N), _p(dN), _p(w), _p(Gref), _p(Mf), _p(coef), _p(Hq),
+                               _p(Rc), _p(Dc), _p(avgD), _p(Ec))
+    assert rc == 0
+    return Hq, Rc, Dc, avgD, Ec
+
+
+def _mesh(kind):
+    if kind == "q1-walls":
+        return vh.Mesh(1, [-1.0, -2.0, -0.5], [1.5, 1.0, 0.75], base=(2, 3, 1), face_bid=(2, 2, 3, 1, 4, 4), n_global_refine=0).finalize(1).tables(0)
+    if kind == "q1-ragged":  # 18 cells: the last warp of the last block is only half full
+        return vh.Mesh(1, [-1.0, -1.0, -1.0], [2.0, 2.0, 1.0], base=(3, 3, 2), face_bid=(1, 1, 1, 1, 4, 4), n_global_refine=0).finalize(1).tables(0)
+    if kind == "q2-walls":
+        return vh.Mesh(2, [-1.0, -2.0, -0.5], [1.5, 1.0, 0.75], base=(2, 1, 1), face_bid=(2, 2, 3, 1, 4, 4), n_global_refine=0).finalize(1).tables(0)
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("kind,bt", [("q1-walls", 0.7), ("q1-ragged", 2.0), ("q1-ragged", 1e10), ("q2-walls", 0.7)])
+def test_emulated_pointwise_kernels_match_oracle_cells(kind, bt):
+    T = _mesh(kind)
+    coef = coef_vector(MATEP_SCC_ON, bt)
+    x = b_phase_state(T, seed=31)
+    fptr, fno, fbid = T.face_csr()
+    dummy = np.zeros(1, np.int32)
+    K, r, e = O.cells(T.degree, T.cell_nodes, T.cell_origin, T.cell_h, x, coef, fptr, fno if fno.size else dummy,
+                      fbid if fbid.size else dummy, want_matrix=True, want_energy=True)
+    dofs = (18 * T.cell_nodes.astype(np.int64)[:, :, None] + np.arange(18)[None, None, :]).reshape(T.n_cells, -1)
+    scale = np.abs(K).max()
+    # assembly mode: cell rhs, cell-matrix diagonal, mean |diag|, and the packed H_q tables (used below)
+    Hq, Rc, Dc, avgD, _ = _run(T, 0, x, coef)
+    assert np.abs(Rc - r).max() <= 1e-12 * np.abs(r).max()
+    diag = np.einsum("eii->ei", K)
+    assert np.abs(Dc - diag).max() <= 1e-12 * scale
+    assert np.abs(avgD - np.abs(diag).mean(axis=1)).max() <= 1e-12 * scale
+    # residual-only mode and the energy
+    _, Rc1, _, _, _ = _run(T, 1, x, coef)
+    assert np.abs(Rc1 - r).max() <= 1e-12 * np.abs(r).max()
+    _, _, _, _, Ec = _run(T, 4, x, coef)
+    assert np.abs(Ec - e).max() <= 1e-12 * np.abs(e).max()
+    # operator apply: from the tables (mode 2) and table-free (mode 3), for two random directions
+    rng = np.random.default_rng(5)
+    for _ in range(2):
+        z = rng.uniform(-1, 1, x.size)
+        want = np.einsum("eij,ej->ei", K, z[dofs])
+        _, Y2, _, _, _ = _run(T, 2, z, coef, Hq=Hq)
+        assert np.abs(Y2 - want).max() <= 1e-12 * np.abs(want).max(), "apply from the H_q tables"
+        _, Y3, _, _, _ = _run(T, 3, z, coef, x_state=x)
+        assert np.abs(Y3 - want).max() <= 1e-12 * np.abs(want).max(), "table-free apply"
