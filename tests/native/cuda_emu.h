@@ -176,6 +176,8 @@ inline T shfl_common(T v, int src_lane)
 #ifndef __global__
 #define __global__
 #endif
+#undef __shared__
+#define __shared__ static /* one copy per kernel instantiation: blocks run one after the other, all fibres of a block share it */
 #endif
 #define threadIdx (emu::cur().tid)
 #define blockIdx (emu::block()->bid)

@@ -12,6 +12,7 @@ using std::min;
 #include "cuda_emu.h"
 
 #include "../../verkko-hem-repo_b200/csrc/vh_points_kernel.cuh"
+#include "../../verkko-hem-repo_b200/csrc/vh_diag_kernel.cuh"
 
 // mode 0: assembly (WANT_H: writes Hq, Rc = -cell residual, Dc, avgD)      x = Newton state
 // mode 1: residual only (Rc)                                                x = trial state
@@ -77,6 +78,28 @@ extern "C" int vht_points_emulated(int degree, int mode, int n_cells, const int3
   catch (const std::exception &e)
     {
       std::fprintf(stderr, "vht_points_emulated: %s\n", e.what());
+      return -1;
+    }
+  return 0;
+}
+
+// diagonal packed blocks of the lattice rows from the H_q tables: k_diag_cells + k_diag_gather (vh_diag_kernel.cuh)
+extern "C" int vht_diag_emulated(int degree, int n_cells, const double *N, const double *wq, const double *Hq, int n_fast,
+                                 const int32_t *fast_rows, const int32_t *fast_cells, const int8_t *fast_a, const int32_t *diag_pos,
+                                 double *Dblk, double *pvals)
+{
+  try
+    {
+      if (degree == 1)
+        emu::launch((unsigned)n_cells, 192, 0, [&] { k_diag_cells<8>(n_cells, N, wq, Hq, Dblk); });
+      else
+        emu::launch((unsigned)n_cells, 192, 0, [&] { k_diag_cells<27>(n_cells, N, wq, Hq, Dblk); });
+      emu::launch((unsigned)n_fast, 192, 0,
+                  [&] { k_diag_gather(n_fast, degree == 1 ? 8 : 27, fast_rows, fast_cells, fast_a, diag_pos, Dblk, pvals); });
+    }
+  catch (const std::exception &e)
+    {
+      std::fprintf(stderr, "vht_diag_emulated: %s\n", e.what());
       return -1;
     }
   return 0;

@@ -160,3 +160,37 @@ def test_table_free_apply_equals_assembled_operator(name):
     its0, _ = ctx.solve(1e-1)
     assert its == its0
     ctx.close()
+
+
+@unverified
+@pytest.mark.parametrize("name", ["q1-cube", "q1-walls-aniso", "q2-cube", "q1-hanging", "q1-periodic"])
+def test_lazy_rows_block_jacobi_and_solve_match_oracle(name, monkeypatch):
+    """VH_MF_LAZY_ROWS=1 with the matrix-free apply: vh_assemble forms only the diagonal blocks of the lattice rows
+    (k_diag_cells + k_diag_gather).  The preconditioner, the GMRES history and the update must equal the oracle's, and the
+    rows must appear on demand (export) identical to an ordinary assembly."""
+    monkeypatch.setenv("VH_SPMV_MF", "1")
+    monkeypatch.setenv("VH_MF_LAZY_ROWS", "1")
+    T, bt = _mesh(name)
+    coef = coef_vector(MATEP_SCC_ON, bt)
+    x = b_phase_state(T, seed=13)
+    A, rhs = O.assemble_global(T, x, coef, True)
+    ctx = vh.Context(T)
+    ctx.set_coef_vector(coef)
+    ctx.set_solution(x)
+    ctx.assemble()
+    Minv = O.block_jacobi_inverse(A, T.n_owned_nodes)
+    z = np.random.default_rng(29).uniform(-1, 1, A.shape[1])
+    p_ora = np.einsum("ijk,ik->ij", Minv, z.reshape(-1, 18)[:T.n_owned_nodes]).ravel()
+    assert np.abs(ctx.precondition(z) - p_ora).max() <= 1e-11 * np.abs(p_ora).max()
+    its, _ = ctx.solve(1e-1)
+    d_ora, its_ora, _, ok = O.gmres_block_jacobi(A, rhs, Minv, 1e-1 * np.linalg.norm(rhs))
+    assert ok and its == its_ora
+    d_ora = O.distribute(T, d_ora)
+    assert np.abs(ctx.get_newton_update() - d_ora).max() <= 1e-9 * np.abs(d_ora).max()
+    from helpers import blockrow_rel_error, bsr_to_csr
+    A_gpu = bsr_to_csr(*ctx.export_matrix_bsr(), T.n_local_nodes)   # assembles the stale rows on demand
+    assert blockrow_rel_error(A_gpu, A) <= 1e-12
+    ctx.set_spmv_matrix_free(0)                                      # and the packed SpMV works afterwards
+    y_ora = A @ z
+    assert np.abs(ctx.spmv(z) - y_ora).max() <= 1e-13 * np.abs(y_ora).max()
+    ctx.close()

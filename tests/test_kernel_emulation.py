@@ -22,7 +22,7 @@ def _lib():
     src = os.path.join(ROOT, "tests", "native", "points_emu_host.cc")
     csrc = os.path.join(ROOT, "verkko-hem-repo_b200", "csrc")
     deps = [src, os.path.join(ROOT, "tests", "native", "cuda_emu.h")] + [os.path.join(csrc, f) for f in
-                                                                          ("vh_points_kernel.cuh", "vh_pointwise.cuh", "vh_internal.h")]
+                                                                          ("vh_points_kernel.cuh", "vh_diag_kernel.cuh", "vh_pointwise.cuh", "vh_internal.h")]
     out = os.path.join(ROOT, "tests", "native", "_build", "libvhpoints_emu.so")
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -106,3 +106,56 @@ def test_emulated_pointwise_kernels_match_oracle_cells(kind, bt):
         assert np.abs(Y2 - want).max() <= 1e-12 * np.abs(want).max(), "apply from the H_q tables"
         _, Y3, _, _, _ = _run(T, 3, z, coef, x_state=x)
         assert np.abs(Y3 - want).max() <= 1e-12 * np.abs(want).max(), "table-free apply"
+
+
+@pytest.mark.parametrize("kind", ["q1-ragged", "q2-walls"])
+def test_emulated_diagonal_block_kernels_match_oracle(kind):
+    """k_diag_cells + k_diag_gather (block-Jacobi's diagonal blocks without assembling the lattice rows): the packed bulk
+    part P_II of every node's diagonal block equals the oracle's, summed over the node's incident cells."""
+    L = _lib()
+    T = _mesh(kind)
+    n = T.cell_nodes.shape[1]
+    coef = coef_vector(MATEP_SCC_ON, 2.0)
+    x = b_phase_state(T, seed=33)
+    Hq, _, _, _, _ = _run(T, 0, x, coef)          # the tables the assembly kernel wrote (emulated)
+    # bulk-only cell matrices from the oracle: gradient coefficients and Robin faces switched off
+    bulk = coef.copy()
+    bulk[0:3] = 0.0
+    bulk[9] = 1e10
+    K, _, _ = O.cells(T.degree, T.cell_nodes, T.cell_origin, T.cell_h, x, bulk, want_matrix=True)
+    want = np.zeros((T.n_local_nodes, 18, 18))
+    for e in range(T.n_cells):
+        for a, node in enumerate(T.cell_nodes[e]):
+            want[node] += K[e, 18 * a:18 * a + 18, 18 * a:18 * a + 18]
+    # row tables as vh_create builds them: incident cells (<= 8) and the local index of the node in each
+    fast_rows = np.arange(T.n_local_nodes, dtype=np.int32)
+    fast_cells = np.full((T.n_local_nodes, 8), -1, dtype=np.int32)
+    fast_a = np.zeros((T.n_local_nodes, 8), dtype=np.int8)
+    fill = np.zeros(T.n_local_nodes, dtype=int)
+    for e in range(T.n_cells):
+        for a, node in enumerate(T.cell_nodes[e]):
+            fast_cells[node, fill[node]] = e
+            fast_a[node, fill[node]] = a
+            fill[node] += 1
+    diag_pos = (3 * np.arange(T.n_local_nodes) + 1).astype(np.int32)  # any scattered block positions
+    N, _, w, _ = O.fe_tables(T.degree)
+    Dblk = np.zeros(T.n_cells * n * 180)
+    pvals = np.full((3 * T.n_local_nodes + 2) * 180, np.nan)
+    rc = L.vht_diag_emulated(T.degree, T.n_cells, _p(N), _p(w), _p(Hq), T.n_local_nodes, _p(fast_rows, ctypes.c_int32),
+                             _p(fast_cells, ctypes.c_int32), _p(fast_a, ctypes.c_int8), _p(diag_pos, ctypes.c_int32), _p(Dblk), _p(pvals))
+    assert rc == 0
+    native = ctypes.CDLL(os.path.join(ROOT, "tests", "native", "_build", "libvhpw.so")) if os.path.exists(
+        os.path.join(ROOT, "tests", "native", "_build", "libvhpw.so")) else None
+    if native is None:
+        import test_host_logic
+        native = test_host_logic._native_pointwise_lib()
+    P = pvals.reshape(-1, 180)
+    scale = np.abs(want).max()
+    for node in range(T.n_local_nodes):
+        blk = P[diag_pos[node]]
+        for c in range(18):
+            for d in range(c, 18):
+                v = blk[native.vht_sym_index(c, d)]
+                assert abs(v - want[node, c, d]) <= 1e-12 * scale, (node, c, d)
+    # untouched blocks stay untouched
+    assert np.isnan(P[0]).all() and np.isnan(P[2]).all()

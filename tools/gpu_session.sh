@@ -12,7 +12,7 @@ if [ "$what" = tests ] || [ "$what" = all ]; then
   timeout 600 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1
   tail -5 gpurun_out/gpu_tests.log
   # opt-in paths that have not run on hardware yet (table-free operator apply)
-  VH_TEST_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_zmatrix_free.py -m gpu -q --tb=short -p no:cacheprovider -k table_free \
+  VH_TEST_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_zmatrix_free.py -m gpu -q --tb=short -p no:cacheprovider -k 'table_free or lazy_rows' \
     > gpurun_out/gpu_tests_unverified.log 2>&1
   tail -5 gpurun_out/gpu_tests_unverified.log
 fi

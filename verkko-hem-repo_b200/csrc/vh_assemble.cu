@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(NQ == 8 ? 192 : 512)
 // 1b. pointwise kernel, one THREAD per quadrature point: csrc/vh_points_kernel.cuh (k_points, VhPt, VH_PT_WARPS)
 // ------------------------------------------------------------------------------------------------
 #include "vh_points_kernel.cuh"
+#include "vh_diag_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // 2. row-owner Jacobian kernel for Q1 rows whose neighbourhood is a piece of a structured lattice
@@ -1504,6 +1505,32 @@ int vhk_apply_fast(vh_ctx *ctx, const double *z_masked, const double *x_orig, do
   k_gather_apply<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n_fast, ctx->dpc, ctx->fast_rows, ctx->fast_cells, ctx->fast_a,
                                                                       ctx->dirmask, ctx->Rc, ctx->cdiag, x_orig, y_owned);
   VH_LAUNCH_CHECK();
+  return VH_OK;
+}
+
+int vhk_diag_fast(vh_ctx *ctx)
+{
+  if (ctx->n_fast == 0 || ctx->n_cells == 0)
+    return VH_OK;
+  if (!ctx->Dblk)
+    VH_TRY(vh_dev_alloc(ctx, &ctx->Dblk, (size_t)ctx->n_cells * ctx->nn * VH_SYMP));
+  if (ctx->degree == 1)
+    k_diag_cells<8><<<ctx->n_cells, 192, 0, ctx->stream>>>(ctx->n_cells, ctx->tab.N, ctx->tab.wq, ctx->Hq, ctx->Dblk);
+  else
+    k_diag_cells<27><<<ctx->n_cells, 192, 0, ctx->stream>>>(ctx->n_cells, ctx->tab.N, ctx->tab.wq, ctx->Hq, ctx->Dblk);
+  VH_LAUNCH_CHECK();
+  k_diag_gather<<<ctx->n_fast, 192, 0, ctx->stream>>>(ctx->n_fast, ctx->nn, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->diag_pos,
+                                                    ctx->Dblk, ctx->pvals);
+  VH_LAUNCH_CHECK();
+  return VH_OK;
+}
+
+int vhk_ensure_rows(vh_ctx *ctx)
+{
+  if (!ctx->rows_stale)
+    return VH_OK;
+  VH_TRY(vhk_rows_fast(ctx)); // from the H_q tables of the last vh_assemble (the pointwise kernel is not rerun)
+  ctx->rows_stale = false;
   return VH_OK;
 }
 

@@ -804,6 +804,7 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   ctx->spmv_mf = ctx->packed && getenv("VH_SPMV_MF") && (getenv("VH_SPMV_MF")[0] == '1' || getenv("VH_SPMV_MF")[0] == '2') &&
                  !(getenv("VH_Q2_POINTWISE_LEGACY") && getenv("VH_Q2_POINTWISE_LEGACY")[0] == '1');
   ctx->spmv_mf_table_free = ctx->spmv_mf && getenv("VH_SPMV_MF")[0] == '2';
+  ctx->rows_lazy          = getenv("VH_MF_LAZY_ROWS") && getenv("VH_MF_LAZY_ROWS")[0] == '1';
   if (ctx->packed)
     {
       VH_TRY(vh_dev_alloc(ctx, &ctx->pvals, (size_t)ctx->nnzb * VH_SYMP));
@@ -1075,7 +1076,7 @@ int vh_destroy(vh_ctx *ctx)
   vh_comm_destroy(ctx);
   void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
                   ctx->diag_pos, ctx->minv, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_first, ctx->spmv_order, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->srow_ptr, ctx->srow_cell, ctx->srow_a, ctx->srow_posb, ctx->srow_wr, ctx->srow_bcons, ctx->srow_posI, ctx->srow_mnode, ctx->srow_mpos, ctx->srow_cons, ctx->push_ptr, ctx->push_dst, ctx->push_peer, ctx->push_ticket, ctx->row_slow,
-                  ctx->slow_cells, ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
+                  ctx->slow_cells, ctx->Hq, ctx->Dblk, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
                   ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
                   ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,
                   ctx->tab.Mf};
@@ -1203,7 +1204,16 @@ static int norm_of(vh_ctx *ctx, const double *v, double *out)
 static int assemble_device(vh_ctx *ctx)
 {
   VH_TRY(vhk_pointwise(ctx, ctx->x_sol, true, false));
-  VH_TRY(vhk_rows_fast(ctx));
+  if (ctx->rows_lazy && ctx->spmv_mf && ctx->packed)
+    { // matrix-free operator: only the diagonal blocks (block-Jacobi) are formed now, the rows on demand
+      VH_TRY(vhk_diag_fast(ctx));
+      ctx->rows_stale = true;
+    }
+  else
+    {
+      VH_TRY(vhk_rows_fast(ctx));
+      ctx->rows_stale = false;
+    }
   VH_TRY(vhk_rhs_fast(ctx, ctx->rhs, true));
   VH_TRY(vhk_rows_slow(ctx, true, ctx->rhs));
   return VH_OK;
@@ -1364,6 +1374,7 @@ int vh_export_matrix_bsr(vh_ctx *ctx, int32_t *row_ptr, int32_t *col, double *va
       VH_CUDA(cudaMemcpy(vals, ctx->vals, sizeof(double) * (size_t)ctx->nnzb * VH_BLK, cudaMemcpyDeviceToHost));
       return VH_OK;
     }
+  VH_TRY(vhk_ensure_rows(ctx)); // lazily assembled lattice rows (VH_MF_LAZY_ROWS=1)
   // packed storage: expand into a temporary full-format copy (tests / diagnostics only)
   double     *tmp = nullptr;
   cudaError_t e   = cudaMalloc((void **)&tmp, sizeof(double) * (size_t)ctx->nnzb * VH_BLK);

@@ -207,6 +207,11 @@ struct vh_ctx
   // with spmv_mf: evaluate H(A_q) z_q from the Newton state instead of reading the H_q tables (VH_SPMV_MF=2 or
   // vh_set_spmv_matrix_free(ctx, 2); written after the round-1 GPU budget was spent: unverified on hardware)
   bool spmv_mf_table_free = false;
+  // VH_MF_LAZY_ROWS=1 (with spmv_mf): vh_assemble does not assemble the lattice rows — only their diagonal blocks, which
+  // block-Jacobi needs (k_diag_cells + k_diag_gather); whoever needs the rows later (packed SpMV after a mode switch,
+  // vh_export_matrix_bsr) assembles them on demand from the H_q tables.  Unverified on hardware in round 1.
+  bool    rows_lazy = false, rows_stale = false;
+  double *Dblk      = nullptr; // [n_cells][nn][180] per-(cell, node) diagonal contributions (allocated on first use)
 
   // state flags
   bool have_matrix = false, have_update = false, have_trial = false;
@@ -274,6 +279,9 @@ int vhk_upload_linalg_constants(vh_ctx *ctx);
 int vhk_expand_packed(vh_ctx *ctx, double *full_vals);
 // matrix-free apply of the lattice rows from the stored H_q tables (ctx->spmv_mf, VH_SPMV_MF=1); see k_points<APPLY>
 int vhk_apply_fast(vh_ctx *ctx, const double *z_masked, const double *x_orig, double *y_owned);
+// diagonal packed blocks of the lattice rows from the H_q tables (rows_lazy); vhk_ensure_rows assembles stale rows on demand
+int vhk_diag_fast(vh_ctx *ctx);
+int vhk_ensure_rows(vh_ctx *ctx);
 int vhk_block_jacobi_setup(vh_ctx *ctx);
 int vhk_block_jacobi_apply(vh_ctx *ctx, const double *x_owned, double *y_owned);
 // push = true (only with ctx->zpush and y_owned == ctx->zbuf): also store the interface values into the neighbours' ghost slots

@@ -917,6 +917,7 @@ int vhk_spmv(vh_ctx *ctx, const double *x_local, double *y_owned, bool x_is_mask
             }
           return VH_OK;
         }
+      VH_TRY(vhk_ensure_rows(ctx)); // lattice rows that were left unassembled for the matrix-free mode (VH_MF_LAZY_ROWS=1)
       static int variant = -1;
       if (variant < 0)
         {
