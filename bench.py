@@ -468,7 +468,7 @@ def run_ours(args):
                "phase_ms_per_step": {k: tm[k] / args.steps for k in ("assemble", "residual", "solve", "vector")},
                "roofline": roof, "assembly": asm,
                "kernels": {"spmv_ms": t_spmv, "spmv_gbs": spmv_gbs, "residual_ms": t_res, "block_jacobi_apply_ms": t_bj,
-                           "operator_apply_mode": ("packed-spmv", "matrix-free", "table-free")[mf_mode], "other_apply_mode": other},
+                           "operator_apply_mode": ("packed-spmv", "matrix-free", "table-free", "matrix-free-v2")[mf_mode], "other_apply_mode": other},
                "e2e": {"value": e2e_val, "unit": "DoF/s", "h2d_bytes_per_step": int(8 * 18 * T.n_owned_nodes),
                        "d2h_bytes_per_step": int(8 * 18 * T.n_owned_nodes), "ms_per_step": ms_e2e / args.steps,
                        "wall_ms_per_step": wall_e2e / args.steps * 1e3},

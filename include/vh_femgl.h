@@ -163,7 +163,8 @@ int vh_timer_stop(vh_ctx *ctx, float *ms);
 int vh_measure_fp64_peak(vh_ctx *ctx, double *tflops);
 /* Operator apply of the lattice rows inside vh_solve / vh_spmv (collective: same value on every rank):
  *   0 = packed SpMV over the assembled blocks (default), 1 = matrix-free from the H_q tables of the last vh_assemble,
- *   2 = matrix-free and table-free: H(A_q) z_q evaluated from the Newton state (unverified on hardware in round 1).
+ *   2 = matrix-free and table-free: H(A_q) z_q evaluated from the Newton state (unverified on hardware in round 1),
+ *   3 = second formulation of mode 1 at Q1 (per-cell geometry table, higher occupancy; unverified on hardware in round 1).
  * The initial value comes from the environment variable VH_SPMV_MF.  VH_ERR_UNSUPPORTED if the context has no packed
  * lattice rows (nothing to apply matrix-free). */
 int vh_set_spmv_matrix_free(vh_ctx *ctx, int on);

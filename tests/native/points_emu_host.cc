@@ -13,6 +13,7 @@ using std::min;
 
 #include "../../verkko-hem-repo_b200/csrc/vh_points_kernel.cuh"
 #include "../../verkko-hem-repo_b200/csrc/vh_diag_kernel.cuh"
+#include "../../verkko-hem-repo_b200/csrc/vh_apply_v2.cuh"
 
 // mode 0: assembly (WANT_H: writes Hq, Rc = -cell residual, Dc, avgD)      x = Newton state
 // mode 1: residual only (Rc)                                                x = trial state
@@ -100,6 +101,39 @@ extern "C" int vht_diag_emulated(int degree, int n_cells, const double *N, const
   catch (const std::exception &e)
     {
       std::fprintf(stderr, "vht_diag_emulated: %s\n", e.what());
+      return -1;
+    }
+  return 0;
+}
+
+// second formulation of the Q1 matrix-free apply (vh_apply_v2.cuh)
+extern "C" int vht_apply_v2_emulated(int n_cells, const int32_t *cell_nodes, const double *cell_h4, const uint32_t *cell_faces,
+                                     const double *z, const double *N, const double *dN, const double *wq, const double *Gref,
+                                     const double *Mf, const double *coef10, const double *Hq, double *Yc)
+{
+  VhTables tab{};
+  tab.degree = 1;
+  tab.nn = tab.nq = 8;
+  tab.N    = const_cast<double *>(N);
+  tab.dN   = const_cast<double *>(dN);
+  tab.wq   = const_cast<double *>(wq);
+  tab.Gref = const_cast<double *>(Gref);
+  tab.Mf   = const_cast<double *>(Mf);
+  VhCoef cf{};
+  cf.K1    = coef10[0];
+  cf.K23   = coef10[1] + coef10[2];
+  cf.alpha = coef10[3];
+  for (int k = 0; k < 5; ++k)
+    cf.beta[k] = coef10[4 + k];
+  cf.bt = coef10[9];
+  try
+    {
+      emu::launch((unsigned)((n_cells + 4 * VH_V2_WARPS - 1) / (4 * VH_V2_WARPS)), VH_V2_WARPS * 32, 0,
+                  [&] { k_apply_q1_v2(n_cells, cell_nodes, cell_h4, cell_faces, z, tab, cf, Hq, Yc); });
+    }
+  catch (const std::exception &e)
+    {
+      std::fprintf(stderr, "vht_apply_v2_emulated: %s\n", e.what());
       return -1;
     }
   return 0;

@@ -137,9 +137,11 @@ unverified = pytest.mark.skipif(os.environ.get("VH_TEST_UNVERIFIED") != "1",
 
 
 @unverified
+@pytest.mark.parametrize("mode", [2, 3])
 @pytest.mark.parametrize("name", NAMES)
-def test_table_free_apply_equals_assembled_operator(name):
-    """Mode 2 of the operator apply: H(A_q) z_q evaluated from the Newton state (vh_hessian_apply), no H_q table read."""
+def test_table_free_apply_equals_assembled_operator(name, mode):
+    """Mode 2 of the operator apply: H(A_q) z_q evaluated from the Newton state (vh_hessian_apply), no H_q table read.
+    Mode 3: second formulation of the table apply at Q1 (csrc/vh_apply_v2.cuh; Q2 contexts fall back to mode 1)."""
     T, bt = _mesh(name)
     coef = coef_vector(MATEP_SCC_ON, bt)
     x = b_phase_state(T, seed=13)
@@ -148,8 +150,8 @@ def test_table_free_apply_equals_assembled_operator(name):
     ctx.set_coef_vector(coef)
     ctx.set_solution(x)
     ctx.assemble()
-    ctx.set_spmv_matrix_free(2)
-    assert ctx.info()["spmv_matrix_free"] == 2
+    ctx.set_spmv_matrix_free(mode)
+    assert ctx.info()["spmv_matrix_free"] == mode
     rng = np.random.default_rng(19)
     for _ in range(2):
         z = rng.uniform(-1, 1, A.shape[1])

@@ -22,7 +22,7 @@ def _lib():
     src = os.path.join(ROOT, "tests", "native", "points_emu_host.cc")
     csrc = os.path.join(ROOT, "verkko-hem-repo_b200", "csrc")
     deps = [src, os.path.join(ROOT, "tests", "native", "cuda_emu.h")] + [os.path.join(csrc, f) for f in
-                                                                          ("vh_points_kernel.cuh", "vh_diag_kernel.cuh", "vh_pointwise.cuh", "vh_internal.h")]
+                                                                          ("vh_points_kernel.cuh", "vh_diag_kernel.cuh", "vh_apply_v2.cuh", "vh_pointwise.cuh", "vh_internal.h")]
     out = os.path.join(ROOT, "tests", "native", "_build", "libvhpoints_emu.so")
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -159,3 +159,39 @@ def test_emulated_diagonal_block_kernels_match_oracle(kind):
                 assert abs(v - want[node, c, d]) <= 1e-12 * scale, (node, c, d)
     # untouched blocks stay untouched
     assert np.isnan(P[0]).all() and np.isnan(P[2]).all()
+
+
+@pytest.mark.parametrize("kind,bt", [("q1-walls", 0.7), ("q1-ragged", 2.0), ("q1-ragged", 1e10)])
+def test_emulated_apply_v2_matches_oracle_cells(kind, bt):
+    """Second formulation of the Q1 matrix-free apply (bulk part through the H_q tables with lane = point, gradient and
+    Robin forms as a per-cell 8x8 table with lane = node): K_cell z_cell of the oracle for every cell."""
+    L = _lib()
+    T = _mesh(kind)
+    coef = coef_vector(MATEP_SCC_ON, bt)
+    x = b_phase_state(T, seed=31)
+    fptr, fno, fbid = T.face_csr()
+    dummy = np.zeros(1, np.int32)
+    K, _, _ = O.cells(1, T.cell_nodes, T.cell_origin, T.cell_h, x, coef, fptr, fno if fno.size else dummy,
+                      fbid if fbid.size else dummy, want_matrix=True)
+    dofs = (18 * T.cell_nodes.astype(np.int64)[:, :, None] + np.arange(18)[None, None, :]).reshape(T.n_cells, -1)
+    Hq, _, _, _, _ = _run(T, 0, x, coef)
+    N, dN, w, _ = O.fe_tables(1)
+    Gref = np.einsum("q,aqx,bqy->abxy", w, dN, dN).copy()
+    Mf = np.zeros((6, 8, 8))
+    for f in range(6):
+        Nf, wf = O.face_tables(1, f)
+        Mf[f] = np.einsum("q,aq,bq->ab", wf, Nf, Nf)
+    h4 = np.concatenate([T.cell_h, T.cell_h.prod(axis=1, keepdims=True)], axis=1).copy()
+    faces = np.zeros(T.n_cells, dtype=np.uint32)
+    for c, f, b in zip(T.wall_face_cell, T.wall_face_no, T.wall_face_bid):
+        faces[c] |= np.uint32(int(b) << (4 * int(f)))
+    nodes = np.ascontiguousarray(T.cell_nodes, dtype=np.int32)
+    rng = np.random.default_rng(6)
+    for _ in range(2):
+        z = rng.uniform(-1, 1, x.size)
+        want = np.einsum("eij,ej->ei", K, z[dofs])
+        Yc = np.full((T.n_cells, 144), np.nan)
+        rc = L.vht_apply_v2_emulated(T.n_cells, _p(nodes, ctypes.c_int32), _p(h4), _p(faces, ctypes.c_uint32), _p(z), _p(N), _p(dN), _p(w),
+                                     _p(Gref), _p(Mf), _p(coef), _p(Hq), _p(Yc))
+        assert rc == 0
+        assert np.abs(Yc - want).max() <= 1e-12 * np.abs(want).max()

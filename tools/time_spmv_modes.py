@@ -26,11 +26,11 @@ ctx.assemble()
 info = ctx.info()
 n = 8 if degree == 1 else 27
 print("Q%d r%d: %d DoFs, %d blocks, setup %.1f s" % (degree, refine, info["n_owned_dofs"], info["nnzb"], time.time() - t0), flush=True)
-modes = (0, 1, 0, 1) + ((2, 2) if os.environ.get("VH_TEST_UNVERIFIED") == "1" else ())
+modes = (0, 1, 0, 1) + ((2, 2, 3, 3) if os.environ.get("VH_TEST_UNVERIFIED") == "1" else ())
 for mode in modes:
     ctx.set_spmv_matrix_free(mode)
     ms = ctx.time_kernel(0, reps, True)
-    byts = (8 * 180 * n * T.n_cells) if mode == 1 else ((8 * 180 * info["n_packed_blocks"]) if mode == 0 else 2 * 8 * 18 * T.n_local_nodes)
-    print("mode %s: %.4f ms per apply, streams %.3f GB -> %.0f GB/s" % (("packed-spmv", "matrix-free", "table-free")[mode], ms, byts / 1e9, byts / ms / 1e6),
+    byts = (8 * 180 * n * T.n_cells) if mode in (1, 3) else ((8 * 180 * info["n_packed_blocks"]) if mode == 0 else 2 * 8 * 18 * T.n_local_nodes)
+    print("mode %s: %.4f ms per apply, streams %.3f GB -> %.0f GB/s" % (("packed-spmv", "matrix-free", "table-free", "matrix-free-v2")[mode], ms, byts / 1e9, byts / ms / 1e6),
           flush=True)
 ctx.close()

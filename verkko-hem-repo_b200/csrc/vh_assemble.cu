@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(NQ == 8 ? 192 : 512)
 // ------------------------------------------------------------------------------------------------
 #include "vh_points_kernel.cuh"
 #include "vh_diag_kernel.cuh"
+#include "vh_apply_v2.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // 2. row-owner Jacobian kernel for Q1 rows whose neighbourhood is a piece of a structured lattice
@@ -1454,6 +1455,17 @@ int vhk_apply_fast(vh_ctx *ctx, const double *z_masked, const double *x_orig, do
 {
   if (ctx->n_fast == 0 || ctx->n_cells == 0)
     return VH_OK;
+  if (ctx->spmv_mf_v2 && ctx->degree == 1)
+    { // second formulation (Q1): lane = point for the bulk part, lane = node with a per-cell geometry table for the rest
+      k_apply_q1_v2<<<(ctx->n_cells + 4 * VH_V2_WARPS - 1) / (4 * VH_V2_WARPS), VH_V2_WARPS * 32, 0, ctx->stream>>>(
+        ctx->n_cells, ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, z_masked, ctx->tab, ctx->coef, ctx->Hq, ctx->Rc);
+      VH_LAUNCH_CHECK();
+      const int64_t n0 = (int64_t)ctx->n_fast * 18;
+      k_gather_apply<<<(unsigned)((n0 + 255) / 256), 256, 0, ctx->stream>>>(ctx->n_fast, ctx->dpc, ctx->fast_rows, ctx->fast_cells, ctx->fast_a,
+                                                                           ctx->dirmask, ctx->Rc, ctx->cdiag, x_orig, y_owned);
+      VH_LAUNCH_CHECK();
+      return VH_OK;
+    }
   if (ctx->spmv_mf_table_free)
     { // table-free variant: the Jacobian is the one of the state the last vh_assemble saw (ctx->x_sol until vh_accept_trial,
       // which invalidates the matrix anyway)

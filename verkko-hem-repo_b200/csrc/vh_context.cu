@@ -801,9 +801,10 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   // ---- matrix, scratch, vectors ----
   // storage format: packed symmetric blocks for the lattice rows unless VH_FULL_BSR=1 (A/B switch, full 18x18 blocks)
   ctx->packed = ctx->n_fast > 0 && (ctx->degree == 2 || !(getenv("VH_FULL_BSR") && getenv("VH_FULL_BSR")[0] == '1'));
-  ctx->spmv_mf = ctx->packed && getenv("VH_SPMV_MF") && (getenv("VH_SPMV_MF")[0] == '1' || getenv("VH_SPMV_MF")[0] == '2') &&
+  ctx->spmv_mf = ctx->packed && getenv("VH_SPMV_MF") && (getenv("VH_SPMV_MF")[0] >= '1' && getenv("VH_SPMV_MF")[0] <= '3') &&
                  !(getenv("VH_Q2_POINTWISE_LEGACY") && getenv("VH_Q2_POINTWISE_LEGACY")[0] == '1');
   ctx->spmv_mf_table_free = ctx->spmv_mf && getenv("VH_SPMV_MF")[0] == '2';
+  ctx->spmv_mf_v2         = ctx->spmv_mf && getenv("VH_SPMV_MF")[0] == '3';
   ctx->rows_lazy          = getenv("VH_MF_LAZY_ROWS") && getenv("VH_MF_LAZY_ROWS")[0] == '1';
   if (ctx->packed)
     {
@@ -1352,7 +1353,7 @@ int vh_get_info(vh_ctx *ctx, vh_info *info)
   info->n_slow_cells = ctx->n_slow_cells;
   info->device_bytes = ctx->device_bytes;
   info->n_packed_blocks = 0;
-  info->spmv_matrix_free = ctx->spmv_mf ? (ctx->spmv_mf_table_free ? 2 : 1) : 0;
+  info->spmv_matrix_free = ctx->spmv_mf ? (ctx->spmv_mf_table_free ? 2 : (ctx->spmv_mf_v2 ? 3 : 1)) : 0;
   if (ctx->packed)
     for (int32_t I = 0; I < ctx->n_owned; ++I)
       if (ctx->h_fast_index.size() && ctx->h_fast_index[I] >= 0)
@@ -1548,6 +1549,7 @@ int vh_set_spmv_matrix_free(vh_ctx *ctx, int on)
     return vh_fail(ctx, VH_ERR_UNSUPPORTED, "matrix-free apply needs the H_q layout of k_points (VH_Q2_POINTWISE_LEGACY is set)");
   ctx->spmv_mf            = on != 0;
   ctx->spmv_mf_table_free = on == 2;
+  ctx->spmv_mf_v2         = on == 3;
   return VH_OK;
 }
 

@@ -207,6 +207,7 @@ struct vh_ctx
   // with spmv_mf: evaluate H(A_q) z_q from the Newton state instead of reading the H_q tables (VH_SPMV_MF=2 or
   // vh_set_spmv_matrix_free(ctx, 2); written after the round-1 GPU budget was spent: unverified on hardware)
   bool spmv_mf_table_free = false;
+  bool spmv_mf_v2         = false; // mode 3 (Q1): second formulation of the table apply, csrc/vh_apply_v2.cuh (unverified on hardware)
   // VH_MF_LAZY_ROWS=1 (with spmv_mf): vh_assemble does not assemble the lattice rows — only their diagonal blocks, which
   // block-Jacobi needs (k_diag_cells + k_diag_gather); whoever needs the rows later (packed SpMV after a mode switch,
   // vh_export_matrix_bsr) assembles them on demand from the H_q tables.  Unverified on hardware in round 1.
