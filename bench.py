@@ -367,12 +367,6 @@ def run_ours(args):
     t_rows = ctx.time_kernel(6, reps=5, flush_l2=True)
     t_res = ctx.time_kernel(2, reps=5, flush_l2=True)
     t_bj = ctx.time_kernel(3, reps=10, flush_l2=True)
-    t_aad = None
-    if world == 1:  # (with several ranks the kernel ends in an all-reduce: a collective, left out of the side measurements)
-        try:
-            t_aad = ctx.time_kernel(4, reps=10, flush_l2=True)  # fused add_and_dot (one modified Gram-Schmidt step)
-        except Exception:
-            t_aad = None
     fp64_peak = ctx.measure_fp64_peak()
     hbm_peak, peak_src = peaks()
     n = 8 if args.degree == 1 else 27
@@ -474,11 +468,11 @@ def run_ours(args):
                "phase_ms_per_step": {k: tm[k] / args.steps for k in ("assemble", "residual", "solve", "vector")},
                "roofline": roof, "assembly": asm,
                # the other HBM-bound kernels with SURVEY.md section 8(d)'s algorithmic bytes: residual assembly 8*dpc*cells (gather)
-               # + 8*N (write); block-Jacobi apply 2592*nb + 16*N; add_and_dot 8*(3 reads + 1 write)*N
+               # + 8*N (write); block-Jacobi apply 2592*nb + 16*N
                "kernels": {"spmv_ms": t_spmv, "spmv_gbs": spmv_gbs, "residual_ms": t_res,
                            "residual_gbs": (8 * 18 * n * T.n_cells + 8 * 18 * nb) / (t_res * 1e-3) / 1e9,
                            "block_jacobi_apply_ms": t_bj, "block_jacobi_apply_gbs": (2592 * nb + 16 * 18 * nb) / (t_bj * 1e-3) / 1e9,
-                           "add_and_dot_ms": t_aad, "add_and_dot_gbs": (32 * 18 * nb) / (t_aad * 1e-3) / 1e9 if t_aad else None,
+
                            "operator_apply_mode": ("packed-spmv", "matrix-free", "table-free", "matrix-free-v2")[mf_mode], "other_apply_mode": other},
                "e2e": {"value": e2e_val, "unit": "DoF/s", "h2d_bytes_per_step": int(8 * 18 * T.n_owned_nodes),
                        "d2h_bytes_per_step": int(8 * 18 * T.n_owned_nodes), "ms_per_step": ms_e2e / args.steps,
