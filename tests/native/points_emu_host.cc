@@ -14,6 +14,7 @@ using std::min;
 #include "../../verkko-hem-repo_b200/csrc/vh_points_kernel.cuh"
 #include "../../verkko-hem-repo_b200/csrc/vh_diag_kernel.cuh"
 #include "../../verkko-hem-repo_b200/csrc/vh_apply_v2.cuh"
+#include "../../verkko-hem-repo_b200/csrc/vh_gather_kernels.cuh"
 
 // mode 0: assembly (WANT_H: writes Hq, Rc = -cell residual, Dc, avgD)      x = Newton state
 // mode 1: residual only (Rc)                                                x = trial state
@@ -134,6 +135,27 @@ extern "C" int vht_apply_v2_emulated(int n_cells, const int32_t *cell_nodes, con
   catch (const std::exception &e)
     {
       std::fprintf(stderr, "vht_apply_v2_emulated: %s\n", e.what());
+      return -1;
+    }
+  return 0;
+}
+
+// the two row gathers (vh_gather_kernels.cuh): which = 0: k_rhs_fast (rhs + cdiag from Rc, Dc, avgD), 1: k_gather_apply
+extern "C" int vht_gather_emulated(int which, int n_fast, int dpc, const int32_t *fast_rows, const int32_t *fast_cells, const int8_t *fast_a,
+                                   const uint32_t *dirmask, const double *cellvec, const double *Dc, const double *avgD, double *cdiag,
+                                   const double *x_orig, double *out)
+{
+  try
+    {
+      const unsigned grid = (unsigned)(((int64_t)n_fast * 18 + 255) / 256);
+      if (which == 0)
+        emu::launch(grid, 256, 0, [&] { k_rhs_fast(n_fast, dpc, fast_rows, fast_cells, fast_a, dirmask, cellvec, out, Dc, avgD, cdiag); });
+      else
+        emu::launch(grid, 256, 0, [&] { k_gather_apply(n_fast, dpc, fast_rows, fast_cells, fast_a, dirmask, cellvec, cdiag, x_orig, out); });
+    }
+  catch (const std::exception &e)
+    {
+      std::fprintf(stderr, "vht_gather_emulated: %s\n", e.what());
       return -1;
     }
   return 0;

@@ -22,7 +22,7 @@ def _lib():
     src = os.path.join(ROOT, "tests", "native", "points_emu_host.cc")
     csrc = os.path.join(ROOT, "verkko-hem-repo_b200", "csrc")
     deps = [src, os.path.join(ROOT, "tests", "native", "cuda_emu.h")] + [os.path.join(csrc, f) for f in
-                                                                          ("vh_points_kernel.cuh", "vh_diag_kernel.cuh", "vh_apply_v2.cuh", "vh_pointwise.cuh", "vh_internal.h")]
+                                                                          ("vh_points_kernel.cuh", "vh_diag_kernel.cuh", "vh_apply_v2.cuh", "vh_gather_kernels.cuh", "vh_pointwise.cuh", "vh_internal.h")]
     out = os.path.join(ROOT, "tests", "native", "_build", "libvhpoints_emu.so")
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -195,3 +195,56 @@ def test_emulated_apply_v2_matches_oracle_cells(kind, bt):
                                      _p(Gref), _p(Mf), _p(coef), _p(Hq), _p(Yc))
         assert rc == 0
         assert np.abs(Yc - want).max() <= 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("kind,bt,apply_mode", [("q1-walls", 0.7, 2), ("q1-walls", 0.7, 3), ("q1-ragged", 2.0, 2), ("q2-walls", 0.7, 2),
+                                                 ("q2-walls", 0.7, 3)])
+def test_emulated_lattice_row_pipeline_matches_oracle_global(kind, bt, apply_mode):
+    """End to end on the CPU, for meshes whose rows are all lattice rows: pointwise assembly kernel -> k_rhs_fast (system_rhs
+    and the constrained-diagonal values of distribute_local_to_global) -> matrix-free operator apply (k_points<APPLY> from the
+    tables or table-free, then k_gather_apply with the Dirichlet rule) against the oracle's GLOBAL rhs and matrix."""
+    L = _lib()
+    T = _mesh(kind)
+    n = T.cell_nodes.shape[1]
+    dpc = 18 * n
+    coef = coef_vector(MATEP_SCC_ON, bt)
+    x = b_phase_state(T, seed=35)
+    A, rhs_ora = O.assemble_global(T, x, coef, True)
+    Hq, Rc, Dc, avgD, _ = _run(T, 0, x, coef)
+    nn = T.n_local_nodes
+    fast_rows = np.arange(nn, dtype=np.int32)
+    fast_cells = np.full((nn, 8), -1, dtype=np.int32)
+    fast_a = np.zeros((nn, 8), dtype=np.int8)
+    fill = np.zeros(nn, dtype=int)
+    for e in range(T.n_cells):
+        for a, node in enumerate(T.cell_nodes[e]):
+            fast_cells[node, fill[node]] = e
+            fast_a[node, fill[node]] = a
+            fill[node] += 1
+    dirmask = np.zeros(nn, dtype=np.uint32)
+    assert T.c_master.size == 0                      # only masked Dirichlet lines on these meshes
+    for dof in T.c_dof:
+        dirmask[dof // 18] |= np.uint32(1 << int(dof % 18))
+    rhs = np.full(18 * nn, np.nan)
+    cdiag = np.full(18 * nn, np.nan)
+    dummy = np.zeros(1)
+    I32, I8, U32 = ctypes.c_int32, ctypes.c_int8, ctypes.c_uint32
+    rc = L.vht_gather_emulated(0, nn, dpc, _p(fast_rows, I32), _p(fast_cells, I32), _p(fast_a, I8), _p(dirmask, U32), _p(Rc), _p(Dc),
+                               _p(avgD), _p(cdiag), _p(dummy), _p(rhs))
+    assert rc == 0
+    assert np.abs(rhs - rhs_ora).max() <= 1e-12 * np.abs(rhs_ora).max()
+    rng = np.random.default_rng(8)
+    z = rng.uniform(-1, 1, 18 * nn)
+    con = np.zeros(18 * nn, dtype=bool)
+    con[T.c_dof] = True
+    zm = np.where(con, 0.0, z)                         # what k_mask_dirichlet hands to the cell kernel
+    if apply_mode == 2:
+        _, Yc, _, _, _ = _run(T, 2, zm, coef, Hq=Hq)
+    else:
+        _, Yc, _, _, _ = _run(T, 3, zm, coef, x_state=x)
+    y = np.full(18 * nn, np.nan)
+    rc = L.vht_gather_emulated(1, nn, dpc, _p(fast_rows, I32), _p(fast_cells, I32), _p(fast_a, I8), _p(dirmask, U32), _p(Yc), _p(Dc),
+                               _p(avgD), _p(cdiag), _p(z), _p(y))
+    assert rc == 0
+    y_ora = A @ z
+    assert np.abs(y - y_ora).max() <= 1e-12 * np.abs(y_ora).max()
