@@ -18,6 +18,7 @@
 #include <cstring>
 #include <functional>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 namespace emu
@@ -43,6 +44,7 @@ struct Block
   int                   cur = -1;
   std::function<void()> body;
 };
+constexpr size_t kGuard = 65536; // bytes, a multiple of 16: wide enough to absorb a whole mis-sized buffer
 inline Block *&block()
 {
   static Block *b = nullptr;
@@ -144,15 +146,20 @@ inline void launch(unsigned grid, unsigned block_threads, size_t smem_bytes, con
       B.bid.x  = b;
       B.bdim.x = block_threads;
       B.gdim.x = grid;
-      B.dyn_smem.assign(smem_bytes + 64, 0);
+      // dynamic shared memory with guard zones on both sides: a kernel that writes outside its launch size is caught
+      B.dyn_smem.assign(smem_bytes + 2 * kGuard + 64, (char)0x5a);
       B.body = body;
       run_block(B, block_threads, stack_bytes);
+      const char *base = reinterpret_cast<const char *>((reinterpret_cast<uintptr_t>(B.dyn_smem.data()) + 15) & ~uintptr_t(15));
+      for (size_t i = 0; i < kGuard; ++i)
+        if (base[i] != (char)0x5a || base[kGuard + smem_bytes + i] != (char)0x5a)
+          throw std::runtime_error("cuda_emu: write outside the dynamic shared memory of the launch (block " + std::to_string(b) + ")");
     }
 }
 inline double *dyn_smem()
 {
   char *p = block()->dyn_smem.data();
-  return reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
+  return reinterpret_cast<double *>(((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15)) + kGuard);
 }
 template <class T>
 inline T shfl_common(T v, int src_lane)
