@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE: the product's pointwise kernel family (csrc/vh_points_kernel.cuh) compiled by g++ and executed
 // lane by lane under tests/native/cuda_emu.h, so that kernel logic written without GPU access (the matrix-free and
 // table-free operator apply) is checked against the oracle in the CPU-only container.  Never part of the product.
+#include <vector>
 #include <cuda_runtime.h> // vector types (double2) and the __global__ / __launch_bounds__ macros for a host compiler
 
 #include <algorithm>
@@ -96,8 +97,13 @@ extern "C" int vht_diag_emulated(int degree, int n_cells, const double *N, const
         emu::launch((unsigned)n_cells, 192, 0, [&] { k_diag_cells<8>(n_cells, N, wq, Hq, Dblk); });
       else
         emu::launch((unsigned)n_cells, 192, 0, [&] { k_diag_cells<27>(n_cells, N, wq, Hq, Dblk); });
+      std::vector<double> dpack((size_t)n_fast * VH_SYMP, 0.0); // the kernel writes [fast row][180]; the test reads block positions
+      double *dp = dpack.data();
       emu::launch((unsigned)n_fast, 192, 0,
-                  [&] { k_diag_gather(n_fast, degree == 1 ? 8 : 27, fast_rows, fast_cells, fast_a, diag_pos, Dblk, pvals); });
+                  [&] { k_diag_gather(n_fast, degree == 1 ? 8 : 27, fast_rows, fast_cells, fast_a, Dblk, dp); });
+      for (int r = 0; r < n_fast; ++r)
+        for (int e = 0; e < VH_SYMP; ++e)
+          pvals[(size_t)diag_pos[fast_rows[r]] * VH_SYMP + e] = dpack[(size_t)r * VH_SYMP + e];
     }
   catch (const std::exception &e)
     {

@@ -49,10 +49,8 @@ def test_q1_all_walls_and_anisotropic_box():
     _check_assembly(T, coef_vector(MATEP_SCC_ON, 0.7), b_phase_state(T), expect_fast=True)
 
 
-@pytest.mark.parametrize("scatter", ["0", "1"])
-def test_q1_hanging_nodes_general_scatter(scatter, monkeypatch):
-    """Rows next to hanging nodes: row-owner kernel k_rows_slow (default) and the atomic cell scatter (VH_SLOW_SCATTER=1)."""
-    monkeypatch.setenv("VH_SLOW_SCATTER", scatter)
+def test_q1_hanging_nodes_general_scatter():
+    """Rows next to hanging nodes: the row-owner kernel k_rows_slow."""
     m = vh.Mesh(1, [-2, -2, -2], [2, 2, 2], n_global_refine=2)
     c = m.cell_centers()
     m.refine((np.abs(c[:, 2]) < 1.1) & (c[:, 0] < 0.1))

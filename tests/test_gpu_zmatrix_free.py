@@ -1,4 +1,4 @@
-"""GPU parity of the matrix-free operator apply (VH_SPMV_MF=1): inside vh_solve / vh_spmv the lattice rows are applied as
+"""GPU parity of the matrix-free operator apply (the default; VH_SPMV_MF=0 selects the assembled packed SpMV): inside vh_solve / vh_spmv the lattice rows are applied as
 sum_cells K_cell z_cell, with the bulk part H_q z_q read back from the packed H_q tables of the assembly and the gradient /
 Robin forms evaluated from z (k_points<APPLY> + k_gather_apply), instead of streaming the assembled blocks.  The result
 must equal the assembled operator: against the oracle's matrix (1e-13) and against the default SpMV of a second context,
@@ -49,10 +49,10 @@ def test_matrix_free_apply_equals_assembled_operator(name, monkeypatch):
     A, _ = O.assemble_global(T, x, coef, True)
     rng = np.random.default_rng(17)
     zs = [rng.uniform(-1, 1, A.shape[1]) for _ in range(2)]
-    monkeypatch.setenv("VH_SPMV_MF", "1")
-    mf = vh.Context(T)
+    mf = vh.Context(T)                       # default: matrix-free apply, lattice rows not assembled
+    monkeypatch.setenv("VH_SPMV_MF", "0")
+    ref = vh.Context(T)                      # assembled packed SpMV
     monkeypatch.delenv("VH_SPMV_MF")
-    ref = vh.Context(T)
     assert mf.info()["spmv_matrix_free"] == 1 and ref.info()["spmv_matrix_free"] == 0
     for ctx in (mf, ref):
         ctx.set_coef_vector(coef)
@@ -131,12 +131,6 @@ def test_matrix_free_newton_history_matches_oracle(monkeypatch):
     ctx.close()
 
 
-unverified = pytest.mark.skipif(os.environ.get("VH_TEST_UNVERIFIED") != "1",
-                                reason="table-free apply (mode 2) was written after the round-1 GPU budget was spent; "
-                                       "run with VH_TEST_UNVERIFIED=1 (tools/gpu_session.sh does) before relying on it")
-
-
-@unverified
 @pytest.mark.parametrize("mode", [2, 3])
 @pytest.mark.parametrize("name", NAMES)
 def test_table_free_apply_equals_assembled_operator(name, mode):
@@ -164,10 +158,9 @@ def test_table_free_apply_equals_assembled_operator(name, mode):
     ctx.close()
 
 
-@unverified
 @pytest.mark.parametrize("name", ["q1-cube", "q1-walls-aniso", "q2-cube", "q1-hanging", "q1-periodic"])
 def test_lazy_rows_block_jacobi_and_solve_match_oracle(name, monkeypatch):
-    """VH_MF_LAZY_ROWS=1 with the matrix-free apply: vh_assemble forms only the diagonal blocks of the lattice rows
+    """The default mode (matrix-free apply, lazy rows): vh_assemble forms only the diagonal blocks of the lattice rows
     (k_diag_cells + k_diag_gather).  The preconditioner, the GMRES history and the update must equal the oracle's, and the
     rows must appear on demand (export) identical to an ordinary assembly."""
     monkeypatch.setenv("VH_SPMV_MF", "1")

@@ -21,9 +21,8 @@ def _random_mesh(degree, seed, rounds, frac=0.15):
     return m.finalize(1)
 
 
-@pytest.mark.parametrize("degree,seed,rounds,scatter", [(1, 11, 3, "0"), (1, 12, 4, "0"), (1, 11, 3, "1"), (2, 13, 2, "0")])
-def test_multilevel_assembly_spmv_and_solve_match_oracle(degree, seed, rounds, scatter, monkeypatch):
-    monkeypatch.setenv("VH_SLOW_SCATTER", scatter)
+@pytest.mark.parametrize("degree,seed,rounds", [(1, 11, 3), (1, 12, 4), (2, 13, 2)])
+def test_multilevel_assembly_spmv_and_solve_match_oracle(degree, seed, rounds):
     m = _random_mesh(degree, seed, rounds)
     assert m.n_hanging_nodes > 0
     T = m.tables(0)

@@ -11,15 +11,11 @@ mkdir -p gpurun_out
 if [ "$what" = tests ] || [ "$what" = all ]; then
   timeout 600 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1
   tail -5 gpurun_out/gpu_tests.log
-  # opt-in paths that have not run on hardware yet (table-free operator apply)
-  VH_TEST_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_zmatrix_free.py -m gpu -q --tb=short -p no:cacheprovider -k 'table_free or lazy_rows' \
-    > gpurun_out/gpu_tests_unverified.log 2>&1
-  tail -5 gpurun_out/gpu_tests_unverified.log
 fi
 if [ "$what" = bench ] || [ "$what" = all ]; then
   timeout 300 python bench.py > gpurun_out/bench_packed.json 2> gpurun_out/bench_packed.err
   timeout 300 python bench.py --spmv-mf --no-cpu-baseline > gpurun_out/bench_mf.json 2> gpurun_out/bench_mf.err
-  VH_TEST_UNVERIFIED=1 timeout 120 python tools/time_spmv_modes.py 1 5 20 > gpurun_out/spmv_modes_q1_r5.txt 2>&1
+  timeout 120 python tools/time_spmv_modes.py 1 5 20 > gpurun_out/spmv_modes_q1_r5.txt 2>&1
   timeout 300 python tools/bench_q2.py 4 5 > gpurun_out/q2_timings.txt 2>&1
   python - <<'PY'
 import json

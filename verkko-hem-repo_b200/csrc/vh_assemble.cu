@@ -4,17 +4,18 @@
 // FemGL::compute_residual (/root/reference/femgl/src/residual.cc:109-297), including the constrained
 // scatter AffineConstraints::distribute_local_to_global (call sites assemble.cc:356-361, residual.cc:287-289).
 //
-// Three kernels instead of the reference's (cell, q, i, j) loop over 3x3 FullMatrix products:
-//   1. k_pointwise    one CTA per cell: gather the cell's DoFs, interpolate A and grad A at the quadrature
-//                     points, evaluate g_q (18) and the symmetric bulk Hessian H_q (171 unique entries) in closed
-//                     form (vh_pointwise.cuh), store H_q, and reduce the cell rhs / cell diagonal / cell energy.
-//   2. k_rows_fast_q1 ROW-OWNER assembly: one CTA per matrix block row.  Each 18x18 block of the row is
-//                     accumulated in registers over the <= 8 incident cells x 8 quadrature points and written
-//                     exactly once with 16-byte stores: no atomics, no memset (write-once traffic = the matrix).
-//                     Gradient (K1, K2+K3) and Robin-face terms are geometry-only and added at write time.
-//                     Component-masked Dirichlet DoFs follow deal.II's rule (zero row/column, |a_ii| on the diagonal).
-//   3. k_cells_slow   general constrained scatter (hanging nodes / any topology / Q2): one CTA per cell,
-//                     constraint lines resolved per entry, atomics into the rows that kernel 2 does not own.
+// Kernels instead of the reference's (cell, q, i, j) loop over 3x3 FullMatrix products:
+//   1. k_points       (vh_points_kernel.cuh) one THREAD per quadrature point: gather the cell's DoFs, interpolate A and
+//                     grad A, evaluate g_q (18) and the symmetric bulk Hessian H_q (171 unique entries) in closed form
+//                     (vh_pointwise.cuh), store the packed H_q table, reduce the cell rhs / cell diagonal / cell energy.
+//                     The same kernel in APPLY mode is the matrix-free operator of the lattice rows.
+//   2. k_diag_cells / k_diag_gather (vh_diag_kernel.cuh) diagonal 18x18 blocks of the lattice rows for block-Jacobi.
+//   3. k_rows_fast_q1 / k_rows_fast_q2  ROW-OWNER assembly of the lattice rows, on demand only (export, assembled SpMV
+//                     mode): one CTA per block row, every packed block accumulated in registers over the <= 8 incident
+//                     cells and written exactly once: no atomics, no memset.  Gradient (K1, K2+K3) and Robin-face terms
+//                     are geometry-only (class_M) and Dirichlet masks are applied by the consumers.
+//   4. k_rows_slow    row-owner assembly of the constrained rows (hanging-node neighbourhoods, periodic seams,
+//                     constraint masters) with deal.II's distribute_local_to_global rule resolved per entry.
 #include "vh_internal.h"
 #include "vh_pointwise.cuh"
 
@@ -22,240 +23,11 @@
 #include <cstdlib>
 
 __constant__ double  c_W1[512];   // Q1: w_q N_a(q) N_b(q), index (a*8+b)*8+q
-__constant__ uint8_t c_symc[VH_SYMP], c_symd[VH_SYMP];
 __constant__ double  c_T2[27];    // Q2, one direction: w_q l_a(q) l_b(q), index (t_a*3 + t_b)*3 + q  (t = 0 low, 1 mid, 2 high)
 __constant__ uint8_t c_q2t[27 * 3]; // Q2: tensor index (t_x, t_y, t_z) of local node a (deal.II hierarchical order)
 
 namespace
 {
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-// sum over the whole block; result valid in thread 0.  s_red needs 32 doubles.
-__device__ __forceinline__ double block_sum(double v, double *s_red)
-{
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0)
-    s_red[wid] = v;
-  __syncthreads();
-  double r = 0;
-  if (wid == 0)
-    {
-      r = lane < nw ? s_red[lane] : 0.0;
-      r = warp_sum(r);
-    }
-  return r;
-}
-
-// ------------------------------------------------------------------------------------------------
-// 1. pointwise kernel
-// ------------------------------------------------------------------------------------------------
-template <int NN, int NQ>
-__global__ void __launch_bounds__(NQ == 8 ? 192 : 512)
-  k_pointwise(const int32_t *__restrict__ cell_nodes, const double *__restrict__ cell_h, const uint32_t *__restrict__ cell_faces,
-              const uint8_t *__restrict__ cell_owned, const double *__restrict__ x, VhTables tab, VhCoef cf, int want_h, int want_e,
-              double *__restrict__ Hq, double *__restrict__ Rc, double *__restrict__ Dc, double *__restrict__ avgD,
-              double *__restrict__ Ec)
-{
-  extern __shared__ double sm[];
-  double *sU   = sm;                // [NN*18]
-  double *sT   = sU + NN * 18;      // [NQ][VH_TQ]  per quadrature point: A(18) | products R,Q,P,S (72) | Z1,Z2 (324)
-  double *sdA  = sT + NQ * VH_TQ;   // [NQ*18*3]
-  double *sg   = sdA + NQ * 54;     // [NQ*18]
-  double *sHd  = sg + NQ * 18;      // [NQ*18]   diagonal of H_q (unscaled)
-  double *sN   = sHd + NQ * 18;     // [NN*NQ]
-  double *sdN  = sN + NN * NQ;      // [NN*NQ*3]
-  double *swq  = sdN + NN * NQ * 3; // [NQ]
-  double *sred = swq + NQ;          // [32]
-
-  const int     t    = threadIdx.x;
-  const int64_t cell = blockIdx.x;
-  for (int i = t; i < NN * NQ; i += blockDim.x)
-    sN[i] = tab.N[i];
-  for (int i = t; i < NN * NQ * 3; i += blockDim.x)
-    sdN[i] = tab.dN[i];
-  if (t < NQ)
-    swq[t] = tab.wq[t];
-  for (int i = t; i < NN * 18; i += blockDim.x)
-    {
-      const int a = i / 18, c = i - 18 * a;
-      sU[i]       = x[18 * (int64_t)cell_nodes[cell * NN + a] + c];
-    }
-  const double h0 = cell_h[4 * cell], h1 = cell_h[4 * cell + 1], h2 = cell_h[4 * cell + 2], vol = cell_h[4 * cell + 3];
-  const double ih[3] = {1.0 / h0, 1.0 / h1, 1.0 / h2};
-  __syncthreads();
-
-  // FE interpolation of the state and its gradient (s_vector2matrix.cc:154-162, 203-213)
-  if (t < 18 * NQ)
-    {
-      const int q = t / 18, c = t - 18 * q;
-      double    A = 0, d0 = 0, d1 = 0, d2 = 0;
-#pragma unroll 4
-      for (int a = 0; a < NN; ++a)
-        {
-          const double u = sU[a * 18 + c];
-          A += sN[a * NQ + q] * u;
-          d0 += sdN[(a * NQ + q) * 3 + 0] * u;
-          d1 += sdN[(a * NQ + q) * 3 + 1] * u;
-          d2 += sdN[(a * NQ + q) * 3 + 2] * u;
-        }
-      sT[q * VH_TQ + VH_TQ_A + c] = A;
-      sdA[3 * t + 0]              = d0 * ih[0];
-      sdA[3 * t + 1]              = d1 * ih[1];
-      sdA[3 * t + 2]              = d2 * ih[2];
-    }
-  __syncthreads();
-  // per quadrature point: 36 product entries (+ 162 Z-table entries for the Hessian)
-  {
-    const int per_q = want_h ? 198 : 36;
-    for (int i = t; i < NQ * per_q; i += blockDim.x)
-      {
-        const int q = i / per_q, e = i - per_q * q;
-        double   *T = sT + q * VH_TQ;
-        if (e < 36)
-          vh_product_entry(T + VH_TQ_A, e, T + VH_TQ_P + 2 * e);
-        else
-          vh_ztable_entry(T + VH_TQ_A, e - 36, T + VH_TQ_Z);
-      }
-  }
-  __syncthreads();
-  if (t < 18 * NQ)
-    {
-      const int q = t / 18, c = t - 18 * q;
-      sg[t]       = vh_g_component(sT + q * VH_TQ + VH_TQ_A, sT + q * VH_TQ + VH_TQ_P, c, cf.alpha, cf.beta);
-    }
-  if (want_h)
-    { // the 171 unique entries of every H_q, stored pre-multiplied by the cell volume (JxW = w_q * vol).
-      // A thread owns ONE packed entry (c,d): its 16-term list is set up once and reused for every quadrature point.
-      const int n_groups = blockDim.x / VH_SYMP, grp = t / VH_SYMP, sidx = t - VH_SYMP * grp;
-      if (grp < n_groups)
-        {
-          double *dst = Hq + cell * (int64_t)(NQ * VH_SYMP) + sidx;
-          if (c_symd[sidx] >= c_symc[sidx])
-            {
-              const int c = c_symc[sidx], d = c_symd[sidx];
-              vh_terms  T;
-              vh_entry_terms(c, d, cf.alpha, cf.beta, T);
-              for (int q = grp; q < NQ; q += n_groups)
-                {
-                  const double v = vh_entry_eval(sT + q * VH_TQ, T);
-                  if (c == d)
-                    sHd[q * 18 + c] = v;
-                  dst[q * VH_SYMP] = v * vol;
-                }
-            }
-          else
-            for (int q = grp; q < NQ; q += n_groups)
-              dst[q * VH_SYMP] = 0.0;
-        }
-    }
-  __syncthreads();
-
-  // cell rhs (assemble.cc:257-276) and cell-matrix diagonal
-  const uint32_t faces = cell_faces[cell];
-  const bool     robin = (cf.bt < 1e10) && faces != 0u;
-  double         absd  = 0.0;
-  if (t < 18 * NN)
-    {
-      const int a = t / 18, c = t - 18 * a, pm = c / 3, xc = c - 3 * pm;
-      double    r = 0.0, dg = 0.0;
-      for (int q = 0; q < NQ; ++q)
-        {
-          const double JxW = swq[q] * vol, Na = sN[a * NQ + q];
-          const double gx = sdN[(a * NQ + q) * 3 + 0] * ih[0], gy = sdN[(a * NQ + q) * 3 + 1] * ih[1],
-                       gz = sdN[(a * NQ + q) * 3 + 2] * ih[2];
-          const double *dA  = sdA + 3 * (q * 18 + c);
-          const double *dAr = sdA + 3 * (q * 18 + 3 * pm);
-          const double  div = dAr[0] + dAr[4] + dAr[8];
-          const double  gxc = xc == 0 ? gx : (xc == 1 ? gy : gz);
-          r += JxW * (Na * sg[q * 18 + c] + cf.K1 * (gx * dA[0] + gy * dA[1] + gz * dA[2]) + cf.K23 * gxc * div);
-          if (want_h)
-            dg += JxW * Na * Na * sHd[q * 18 + c];
-        }
-      if (want_h)
-        {
-          const double *G = tab.Gref + (size_t)(a * NN + a) * 9;
-          dg += vol * (cf.K1 * (G[0] * ih[0] * ih[0] + G[4] * ih[1] * ih[1] + G[8] * ih[2] * ih[2]) +
-                       cf.K23 * G[4 * xc] * ih[xc] * ih[xc]);
-        }
-      if (robin)
-        for (int f = 0; f < 6; ++f)
-          {
-            const int bid = (faces >> (4 * f)) & 15u;
-            if (bid < 2 || bid > 4 || xc == bid - 2)
-              continue;
-            const double  hn   = f / 2 == 0 ? h0 : (f / 2 == 1 ? h1 : h2);
-            const double  s    = cf.K1 / cf.bt * (vol / hn);
-            const double *M    = tab.Mf + (size_t)(f * NN + a) * NN;
-            double        accf = 0.0;
-            for (int b = 0; b < NN; ++b)
-              accf += M[b] * sU[b * 18 + c];
-            r += s * accf;
-            dg += s * M[a];
-          }
-      Rc[cell * (int64_t)(18 * NN) + t] = -r;
-      if (want_h)
-        {
-          Dc[cell * (int64_t)(18 * NN) + t] = dg;
-          absd                              = fabs(dg);
-        }
-    }
-  if (want_h)
-    {
-      const double s = block_sum(absd, sred);
-      if (t == 0)
-        avgD[cell] = s / (double)(18 * NN);
-    }
-  if (want_e)
-    { // GL functional, SURVEY.md A.1 (only locally owned cells count; ghost cells are assembled redundantly)
-      double e = 0.0;
-      if (t < 18 * NQ && cell_owned[cell])
-        {
-          const int     q = t / 18, c = t - 18 * q;
-          const double  JxW = swq[q] * vol;
-          const double *dA  = sdA + 3 * t;
-          e                 = cf.K1 * (dA[0] * dA[0] + dA[1] * dA[1] + dA[2] * dA[2]);
-          if (c < 6)
-            {
-              const double *dAr = sdA + 3 * (q * 18 + 3 * c);
-              const double  div = dAr[0] + dAr[4] + dAr[8];
-              e += cf.K23 * div * div;
-            }
-          if (c == 6)
-            e += vh_bulk_energy(sT + q * VH_TQ + VH_TQ_P, cf.alpha, cf.beta);
-          e *= JxW;
-        }
-      if (robin && t < 18 && cell_owned[cell])
-        for (int f = 0; f < 6; ++f)
-          {
-            const int bid = (faces >> (4 * f)) & 15u;
-            if (bid < 2 || bid > 4 || (t % 3) == bid - 2)
-              continue;
-            const double hn = f / 2 == 0 ? h0 : (f / 2 == 1 ? h1 : h2);
-            const double s  = cf.K1 / cf.bt * (vol / hn);
-            double       ef = 0.0;
-            for (int a = 0; a < NN; ++a)
-              {
-                const double *M = tab.Mf + (size_t)(f * NN + a) * NN;
-                double        m = 0.0;
-                for (int b = 0; b < NN; ++b)
-                  m += M[b] * sU[b * 18 + t];
-                ef += sU[a * 18 + t] * m;
-              }
-            e += s * ef;
-          }
-      const double s = block_sum(e, sred);
-      if (t == 0)
-        Ec[cell] = s;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // 1b. pointwise kernel, one THREAD per quadrature point: csrc/vh_points_kernel.cuh (k_points, VhPt, VH_PT_WARPS)
 // ------------------------------------------------------------------------------------------------
@@ -267,8 +39,8 @@ __global__ void __launch_bounds__(NQ == 8 ? 192 : 512)
 // 2. row-owner Jacobian kernel for Q1 rows whose neighbourhood is a piece of a structured lattice
 // ------------------------------------------------------------------------------------------------
 #define VH_FAST_STAGES 4
-#define VH_CELL_H_BYTES (8 * VH_SYMP * 8) /* one cell's 8 x 172 doubles: 11008 B, a multiple of 16 */
-#define VH_FAST_SMEM (VH_FAST_STAGES * VH_CELL_H_BYTES + VH_BLK * 8 + 32 * 8 + VH_FAST_STAGES * 8 + (36 + 28) * 4)
+#define VH_CELL_H_BYTES (8 * VH_SYMP * 8) /* one cell's 8 x 180 doubles: 11520 B, a multiple of 16 */
+#define VH_FAST_SMEM (VH_FAST_STAGES * VH_CELL_H_BYTES + VH_FAST_STAGES * 8 + (8 + 28) * 4)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
@@ -300,32 +72,23 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                : "memory");
 }
 
-// EPT = packed Hessian entries per thread: 2 -> 96 threads/row (86 active), 108 accumulator registers, 12 warps/SM;
-//                                          1 -> 192 threads/row (172 active), 54 accumulator registers, 24 warps/SM.
-// PACK = true: the row is stored as packed symmetric blocks (172 doubles each): the accumulators go straight from
-//               registers to global memory with coalesced stores; geometry terms and Dirichlet masks are applied by the
-//               consumers (SpMV, block-Jacobi setup, export), so the expansion stage disappears.
-template <int EPT, bool PACK>
-__global__ void __launch_bounds__(192 / EPT, 4)
+// One thread per packed Hessian entry (192 threads per row, 180 active, 27 accumulator registers, 24 warps/SM).  The row is
+// stored as packed symmetric blocks (180 doubles each): the accumulators go straight from registers to global memory with
+// coalesced stores; geometry terms and Dirichlet masks are applied by the consumers (SpMV, block-Jacobi setup, export).
+__global__ void __launch_bounds__(192, 4)
   k_rows_fast_q1(const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells,
-                 const int8_t *__restrict__ fast_slot, const int32_t *__restrict__ fast_class,
-                 const double *__restrict__ class_M, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
-                 const uint32_t *__restrict__ dirmask, const double *__restrict__ Hq, const double *__restrict__ Dc,
-                 const double *__restrict__ avgD, VhCoef cf, double *__restrict__ vals)
+                 const int8_t *__restrict__ fast_slot, const int32_t *__restrict__ row_ptr, const double *__restrict__ Hq,
+                 double *__restrict__ vals)
 {
   extern __shared__ __align__(128) unsigned char smraw[];
-  double   *s_H    = reinterpret_cast<double *>(smraw);                                     // [4][8*172], later [27][172]
-  double   *s_cls  = reinterpret_cast<double *>(smraw + VH_FAST_STAGES * VH_CELL_H_BYTES);  // [27][12]: GS(9), FS(3)
-  double   *s_tr   = s_cls + VH_BLK;                                                        // [27] tr(GS), padded to 32
-  uint64_t *s_bar  = reinterpret_cast<uint64_t *>(s_tr + 32);                               // [4]
-  int      *s_cells = reinterpret_cast<int *>(s_bar + VH_FAST_STAGES);                      // [8]
-  int      *s_pos   = s_cells + 8;                                                          // [27] (+1 pad)
-  uint32_t *s_maskJ = reinterpret_cast<uint32_t *>(s_pos + 28);                             // [27]
+  double   *s_H     = reinterpret_cast<double *>(smraw);                                      // [4][8*180]
+  uint64_t *s_bar   = reinterpret_cast<uint64_t *>(smraw + VH_FAST_STAGES * VH_CELL_H_BYTES); // [4]
+  int      *s_cells = reinterpret_cast<int *>(s_bar + VH_FAST_STAGES);                        // [8]
+  int      *s_pos   = s_cells + 8;                                                            // [27] (+1 pad)
 
-  constexpr int NT = 192 / EPT, ACT = VH_SYMP / EPT;
-  const int     t = threadIdx.x;
-  const int     r = blockIdx.x;
-  const int     I = fast_rows[r];
+  const int t = threadIdx.x;
+  const int r = blockIdx.x;
+  const int I = fast_rows[r];
   if (t == 0)
     { // TMA producer, first thing in the CTA: the DRAM/L2 latency of the first four cells' tables overlaps the prologue
 #pragma unroll
@@ -347,15 +110,9 @@ __global__ void __launch_bounds__(192 / EPT, 4)
     s_cells[t - 64] = fast_cells[(size_t)r * 8 + (t - 64)];
   if (t >= 32 && t < 59)
     s_pos[t - 32] = fast_slot[(size_t)r * 32 + (t - 32)];
-  if constexpr (!PACK)
-    { // geometry-only part of every block of this row's stencil: block += kron(I_6, M_s), M_s 3x3 (stride 10, [9] = 0)
-      const double *cls = class_M + (size_t)fast_class[r] * 270;
-      for (int i = t; i < 270; i += NT)
-        s_cls[i] = cls[i];
-    }
   __syncthreads();
 
-  // TMA producer: thread 0 streams the incident cells' pre-scaled H_q tables (11 KB each, contiguous) into the ring
+  // TMA producer: thread 0 streams the incident cells' pre-scaled H_q tables (11.5 KB each, contiguous) into the ring
   auto issue = [&](int o) {
     const int e = s_cells[o];
     if (e >= 0)
@@ -366,12 +123,10 @@ __global__ void __launch_bounds__(192 / EPT, 4)
       }
   };
   // bulk part:  acc[s](c,d) = sum_o sum_q sum_b->s  w_q N_a(q) N_b(q) (vol_o H_{o,q})(c,d)
-  double acc[EPT][27];
+  double acc[27];
 #pragma unroll
   for (int s = 0; s < 27; ++s)
-#pragma unroll
-    for (int k = 0; k < EPT; ++k)
-      acc[k][s] = 0.0;
+    acc[s] = 0.0;
   uint32_t uses = 0; // bit k: parity of the next completed phase of stage k
 #pragma unroll
   for (int o = 0; o < 8; ++o)
@@ -391,141 +146,39 @@ __global__ void __launch_bounds__(192 / EPT, 4)
           const int st = o & (VH_FAST_STAGES - 1);
           mbar_wait(s_bar + st, (uses >> st) & 1u);
           uses ^= 1u << st;
-          if (t < ACT)
+          if (t < VH_SYMP)
             {
               // cell table layout [pair][q XOR (pair & 7)] (vh_hq8_index): the stage base is 128-byte aligned, so the
               // address of point q is the address of point 0 with bits 4..6 flipped by q
-              const int      pr0 = (EPT * t) >> 1;
-              const uint32_t Hs0 = smem_u32(s_H + (size_t)st * (8 * VH_SYMP)) + (uint32_t)((pr0 << 7) + ((pr0 & 7) << 4) + ((EPT * t) & 1) * 8);
+              const int      pr0 = t >> 1;
+              const uint32_t Hs0 = smem_u32(s_H + (size_t)st * (8 * VH_SYMP)) + (uint32_t)((pr0 << 7) + ((pr0 & 7) << 4) + (t & 1) * 8);
 #pragma unroll
               for (int q = 0; q < 8; ++q)
                 {
-                  double hv[EPT];
-                  if constexpr (EPT == 2)
-                    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(hv[0]), "=d"(hv[1]) : "r"(Hs0 ^ (uint32_t)(q << 4)));
-                  else
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(hv[0]) : "r"(Hs0 ^ (uint32_t)(q << 4)));
+                  double hv;
+                  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(hv) : "r"(Hs0 ^ (uint32_t)(q << 4)));
 #pragma unroll
                   for (int b = 0; b < 8; ++b)
                     {
                       const int    s = ((o & 1) + (b & 1)) + 3 * (((o >> 1) & 1) + ((b >> 1) & 1)) + 9 * ((o >> 2) + (b >> 2));
                       const double w = c_W1[((7 - o) * 8 + b) * 8 + q];
-#pragma unroll
-                      for (int k = 0; k < EPT; ++k)
-                        acc[k][s] = fma(w, hv[k], acc[k][s]);
+                      acc[s]         = fma(w, hv, acc[s]);
                     }
                 }
             }
         }
     }
-
-  if constexpr (PACK)
-    { // packed storage: block (rp+pos) holds the 172 packed entries contiguously; thread t owns entries EPT*t..
-      const int rp = row_ptr[I];
-      if (t < ACT)
-        {
-#pragma unroll
-          for (int s = 0; s < 27; ++s)
-            {
-              const int pos = s_pos[s];
-              if (pos < 0)
-                continue;
-              double *dst = vals + (size_t)(rp + pos) * VH_SYMP + EPT * t;
-              if constexpr (EPT == 2)
-                __stcs(reinterpret_cast<double2 *>(dst), make_double2(acc[0][s], acc[1][s]));
-              else
-                __stcs(dst, acc[0][s]);
-            }
-        }
-      return;
-    }
-
-  // ---- write the block row ----
-  // 1. dump the packed symmetric accumulators of all 27 slots into the (now idle) TMA ring: [27][172] doubles
-  __syncthreads();
-  double *s_sym = s_H;
-  if (t < ACT)
+  // block (rp + pos) holds the 180 packed entries contiguously; thread t owns entry t of every block of the row
+  const int rp = row_ptr[I];
+  if (t < VH_SYMP)
     {
 #pragma unroll
       for (int s = 0; s < 27; ++s)
         {
-          if constexpr (EPT == 2)
-            reinterpret_cast<double2 *>(s_sym + s * VH_SYMP)[t] = make_double2(acc[0][s], acc[1][s]);
-          else
-            s_sym[s * VH_SYMP + t] = acc[0][s];
+          const int pos = s_pos[s];
+          if (pos >= 0)
+            __stcs(vals + (size_t)(rp + pos) * VH_SYMP + t, acc[s]);
         }
-    }
-  const uint32_t maskI = dirmask[I];
-  const int      rp    = row_ptr[I];
-  if (t < 27)
-    { // per-slot column Dirichlet masks, so the store loop has no dependent global loads
-      const int pos = s_pos[t];
-      s_maskJ[t]    = pos >= 0 ? dirmask[col[rp + pos]] : 0u;
-    }
-  __syncthreads();
-  // 2. every thread owns EPT fixed 16-byte pieces of the 18x18 block (double2 #t [and #t+96]): the packed offsets and
-  //    geometry selectors of its entries are loop invariants; the slot loop is rolled and barrier-free.
-  constexpr int NE = 2 * EPT;
-  int           soff[NE], gsel[NE];
-  uint32_t      rbit[NE], cbit[NE];
-#pragma unroll
-  for (int k = 0; k < NE; ++k)
-    {
-      const int i = t + NT * (k >> 1); // double2 index inside the block
-      const int c = min((2 * i) / 18, 17), d = (2 * i) % 18 + (k & 1);
-      soff[k] = c <= d ? vh_sym_index(c, d) : vh_sym_index(d, c);
-      gsel[k] = (c / 3 == d / 3) ? (c % 3) * 3 + d % 3 : 9; // entry 9 of every M_s is 0
-      rbit[k] = 1u << c;
-      cbit[k] = 1u << d;
-    }
-  const bool first = t < VH_BLK / 2, second = EPT == 2 && t + NT < VH_BLK / 2;
-#pragma unroll 3
-  for (int s = 0; s < 27; ++s)
-    {
-      const int pos = s_pos[s];
-      if (pos < 0)
-        continue; // block-uniform
-      const double  *sy    = s_sym + s * VH_SYMP;
-      const double  *M     = s_cls + s * 10;
-      const uint32_t maskJ = s_maskJ[s];
-      double         v[NE];
-#pragma unroll
-      for (int k = 0; k < NE; ++k)
-        v[k] = sy[soff[k]] + M[gsel[k]];
-      if ((maskI | maskJ) != 0u)
-        { // component-masked Dirichlet DoFs (block-uniform branch): row and column dropped (distribute_local_to_global)
-#pragma unroll
-          for (int k = 0; k < NE; ++k)
-            if ((maskI & rbit[k]) || (maskJ & cbit[k]))
-              v[k] = 0.0;
-          if (s == 13)
-            { // constrained diagonal: sum over cells of |a_ii| (mean |diag| of the cell if a_ii == 0)
-#pragma unroll
-              for (int k = 0; k < NE; ++k)
-                if (rbit[k] == cbit[k] && (maskI & rbit[k]))
-                  {
-                    const int c    = 31 - __clz(rbit[k]);
-                    double    dsum = 0.0;
-                    for (int o = 0; o < 8; ++o)
-                      {
-                        const int e = s_cells[o];
-                        if (e < 0)
-                          continue;
-                        double dv = fabs(Dc[(size_t)e * 144 + (7 - o) * 18 + c]);
-                        if (dv == 0.0)
-                          dv = avgD[e];
-                        dsum += dv;
-                      }
-                    v[k] = dsum;
-                  }
-            }
-        }
-      double2 *dst = reinterpret_cast<double2 *>(vals + (size_t)(rp + pos) * VH_BLK);
-      if (first)
-        __stcs(dst + t, make_double2(v[0], v[1])); // streaming stores: the block is not re-read by this kernel
-      if constexpr (EPT == 2)
-        if (second)
-          __stcs(dst + t + NT, make_double2(v[2], v[3]));
     }
 }
 
@@ -540,8 +193,7 @@ __global__ void __launch_bounds__(192 / EPT, 4)
 // 729 (the full Q2 cell matrix costs 2.36 MFLOP instead of SURVEY's 13.2 MFLOP).  Slots fed by several cells are
 // accumulated by the SAME thread with plain load-add-store on its own entry (first-writer mask from the host): no
 // atomics, no memset, and the row (<= 180 KB) stays in L2 between the visits.
-template <int MINB>
-__global__ void __launch_bounds__(192, MINB)
+__global__ void __launch_bounds__(192, 4)
   k_rows_fast_q2(const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells, const int8_t *__restrict__ fast_a,
                  const int8_t *__restrict__ fast_slot, const uint32_t *__restrict__ fast_first, const int32_t *__restrict__ row_ptr,
                  const double *__restrict__ Hq, double *__restrict__ vals)
@@ -618,239 +270,6 @@ __global__ void __launch_bounds__(192, MINB)
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// 2c. row-owner kernel with the contraction on the FP64 tensor cores (mma.sync m8n8k4 -> SASS DMMA.8x8x4).
-//     For one incident cell o the row's contribution is the GEMM  out[b][entry] = sum_q W_o[b][q] * H_o[q][entry]
-//     with M = 8 column nodes b, K = 8 quadrature points (two k-steps of 4), N = 172 packed entries (22 tiles of 8).
-//     On B200 DMMA has the same FLOP/s as DFMA (measured 37.1 vs 36.7 TFLOP/s, tools/dmma_peak.cu) but needs 8x fewer
-//     issue slots, which is what the scalar kernel is short of.
-//     Row permutation: MMA row m of octant o holds column node b = m XOR o, so that row m always accumulates slots of
-//     parity m (slot coordinate s_d = 1 if m_d else 2*o_d): contributions of different cells to one slot stay in the
-//     same lane and are reduced in registers; no cross-lane traffic, no atomics.  C fragments: one set per octant.
-//     6 warps x 4 tiles; A fragments (weights) come from a 4 KB shared table, B fragments from the TMA ring.
-// ------------------------------------------------------------------------------------------------
-#define VH_MMA_THREADS 192
-#define VH_MMA_STAGES 8 /* all incident cells' tables in flight at once: 88 KB ring, two CTAs per SM */
-#define VH_MMA_SMEM (VH_MMA_STAGES * VH_CELL_H_BYTES + 272 * 8 + 512 * 8 + VH_MMA_STAGES * 8 + 64 * 4)
-
-__global__ void __launch_bounds__(VH_MMA_THREADS, 2)
-  k_rows_mma_q1(const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells, const int8_t *__restrict__ fast_slot,
-                const int32_t *__restrict__ fast_class, const double *__restrict__ class_M, const double *__restrict__ afrag,
-                const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, const uint32_t *__restrict__ dirmask,
-                const double *__restrict__ Hq, const double *__restrict__ Dc, const double *__restrict__ avgD,
-                double *__restrict__ vals)
-{
-  extern __shared__ __align__(128) unsigned char smraw[];
-  double   *s_H     = reinterpret_cast<double *>(smraw);                                   // [8][8*172], later [27][172]
-  double   *s_cls   = reinterpret_cast<double *>(smraw + VH_MMA_STAGES * VH_CELL_H_BYTES); // [27][10] (+2)
-  double   *s_A     = s_cls + 272;                                                         // [8 o][2 kstep][32 lanes]
-  uint64_t *s_bar   = reinterpret_cast<uint64_t *>(s_A + 512);                             // [8]
-  int      *s_cells = reinterpret_cast<int *>(s_bar + VH_MMA_STAGES);                      // [8]
-  int      *s_pos   = s_cells + 8;                                                         // [27] (+1)
-  uint32_t *s_maskJ = reinterpret_cast<uint32_t *>(s_pos + 28);                            // [27]
-
-  constexpr int NT = VH_MMA_THREADS;
-  const int     t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int     r = blockIdx.x;
-  const int     I = fast_rows[r];
-  if (t == 0)
-    { // TMA producer, first thing in the CTA: every incident cell's table (11 KB each) is requested at once
-#pragma unroll
-      for (int k = 0; k < VH_MMA_STAGES; ++k)
-        mbar_init(s_bar + k, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-      for (int o = 0; o < 8; ++o)
-        {
-          const int e = fast_cells[(size_t)r * 8 + o];
-          if (e >= 0)
-            {
-              mbar_expect_tx(s_bar + o, VH_CELL_H_BYTES);
-              bulk_g2s(s_H + (size_t)o * (8 * VH_SYMP), Hq + (size_t)e * (8 * VH_SYMP), VH_CELL_H_BYTES, s_bar + o);
-            }
-        }
-    }
-  // all row metadata is fetched now, behind the TMA latency: nothing global is touched again until the stores
-  const uint32_t maskI = dirmask[I];
-  const int      rp    = row_ptr[I];
-  if (t >= 64 && t < 72)
-    s_cells[t - 64] = fast_cells[(size_t)r * 8 + (t - 64)];
-  if (t >= 32 && t < 59)
-    {
-      const int pos     = fast_slot[(size_t)r * 32 + (t - 32)];
-      s_pos[t - 32]     = pos;
-      s_maskJ[t - 32]   = pos >= 0 ? dirmask[col[rp + pos]] : 0u;
-    }
-  {
-    const double *cls = class_M + (size_t)fast_class[r] * 270;
-    for (int i = t; i < 270; i += NT)
-      s_cls[i] = cls[i];
-    for (int i = t; i < 512; i += NT)
-      s_A[i] = afrag[i];
-  }
-  __syncthreads();
-
-  // B-fragment offsets of this lane inside a cell table: row q = 4*kstep + lane%4, column = packed entry of tile + lane/4
-  int boff[2][4];
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-    for (int tl = 0; tl < 4; ++tl)
-      {
-        const int e  = 8 * (4 * warp + tl) + (lane >> 2);
-        boff[ks][tl] = vh_hq8_index(4 * ks + (lane & 3), e < VH_SYMP ? e : 18); // out-of-range columns read the zero dummy (1,0)
-      }
-  double acc[8][4][2];
-#pragma unroll
-  for (int o = 0; o < 8; ++o)
-#pragma unroll
-    for (int tl = 0; tl < 4; ++tl)
-      acc[o][tl][0] = acc[o][tl][1] = 0.0;
-
-#pragma unroll
-  for (int o = 0; o < 8; ++o)
-    {
-      const int e = s_cells[o];
-      if (e >= 0)
-        {
-          mbar_wait(s_bar + o, 0u);
-          const double *Hs = s_H + (size_t)o * (8 * VH_SYMP);
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-            {
-              const double a = s_A[(o * 2 + ks) * 32 + lane];
-#pragma unroll
-              for (int tl = 0; tl < 4; ++tl)
-                {
-                  const double b = Hs[boff[ks][tl]];
-                  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                               : "+d"(acc[o][tl][0]), "+d"(acc[o][tl][1])
-                               : "d"(a), "d"(b));
-                }
-            }
-        }
-    }
-
-  // ---- reduce the octant sets inside each lane and dump the packed accumulators: [27][172] in the idle TMA ring ----
-  __syncthreads();
-  double   *s_sym = s_H;
-  const int m = lane >> 2; // MMA row = slot parity class (m_x, m_y, m_z)
-#pragma unroll
-  for (int d = 0; d < 3; ++d)
-    if ((m >> d) & 1)
-      { // coordinate d of the slot is 1 whatever the octant: octants o and o|(1<<d) feed the same slot
-#pragma unroll
-        for (int o = 0; o < 8; ++o)
-          if (!((o >> d) & 1))
-#pragma unroll
-            for (int tl = 0; tl < 4; ++tl)
-              {
-                acc[o][tl][0] += acc[o | (1 << d)][tl][0];
-                acc[o][tl][1] += acc[o | (1 << d)][tl][1];
-              }
-      }
-#pragma unroll
-  for (int o = 0; o < 8; ++o)
-    if ((o & m) == 0)
-      {
-        const int sx = (m & 1) ? 1 : 2 * (o & 1), sy = (m & 2) ? 1 : 2 * ((o >> 1) & 1), sz = (m & 4) ? 1 : 2 * (o >> 2);
-        double   *dst = s_sym + (sx + 3 * sy + 9 * sz) * VH_SYMP;
-#pragma unroll
-        for (int tl = 0; tl < 4; ++tl)
-          {
-            const int e = 8 * (4 * warp + tl) + 2 * (lane & 3);
-            if (e < VH_SYMP)
-              *reinterpret_cast<double2 *>(dst + e) = make_double2(acc[o][tl][0], acc[o][tl][1]);
-          }
-      }
-  __syncthreads();
-
-  // ---- store: thread t < 162 owns double2 #t of every 18x18 block ----
-  if (t < VH_BLK / 2)
-    {
-      int      soff[2], gsel[2];
-      uint32_t rbit[2], cbit[2];
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-        {
-          const int c = (2 * t) / 18, d = (2 * t) % 18 + k;
-          soff[k] = c <= d ? vh_sym_index(c, d) : vh_sym_index(d, c);
-          gsel[k] = (c / 3 == d / 3) ? (c % 3) * 3 + d % 3 : 9;
-          rbit[k] = 1u << c;
-          cbit[k] = 1u << d;
-        }
-      // fully unrolled: the 108 shared-memory loads of the 27 slots are batched ahead of the adds and the stores
-      double2 v[27];
-#pragma unroll
-      for (int s = 0; s < 27; ++s)
-        {
-          const double *sy = s_sym + s * VH_SYMP;
-          const double *G  = s_cls + s * 10;
-          v[s]             = make_double2(sy[soff[0]] + G[gsel[0]], sy[soff[1]] + G[gsel[1]]);
-        }
-#pragma unroll
-      for (int s = 0; s < 27; ++s)
-        {
-          const int pos = s_pos[s];
-          if (pos < 0)
-            continue; // block-uniform
-          const uint32_t maskJ = s_maskJ[s];
-          double         v0 = v[s].x, v1 = v[s].y;
-          if ((maskI | maskJ) != 0u)
-            {
-              if ((maskI & rbit[0]) || (maskJ & cbit[0]))
-                v0 = 0.0;
-              if ((maskI & rbit[1]) || (maskJ & cbit[1]))
-                v1 = 0.0;
-              if (s == 13)
-                {
-#pragma unroll
-                  for (int k = 0; k < 2; ++k)
-                    if (rbit[k] == cbit[k] && (maskI & rbit[k]))
-                      { // constrained diagonal: sum over cells of |a_ii| (mean |diag| of the cell if a_ii == 0)
-                        const int c    = 31 - __clz(rbit[k]);
-                        double    dsum = 0.0;
-                        for (int o = 0; o < 8; ++o)
-                          {
-                            const int e = s_cells[o];
-                            if (e < 0)
-                              continue;
-                            double dv = fabs(Dc[(size_t)e * 144 + (7 - o) * 18 + c]);
-                            if (dv == 0.0)
-                              dv = avgD[e];
-                            dsum += dv;
-                          }
-                        if (k == 0)
-                          v0 = dsum;
-                        else
-                          v1 = dsum;
-                      }
-                }
-            }
-          __stcs(reinterpret_cast<double2 *>(vals + (size_t)(rp + pos) * VH_BLK) + t, make_double2(v0, v1));
-        }
-    }
-}
-
-// Store-bandwidth probe with the row kernel's write pattern (one CTA per block row, 16-byte stores, no other work):
-// what the write-once matrix store costs on its own.  Used by vh_time_kernel(what=7) only.
-__global__ void __launch_bounds__(192) k_store_probe(int n_rows, const int32_t *__restrict__ row_ptr, double *__restrict__ vals, int mode)
-{
-  const int r = blockIdx.x;
-  if (r >= n_rows)
-    return;
-  double2      *dst = reinterpret_cast<double2 *>(vals + (size_t)row_ptr[r] * VH_BLK);
-  const int     n2  = (row_ptr[r + 1] - row_ptr[r]) * (VH_BLK / 2);
-  const double2 v   = make_double2(1.0, 2.0);
-  for (int i = threadIdx.x; i < n2; i += blockDim.x)
-    {
-      if (mode == 0)
-        __stcs(dst + i, v);
-      else
-        dst[i] = v;
-    }
-}
-
 // rhs gather of the lattice rows and the gather of the matrix-free apply: csrc/vh_gather_kernels.cuh
 #include "vh_gather_kernels.cuh"
 
@@ -902,139 +321,6 @@ __global__ void k_zero_slow_rows(int n_slow_rows, const int32_t *__restrict__ sl
     vals[i] = 0.0;
 }
 
-struct SlowArgs
-{
-  const int32_t *slow_cells, *cell_nodes, *row_ptr, *col;
-  const double  *cell_h;
-  const uint32_t *cell_faces;
-  const uint8_t *row_slow;
-  const int32_t *line_of, *cptr, *cmaster;
-  const double  *cweight;
-  const double  *Hq, *Rc, *avgD;
-  int            n_owned;
-};
-
-__device__ __forceinline__ void slow_add(const SlowArgs &A, int I, int c, int J, int d, double v, double *vals)
-{
-  if (I >= A.n_owned || !A.row_slow[I])
-    return;
-  int lo = A.row_ptr[I], hi = A.row_ptr[I + 1] - 1;
-  while (lo < hi)
-    {
-      const int mid = (lo + hi) >> 1;
-      if (A.col[mid] < J)
-        lo = mid + 1;
-      else
-        hi = mid;
-    }
-  if (A.col[lo] == J)
-    atomicAdd(vals + (size_t)lo * VH_BLK + c * 18 + d, v);
-}
-
-template <int NN, int NQ>
-__global__ void k_cells_slow(SlowArgs A, VhTables tab, VhCoef cf, int want_matrix, double *__restrict__ vals,
-                             double *__restrict__ rhs)
-{
-  extern __shared__ double sm[];
-  double *sH  = sm;                  // [NQ*172]
-  double *sN  = sH + NQ * VH_SYMP;   // [NN*NQ]
-  double *swq = sN + NN * NQ;        // [NQ]
-  __shared__ int s_nodes[NN];
-
-  const int     t    = threadIdx.x;
-  const int64_t cell = A.slow_cells[blockIdx.x];
-  if (want_matrix)
-    for (int i = t; i < NQ * VH_SYMP; i += blockDim.x)
-      sH[i] = A.Hq[cell * (int64_t)(NQ * VH_SYMP) + i];
-  for (int i = t; i < NN * NQ; i += blockDim.x)
-    sN[i] = tab.N[i];
-  if (t < NQ)
-    swq[t] = tab.wq[t];
-  if (t < NN)
-    s_nodes[t] = A.cell_nodes[cell * NN + t];
-  __syncthreads();
-  const double *h   = A.cell_h + 4 * cell;
-  const double  vol = h[3];
-  const double  ih[3] = {1.0 / h[0], 1.0 / h[1], 1.0 / h[2]};
-  const uint32_t faces = A.cell_faces[cell];
-  const bool     robin = (cf.bt < 1e10) && faces != 0u;
-
-  if (want_matrix)
-    for (int pair = 0; pair < NN * NN; ++pair)
-      {
-        const int     a = pair / NN, b = pair - NN * a;
-        const double *G = tab.Gref + (size_t)pair * 9;
-        for (int e = t; e < VH_BLK; e += blockDim.x)
-          {
-            const int c = e / 18, d = e - 18 * c;
-            const int sidx = c <= d ? vh_sym_index(c, d) : vh_sym_index(d, c);
-            double    v = 0.0;
-            for (int q = 0; q < NQ; ++q)
-              v += swq[q] * sN[a * NQ + q] * sN[b * NQ + q] * sH[NQ == 8 ? vh_hq8_index(q, sidx) : q * VH_SYMP + sidx]; // pre-scaled by vol
-            if (c == d)
-              v += vol * cf.K1 * (G[0] * ih[0] * ih[0] + G[4] * ih[1] * ih[1] + G[8] * ih[2] * ih[2]);
-            if (c / 3 == d / 3)
-              v += vol * cf.K23 * G[(c % 3) * 3 + d % 3] * ih[c % 3] * ih[d % 3];
-            if (robin && c == d)
-              for (int f = 0; f < 6; ++f)
-                {
-                  const int bid = (faces >> (4 * f)) & 15u;
-                  if (bid < 2 || bid > 4 || (c % 3) == bid - 2)
-                    continue;
-                  v += cf.K1 / cf.bt * (vol / h[f / 2]) * tab.Mf[(size_t)(f * NN + a) * NN + b];
-                }
-            // AffineConstraints::distribute_local_to_global
-            const int gi = 18 * s_nodes[a] + c, gj = 18 * s_nodes[b] + d;
-            const int li = A.line_of[gi], lj = A.line_of[gj];
-            if (li < 0 && lj < 0)
-              slow_add(A, s_nodes[a], c, s_nodes[b], d, v, vals);
-            else
-              {
-                const int r0 = li < 0 ? 0 : A.cptr[li], r1 = li < 0 ? 1 : A.cptr[li + 1];
-                const int q0 = lj < 0 ? 0 : A.cptr[lj], q1 = lj < 0 ? 1 : A.cptr[lj + 1];
-                for (int rr = r0; rr < r1; ++rr)
-                  {
-                    const int    rd = li < 0 ? gi : A.cmaster[rr];
-                    const double rw = li < 0 ? 1.0 : A.cweight[rr];
-                    for (int qq = q0; qq < q1; ++qq)
-                      {
-                        const int    cd = lj < 0 ? gj : A.cmaster[qq];
-                        const double cw = lj < 0 ? 1.0 : A.cweight[qq];
-                        slow_add(A, rd / 18, rd % 18, cd / 18, cd % 18, rw * cw * v, vals);
-                      }
-                  }
-                if (gi == gj && li >= 0)
-                  {
-                    double dv = fabs(v);
-                    if (dv == 0.0)
-                      dv = A.avgD[cell];
-                    slow_add(A, s_nodes[a], c, s_nodes[a], c, dv, vals);
-                  }
-              }
-          }
-      }
-  // vector part (rhs[m_k] += w_k r_i; constrained entries stay 0)
-  for (int i = t; i < 18 * NN; i += blockDim.x)
-    {
-      const int    a = i / 18, c = i - 18 * a;
-      const double r = A.Rc[cell * (int64_t)(18 * NN) + i];
-      const int    gi = 18 * s_nodes[a] + c, li = A.line_of[gi];
-      if (li < 0)
-        {
-          const int I = s_nodes[a];
-          if (I < A.n_owned && A.row_slow[I])
-            atomicAdd(rhs + gi, r);
-        }
-      else
-        for (int rr = A.cptr[li]; rr < A.cptr[li + 1]; ++rr)
-          {
-            const int rd = A.cmaster[rr], I = rd / 18;
-            if (I < A.n_owned && A.row_slow[I])
-              atomicAdd(rhs + rd, A.cweight[rr] * r);
-          }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // 3b. row-owner assembly of the constrained rows (hanging-node neighbourhoods, constraint masters)
 // ------------------------------------------------------------------------------------------------
@@ -1045,8 +331,8 @@ __global__ void k_cells_slow(SlowArgs A, VhTables tab, VhCoef cf, int want_matri
 // distribute_local_to_global rule: row weight of (a,c) -> (I,c), column b either direct or spread over
 // the masters of its line, constrained rows reduced to  sum_cells |a_ii|  on the diagonal.  The row belongs to this CTA
 // alone and entry (c,d) to one thread, so the accumulation is a plain read-modify-write on pre-zeroed blocks: no atomics.
-// (Constraint lines that couple different components - none are generated by the hosts in this repository - would let
-// two threads meet in one entry; such contexts keep the atomic cell scatter k_cells_slow.)
+// (Constraint lines that couple different components - none exist in the reference: Dirichlet, hanging-node and periodic
+// lines all stay within one component - would let two threads meet in one entry; vh_create rejects such tables.)
 struct SlowRowArgs
 {
   const int32_t *slow_rows, *srow_ptr, *srow_cell;
@@ -1295,24 +581,7 @@ __global__ void __launch_bounds__(352, NN == 8 ? 2 : 1)
     }
 }
 
-template <int NN, int NQ>
-size_t pointwise_smem(bool want_h)
-{
-  (void)want_h;
-  size_t n = (size_t)NN * 18 + (size_t)NQ * VH_TQ + NQ * 54 + NQ * 18 + NQ * 18 + NN * NQ + NN * NQ * 3 + NQ + 32;
-  return n * sizeof(double);
-}
 } // namespace
-
-int vhk_upload_constants(vh_ctx *ctx)
-{
-  // symmetric packing tables
-  uint8_t sc[VH_SYMP], sd[VH_SYMP];
-  vh_sym_tables(sc, sd); // dummies (d < c) are written as 0 by the pointwise kernel and never read back as entries
-  VH_CUDA(cudaMemcpyToSymbol(c_symc, sc, sizeof(sc)));
-  VH_CUDA(cudaMemcpyToSymbol(c_symd, sd, sizeof(sd)));
-  return VH_OK;
-}
 
 int vhk_upload_q2(vh_ctx *ctx, const double *T2, const uint8_t *q2t)
 {
@@ -1331,7 +600,6 @@ int vhk_pointwise(vh_ctx *ctx, const double *x_local, bool want_h, bool want_e)
 {
   if (ctx->n_cells == 0)
     return VH_OK;
-  const bool legacy_q2 = getenv("VH_Q2_POINTWISE_LEGACY") && getenv("VH_Q2_POINTWISE_LEGACY")[0] == '1';
   const vh_hweights hw = vh_make_hweights(ctx->coef.alpha, ctx->coef.beta);
 #define VH_LAUNCH_POINTS(NN, H, E)                                                                                                \
   k_points<NN, H, E><<<grid, VH_PT_WARPS * 32, VhPt<NN>::SMEM, ctx->stream>>>(ctx->n_cells, ctx->cell_nodes, ctx->cell_h,         \
@@ -1363,7 +631,7 @@ int vhk_pointwise(vh_ctx *ctx, const double *x_local, bool want_h, bool want_e)
       const int grid = (ctx->n_cells + 4 * VH_PT_WARPS - 1) / (4 * VH_PT_WARPS);
       VH_LAUNCH_POINTS_MODE(8);
     }
-  else if (!legacy_q2)
+  else
     {
       const int grid = (ctx->n_cells + VH_PT_WARPS - 1) / VH_PT_WARPS;
       VH_LAUNCH_POINTS_MODE(27);
@@ -1371,17 +639,6 @@ int vhk_pointwise(vh_ctx *ctx, const double *x_local, bool want_h, bool want_e)
 #undef VH_LAUNCH_POINTS
 #undef VH_LAUNCH_POINTS_MODE
 #undef VH_POINTS_ATTR
-  else
-    {
-      const size_t smem = pointwise_smem<27, 27>(want_h);
-      static unsigned long long attr_mask2 = 0;
-      if (vh_first_time_on_device(attr_mask2, ctx->device))
-        VH_CUDA(cudaFuncSetAttribute(k_pointwise<27, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)pointwise_smem<27, 27>(true)));
-      k_pointwise<27, 27><<<ctx->n_cells, 512, smem, ctx->stream>>>(ctx->cell_nodes, ctx->cell_h, ctx->cell_faces,
-                                                                   ctx->cell_owned, x_local, ctx->tab, ctx->coef, want_h, want_e,
-                                                                   ctx->Hq, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec);
-    }
   VH_LAUNCH_CHECK();
   return VH_OK;
 }
@@ -1469,9 +726,18 @@ int vhk_diag_fast(vh_ctx *ctx)
   else
     k_diag_cells<27><<<ctx->n_cells, 192, 0, ctx->stream>>>(ctx->n_cells, ctx->tab.N, ctx->tab.wq, ctx->Hq, ctx->Dblk);
   VH_LAUNCH_CHECK();
-  k_diag_gather<<<ctx->n_fast, 192, 0, ctx->stream>>>(ctx->n_fast, ctx->nn, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->diag_pos,
-                                                    ctx->Dblk, ctx->pvals);
+  if (!ctx->dpack)
+    VH_TRY(vh_dev_alloc(ctx, &ctx->dpack, (size_t)ctx->n_fast * VH_SYMP));
+  k_diag_gather<<<ctx->n_fast, 192, 0, ctx->stream>>>(ctx->n_fast, ctx->nn, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->Dblk,
+                                                    ctx->dpack);
   VH_LAUNCH_CHECK();
+  return VH_OK;
+}
+
+int vhk_alloc_rows(vh_ctx *ctx)
+{
+  if (ctx->packed && !ctx->pvals)
+    VH_TRY(vh_dev_alloc(ctx, &ctx->pvals, (size_t)ctx->nnzb * VH_SYMP));
   return VH_OK;
 }
 
@@ -1488,75 +754,18 @@ int vhk_rows_fast(vh_ctx *ctx)
 {
   if (ctx->n_fast == 0)
     return VH_OK;
+  VH_TRY(vhk_alloc_rows(ctx));
   if (ctx->degree == 2)
-    {
-      static int minb = 0;
-      if (!minb)
-        {
-          const char *e = getenv("VH_Q2_ROWS_MINB"); // tuning knob: resident CTAs per SM the kernel is compiled for (2, 3 or 4)
-          minb          = e ? atoi(e) : 4;
-        }
-      if (minb == 2)
-        k_rows_fast_q2<2><<<ctx->n_fast, 192, 0, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_slot,
-                                                               ctx->fast_first, ctx->row_ptr, ctx->Hq, ctx->pvals);
-      else if (minb == 4)
-        k_rows_fast_q2<4><<<ctx->n_fast, 192, 0, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_slot,
-                                                               ctx->fast_first, ctx->row_ptr, ctx->Hq, ctx->pvals);
-      else
-        k_rows_fast_q2<3><<<ctx->n_fast, 192, 0, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_slot,
-                                                               ctx->fast_first, ctx->row_ptr, ctx->Hq, ctx->pvals);
-      VH_LAUNCH_CHECK();
-      return VH_OK;
-    }
-  static int                ept = 0;
-  static unsigned long long rows_attr_mask = 0;
-  if (!ept)
-    {
-      const char *e = getenv("VH_ROWS_EPT"); // tuning knob: packed entries per thread (1 or 2)
-      ept           = (e && e[0] == '2') ? 2 : 1;
-    }
-  if (vh_first_time_on_device(rows_attr_mask, ctx->device))
-    {
-      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
-      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
-      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
-      VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
-    }
-  static int use_mma = -1;
-  if (use_mma < 0)
-    {
-      const char *e = getenv("VH_ROWS_MMA"); // tuning knob (full-format storage only): 1 = FP64 tensor-core kernel, 0 = scalar DFMA kernel (default, faster)
-      use_mma       = (e && e[0] == '1') ? 1 : 0;
-    }
-  static unsigned long long mma_attr_mask = 0;
-  if (use_mma && vh_first_time_on_device(mma_attr_mask, ctx->device))
-    VH_CUDA(cudaFuncSetAttribute(k_rows_mma_q1, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_MMA_SMEM));
-  if (ctx->packed)
-    { // packed symmetric storage: no expansion stage, half the bytes
-      if (ept == 2)
-        k_rows_fast_q1<2, true><<<ctx->n_fast, 96, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot,
-                                                                               ctx->fast_class, ctx->class_M, ctx->row_ptr, ctx->col,
-                                                                               ctx->dirmask, ctx->Hq, ctx->Dc, ctx->avgD, ctx->coef,
-                                                                               ctx->pvals);
-      else
-        k_rows_fast_q1<1, true><<<ctx->n_fast, 192, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot,
-                                                                                ctx->fast_class, ctx->class_M, ctx->row_ptr, ctx->col,
-                                                                                ctx->dirmask, ctx->Hq, ctx->Dc, ctx->avgD, ctx->coef,
-                                                                                ctx->pvals);
-    }
-  else if (use_mma)
-    k_rows_mma_q1<<<ctx->n_fast, VH_MMA_THREADS, VH_MMA_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot,
-                                                                           ctx->fast_class, ctx->class_M, ctx->afrag, ctx->row_ptr,
-                                                                           ctx->col, ctx->dirmask, ctx->Hq, ctx->Dc, ctx->avgD,
-                                                                           ctx->vals);
-  else if (ept == 2)
-    k_rows_fast_q1<2, false><<<ctx->n_fast, 96, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class,
-                                                                     ctx->class_M, ctx->row_ptr, ctx->col, ctx->dirmask, ctx->Hq,
-                                                                     ctx->Dc, ctx->avgD, ctx->coef, ctx->vals);
+    k_rows_fast_q2<<<ctx->n_fast, 192, 0, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_slot, ctx->fast_first,
+                                                        ctx->row_ptr, ctx->Hq, ctx->pvals);
   else
-    k_rows_fast_q1<1, false><<<ctx->n_fast, 192, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->fast_class,
-                                                                      ctx->class_M, ctx->row_ptr, ctx->col, ctx->dirmask, ctx->Hq,
-                                                                      ctx->Dc, ctx->avgD, ctx->coef, ctx->vals);
+    {
+      static unsigned long long rows_attr_mask = 0;
+      if (vh_first_time_on_device(rows_attr_mask, ctx->device))
+        VH_CUDA(cudaFuncSetAttribute(k_rows_fast_q1, cudaFuncAttributeMaxDynamicSharedMemorySize, VH_FAST_SMEM));
+      k_rows_fast_q1<<<ctx->n_fast, 192, VH_FAST_SMEM, ctx->stream>>>(ctx->fast_rows, ctx->fast_cells, ctx->fast_slot, ctx->row_ptr,
+                                                                     ctx->Hq, ctx->pvals);
+    }
   VH_LAUNCH_CHECK();
   return VH_OK;
 }
@@ -1567,13 +776,6 @@ int vhk_expand_packed(vh_ctx *ctx, double *full_vals)
     return VH_OK;
   k_expand_packed<<<ctx->n_fast, 256, 0, ctx->stream>>>(ctx->n_fast, ctx->slot_stride, ctx->n_slots * 10, ctx->fast_rows, ctx->fast_posslot, ctx->fast_class, ctx->class_M,
                                                        ctx->row_ptr, ctx->col, ctx->dirmask, ctx->pvals, ctx->cdiag, full_vals);
-  VH_LAUNCH_CHECK();
-  return VH_OK;
-}
-
-int vhk_store_probe(vh_ctx *ctx, int mode)
-{
-  k_store_probe<<<ctx->n_owned, 192, 0, ctx->stream>>>(ctx->n_owned, ctx->row_ptr, ctx->vals, mode);
   VH_LAUNCH_CHECK();
   return VH_OK;
 }
@@ -1600,78 +802,46 @@ int vhk_rows_slow(vh_ctx *ctx, bool want_matrix, double *rhs_out)
   VH_LAUNCH_CHECK();
   if (ctx->n_slow_cells == 0)
     return VH_OK;
-  if (ctx->slow_row_owner)
-    { // row-owner kernel: no atomics (constraint lines stay within one component)
-      SlowRowArgs R;
-      R.slow_rows  = ctx->slow_rows;
-      R.srow_ptr   = ctx->srow_ptr;
-      R.srow_cell  = ctx->srow_cell;
-      R.srow_a     = ctx->srow_a;
-      R.srow_posb  = ctx->srow_posb;
-      R.srow_wr    = ctx->srow_wr;
-      R.srow_bcons = ctx->srow_bcons;
-      R.srow_mnode = ctx->srow_mnode;
-      R.srow_mpos  = ctx->srow_mpos;
-      R.srow_posI  = ctx->srow_posI;
-      R.srow_cons  = ctx->srow_cons;
-      R.cell_nodes = ctx->cell_nodes;
-      R.row_ptr    = ctx->row_ptr;
-      R.col        = ctx->col;
-      R.cell_h     = ctx->cell_h;
-      R.cell_faces = ctx->cell_faces;
-      R.line_of    = ctx->cons[0].line_of;
-      R.cptr       = ctx->cons[0].ptr;
-      R.cmaster    = ctx->cons[0].master;
-      R.cweight    = ctx->cons[0].weight;
-      R.Hq         = ctx->Hq;
-      R.Rc         = ctx->Rc;
-      R.Dc         = ctx->Dc;
-      R.avgD       = ctx->avgD;
-      k_rhs_slow<<<(ctx->n_slow_rows * 18 + 127) / 128, 128, 0, ctx->stream>>>(ctx->n_slow_rows, ctx->nn, R, rhs_out);
-      VH_LAUNCH_CHECK();
-      if (!want_matrix)
-        return VH_OK;
-      if (ctx->degree == 1)
-        k_rows_slow<8, 8><<<ctx->n_slow_rows, 352, (8 * VH_SYMP + 64 + 8) * sizeof(double), ctx->stream>>>(R, ctx->tab, ctx->coef, ctx->vals);
-      else
-        {
-          static unsigned long long attr_mask = 0;
-          if (vh_first_time_on_device(attr_mask, ctx->device))
-            VH_CUDA(cudaFuncSetAttribute(k_rows_slow<27, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((27 * VH_SYMP + 729 + 27) * sizeof(double))));
-          k_rows_slow<27, 27><<<ctx->n_slow_rows, 352, (27 * VH_SYMP + 729 + 27) * sizeof(double), ctx->stream>>>(R, ctx->tab, ctx->coef,
-                                                                                                                 ctx->vals);
-        }
-      VH_LAUNCH_CHECK();
-      return VH_OK;
-    }
-  SlowArgs A;
-  A.slow_cells = ctx->slow_cells;
-  A.cell_nodes = ctx->cell_nodes;
-  A.row_ptr    = ctx->row_ptr;
-  A.col        = ctx->col;
-  A.cell_h     = ctx->cell_h;
-  A.cell_faces = ctx->cell_faces;
-  A.row_slow   = ctx->row_slow;
-  A.line_of    = ctx->cons[0].line_of;
-  A.cptr       = ctx->cons[0].ptr;
-  A.cmaster    = ctx->cons[0].master;
-  A.cweight    = ctx->cons[0].weight;
-  A.Hq         = ctx->Hq;
-  A.Rc         = ctx->Rc;
-  A.avgD       = ctx->avgD;
-  A.n_owned    = ctx->n_owned;
+  // row-owner kernel: no atomics (constraint lines stay within one component: checked in vh_create)
+  SlowRowArgs R;
+  R.slow_rows  = ctx->slow_rows;
+  R.srow_ptr   = ctx->srow_ptr;
+  R.srow_cell  = ctx->srow_cell;
+  R.srow_a     = ctx->srow_a;
+  R.srow_posb  = ctx->srow_posb;
+  R.srow_wr    = ctx->srow_wr;
+  R.srow_bcons = ctx->srow_bcons;
+  R.srow_mnode = ctx->srow_mnode;
+  R.srow_mpos  = ctx->srow_mpos;
+  R.srow_posI  = ctx->srow_posI;
+  R.srow_cons  = ctx->srow_cons;
+  R.cell_nodes = ctx->cell_nodes;
+  R.row_ptr    = ctx->row_ptr;
+  R.col        = ctx->col;
+  R.cell_h     = ctx->cell_h;
+  R.cell_faces = ctx->cell_faces;
+  R.line_of    = ctx->cons[0].line_of;
+  R.cptr       = ctx->cons[0].ptr;
+  R.cmaster    = ctx->cons[0].master;
+  R.cweight    = ctx->cons[0].weight;
+  R.Hq         = ctx->Hq;
+  R.Rc         = ctx->Rc;
+  R.Dc         = ctx->Dc;
+  R.avgD       = ctx->avgD;
+  k_rhs_slow<<<(ctx->n_slow_rows * 18 + 127) / 128, 128, 0, ctx->stream>>>(ctx->n_slow_rows, ctx->nn, R, rhs_out);
+  VH_LAUNCH_CHECK();
+  if (!want_matrix)
+    return VH_OK;
   if (ctx->degree == 1)
-    {
-      const size_t smem = (size_t)(8 * VH_SYMP + 64 + 8) * sizeof(double);
-      k_cells_slow<8, 8><<<ctx->n_slow_cells, 352, smem, ctx->stream>>>(A, ctx->tab, ctx->coef, want_matrix ? 1 : 0, ctx->vals,
-                                                                       rhs_out);
-    }
+    k_rows_slow<8, 8><<<ctx->n_slow_rows, 352, (8 * VH_SYMP + 64 + 8) * sizeof(double), ctx->stream>>>(R, ctx->tab, ctx->coef, ctx->vals);
   else
     {
-      const size_t smem = (size_t)(27 * VH_SYMP + 729 + 27) * sizeof(double);
-      k_cells_slow<27, 27><<<ctx->n_slow_cells, 352, smem, ctx->stream>>>(A, ctx->tab, ctx->coef, want_matrix ? 1 : 0, ctx->vals,
-                                                                         rhs_out);
+      static unsigned long long attr_mask = 0;
+      if (vh_first_time_on_device(attr_mask, ctx->device))
+        VH_CUDA(cudaFuncSetAttribute(k_rows_slow<27, 27>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((27 * VH_SYMP + 729 + 27) * sizeof(double))));
+      k_rows_slow<27, 27><<<ctx->n_slow_rows, 352, (27 * VH_SYMP + 729 + 27) * sizeof(double), ctx->stream>>>(R, ctx->tab, ctx->coef,
+                                                                                                             ctx->vals);
     }
   VH_LAUNCH_CHECK();
   return VH_OK;

@@ -456,7 +456,7 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
             ps[pos27[sl]] = (uint8_t)sl;
         fast_posslot.insert(fast_posslot.end(), ps, ps + 32);
       }
-  if (ctx->degree == 2 && !(getenv("VH_Q2_SCATTER") && getenv("VH_Q2_SCATTER")[0] == '1'))
+  if (ctx->degree == 2)
     { // Q2 lattice rows: vertex / edge / face / interior nodes with 8 / 4 / 2 / 1 incident cells and 125 / 75 / 45 / 27 blocks
       std::vector<std::pair<int32_t, int32_t>> order; // (first incident cell, row): rows of one cell are launched together
       for (int I = 0; I < n_owned; ++I)
@@ -744,9 +744,11 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
       for (int p = C.ptr[l]; p < C.ptr[l + 1]; ++p)
         if (C.master[p] % 18 != C.dof[l] % 18)
           mixes = true;
-    ctx->slow_row_owner = !mixes && !too_many_masters && !(getenv("VH_SLOW_SCATTER") && getenv("VH_SLOW_SCATTER")[0] == '1');
+    if (!slow_rows.empty() && (mixes || too_many_masters))
+      return vh_fail(ctx, VH_ERR_UNSUPPORTED,
+                     mixes ? "constraint lines that couple different components are not supported (the reference has none)"
+                           : "a hanging node with more masters than a face of its degree allows");
   }
-  VH_TRY(vh_dev_upload(ctx, &ctx->slow_cells, slow_cells.data(), slow_cells.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->row_slow, row_slow.data(), row_slow.size()));
 
   // ---- reference-cell tables ----
@@ -758,19 +760,8 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
   VH_TRY(vh_dev_upload(ctx, &ctx->tab.wq, T.wq.data(), T.wq.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->tab.Gref, T.Gref.data(), T.Gref.size()));
   VH_TRY(vh_dev_upload(ctx, &ctx->tab.Mf, T.Mf.data(), T.Mf.size()));
-  VH_TRY(vhk_upload_constants(ctx));
   if (ctx->degree == 1)
-    {
-      VH_TRY(vhk_upload_w1(ctx, T.W1.data()));
-      // A fragments of mma.m8n8k4 (row-major 8x4: lane holds row lane/4, column lane%4) for every octant and k-step:
-      // row m of octant o carries column node b = m XOR o, the row node is local vertex a = 7 - o.
-      std::vector<double> af(512);
-      for (int o = 0; o < 8; ++o)
-        for (int ks = 0; ks < 2; ++ks)
-          for (int l = 0; l < 32; ++l)
-            af[(o * 2 + ks) * 32 + l] = T.W1[((7 - o) * 8 + ((l >> 2) ^ o)) * 8 + 4 * ks + (l & 3)];
-      VH_TRY(vh_dev_upload(ctx, &ctx->afrag, af.data(), af.size()));
-    }
+    VH_TRY(vhk_upload_w1(ctx, T.W1.data()));
 
   // ---- halo plan ----
   if (d->n_peers < 0)
@@ -799,20 +790,22 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
     return vh_fail(ctx, VH_ERR_ARG, "ghost nodes without a halo plan");
 
   // ---- matrix, scratch, vectors ----
-  // storage format: packed symmetric blocks for the lattice rows unless VH_FULL_BSR=1 (A/B switch, full 18x18 blocks)
-  ctx->packed = ctx->n_fast > 0 && (ctx->degree == 2 || !(getenv("VH_FULL_BSR") && getenv("VH_FULL_BSR")[0] == '1'));
-  ctx->spmv_mf = ctx->packed && getenv("VH_SPMV_MF") && (getenv("VH_SPMV_MF")[0] >= '1' && getenv("VH_SPMV_MF")[0] <= '3') &&
-                 !(getenv("VH_Q2_POINTWISE_LEGACY") && getenv("VH_Q2_POINTWISE_LEGACY")[0] == '1');
-  ctx->spmv_mf_table_free = ctx->spmv_mf && getenv("VH_SPMV_MF")[0] == '2';
-  ctx->spmv_mf_v2         = ctx->spmv_mf && getenv("VH_SPMV_MF")[0] == '3';
-  ctx->rows_lazy          = getenv("VH_MF_LAZY_ROWS") && getenv("VH_MF_LAZY_ROWS")[0] == '1';
+  ctx->packed = ctx->n_fast > 0;
+  // Operator apply of the lattice rows.  Default: matrix-free from the H_q tables, and the rows are
+  // not assembled at all (solve.cc:171-174 needs only vmult; block-Jacobi needs only the diagonal blocks).  VH_SPMV_MF=0
+  // selects the assembled packed SpMV (A/B runs), VH_MF_LAZY_ROWS=0 assembles the rows in every vh_assemble anyway.
+  const char *mf_env = getenv("VH_SPMV_MF");
+  const int   mf_mode = (mf_env && mf_env[0] >= '0' && mf_env[0] <= '3') ? mf_env[0] - '0' : 1;
+  ctx->spmv_mf            = ctx->packed && mf_mode != 0;
+  ctx->spmv_mf_table_free = ctx->spmv_mf && mf_mode == 2;
+  ctx->spmv_mf_v2         = ctx->spmv_mf && mf_mode == 3;
+  ctx->rows_lazy          = !(getenv("VH_MF_LAZY_ROWS") && getenv("VH_MF_LAZY_ROWS")[0] == '0');
   if (ctx->packed)
-    {
-      VH_TRY(vh_dev_alloc(ctx, &ctx->pvals, (size_t)ctx->nnzb * VH_SYMP));
+    { // pvals (the packed rows, 1440 B per block) is allocated on first use: vhk_alloc_rows
       VH_TRY(vh_dev_alloc(ctx, &ctx->cdiag, (size_t)n_owned * 18));
       VH_CUDA(cudaMemset(ctx->cdiag, 0, sizeof(double) * (size_t)std::max(n_owned, 1) * 18));
     }
-  if (!ctx->packed || ctx->n_slow_rows > 0)
+  if (ctx->n_slow_rows > 0)
     VH_TRY(vh_dev_alloc(ctx, &ctx->vals, (size_t)ctx->nnzb * VH_BLK));
   VH_TRY(vhk_upload_linalg_constants(ctx));
   VH_TRY(vh_dev_alloc(ctx, &ctx->minv, (size_t)n_owned * VH_BLK));
@@ -1076,8 +1069,8 @@ int vh_destroy(vh_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
   vh_comm_destroy(ctx);
   void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
-                  ctx->diag_pos, ctx->minv, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_first, ctx->spmv_order, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->afrag, ctx->slow_rows, ctx->srow_ptr, ctx->srow_cell, ctx->srow_a, ctx->srow_posb, ctx->srow_wr, ctx->srow_bcons, ctx->srow_posI, ctx->srow_mnode, ctx->srow_mpos, ctx->srow_cons, ctx->push_ptr, ctx->push_dst, ctx->push_peer, ctx->push_ticket, ctx->row_slow,
-                  ctx->slow_cells, ctx->Hq, ctx->Dblk, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
+                  ctx->diag_pos, ctx->minv, ctx->pvals, ctx->dpack, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_first, ctx->spmv_order, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->slow_rows, ctx->srow_ptr, ctx->srow_cell, ctx->srow_a, ctx->srow_posb, ctx->srow_wr, ctx->srow_bcons, ctx->srow_posI, ctx->srow_mnode, ctx->srow_mpos, ctx->srow_cons, ctx->push_ptr, ctx->push_dst, ctx->push_peer, ctx->push_ticket, ctx->row_slow,
+                  ctx->Hq, ctx->Dblk, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
                   ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
                   ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,
                   ctx->tab.Mf};
@@ -1324,7 +1317,8 @@ int vh_accept_trial(vh_ctx *ctx)
   VH_CUDA(cudaSetDevice(ctx->device));
   VH_CUDA(cudaMemcpyAsync(ctx->x_sol, ctx->x_trial, sizeof(double) * ctx->NL, cudaMemcpyDeviceToDevice, ctx->stream));
   VH_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->have_matrix = false;
+  // the matrix, the Newton update and the trial vector all belong to the state that was just replaced
+  ctx->have_matrix = ctx->have_update = ctx->have_trial = false;
   return VH_OK;
 }
 
@@ -1458,13 +1452,6 @@ int vh_time_kernel(vh_ctx *ctx, int what, int reps, int do_flush, float *ms_avg)
         case 6:
           VH_TRY(vhk_rows_fast(ctx));
           break;
-        case 7: // destroys the matrix values: bandwidth probe only
-        case 8:
-          if (!ctx->vals)
-            return vh_fail(ctx, VH_ERR_STATE, "store probe needs full-format storage (VH_FULL_BSR=1)");
-          VH_TRY(vhk_store_probe(ctx, what - 7));
-          ctx->have_matrix = false;
-          break;
         case 9: // collective: 20 ghost refreshes back to back (ms_avg is per batch of 20)
           for (int k = 0; k < 20; ++k)
             VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
@@ -1544,9 +1531,7 @@ int vh_set_spmv_matrix_free(vh_ctx *ctx, int on)
 {
   VH_REQUIRE(ctx);
   if (on && !ctx->packed)
-    return vh_fail(ctx, VH_ERR_UNSUPPORTED, "matrix-free apply needs packed lattice rows (none here, or VH_FULL_BSR=1)");
-  if (on && getenv("VH_Q2_POINTWISE_LEGACY") && getenv("VH_Q2_POINTWISE_LEGACY")[0] == '1')
-    return vh_fail(ctx, VH_ERR_UNSUPPORTED, "matrix-free apply needs the H_q layout of k_points (VH_Q2_POINTWISE_LEGACY is set)");
+    return vh_fail(ctx, VH_ERR_UNSUPPORTED, "matrix-free apply needs lattice rows (this context has none)");
   ctx->spmv_mf            = on != 0;
   ctx->spmv_mf_table_free = on == 2;
   ctx->spmv_mf_v2         = on == 3;

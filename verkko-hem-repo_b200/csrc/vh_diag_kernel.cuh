@@ -2,8 +2,8 @@
 // applied matrix-free and the lattice rows are therefore not assembled (VH_MF_LAZY_ROWS=1):
 //   P_II = sum_{cells e containing node I} sum_q w_q N_a(q)^2 (vol H_q)(e)        (a = local index of I in e)
 // k_diag_cells writes the per-(cell, node) contributions in the packed layout (coalesced over the 180 packed entries),
-// k_diag_gather sums the <= 8 contributions of a row in a fixed order into the diagonal block's usual place in pvals, so
-// k_block_invert and its class_M / Dirichlet handling stay as they are.  Same header for nvcc and for the CPU emulation
+// k_diag_gather sums the <= 8 contributions of a row in a fixed order into dpack[fast row] (packed layout), which
+// k_block_invert reads instead of the assembled diagonal block; its class_M / Dirichlet handling stays as it is.  Same header for nvcc and for the CPU emulation
 // (tests/native/cuda_emu.h, tests/test_kernel_emulation.py).
 #ifndef VH_DIAG_KERNEL_CUH
 #define VH_DIAG_KERNEL_CUH
@@ -41,14 +41,12 @@ __global__ void __launch_bounds__(192)
 
 __global__ void __launch_bounds__(192)
   k_diag_gather(int n_fast, int nn, const int32_t *__restrict__ fast_rows, const int32_t *__restrict__ fast_cells,
-                const int8_t *__restrict__ fast_a, const int32_t *__restrict__ diag_pos, const double *__restrict__ Dblk,
-                double *__restrict__ pvals)
+                const int8_t *__restrict__ fast_a, const double *__restrict__ Dblk, double *__restrict__ dpack)
 {
   const int r = blockIdx.x, e = threadIdx.x;
   if (r >= n_fast || e >= VH_SYMP)
     return;
-  const int I = fast_rows[r];
-  double    s = 0.0;
+  double s = 0.0;
 #pragma unroll
   for (int o = 0; o < 8; ++o)
     {
@@ -56,7 +54,7 @@ __global__ void __launch_bounds__(192)
       if (c >= 0)
         s += Dblk[((int64_t)c * nn + fast_a[(size_t)r * 8 + o]) * VH_SYMP + e];
     }
-  pvals[(size_t)diag_pos[I] * VH_SYMP + e] = s;
+  dpack[(size_t)r * VH_SYMP + e] = s;
 }
 
 #endif

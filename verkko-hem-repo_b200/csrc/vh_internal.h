@@ -108,11 +108,11 @@ struct vh_ctx
   // BSR(18) matrix over owned rows
   int32_t *row_ptr  = nullptr; // [n_owned+1]
   int32_t *col      = nullptr; // [nnzb] local node ids, ascending inside a row
-  double  *vals     = nullptr; // [nnzb][18][18]  full blocks (general-scatter rows; all rows when !packed)
+  double  *vals     = nullptr; // [nnzb][18][18]  full blocks of the constrained (row-owner scatter) rows
   // Packed storage of the lattice ("fast") rows: block = Sym(P) + kron(I_6, M_slot) with Dirichlet masks applied on
-  // the fly, P = 171 unique entries of the symmetric bulk part (+1 pad): 1376 B per block instead of 2592 B.
-  bool     packed   = false;
-  double  *pvals    = nullptr; // [nnzb][172]
+  // the fly, P = 171 unique entries of the symmetric bulk part (+9 zero dummies): 1440 B per block instead of 2592 B.
+  bool     packed   = false;   // the context has lattice rows
+  double  *pvals    = nullptr; // [nnzb][180], allocated on first use (vhk_alloc_rows)
   uint32_t *spmv_lane_tab   = nullptr; // [3][32]  lane constants of k_spmv_sym18
   uint16_t *spmv_gather_tab = nullptr; // [26][18] row-end gather lists of k_spmv_sym18
   double   *xmask   = nullptr; // [NL] scratch: Dirichlet-masked copy of an SpMV input (public vh_spmv only)
@@ -135,12 +135,10 @@ struct vh_ctx
   int32_t *fast_class = nullptr; // [n_fast]      geometry class of the row's stencil
   double  *class_tab  = nullptr; // [n_classes][27][12] per slot: GS[3][3] = sum vol/(h_x h_y) Gref, FS[3] = sum area Mf (x != normal)
   int32_t  n_classes  = 0;
-  double  *afrag      = nullptr; // [8 octants][2 k-steps][32 lanes] A fragments of the DMMA row kernel (weights w_q N_a N_b)
   double  *class_M    = nullptr; // [n_classes][27][10] coefficient-dependent 3x3 geometry block per slot (entry 9 = 0)
   std::vector<double> h_class_tab;
   int32_t *slow_rows  = nullptr; // [n_slow_rows]
   uint8_t *row_slow   = nullptr; // [n_owned]
-  int32_t *slow_cells = nullptr; // [n_slow_cells]
   // row-owner lists of the constrained rows: (cell, local node) pairs feeding slow row r (the node itself or a hanging
   // node that names it as a master)
   int32_t *srow_ptr = nullptr, *srow_cell = nullptr; // [n_slow_rows + 1], [srow_ptr[n_slow_rows]]
@@ -150,12 +148,11 @@ struct vh_ctx
   uint32_t *srow_bcons = nullptr, *srow_cons = nullptr;
   int32_t *srow_posI = nullptr, *srow_mnode = nullptr;
   int16_t *srow_mpos = nullptr;
-  bool     slow_row_owner = false; // false: constraint lines couple components (or VH_SLOW_SCATTER=1) -> atomic cell scatter
   // node -> incident (cell, local node) lists for the deterministic rhs gather of fast rows
   // (fast rows use fast_cells; kept for Q2 later)
 
   // per-cell scratch written by the pointwise kernel
-  double *Hq   = nullptr; // [n_cells][nq][172]  symmetric bulk Hessian at every quadrature point
+  double *Hq   = nullptr; // [n_cells][nq][180]  packed symmetric bulk Hessian (x cell volume) at every quadrature point
   double *Rc   = nullptr; // [n_cells][dpc]      cell rhs (= -cell residual)
   double *Dc   = nullptr; // [n_cells][dpc]      cell matrix diagonal (for the constrained-diagonal rule)
   double *avgD = nullptr; // [n_cells]           mean |diag| of the cell matrix
@@ -213,6 +210,7 @@ struct vh_ctx
   // vh_export_matrix_bsr) assembles them on demand from the H_q tables.  Unverified on hardware in round 1.
   bool    rows_lazy = false, rows_stale = false;
   double *Dblk      = nullptr; // [n_cells][nn][180] per-(cell, node) diagonal contributions (allocated on first use)
+  double *dpack     = nullptr; // [n_fast][180] packed diagonal blocks of the lattice rows (what block-Jacobi reads while rows_stale)
 
   // state flags
   bool have_matrix = false, have_update = false, have_trial = false;
@@ -268,8 +266,6 @@ int vhk_pointwise(vh_ctx *ctx, const double *x_local, bool want_hessian, bool wa
 int vhk_rows_fast(vh_ctx *ctx);
 int vhk_rows_slow(vh_ctx *ctx, bool want_matrix, double *rhs_out);
 int vhk_rhs_fast(vh_ctx *ctx, double *rhs_out, bool with_cdiag);
-int vhk_store_probe(vh_ctx *ctx, int mode);
-int vhk_upload_constants(vh_ctx *ctx);
 int vhk_upload_w1(vh_ctx *ctx, const double *W1);
 int vhk_upload_q2(vh_ctx *ctx, const double *T2, const uint8_t *q2t);
 
@@ -283,6 +279,7 @@ int vhk_apply_fast(vh_ctx *ctx, const double *z_masked, const double *x_orig, do
 // diagonal packed blocks of the lattice rows from the H_q tables (rows_lazy); vhk_ensure_rows assembles stale rows on demand
 int vhk_diag_fast(vh_ctx *ctx);
 int vhk_ensure_rows(vh_ctx *ctx);
+int vhk_alloc_rows(vh_ctx *ctx); // packed row storage (pvals) is allocated on first use: the matrix-free default never needs it
 int vhk_block_jacobi_setup(vh_ctx *ctx);
 int vhk_block_jacobi_apply(vh_ctx *ctx, const double *x_owned, double *y_owned);
 // push = true (only with ctx->zpush and y_owned == ctx->zbuf): also store the interface values into the neighbours' ghost slots

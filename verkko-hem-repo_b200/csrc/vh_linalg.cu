@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(128)
   k_block_invert(int n_rows, const int32_t *__restrict__ diag_pos, const double *__restrict__ vals, double *__restrict__ minv,
                  int *__restrict__ n_singular, const double *__restrict__ pvals, int cm_stride, int diag_slot, const int32_t *__restrict__ fast_index,
                  const int32_t *__restrict__ fast_class, const double *__restrict__ class_M, const uint32_t *__restrict__ dirmask,
-                 const double *__restrict__ cdiag)
+                 const double *__restrict__ cdiag, const double *__restrict__ dpack, int packed)
 {
   // Register-resident Gauss-Jordan, one warp per block; the scaled pivot row is broadcast through shared memory
   // (shuffles would be the bottleneck: ~650 per block).
@@ -260,10 +260,11 @@ __global__ void __launch_bounds__(128)
     return;
   const int rr = lane < 18 ? lane : 17;
   double    a[18];
-  const int fi = pvals ? fast_index[row] : -1;
+  const int fi = packed ? fast_index[row] : -1;
   if (fi >= 0)
-    { // packed row: diagonal block = Sym(P) + kron(I_6, M_13), Dirichlet rows/columns -> sum_cells |a_ii| on the diagonal
-      const double  *P  = pvals + (size_t)diag_pos[row] * VH_SYMP;
+    { // packed row: diagonal block = Sym(P) + kron(I_6, M_13), Dirichlet rows/columns -> sum_cells |a_ii| on the diagonal;
+      // P comes from dpack[fast row] while the lattice rows are not assembled (matrix-free default), else from the row itself
+      const double  *P  = dpack ? dpack + (size_t)fi * VH_SYMP : pvals + (size_t)diag_pos[row] * VH_SYMP;
       const double  *M  = class_M + (size_t)fast_class[fi] * cm_stride + diag_slot * 10;
       const uint32_t mI = dirmask[row];
 #pragma unroll
@@ -918,25 +919,12 @@ int vhk_spmv(vh_ctx *ctx, const double *x_local, double *y_owned, bool x_is_mask
           return VH_OK;
         }
       VH_TRY(vhk_ensure_rows(ctx)); // lattice rows that were left unassembled for the matrix-free mode (VH_MF_LAZY_ROWS=1)
-      static int variant = -1;
-      if (variant < 0)
-        {
-          const char *e = getenv("VH_SPMV_VARIANT"); // tuning knob: blocks in flight / resident CTAs
-          variant       = e ? atoi(e) : 0;
-        }
 #define VH_LAUNCH_PSPMV(NB, MINB)                                                                                                  \
   k_spmv_sym18<NB, MINB><<<grid, VH_PSPMV_WARPS * 32, 0, ctx->stream>>>(ctx->n_fast, ctx->slot_stride, ctx->n_slots * 10, ctx->spmv_order, ctx->fast_rows, ctx->fast_posslot, \
                                                                        ctx->fast_class, ctx->class_M, ctx->row_ptr, ctx->col,      \
                                                                        ctx->dirmask, ctx->pvals, ctx->cdiag, ctx->spmv_lane_tab,   \
                                                                        ctx->spmv_gather_tab, xg, x_local, y_owned)
-      if (variant == 1)
-        VH_LAUNCH_PSPMV(3, 3);
-      else if (variant == 2)
-        VH_LAUNCH_PSPMV(2, 4);
-      else if (variant == 3)
-        VH_LAUNCH_PSPMV(6, 2);
-      else
-        VH_LAUNCH_PSPMV(4, 2);
+      VH_LAUNCH_PSPMV(4, 2); // four blocks in flight per warp, two CTAs per SM (2/3/6 in flight measured 0.26-0.30 vs 0.256 ms at C2)
 #undef VH_LAUNCH_PSPMV
       VH_LAUNCH_CHECK();
       if (ctx->n_slow_rows > 0)
@@ -963,7 +951,8 @@ int vhk_block_jacobi_setup(vh_ctx *ctx)
   VH_CUDA(cudaMemsetAsync(d_sing, 0, sizeof(int), ctx->stream));
   k_block_invert<<<(ctx->n_owned + 3) / 4, 128, 0, ctx->stream>>>(ctx->n_owned, ctx->diag_pos, ctx->vals, ctx->minv, d_sing,
                                                                   ctx->packed ? ctx->pvals : nullptr, ctx->n_slots * 10, ctx->diag_slot, ctx->fast_index, ctx->fast_class,
-                                                                  ctx->class_M, ctx->dirmask, ctx->cdiag);
+                                                                  ctx->class_M, ctx->dirmask, ctx->cdiag,
+                                                                  ctx->rows_stale ? ctx->dpack : nullptr, ctx->packed ? 1 : 0);
   VH_LAUNCH_CHECK();
   int h_sing = 0;
   VH_CUDA(cudaMemcpyAsync(&h_sing, d_sing, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
