@@ -4,16 +4,22 @@
     python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, through the C ABI)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code (oracle/_ref) on the host cores
 
-A "step" is one Newton step of run.cc:214-218 (assemble_system, solve(tol), newton_iteration) on the synthetic
-cube of BASELINE.json configs[1]: Q1, hyper_cube(-20,20), global refinement 5, 646 866 DoFs per GPU
-(weak scaling: N GPUs solve an N-times taller box, partitioned along the Morton curve).
-The W warm-up steps and the K timed steps both start from the uniform B-phase initial condition
-(setup_uniform_B-phase.cc:245-259), so the timed region is Newton iterations 1..K of a real run.
+Workload (default, every N): BASELINE.json configs[4] = the north-star target — ONE cube, Q1, global refinement 7,
+38 640 402 DoFs, Morton-partitioned over the N GPUs (strong scaling: same problem, same iterates at every N).  It fits
+one B200 because the operator is applied matrix-free (no 148 GB matrix).  At N=1 the line also carries "c2": the same
+measurement on configs[1] (Q1 r5, 646 866 DoFs).  `--workload c2|c3|c5` or --refine/--global-refine/--degree select others.
 
-Prints ONE JSON line.  `value` = DoFs advanced one Newton step per second, whole job (ms_per_step is the
-Newton-step wall time the BASELINE metric names); `roofline` is the SpMV kernel (HBM-bound) timed live with CUDA
-events; `assembly` and `kernels` break the step down; `e2e` repeats the step through the C ABI with host
-buffers in and out every step; `cpu_baseline` is the reference's literal term code on a bounded cell sample.
+A "step" is one Newton step of run.cc:214-218 (assemble_system, solve(tol), newton_iteration).  The run follows the
+reference's stop rule (run.cc:234-250, converge accuracy 5e-6): when the residual drops below it the run is over and the
+next step starts a new run from the initial condition, so all K timed steps are steps a real run executes.  Steps are timed
+one by one with CUDA events on the library's stream (the reset to the initial condition is outside the timed region);
+`ms_per_step` = (max over ranks of the summed step times) / K.
+
+Prints ONE JSON line.  `value` = DoFs advanced one Newton step per second, whole job; `roofline` is the dominant kernel
+(the operator apply inside GMRES, HBM-bound) timed live; `e2e` repeats the steps through the C ABI with pinned HOST buffers
+in and out every step; `cpu_baseline` is the reference's literal term code on a bounded cell sample, `cpu_port` the
+optimised CPU restatement (fair CPU number); for N > 1 `multi_gpu_parity` compares the first Newton steps with a single-GPU
+context of the same global mesh built on rank 0.
 """
 import argparse
 import json
@@ -39,6 +45,14 @@ LIN_TOL = 1e-1       # "Cycle 0 linear solver tol" default, declare.cc:203
 LS_STEP = 0.83       # "primary step length of dampped newton iteration" default, declare.cc:287
 MAX_LIN_IT = 10000   # declare.cc:277
 RESTART = 30         # SolverFGMRES default max_basis_size
+CONVERGE_ACC = 5e-6  # "converge accuracy" default, declare.cc:249 (run.cc:234-250)
+MAX_NEWTON = 41      # "Number of interations" default 40, inclusive upper bound (run.cc:207)
+
+WORKLOADS = {  # name -> (degree, refine per GPU (weak) or None, global refine (strong) or None)
+    "c2": (1, 5, None),   # BASELINE configs[1]; for N > 1: N root cubes stacked along z (weak)
+    "c3": (2, None, 5),   # BASELINE configs[2]
+    "c5": (1, None, 7),   # BASELINE configs[4], the north-star target
+}
 
 
 def coef_vector():
@@ -116,25 +130,33 @@ class ClockSampler:
 
 def build_mesh(n_gpus, refine, degree, global_refine=None):
     import verkko_hem_repo_b200 as vh
+    L = 20.0  # "cube half side length" default (declare.cc:159)
     if global_refine is not None:
         # strong scaling (BASELINE configs[4]): ONE cube refined `global_refine` times, Morton-partitioned over the ranks
-        L = 20.0
         m = vh.Mesh(degree, [-L, -L, -L], [L, L, L], base=(1, 1, 1), face_bid=(1, 1, 1, 1, 4, 4), n_global_refine=global_refine)
         m.finalize(n_gpus)
         return m
     # weak scaling: N root cubes stacked along z, each refined `refine` times; Morton order keeps each root
     # contiguous, so rank r owns root r (the p4est partition of a 1 x 1 x N brick).
-    L = 20.0  # "cube half side length" default (declare.cc:159)
     m = vh.Mesh(degree, [-L, -L, -L], [L, L, -L + 2 * L * n_gpus], base=(1, 1, n_gpus), face_bid=(1, 1, 1, 1, 4, 4),
                 n_global_refine=refine)
     m.finalize(n_gpus)
     return m
 
 
+def problem_size(degree, refine, global_refine, n_gpus):
+    """(n_dofs, n_cells) of the workload without building it (the reference arm needs no mesh)."""
+    if global_refine is None:
+        n_side, n_z = 2 ** refine, 2 ** refine * n_gpus
+    else:
+        n_side = n_z = 2 ** global_refine
+    return 18 * (degree * n_side + 1) ** 2 * (degree * n_z + 1), n_side * n_side * n_z
+
+
 def workload_string(degree, refine, global_refine, n_dofs, n_cells):
     """config.workload — identical in both arms (the driver compares the two lines)."""
     return ("femgl 3D cube Q%d, global refinement %s (%d DoFs total, %d cells), B-phase IC, "
-            "z walls AdGR diffuse (bt=2), p=25 bar t=0.5 SCC on, linear tol 1e-1, damped Newton 0.83"
+            "z walls AdGR diffuse (bt=2), p=25 bar t=0.5 SCC on, linear tol 1e-1, damped Newton 0.83, converge accuracy 5e-6"
             % (degree, ("%d per GPU" % refine) if global_refine is None else ("%d, one cube split over the GPUs" % global_refine),
                n_dofs, n_cells))
 
@@ -145,7 +167,7 @@ def initial_state(T):
 
 
 def newton_step(ctx):
-    """run.cc:214-218 + iteration.cc:128-210 through the C ABI.  Returns (lin_its, n_trials, res_norm)."""
+    """run.cc:214-218 + iteration.cc:128-210 through the C ABI.  Returns (lin_its, n_trials, res_norm, rhs_norm)."""
     bn = ctx.assemble()
     its, _ = ctx.solve(LIN_TOL, MAX_LIN_IT, RESTART)
     n_trials = 0
@@ -157,11 +179,55 @@ def newton_step(ctx):
         if cur < bn:
             break
     ctx.accept_trial()
-    return its, n_trials, cur
+    return its, n_trials, cur, bn
+
+
+def run_steps(ctx, x0, steps, host_buffer=None):
+    """`steps` Newton steps under the reference's stop rule (run.cc:234-250): a run ends when the residual is <= the converge
+    accuracy (or after MAX_NEWTON steps) and the next step starts a new run from the initial condition x0.  Each step is
+    timed on its own with CUDA events on the library's stream; resets are not timed.  host_buffer (pinned): the e2e variant
+    — the step's input goes host->device and its result device->host inside the timed region.
+    Returns (summed ms, list of runs, each a list of (its, trials, residual, rhs_norm))."""
+    runs, cur_run, total_ms = [], [], 0.0
+    if host_buffer is None:
+        ctx.set_solution(x0)
+    else:
+        host_buffer[:] = x0
+    for _ in range(steps):
+        ctx.timer_start()
+        if host_buffer is not None:
+            ctx.set_solution(host_buffer)        # H2D of the step's input
+        h = newton_step(ctx)
+        if host_buffer is not None:
+            ctx.get_solution(out=host_buffer)    # D2H of the step's result, straight into the pinned buffer
+        total_ms += ctx.timer_stop()
+        cur_run.append(h)
+        if h[2] <= CONVERGE_ACC or len(cur_run) >= MAX_NEWTON:
+            runs.append(cur_run)
+            cur_run = []
+            if host_buffer is None:
+                ctx.set_solution(x0)
+            else:
+                host_buffer[:] = x0
+    if cur_run:
+        runs.append(cur_run)
+    return total_ms, runs
+
+
+def summarize_runs(runs):
+    """Compact keys that survive a truncated log: totals over the timed steps and the first run's history."""
+    steps = [h for r in runs for h in r]
+    first = runs[0] if runs else []
+    return {"newton_steps": len(steps), "gmres_its_total": int(sum(h[0] for h in steps)),
+            "line_search_trials_total": int(sum(h[1] for h in steps)),
+            "runs_completed": int(sum(1 for r in runs if r and r[-1][2] <= CONVERGE_ACC)),
+            "steps_to_converge": (len(first) if first and first[-1][2] <= CONVERGE_ACC else None),
+            "first_run_gmres_its": [int(h[0]) for h in first], "first_run_trials": [int(h[1]) for h in first],
+            "first_run_residuals": [float("%.6e" % h[2]) for h in first]}
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm: the reference's own term files (oracle/_ref) on the host cores
+# CPU legs (the only places that touch oracle/): reference arm, cpu_baseline, cpu_port
 # ------------------------------------------------------------------------------------------
 def _ref_worker(args):
     seed, n_cells_each, h, coef = args
@@ -169,31 +235,37 @@ def _ref_worker(args):
     rng = np.random.default_rng(seed)
     amp = COEF["gapB"] * float(np.float32(0.577350269))
     t0 = time.time()
+    t_mat = t_res = 0.0
     for _ in range(n_cells_each):
         U = np.zeros((8, 18))
         U[:, [0, 4, 8]] = amp
         U += 0.05 * COEF["gapB"] * rng.uniform(-1, 1, U.shape)
+        t = time.time()
         O.ref_cell(1, [0, 0, 0], h, U.ravel(), coef, [(4, 4)], want_matrix=True)   # assemble_system cell
+        t_mat += time.time() - t
+        t = time.time()
         O.ref_cell(1, [0, 0, 0], h, U.ravel(), coef, [(4, 4)], want_matrix=False)  # one compute_residual cell
-    return time.time() - t0
+        t_res += time.time() - t
+    return time.time() - t0, t_mat, t_res
 
 
-def reference_sample(refine, cells_per_core=1):
+def reference_sample(h_cell, cells_per_core=1):
     """Time the reference's literal (q,i,j) loops + term functions on `cores * cells_per_core` Q1 cells, one worker
     process per host core (the reference is 1 thread per MPI rank, sol/src/main.cc:108)."""
     import femgl_oracle as O
     if not O.have_ref():
         return None
     cores = os.cpu_count() or 1
-    n_side = 2 ** refine
-    h = [40.0 / n_side] * 3
     coef = coef_vector()
     t0 = time.time()
     with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_ref_worker, [(1000 + k, cells_per_core, h, coef) for k in range(cores)])
+        parts = pool.map(_ref_worker, [(1000 + k, cells_per_core, [h_cell] * 3, coef) for k in range(cores)])
     wall = time.time() - t0
     n_cells = cores * cells_per_core
-    return dict(cores=cores, cells=n_cells, wall_s=wall, cells_per_s=n_cells / wall)
+    t_mat = sum(p[1] for p in parts) / cores   # mean per-worker seconds spent in the Jacobian / residual cells
+    t_res = sum(p[2] for p in parts) / cores
+    return dict(cores=cores, cells=n_cells, wall_s=wall, cells_per_s=n_cells / wall,
+                assembly_cells_per_s=n_cells / max(t_mat, 1e-9), residual_cells_per_s=n_cells / max(t_res, 1e-9))
 
 
 def run_reference(args):
@@ -201,33 +273,34 @@ def run_reference(args):
     if rank != 0:
         return
     p = args.degree
-    if args.global_refine is None:  # weak scaling: `gpus` root cubes stacked along z (build_mesh)
-        n_side, n_z = 2 ** args.refine, 2 ** args.refine * args.gpus
-    else:                           # strong scaling: one cube
-        n_side = n_z = 2 ** args.global_refine
-    n_nodes = (p * n_side + 1) ** 2 * (p * n_z + 1)
-    n_cells = n_side * n_side * n_z
-    n_dofs = 18 * n_nodes
+    n_dofs, n_cells = problem_size(p, args.refine, args.global_refine, args.gpus)
+    n_side = 2 ** (args.refine if args.global_refine is None else args.global_refine)
+    h_cell = 40.0 / n_side
     for _ in range(args.warmup if args.warmup < 2 else 1):
-        reference_sample(args.refine, 1)
-    t_list, last = [], None
+        reference_sample(h_cell, 1)
+    t_list, last, asm_cps, res_cps = [], None, [], []
     for _ in range(args.steps):
-        last = reference_sample(args.refine, 2)
+        last = reference_sample(h_cell, 2)
         if last is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvhref.so not built"}))
             return
         t_list.append(last["wall_s"])
+        asm_cps.append(last["assembly_cells_per_s"])
+        res_cps.append(last["residual_cells_per_s"])
     cps = last["cells"] * len(t_list) / sum(t_list)
+    scale = 1.0
     q2_note = ""
     if p == 2:
         # the sample is timed on Q1 cells (one Q2 cell takes ~100 s in the reference's loops); a Q2 cell visits
         # (486^2 * 27) / (144^2 * 8) = 38.4x as many (q,i,j) triples, each the same work (assemble.cc:188-252)
-        cps /= (486.0 ** 2 * 27.0) / (144.0 ** 2 * 8.0)
+        scale = (486.0 ** 2 * 27.0) / (144.0 ** 2 * 8.0)
         q2_note = "; Q2 rate = Q1 rate / 38.4 (ratio of (q,i,j) triples per cell)"
+    cps /= scale
     # one Newton step of the reference = one assembly + >= 1 residual evaluation over all cells; its ML-AMG solve is
     # not reproducible here and is left out, so this is an UPPER bound on the reference's throughput.
     step_s = n_cells / cps
     val = n_dofs / step_s
+    dofs_per_cell = n_dofs / n_cells
     out = {"impl": "reference", "metric": "femgl Newton-step throughput",
            "value": val, "unit": "DoF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak" if args.global_refine is None else "strong",
@@ -237,6 +310,12 @@ def run_reference(args):
                                        "driven by its literal (q,i,j) loops) on all host cores; %d-cell sample per step, extrapolated "
                                        "linearly to the workload; its ML-AMG solve is left out (upper bound on its throughput)"
                                        % last["cells"]},
+           # NOT like-for-like with the GPU arm's Newton step (which includes the GMRES solve): compare phase by phase
+           "comparable": False,
+           "phases": {"assembly_dofs_per_s": float(np.mean(asm_cps)) / scale * dofs_per_cell,
+                      "residual_dofs_per_s": float(np.mean(res_cps)) / scale * dofs_per_cell,
+                      "note": "per-phase rates of the reference's literal loops on all cores (sampled cells, extrapolated): compare "
+                              "with the GPU line's assembly.dofs_per_s and kernels.residual_ms; the solve is not in this arm"},
            "cpu_baseline": {"value": val, "unit": "DoF/s", "cores": last["cores"], "kind": "reference",
                             "sample": "%d Q1 cells/step (Jacobian + 1 residual) by the reference's verbatim cell_mat_vec "
                                       "term files driven by its literal (q,i,j) loops; %.2f cells/s on %d cores, "
@@ -245,9 +324,222 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def cpu_port_numbers(its_per_step, trials_per_step, n_cells_workload, n_dofs_workload):
+    """The optimised CPU restatement (oracle O2: closed-form H_q in C with one pthread per core, scipy BSR SpMV, numpy
+    vectors) on a BOUNDED sample — a Q1 r4 cube (4 096 cells, 88 434 DoFs) with the workload's coefficients — scaled
+    linearly in cells/DoFs to the workload.  The "fair CPU" numbers SURVEY.md section 8(d) / BASELINE.md section 3 ask for:
+    assembly DoF/s, SpMV GB/s and a full Newton step with the same GMRES(30)+block-Jacobi iteration count as the GPU run."""
+    import femgl_oracle as O
+    import scipy.sparse as sp
+    import verkko_hem_repo_b200 as vh
+    from helpers import MATEP_SCC_ON, b_phase_state
+    T = vh.Mesh(1, [-20.0] * 3, [20.0] * 3, base=(1, 1, 1), face_bid=(1, 1, 1, 1, 4, 4), n_global_refine=4).finalize(1).tables(0)
+    coef = coef_vector()
+    x = b_phase_state(T, MATEP_SCC_ON, noise=0.0)
+    fptr, fno, fbid = T.face_csr()
+    dummy = np.zeros(1, np.int32)
+    t0 = time.perf_counter()
+    O.cells(1, T.cell_nodes, T.cell_origin, T.cell_h, x, coef, fptr, fno if fno.size else dummy, fbid if fbid.size else dummy,
+            want_matrix=True)
+    t_cells = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.cells(1, T.cell_nodes, T.cell_origin, T.cell_h, x, coef, fptr, fno if fno.size else dummy, fbid if fbid.size else dummy,
+            want_matrix=False)
+    t_res = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    A, rhs = O.assemble_global(T, x, coef, True)       # cells + constrained scatter (scipy)
+    t_asm = time.perf_counter() - t0
+    B = sp.bsr_matrix(A, blocksize=(18, 18))
+    z = np.random.default_rng(3).uniform(-1, 1, A.shape[1])
+    B @ z
+    t0 = time.perf_counter()
+    for _ in range(5):
+        B @ z
+    t_spmv = (time.perf_counter() - t0) / 5
+    spmv_bytes = 8 * 324 * B.indices.size + 4 * B.indices.size + 4 * B.indptr.size + 16 * A.shape[0]
+    Minv = O.block_jacobi_inverse(A, T.n_owned_nodes)
+    t0 = time.perf_counter()
+    _, its_s, _, _ = O.gmres_block_jacobi(A, rhs, Minv, LIN_TOL * np.linalg.norm(rhs))
+    t_solve = time.perf_counter() - t0
+    per_it = t_solve / max(its_s, 1)
+    sc = n_cells_workload / T.n_cells
+    step_s = sc * (t_cells + max(t_asm - t_cells, 0.0) + its_per_step * per_it + trials_per_step * t_res)
+    return {"kind": "port", "cores": os.cpu_count(),
+            "sample": "Q1 r4 cube (%d cells, %d DoFs): cell matrices by oracle/femgl_oracle.c (closed-form H_q, one pthread per "
+                      "core) %.2f s, constrained scatter (scipy, 1 core) %.2f s, residual cells %.3f s, BSR18 SpMV (scipy, 1 core) "
+                      "%.3f s, GMRES(30)+block-Jacobi %.3f s per iteration (numpy); scaled x%.0f in cells to the workload with the "
+                      "GPU run's %.1f linear iterations and %.1f residual evaluations per Newton step"
+                      % (T.n_cells, 18 * T.n_owned_nodes, t_cells, max(t_asm - t_cells, 0.0), t_res, t_spmv, per_it, sc, its_per_step,
+                         trials_per_step),
+            "assembly_dofs_per_s": 18 * T.n_owned_nodes / t_cells, "assembly_with_scatter_dofs_per_s": 18 * T.n_owned_nodes / t_asm,
+            "residual_dofs_per_s": 18 * T.n_owned_nodes / t_res,
+            "spmv_gbs": spmv_bytes / t_spmv / 1e9, "newton_step_ms": step_s * 1e3, "newton_step_dofs_per_s": n_dofs_workload / step_s}
+
+
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def kernel_numbers(ctx, T, info, degree, hbm_peak, peak_src, traffic_key):
+    """Live kernel timings (CUDA events, L2 flushed between launches) of rank 0's kernels and the roofline of the dominant one."""
+    nnzb, nb = info["nnzb"], T.n_owned_nodes
+    n = 8 if degree == 1 else 27
+    n_fast_blocks = info["n_packed_blocks"]
+    mf_mode = int(info.get("spmv_matrix_free", 0))
+    # SURVEY.md section 8(d): algorithmic bytes of one operator apply (BSR18, every 18x18 block stored in full)
+    spmv_alg = 8 * 324 * nnzb + 4 * nnzb + 4 * (nb + 1) + 16 * 18 * nb
+    # bytes this implementation really moves per apply:
+    #   matrix-free: the packed H_q tables (8*180*n_q B per cell) + the cell gather (8*dpc) + the cell products written and
+    #   re-read once (2 * 8*dpc) + y; constrained rows (full blocks) as stored
+    slow = 8 * 324 * (nnzb - n_fast_blocks)
+    mf_moved = 8 * 180 * n * T.n_cells + 3 * 8 * 18 * n * T.n_cells + slow + 8 * 18 * nb
+    packed_moved = 8 * 180 * n_fast_blocks + slow + 4 * nnzb + 4 * (nb + 1) + 16 * 18 * nb
+    moved = mf_moved if mf_mode else packed_moved
+    t_apply = ctx.time_kernel(0, reps=10, flush_l2=True)
+    t_asm = ctx.time_kernel(1, reps=3, flush_l2=True)
+    t_pw = ctx.time_kernel(5, reps=3, flush_l2=True)
+    t_res = ctx.time_kernel(2, reps=3, flush_l2=True)
+    t_bj = ctx.time_kernel(3, reps=5, flush_l2=True)
+    fp64_peak = ctx.measure_fp64_peak()
+    traffic = None
+    try:  # DRAM bytes per launch measured once with `ncu --set full` for this exact workload (profiles/traffic.json)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        kname = "k_points_apply" if mf_mode else "k_spmv_sym18"
+        if traffic_key in tj and kname in tj[traffic_key]:
+            traffic = tj[traffic_key][kname]["read_bytes"] + tj[traffic_key][kname]["write_bytes"]
+    except Exception:
+        traffic = None
+    gbs = moved / (t_apply * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": ("k_points<APPLY>+k_gather_apply" if mf_mode else "k_spmv_sym18") if n_fast_blocks else "k_spmv_bsr18",
+            "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic,
+            "peak_source": peak_src, "ms_per_launch": t_apply, "moved_bytes_per_launch": moved,
+            "achieved_algorithmic": spmv_alg / (t_apply * 1e-3) / 1e9, "algorithmic_bytes_per_launch": spmv_alg,
+            "note": "achieved/frac = bytes this implementation moves per operator apply / time (/ measured HBM peak); "
+                    "achieved_algorithmic uses SURVEY 8(d)'s BSR18 bytes (every 18x18 block streamed in full)"}
+    asm_flops = 2.0 * n * n * n * 336 * T.n_cells
+    asm = {"ms": t_asm, "dofs_per_s": 18 * nb / (t_asm * 1e-3), "pointwise_ms": t_pw,
+           "note": "Jacobian phase of vh_assemble in the matrix-free default: pointwise kernel (H_q tables, cell rhs) + diagonal "
+                   "blocks for block-Jacobi + rhs gather; the lattice rows are never assembled",
+           "algorithmic_flops": asm_flops, "tflops_fp64_algorithmic": asm_flops / (t_asm * 1e-3) / 1e12,
+           "fp64_peak_tflops_measured": fp64_peak,
+           "frac_fp64_algorithmic": asm_flops / (t_asm * 1e-3) / 1e12 / fp64_peak if fp64_peak else None}
+    kern = {"apply_ms": t_apply, "residual_ms": t_res,
+            "residual_gbs": (8 * 18 * n * T.n_cells + 8 * 18 * nb) / (t_res * 1e-3) / 1e9,
+            "block_jacobi_apply_ms": t_bj, "block_jacobi_apply_gbs": (2592 * nb + 16 * 18 * nb) / (t_bj * 1e-3) / 1e9,
+            "operator_apply_mode": ("packed-spmv", "matrix-free", "table-free", "matrix-free-v2")[mf_mode]}
+    return roof, asm, kern
+
+
+def measure(vh, torch, dist, rank, world, local_rank, degree, refine, global_refine, steps, warmup, want_kernels, want_parity):
+    """Build the workload on `world` ranks and measure it.  Returns the dict of results (rank 0) or None."""
+    mesh = build_mesh(world, refine, degree, global_refine)
+    T = mesh.tables(rank)
+    t0 = time.perf_counter()
+    ctx = vh.Context(T, device=local_rank)
+    create_s = time.perf_counter() - t0
+    if world > 1:
+        uid = [vh.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+    ctx.set_coef_vector(coef_vector())
+    x0 = initial_state(T)[:18 * T.n_owned_nodes]
+    n_dofs = 18 * mesh.n_nodes
+    info = ctx.info()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up ----
+    run_steps(ctx, x0, warmup)
+    # ---- timed: K Newton steps, state resident in HBM ----
+    ctx.timers(reset=True)
+    barrier()
+    ms, runs = run_steps(ctx, x0, steps)
+    barrier()
+    tm = ctx.timers()
+    ms = max_over_ranks(ms)
+    # GL free energy at the end of the first run (outside the timed region; SURVEY.md section 0.6)
+    try:
+        final_energy = ctx.energy(0)
+    except Exception:
+        final_energy = None
+    # ---- e2e: same steps, host buffers in and out of the C ABI every step (pinned host memory) ----
+    xh = torch.from_numpy(x0.copy()).pin_memory().numpy()
+    barrier()
+    t0 = time.perf_counter()
+    ms_e2e, _ = run_steps(ctx, x0, steps, host_buffer=xh)
+    wall_e2e = time.perf_counter() - t0
+    ms_e2e = max_over_ranks(ms_e2e)
+    barrier()
+
+    summ = summarize_runs(runs)
+    its_total = max(summ["gmres_its_total"], 1)
+    res = {"n_dofs": n_dofs, "n_cells": mesh.n_cells, "ms_per_step": ms / steps, "value": n_dofs / (ms / steps * 1e-3),
+           "newton": summ, "final_energy": final_energy,
+           "phase_ms_per_step": {k: tm[k] / steps for k in ("assemble", "residual", "solve", "vector")},
+           "ms_per_gmres_it": tm["solve"] / its_total, "gmres_its_per_step": summ["gmres_its_total"] / steps,
+           "e2e": {"value": n_dofs / (ms_e2e / steps * 1e-3), "unit": "DoF/s", "h2d_bytes_per_step": int(8 * 18 * T.n_owned_nodes),
+                   "d2h_bytes_per_step": int(8 * 18 * T.n_owned_nodes), "ms_per_step": ms_e2e / steps,
+                   "wall_ms_per_step": wall_e2e / steps * 1e3},
+           "gpu_launches": tm["launches"], "context_create_s": create_s, "n_owned_dofs_rank0": int(18 * T.n_owned_nodes),
+           "memory": {"device_bytes_rank0": info["device_bytes"], "nnzb": info["nnzb"], "fast_rows": info["n_fast_rows"],
+                      "slow_cells": info["n_slow_cells"]}}
+    if world > 1:  # per-iteration cost of the two exchange steps (collective calls: 20 back-to-back each)
+        try:
+            res["halo_ms_per_exchange"] = max_over_ranks(ctx.time_kernel(9, reps=3, flush_l2=False)) / 20.0
+            res["allreduce_ms_per_dot"] = max_over_ranks(ctx.time_kernel(10, reps=3, flush_l2=False)) / 20.0
+        except Exception as exc:
+            res["exchange_timing_error"] = str(exc)
+    if want_kernels:
+        ctx.set_solution(x0)
+        ctx.assemble()
+        hbm_peak, peak_src = peaks()
+        key = "q%d_%s_%dgpu" % (degree, ("r%d" % refine) if global_refine is None else ("g%d" % global_refine), world)
+        roof, asm, kern = kernel_numbers(ctx, T, info, degree, hbm_peak, peak_src, key)
+        res.update(roofline=roof, assembly=asm, kernels=kern)
+
+    # ---- multi-GPU parity: rank 0 repeats the first Newton steps on ONE GPU with the same global mesh ----
+    if want_parity and world > 1:
+        par = None
+        if rank == 0:
+            try:
+                m1 = build_mesh(1, refine, degree, global_refine) if global_refine is not None else \
+                    vh.Mesh(degree, [-20.0] * 3, [20.0, 20.0, -20.0 + 40.0 * world], base=(1, 1, world),
+                            face_bid=(1, 1, 1, 1, 4, 4), n_global_refine=refine).finalize(1)
+                T1 = m1.tables(0)
+                c1 = vh.Context(T1, device=local_rank)
+                c1.set_coef_vector(coef_vector())
+                x1 = initial_state(T1)[:18 * T1.n_owned_nodes]
+                n_par = min(3, len(runs[0]))
+                ms1, runs1 = run_steps(c1, x1, n_par)
+                a, b = runs[0][:n_par], runs1[0][:n_par]
+                par = {"steps_compared": n_par,
+                       "max_rel_residual_diff": float(max(abs(p[2] - q[2]) / abs(q[2]) for p, q in zip(a, b))),
+                       "max_rel_rhs_norm_diff": float(max(abs(p[3] - q[3]) / abs(q[3]) for p, q in zip(a, b))),
+                       "its_equal": bool(all(p[0] == q[0] and p[1] == q[1] for p, q in zip(a, b))),
+                       "gmres_its_n_gpus": [int(p[0]) for p in a], "gmres_its_1_gpu": [int(q[0]) for q in b],
+                       "single_gpu_ms_per_step_first_steps": ms1 / n_par,
+                       "n_gpu_ms_first_steps_note": "the 1-GPU time covers only the first %d steps of a run (fewer linear "
+                                                    "iterations than the average step)" % n_par}
+                c1.close()
+            except Exception as exc:
+                par = {"error": str(exc)}
+        barrier()
+        res["multi_gpu_parity"] = par
+    ctx.close()
+    return res
+
+
 def run_ours(args):
     # NCCL / torch print banners on stdout; the contract is ONE JSON line there, so everything else goes to stderr.
     sys.stdout.flush()
@@ -270,221 +562,80 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    mesh = build_mesh(world, args.refine, args.degree, args.global_refine)
-    T = mesh.tables(rank)
-    ctx = vh.Context(T, device=local_rank)
-    if world > 1:
-        uid = [vh.Context.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(rank, world, uid[0])
-    ctx.set_coef_vector(coef_vector())
-    if args.spmv_mf:  # whole run with the matrix-free operator apply inside GMRES (opt-in this round)
-        ctx.set_spmv_matrix_free(True)
-    # the mode this run really uses (the library's default may come from VH_SPMV_MF): 0 packed SpMV, 1 matrix-free, 2 table-free
-    mf_mode = int(ctx.info().get("spmv_matrix_free", 0))
-    use_mf = mf_mode != 0
-    x0 = initial_state(T)[:18 * T.n_owned_nodes]
-    n_dofs = 18 * mesh.n_nodes
-    info = ctx.info()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # clocks and throttle reasons are polled (nvidia-smi, ~5 Hz) from the first warm-up step to the end of the e2e loop: the
-    # same workload runs throughout, and the device-timed K steps alone (tens of milliseconds) are shorter than one poll
+    # clocks and throttle reasons are polled (nvidia-smi, ~5 Hz) over warm-up + timed + e2e steps of the headline workload
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-
-    # ---- warm-up ----
-    ctx.set_solution(x0)
-    for _ in range(args.warmup):
-        newton_step(ctx)
-
-    # ---- timed: K Newton steps from the initial condition, state resident in HBM ----
-    ctx.set_solution(x0)
-    ctx.timers(reset=True)
-    hist = []
-    barrier()
-    ctx.timer_start()
-    for _ in range(args.steps):
-        hist.append(newton_step(ctx))
-    ms = ctx.timer_stop()
-    barrier()
-    tm = ctx.timers()
-    # GL free energy of the state the timed steps ended in (outside the timed region; the reference never evaluates the
-    # functional, SURVEY.md section 0.6 — vh_energy integrates the functional whose half-gradient is the residual)
-    try:
-        final_energy = ctx.energy(0)
-    except Exception:
-        final_energy = None
-    ms = max_over_ranks(ms)
-    ms_per_step = ms / args.steps
-    value = n_dofs / (ms_per_step * 1e-3)
-
-    # ---- e2e: same steps, host buffers in and out of the C ABI every step (pinned host memory) ----
-    xh = torch.from_numpy(x0.copy()).pin_memory().numpy()
-    barrier()
-    t0 = time.perf_counter()
-    ctx.timer_start()
-    for _ in range(args.steps):
-        ctx.set_solution(xh)          # H2D of the step's input
-        newton_step(ctx)
-        ctx.get_solution(out=xh)      # D2H of the step's result, straight into the pinned buffer
-    ms_e2e = max_over_ranks(ctx.timer_stop())
-    wall_e2e = time.perf_counter() - t0
-    barrier()
-    e2e_val = n_dofs / (ms_e2e / args.steps * 1e-3)
+    main = measure(vh, torch, dist, rank, world, local_rank, args.degree, args.refine, args.global_refine, args.steps, args.warmup,
+                   want_kernels=True, want_parity=not args.no_parity)
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
-        clocks["window"] = "warm-up + timed + e2e Newton steps (same workload)"
+        clocks["window"] = "warm-up + timed + e2e Newton steps of the headline workload"
 
-    # ---- live kernel timings for the roofline (rank 0's kernels; inputs larger than L2 or L2 flushed) ----
-    ctx.set_solution(x0)
-    ctx.assemble()
-    nnzb, nb = info["nnzb"], T.n_owned_nodes
-    # algorithmic bytes of one SpMV by SURVEY.md §8(d) (BSR18: every 18x18 block stored in full) ...
-    spmv_bytes = 8 * 324 * nnzb + 4 * nnzb + 4 * (nb + 1) + 16 * 18 * nb
-    # ... and the bytes this implementation really has to move: lattice rows are stored as packed symmetric blocks
-    # (180 doubles instead of 324), general-scatter rows in full
-    n_fast_blocks = info["n_packed_blocks"]
-    packed = n_fast_blocks > 0
-    spmv_moved = 8 * (180 * n_fast_blocks + 324 * (nnzb - n_fast_blocks)) + 4 * nnzb + 4 * (nb + 1) + 16 * 18 * nb
-    spmv_moved_packed = spmv_moved
-    t_spmv = ctx.time_kernel(0, reps=20, flush_l2=True)
-    t_asm = ctx.time_kernel(1, reps=5, flush_l2=True)
-    t_pw = ctx.time_kernel(5, reps=5, flush_l2=True)
-    t_rows = ctx.time_kernel(6, reps=5, flush_l2=True)
-    t_res = ctx.time_kernel(2, reps=5, flush_l2=True)
-    t_bj = ctx.time_kernel(3, reps=10, flush_l2=True)
-    fp64_peak = ctx.measure_fp64_peak()
-    hbm_peak, peak_src = peaks()
-    n = 8 if args.degree == 1 else 27
-    asm_flops = 2.0 * n * n * n * 336 * T.n_cells
-    asm_bytes = 8 * 324 * nnzb + 8 * 18 * n * T.n_cells  # SURVEY's write-once figure (full blocks)
-    asm_moved = 8 * (180 * n_fast_blocks + 324 * (nnzb - n_fast_blocks)) + 8 * 18 * n * T.n_cells
-    spmv_gbs = spmv_bytes / (t_spmv * 1e-3) / 1e9
-    traffic = None
-    try:  # DRAM bytes per launch measured once with `ncu --set full` for this exact workload (profiles/traffic.json)
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            tj = json.load(f)
-        key = "q%d_r%d_%dgpu" % (args.degree, args.refine, world)
-        if args.global_refine is None and key in tj:
-            kname = "k_spmv_sym18" if packed else "k_spmv_bsr18"
-            traffic = tj[key][kname]["read_bytes"] + tj[key][kname]["write_bytes"]
-    except Exception:
-        traffic = None
-    # matrix-free apply: the H_q tables (8*180*n_q bytes per cell) + the per-cell products written and gathered once
-    mf_moved = 8 * 180 * n * T.n_cells + 2 * 8 * 18 * n * T.n_cells + 8 * 324 * (nnzb - n_fast_blocks) + 16 * 18 * nb
-    if use_mf:
-        spmv_moved, traffic = mf_moved, None
-    moved_gbs = spmv_moved / (t_spmv * 1e-3) / 1e9
-    kernel_name = ("k_points<APPLY>+k_gather_apply" if use_mf else "k_spmv_sym18") if n_fast_blocks else "k_spmv_bsr18"
-    roof = {"bound": "hbm", "kernel": kernel_name, "achieved": spmv_gbs, "peak": hbm_peak,
-            "unit": "GB/s", "frac": spmv_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src, "ms_per_launch": t_spmv,
-            "algorithmic_bytes_per_launch": spmv_bytes, "moved_bytes_per_launch": spmv_moved, "moved_gbs": moved_gbs,
-            "hbm_utilization": moved_gbs / hbm_peak,
-            "note": "achieved/frac use SURVEY's algorithmic bytes (full 18x18 blocks); the packed symmetric storage moves "
-                    "moved_bytes_per_launch (0.56x), so frac can exceed 1 while hbm_utilization (= real DRAM bytes / time / peak) "
-                    "stays below 1"}
-    asm = {"ms": t_asm, "dofs_per_s": 18 * nb / (t_asm * 1e-3), "tflops_fp64": asm_flops / (t_asm * 1e-3) / 1e12,
-           "fp64_peak_tflops_measured": fp64_peak, "frac_fp64": asm_flops / (t_asm * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
-           "store_gbs": asm_bytes / (t_asm * 1e-3) / 1e9, "frac_hbm": asm_bytes / (t_asm * 1e-3) / 1e9 / hbm_peak,
-           "pointwise_ms": t_pw, "rows_ms": t_rows, "algorithmic_flops": asm_flops, "algorithmic_bytes": asm_bytes,
-           "moved_bytes": asm_moved,
-           # flops the row-owner kernels really execute: packed symmetric entries (180 of 324) and, at Q2, the
-           # sum-factorised contraction (3 x 81 FMAs per entry and row node instead of 27 x 27)
-           "executed_flops": 2.0 * 180 * T.n_cells * (8 * 64 if args.degree == 1 else 27 * 243)}
-
-    # the other operator-apply mode, kernel-only (the timed Newton steps above used the mode of this run)
-    other = None
-    if packed:
+    # configs[1] (C2) next to the headline on one GPU: the same measurement, kernels included
+    c2 = None
+    if world == 1 and args.workload == "c5" and not args.no_c2:
         try:
-            ctx.set_spmv_matrix_free(0 if use_mf else 1)
-            t_other = ctx.time_kernel(0, reps=20, flush_l2=True)
-            om = spmv_moved_packed if use_mf else mf_moved
-            other = {"mode": "packed-spmv" if use_mf else "matrix-free", "ms": t_other, "moved_bytes": om,
-                     "moved_gbs": om / (t_other * 1e-3) / 1e9, "hbm_utilization": om / (t_other * 1e-3) / 1e9 / hbm_peak}
-        except Exception as exc:  # never let the side measurement take the bench line down
-            other = {"error": str(exc)}
-        finally:
-            try:
-                ctx.set_spmv_matrix_free(mf_mode)
-            except Exception:
-                pass
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        s = reference_sample(args.refine, 6)
-        if s is not None:
-            n_cells = mesh.n_cells
-            step_s = n_cells / s["cells_per_s"]
-            cpu = {"value": n_dofs / step_s, "unit": "DoF/s", "cores": s["cores"], "kind": "reference",
-                   "sample": "%d Q1 cells (Jacobian + 1 residual each) through the reference's verbatim term files and literal "
-                             "(q,i,j) loops in %.1f s on %d cores; extrapolated linearly to %d cells; solve excluded"
-                             % (s["cells"], s["wall_s"], s["cores"], n_cells)}
-
-    # the optimised CPU restatement (oracle O2, C, one pthread per host core) on the same cells: the "fair CPU" assembly
-    # rate SURVEY.md section 8(d) asks for next to the reference's literal loops (reported baseline, not a target)
-    if cpu is not None and args.degree == 1:
-        try:
-            import femgl_oracle as O
-            nsmp = min(T.n_cells, 2048)
-            xs = np.zeros(18 * T.n_local_nodes)
-            xs[:x0.size] = x0
-            fptr, fno, fbid = T.face_csr()
-            dummy = np.zeros(1, np.int32)
-            t0 = time.perf_counter()
-            O.cells(1, T.cell_nodes[:nsmp], T.cell_origin[:nsmp], T.cell_h[:nsmp], xs, coef_vector(), fptr[:nsmp + 1],
-                    fno if fno.size else dummy, fbid if fbid.size else dummy, want_matrix=True)
-            dt = time.perf_counter() - t0
-            asm["cpu_port"] = {"dofs_per_s": 18 * nb / (T.n_cells / (nsmp / dt)), "unit": "DoF/s", "cores": os.cpu_count(), "kind": "port",
-                               "sample": "%d Q1 cell matrices + rhs by oracle/femgl_oracle.c (closed-form H_q, pthreads) in %.2f s; "
-                                         "scatter excluded; extrapolated linearly to %d cells" % (nsmp, dt, T.n_cells)}
+            c2 = measure(vh, torch, dist, rank, world, local_rank, 1, 5, None, args.steps, args.warmup, want_kernels=True,
+                         want_parity=False)
+            c2["workload"] = workload_string(1, 5, None, c2["n_dofs"], c2["n_cells"])
         except Exception as exc:
-            asm["cpu_port"] = {"error": str(exc)}
+            c2 = {"error": str(exc)}
+
+    cpu = port = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_side = 2 ** (args.refine if args.global_refine is None else args.global_refine)
+        s = reference_sample(40.0 / n_side, 6)
+        if s is not None:
+            step_s = main["n_cells"] / s["cells_per_s"]
+            cpu = {"value": main["n_dofs"] / step_s, "unit": "DoF/s", "cores": s["cores"], "kind": "reference",
+                   "sample": "%d Q1 cells (Jacobian + 1 residual each) through the reference's verbatim term files and literal "
+                             "(q,i,j) loops in %.1f s on %d cores; extrapolated linearly to %d cells; solve excluded (upper bound "
+                             "on the reference's throughput)" % (s["cells"], s["wall_s"], s["cores"], main["n_cells"]),
+                   "assembly_dofs_per_s": s["assembly_cells_per_s"] * main["n_dofs"] / main["n_cells"],
+                   "residual_dofs_per_s": s["residual_cells_per_s"] * main["n_dofs"] / main["n_cells"]}
+        if args.degree == 1:
+            try:
+                nst = max(main["newton"]["newton_steps"], 1)
+                port = cpu_port_numbers(main["newton"]["gmres_its_total"] / nst, main["newton"]["line_search_trials_total"] / nst,
+                                        main["n_cells"], main["n_dofs"])
+            except Exception as exc:
+                port = {"error": str(exc)}
 
     if rank == 0:
-        out = {"metric": "femgl Newton-step throughput",
-               "value": value, "unit": "DoF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.global_refine is None else "strong", "vs_baseline": None, "dtype": "f64",
-               "data": "synthetic",
-               "config": {"workload": workload_string(args.degree, args.refine, args.global_refine, n_dofs, mesh.n_cells),
-                          "l2": "matrix (%.2f GB/GPU) exceeds the 126 MB L2; kernel timings flush L2 between launches"
-                                % (8 * 324 * nnzb / 1e9),
-                          "parallelism": "subdomain x%d (Morton partition, NCCL halo + all-reduce)" % world},
-               "newton_history": [{"gmres_its": h[0], "line_search_trials": h[1], "residual": h[2]} for h in hist],
-               "final_energy": final_energy,
-               "phase_ms_per_step": {k: tm[k] / args.steps for k in ("assemble", "residual", "solve", "vector")},
-               "roofline": roof, "assembly": asm,
-               # the other HBM-bound kernels with SURVEY.md section 8(d)'s algorithmic bytes: residual assembly 8*dpc*cells (gather)
-               # + 8*N (write); block-Jacobi apply 2592*nb + 16*N
-               "kernels": {"spmv_ms": t_spmv, "spmv_gbs": spmv_gbs, "residual_ms": t_res,
-                           "residual_gbs": (8 * 18 * n * T.n_cells + 8 * 18 * nb) / (t_res * 1e-3) / 1e9,
-                           "block_jacobi_apply_ms": t_bj, "block_jacobi_apply_gbs": (2592 * nb + 16 * 18 * nb) / (t_bj * 1e-3) / 1e9,
-
-                           "operator_apply_mode": ("packed-spmv", "matrix-free", "table-free", "matrix-free-v2")[mf_mode], "other_apply_mode": other},
-               "e2e": {"value": e2e_val, "unit": "DoF/s", "h2d_bytes_per_step": int(8 * 18 * T.n_owned_nodes),
-                       "d2h_bytes_per_step": int(8 * 18 * T.n_owned_nodes), "ms_per_step": ms_e2e / args.steps,
-                       "wall_ms_per_step": wall_e2e / args.steps * 1e3},
-               "gpu_launches": tm["launches"], "clocks": clocks, "cpu_baseline": cpu,
-               "matrix": {"nnzb": nnzb, "fast_rows": info["n_fast_rows"], "slow_cells": info["n_slow_cells"],
-                          "device_bytes": info["device_bytes"]}}
+        strong = args.global_refine is not None
+        out = {"metric": "femgl Newton-step throughput", "value": main["value"], "unit": "DoF/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+               "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": workload_string(args.degree, args.refine, args.global_refine, main["n_dofs"], main["n_cells"]),
+                          "l2": "working set per operator apply (%.2f GB on rank 0) exceeds the 126 MB L2; kernel timings flush L2 "
+                                "between launches" % (main["roofline"]["moved_bytes_per_launch"] / 1e9),
+                          "parallelism": "subdomain x%d (Morton partition, NCCL halo + peer-memory all-reduce)" % world,
+                          "stop_rule": "run.cc:234-250: a run ends at residual <= 5e-6, the next timed step starts a new run from the IC"}}
+        for k in ("newton", "final_energy", "phase_ms_per_step", "gmres_its_per_step", "ms_per_gmres_it", "halo_ms_per_exchange",
+                  "allreduce_ms_per_dot", "roofline", "assembly", "kernels", "e2e", "gpu_launches", "multi_gpu_parity", "memory",
+                  "context_create_s"):
+            if k in main:
+                out[k] = main[k]
+        out["clocks"] = clocks
+        out["cpu_baseline"] = cpu
+        out["cpu_port"] = port
+        if cpu is not None or port is not None:
+            vs = {"note": "phase-by-phase GPU/CPU ratios (reported baseline, not a target); the reference's literal loops have no "
+                          "solve leg, so a whole-step ratio is only formed against the port"}
+            if cpu is not None:
+                vs["assembly_vs_reference_literal"] = main["assembly"]["dofs_per_s"] / cpu["assembly_dofs_per_s"]
+                vs["residual_vs_reference_literal"] = (main["n_owned_dofs_rank0"] / (main["kernels"]["residual_ms"] * 1e-3)) / cpu["residual_dofs_per_s"]
+            if port is not None and "error" not in port:
+                vs["assembly_vs_port"] = main["assembly"]["dofs_per_s"] / port["assembly_with_scatter_dofs_per_s"]
+                vs["newton_step_vs_port"] = port["newton_step_ms"] / main["ms_per_step"]
+            out["vs_cpu"] = vs
+        if c2 is not None:
+            out["c2"] = c2
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(out), flush=True)
         os.dup2(2, 1)
-    ctx.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -495,14 +646,28 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--refine", type=int, default=5)
-    ap.add_argument("--degree", type=int, default=1)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--spmv-mf", action="store_true",
-                    help="run GMRES with the matrix-free operator apply (vh_set_spmv_matrix_free) instead of the packed SpMV")
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS),
+                    help="c5 (default): BASELINE configs[4], Q1 global refinement 7 split over the GPUs (strong scaling); "
+                         "c2: configs[1], Q1 r5 per GPU (weak); c3: configs[2], Q2 r5 split over the GPUs")
+    ap.add_argument("--refine", type=int, default=None, help="override: refinements per GPU (weak scaling)")
+    ap.add_argument("--degree", type=int, default=None)
     ap.add_argument("--global-refine", type=int, default=None,
-                    help="strong scaling: one cube with this many global refinements split over the GPUs (7 = BASELINE C5, 38.6M DoFs)")
+                    help="override: one cube with this many global refinements split over the GPUs (strong scaling)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c2", action="store_true", help="skip the configs[1] measurement next to the headline (N = 1)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the single-GPU parity run of rank 0 (N > 1)")
     args = ap.parse_args()
+    d, r, g = WORKLOADS[args.workload]
+    if args.refine is not None or args.global_refine is not None:
+        r, g = args.refine, args.global_refine
+        args.workload = "custom"
+    if args.degree is not None:
+        d = args.degree
+        if d != WORKLOADS.get(args.workload, (d,))[0]:
+            args.workload = "custom"
+    args.degree, args.refine, args.global_refine = d, r, g
+    if args.refine is None and args.global_refine is None:
+        raise SystemExit("--refine or --global-refine needed")
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -130,8 +130,13 @@ def test_spmv_and_block_jacobi_match_oracle(degree, refine):
     ctx.close()
 
 
+@pytest.mark.parametrize("mgs", ["auto", "64", "1000"])
 @pytest.mark.parametrize("degree,refine,tol", [(1, 3, 1e-1), (1, 3, 1e-8), (2, 2, 1e-6)])
-def test_gmres_history_matches_oracle(degree, refine, tol):
+def test_gmres_history_matches_oracle(degree, refine, tol, mgs, monkeypatch):
+    """mgs: variant of the modified Gram-Schmidt step — register-resident fused kernel (auto at this size), the streaming
+    fused kernel that long vectors (C5) take, and the kernel chain (no cooperative launch)."""
+    if mgs != "auto":
+        monkeypatch.setenv("VH_MGS_MODE", mgs)
     T = vh.unit_cube(degree, refine, half=2.0).tables(0)
     coef = coef_vector(MATEP_SCC_ON, 2.0)
     x = b_phase_state(T)

@@ -175,7 +175,7 @@ struct vh_ctx
   int                  rank = 0, n_ranks = 1;
   void                *nccl_comm = nullptr;
   // peer-memory mailboxes (NVLink P2P through CUDA IPC) for latency-bound scalar all-reduces; see vh_halo.cu
-  int                  mgs_mode = -1;      // fused Gram-Schmidt: elements per thread (8 / 32), 1000 = kernel chain, -1 = undecided
+  int                  mgs_mode = -1;      // fused Gram-Schmidt: elements per thread (8 / 32), 64 = streaming variant, 1000 = kernel chain, -1 = undecided
   bool                 p2p = false;
   VhP2P                p2p_dev;            // by-value kernel argument
   void                *p2p_mbox = nullptr; // this rank's mailbox (device)

@@ -491,9 +491,13 @@ __global__ void k_halo_wait(VhPush H, unsigned long long seq)
 // are summed in the same fixed order by every block.
 // ------------------------------------------------------------------------------------------------
 #define VH_MGS_THREADS 256
-// EPT = elements of w per thread held in registers (as double2): 8 covers 1.2 M DoFs per GPU, 32 covers 4.8 M (C5 on 8 GPUs)
+// EPT = elements of w per thread held in registers (as double2): 8 covers 1.2 M DoFs per GPU, 32 up to 4.8 M.
+// EPT = 0 is the STREAMING variant for vectors of any length: w stays in global memory and is updated in place by the
+// thread that owns the element (grid-stride slices), so there is still no kernel boundary and no host round trip between
+// the j+2 dependent reductions; with 4.8 M DoFs per rank (C5 on 8 GPUs) w and the last basis vector stay L2-resident and
+// only the next basis vector streams from HBM.
 template <int EPT>
-__global__ void __launch_bounds__(VH_MGS_THREADS, EPT == 8 ? 3 : 1)
+__global__ void __launch_bounds__(VH_MGS_THREADS, EPT == 8 ? 3 : (EPT == 0 ? 2 : 1))
   k_mgs_fused(int64_t n, double *__restrict__ w, const double *__restrict__ V, int64_t ld, int j, double *__restrict__ hcol,
               double *__restrict__ partials, unsigned int *__restrict__ tickets, VhP2P P, unsigned long long seq0,
               double *__restrict__ nrm2_out, volatile double *host_out, unsigned long long host_seq)
@@ -505,7 +509,7 @@ __global__ void __launch_bounds__(VH_MGS_THREADS, EPT == 8 ? 3 : 1)
   const int         lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t     base = ((int64_t)blockIdx.x * VH_MGS_THREADS + threadIdx.x) * 2;
   const int64_t     stride = (int64_t)gridDim.x * VH_MGS_THREADS * 2;
-  double2           wr[EPT / 2];
+  double2           wr[EPT > 0 ? EPT / 2 : 1];
 #pragma unroll
   for (int k = 0; k < EPT / 2; ++k)
     {
@@ -538,7 +542,35 @@ __global__ void __launch_bounds__(VH_MGS_THREADS, EPT == 8 ? 3 : 1)
   for (int step = 0; step <= j + 1; ++step)
     {
       double s = 0.0;
-      if constexpr (PF)
+      if constexpr (EPT == 0)
+        { // streaming: this thread's slice of w is updated in global memory (nobody else touches these elements)
+          const double *vp = step > 0 ? V + (size_t)(step - 1) * ld : nullptr; // subtract hprev * v_{step-1}
+          const double *vu = step <= j ? V + (size_t)step * ld : nullptr;      // dot with v_step (or with w itself)
+          double        s1 = 0.0;
+#pragma unroll 4
+          for (int64_t i = base; i < n; i += stride)
+            {
+              const bool two = i + 1 < n;
+              double2    wv  = two ? *reinterpret_cast<const double2 *>(w + i) : make_double2(w[i], 0.0);
+              if (vp)
+                {
+                  const double2 pv = two ? __ldcs(reinterpret_cast<const double2 *>(vp + i)) : make_double2(vp[i], 0.0);
+                  wv.x             = fma(-hprev, pv.x, wv.x);
+                  wv.y             = fma(-hprev, pv.y, wv.y);
+                  if (two)
+                    *reinterpret_cast<double2 *>(w + i) = wv;
+                  else
+                    w[i] = wv.x;
+                }
+              double2 uv = wv;
+              if (vu)
+                uv = two ? *reinterpret_cast<const double2 *>(vu + i) : make_double2(vu[i], 0.0);
+              s  = fma(wv.x, uv.x, s);
+              s1 = fma(wv.y, uv.y, s1);
+            }
+          s += s1;
+        }
+      else if constexpr (PF)
         {
           // w -= hprev * V[step-1]  (cu still holds V[step-1] from the previous step)
           if (step > 0)
@@ -1003,21 +1035,32 @@ static int64_t mgs_capacity(vh_ctx *ctx, int ept)
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   if (ept == 8)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mgs_fused<8>, VH_MGS_THREADS, 0);
-  else
+  else if (ept == 32)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mgs_fused<32>, VH_MGS_THREADS, 0);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mgs_fused<0>, VH_MGS_THREADS, 0);
   if (!coop)
     return 0;
+  if (ept == 0) // streaming variant: the number of co-resident blocks (any vector length)
+    return (int64_t)sms * (per_sm < 2 ? per_sm : 2);
   return (int64_t)sms * (per_sm < 4 ? per_sm : 4) * VH_MGS_THREADS * ept;
 }
-// 8 or 32 = elements per thread this rank needs for its owned vector, 1000 = cannot fuse
+// 8 or 32 = elements per thread this rank needs for its owned vector, 64 = streaming variant (any length), 1000 = cannot fuse
+// (no cooperative launch).  Ordered so that the maximum over the ranks is the mode every rank can run.
 int vhk_mgs_mode_local(vh_ctx *ctx)
 {
+  if (const char *e = getenv("VH_MGS_MODE")) // test hook: force a variant (8, 32, 64 = streaming, 1000 = kernel chain)
+    {
+      const int m = atoi(e);
+      if (m == 8 || m == 32 || m == 64 || m == 1000)
+        return (m == 64 && mgs_capacity(ctx, 0) == 0) ? 1000 : m;
+    }
   if (ctx->NO == 0)
     return 8;
   for (int ept : {8, 32})
     if (ctx->NO <= mgs_capacity(ctx, ept) && (int64_t)(VH_MAX_RESTART + 2) * ((ctx->NO + VH_MGS_THREADS * ept - 1) / (VH_MGS_THREADS * ept)) <= (int64_t)VH_MAX_RED_BLOCKS * 32)
       return ept;
-  return 1000;
+  return mgs_capacity(ctx, 0) > 0 ? 64 : 1000;
 }
 
 int vhk_mgs_fused(vh_ctx *ctx, double *w, const double *V, int64_t ld, int j, double *hcol_dev, bool *used)
@@ -1025,11 +1068,13 @@ int vhk_mgs_fused(vh_ctx *ctx, double *w, const double *V, int64_t ld, int j, do
   *used = false;
   if (ctx->mgs_mode < 0) // single rank: decided here; multi-rank: agreed over all ranks in vh_comm_init
     ctx->mgs_mode = ctx->n_ranks == 1 ? vhk_mgs_mode_local(ctx) : 1000;
-  if (ctx->mgs_mode > 32 || (ctx->n_ranks > 1 && !ctx->p2p) || (ctx->n_ranks == 1 && ctx->NO == 0))
+  if (ctx->mgs_mode > 64 || (ctx->n_ranks > 1 && !ctx->p2p) || (ctx->n_ranks == 1 && ctx->NO == 0))
     return VH_OK;
-  const int     ept       = ctx->mgs_mode;
-  const int64_t per_block = (int64_t)VH_MGS_THREADS * ept;
+  const int     ept       = ctx->mgs_mode == 64 ? 0 : ctx->mgs_mode;
+  const int64_t per_block = (int64_t)VH_MGS_THREADS * (ept ? ept : 2);
   int64_t       grid      = std::max<int64_t>(1, (ctx->NO + per_block - 1) / per_block);
+  if (ept == 0)
+    grid = std::min<int64_t>(grid, std::max<int64_t>(1, mgs_capacity(ctx, 0)));
   int64_t       n         = ctx->NO;
   VhP2P         P         = ctx->p2p_dev; // single rank: the mailbox is this context's own buffer (set up in vh_create)
   unsigned long long seq0 = ctx->p2p_seq + 1;
@@ -1037,7 +1082,7 @@ int vhk_mgs_fused(vh_ctx *ctx, double *w, const double *V, int64_t ld, int j, do
   double            *host_out = ctx->h_mgs;
   unsigned long long host_seq = ++ctx->h_mgs_seq;
   void *args[] = {&n, &w, (void *)&V, &ld, &j, &hcol_dev, &ctx->partials, &ctx->mgs_tickets, &P, &seq0, &nrm2_out, &host_out, &host_seq};
-  cudaError_t e = cudaLaunchCooperativeKernel(ept == 8 ? (void *)k_mgs_fused<8> : (void *)k_mgs_fused<32>, dim3((unsigned)grid),
+  cudaError_t e = cudaLaunchCooperativeKernel(ept == 8 ? (void *)k_mgs_fused<8> : (ept == 32 ? (void *)k_mgs_fused<32> : (void *)k_mgs_fused<0>), dim3((unsigned)grid),
                                               dim3(VH_MGS_THREADS), args, 0, ctx->stream);
   if (e != cudaSuccess)
     return vh_fail(ctx, VH_ERR_CUDA, std::string("cooperative launch: ") + cudaGetErrorString(e));
