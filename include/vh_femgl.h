@@ -114,6 +114,16 @@ int vh_get_newton_update(vh_ctx *ctx, double *owned);      /* locally_relevant_n
 int vh_get_rhs(vh_ctx *ctx, double *owned);                /* system_rhs (femgl.h:315)      */
 int vh_get_residual(vh_ctx *ctx, double *owned);           /* residual_vector (femgl.h:316) */
 
+/* ---- refine_grid(): SolutionTransfer::interpolate + constraints_solution.distribute + ghosted copy on the device
+ *      (refine.cc:128-130, 171-175; run.cc:182-195).  `dst` is the context of the NEW mesh, `src` the one of the old mesh
+ *      (same device, still alive); row i of the CSR table belongs to owned node i of dst and lists the nodes of src
+ *      (LOCAL ids, owned or ghost) whose shape functions are non-zero at that node, with their values:
+ *          dst.local_solution[i][c] = sum_{k in [ptr[i], ptr[i+1])} weight[k] * src.local_solution[src_node[k]][c].
+ *      The host builds the table from the parent/child relation of the cells it refined (deal.II: the same data
+ *      SolutionTransfer uses); nodes whose old cell lives on another rank must be filled by the host (vh_set_solution). ---- */
+int vh_transfer_solution(vh_ctx *dst, vh_ctx *src, int32_t n_rows, const int32_t *ptr, const int32_t *src_node,
+                         const double *weight);
+
 /* ---- assemble_system(): system_matrix = R'(x), system_rhs = -R(x) at local_solution; returns ||rhs||_2 ---- */
 int vh_assemble(vh_ctx *ctx, double *rhs_l2);
 

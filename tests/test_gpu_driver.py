@@ -185,3 +185,37 @@ def test_slab_adaptive_cycles_run_to_completion():
     # the refinement concentrates on the A/B interface: the mesh grows but stays far below uniform refinement
     n0 = 18 * 5 * 5 * 5
     assert n0 < out["solution"].size < 18 * 17 ** 3
+
+
+def test_device_side_solution_transfer_matches_host_interpolation():
+    """refine.cc:128-130/171-175 on the device (vh_transfer_solution): the state transferred to the refined mesh equals the
+    host's FE interpolation followed by constraints_solution.distribute, hanging nodes included; the driver reports the
+    rebuild time of the cycle."""
+    old = vh.Mesh(1, [-3, -2, -4], [3, 2, 4], n_global_refine=2).finalize(1)
+    new = old.clone()
+    d = np.abs(new.cell_centers()[:, 2] - 0.4)
+    new.refine(d <= np.sort(d)[int(0.3 * new.n_cells)])
+    new.finalize(1)
+    assert new.n_hanging_nodes > 0
+    To, Tn = old.tables(0), new.tables(0)
+    coef = coef_vector(MATEP_SCC_ON, 2.0)
+    xo = b_phase_state(To, seed=21)
+    co, cn = vh.Context(To), vh.Context(Tn)
+    for c in (co, cn):
+        c.set_coef_vector(coef)
+    co.set_solution(xo)
+    cn.transfer_solution_from(co, *new.transfer_table(old))
+    from helpers import distribute_constraints
+    want = distribute_constraints(Tn, new.interpolate_from(old, xo))
+    got = cn.get_solution()
+    assert np.abs(got - want).max() <= 1e-14 * np.abs(want).max()
+    # the transferred state is a usable Newton state: one step on the new mesh equals the oracle's from the same state
+    bn = cn.assemble()
+    o = O.newton_step(Tn, want, coef, 1e-1)
+    assert abs(bn - o["rhs_norm"]) <= 1e-10 * o["rhs_norm"]
+    co.close()
+    cn.close()
+    out = vh.run_prm(SLAB_PRM % (1, 1e3))
+    first = [h for h in out["history"] if h["iteration"] == 0]
+    assert len(first) == 2 and all(h["t_setup_ms"] > 0 for h in first)
+    assert "solution transfer" in out["log"]

@@ -74,6 +74,9 @@ def host_lib():
         L.vhh_prm_dump.restype = ctypes.c_char_p
         L.vhh_prm_dump.argtypes = [ctypes.c_char_p]
         L.vhh_mesh_interpolate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, _dp, _dp]
+        L.vhh_mesh_transfer_table.restype = ctypes.c_int64
+        L.vhh_mesh_transfer_table.argtypes = [ctypes.c_void_p, ctypes.c_void_p, _i32p, _i32p, _dp]
+        L.vhh_mesh_kelly.argtypes = [ctypes.c_void_p, _dp, _dp]
         L.vhh_mesh_clone.restype = ctypes.c_void_p
         L.vhh_mesh_clone.argtypes = [ctypes.c_void_p]
         L.vhh_mesh_node_xyz.argtypes = [ctypes.c_void_p, _dp]
@@ -207,6 +210,26 @@ class Mesh:
         if host_lib().vhh_mesh_interpolate(self._h, old_mesh._h, ov.ctypes.data_as(_dp), nv.ctypes.data_as(_dp)) != 0:
             raise RuntimeError(host_lib().vhh_last_error().decode())
         return nv
+
+    def transfer_table(self, old_mesh):
+        """The interpolation of interpolate_from as a CSR table (ptr, old node ids, weights) for vh_transfer_solution."""
+        nn = 8 if self.degree == 1 else 27
+        ptr = np.zeros(self.n_nodes + 1, dtype=np.int32)
+        src = np.zeros(self.n_nodes * nn, dtype=np.int32)
+        w = np.zeros(self.n_nodes * nn)
+        nnz = host_lib().vhh_mesh_transfer_table(self._h, old_mesh._h, ptr.ctypes.data_as(_i32p), src.ctypes.data_as(_i32p),
+                                                 w.ctypes.data_as(_dp))
+        if nnz < 0:
+            raise RuntimeError(host_lib().vhh_last_error().decode())
+        return ptr, src[:nnz].copy(), w[:nnz].copy()
+
+    def kelly_indicator(self, values):
+        """Kelly-type face-jump indicator per cell (refine.cc:144-148 stand-in); values in global node order."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        eta = np.zeros(self.n_cells)
+        if host_lib().vhh_mesh_kelly(self._h, v.ctypes.data_as(_dp), eta.ctypes.data_as(_dp)) != 0:
+            raise RuntimeError(host_lib().vhh_last_error().decode())
+        return eta
 
     def __del__(self):
         try:

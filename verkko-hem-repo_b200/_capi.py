@@ -46,6 +46,7 @@ def cuda_lib():
                                           ctypes.c_double]
         for f in ("vh_set_solution", "vh_get_solution", "vh_get_newton_update", "vh_get_rhs", "vh_get_residual"):
             getattr(L, f).argtypes = [_vp, _dp]
+        L.vh_transfer_solution.argtypes = [_vp, _vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _dp]
         L.vh_assemble.argtypes = [_vp, _dp]
         L.vh_solve.argtypes = [_vp, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), _dp]
         L.vh_line_search_trial.argtypes = [_vp, ctypes.c_double]
@@ -149,6 +150,15 @@ class Context:
 
     def get_residual(self):
         return self._get(self.L.vh_get_residual)
+
+    def transfer_solution_from(self, src_ctx, ptr, src_node, weight):
+        """Device-side SolutionTransfer::interpolate + constraints_solution.distribute (vh_transfer_solution)."""
+        ptr = np.ascontiguousarray(ptr, dtype=np.int32)
+        src_node = np.ascontiguousarray(src_node, dtype=np.int32)
+        weight = np.ascontiguousarray(weight, dtype=np.float64)
+        i32 = ctypes.POINTER(ctypes.c_int32)
+        self._chk(self.L.vh_transfer_solution(self._h, src_ctx._h, ptr.size - 1, ptr.ctypes.data_as(i32),
+                                              src_node.ctypes.data_as(i32), weight.ctypes.data_as(_dp)))
 
     # --- hot path ---
     def assemble(self):
@@ -275,9 +285,9 @@ def run_prm(prm_text):
         if err:
             raise RuntimeError(err + "\n--- log ---\n" + log[-2000:])
         keys = ["cycle", "iteration", "rhs_norm", "linear_its", "residual", "alpha", "trials", "energy", "t_assemble_ms",
-                "t_solve_ms", "t_newton_ms"]
+                "t_solve_ms", "t_newton_ms", "t_setup_ms"]
         hist = []
-        buf = np.zeros(11)
+        buf = np.zeros(12)
         for i in range(L.vhd_n_steps(h)):
             L.vhd_step(h, i, buf.ctypes.data_as(_dp))
             d = dict(zip(keys, buf.tolist()))

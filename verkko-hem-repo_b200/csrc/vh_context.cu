@@ -1186,6 +1186,73 @@ int vh_get_residual(vh_ctx *ctx, double *owned)
   return download_owned(ctx, ctx->resid, owned);
 }
 
+// dst[i][c] = sum_k w_k src[node_k][c]: one thread per (row, component), rows of at most 27 entries
+__global__ void k_transfer(int n_rows, const int32_t *__restrict__ ptr, const int32_t *__restrict__ node, const double *__restrict__ w,
+                           const double *__restrict__ xs, double *__restrict__ xd)
+{
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)n_rows * 18)
+    return;
+  const int i = (int)(gid / 18), c = (int)(gid - 18 * (int64_t)i);
+  double    s = 0.0;
+  for (int k = ptr[i]; k < ptr[i + 1]; ++k)
+    s = fma(w[k], xs[18 * (int64_t)node[k] + c], s);
+  xd[gid] = s;
+}
+
+int vh_transfer_solution(vh_ctx *ctx, vh_ctx *src, int32_t n_rows, const int32_t *ptr, const int32_t *src_node, const double *weight)
+{
+  VH_REQUIRE(ctx);
+  if (!src || src == ctx || src->device != ctx->device)
+    return vh_fail(ctx, VH_ERR_ARG, "vh_transfer_solution: the source context must be another context on the same device");
+  if (n_rows != ctx->n_owned || (n_rows > 0 && (!ptr || !src_node || !weight)) || (n_rows > 0 && ptr[0] != 0))
+    return vh_fail(ctx, VH_ERR_ARG, "vh_transfer_solution: the table must have one row per owned node of the new mesh");
+  for (int i = 0; i < n_rows; ++i)
+    if (ptr[i + 1] < ptr[i])
+      return vh_fail(ctx, VH_ERR_ARG, "vh_transfer_solution: ptr not monotone");
+  const int nent = n_rows ? ptr[n_rows] : 0;
+  for (int k = 0; k < nent; ++k)
+    if (src_node[k] < 0 || src_node[k] >= src->n_local)
+      return vh_fail(ctx, VH_ERR_ARG, "vh_transfer_solution: source node out of range (not local on this rank)");
+  VH_CUDA(cudaSetDevice(ctx->device));
+  VH_CUDA(cudaStreamSynchronize(src->stream)); // the old state is final
+  int32_t *d_ptr = nullptr, *d_node = nullptr;
+  double  *d_w   = nullptr;
+  int      rc    = VH_OK;
+  auto     done  = [&](int r) {
+    cudaFree(d_ptr);
+    cudaFree(d_node);
+    cudaFree(d_w);
+    return r;
+  };
+  if (cudaMalloc((void **)&d_ptr, sizeof(int32_t) * ((size_t)n_rows + 1)) != cudaSuccess ||
+      cudaMalloc((void **)&d_node, sizeof(int32_t) * (size_t)std::max(nent, 1)) != cudaSuccess ||
+      cudaMalloc((void **)&d_w, sizeof(double) * (size_t)std::max(nent, 1)) != cudaSuccess)
+    return done(vh_fail(ctx, VH_ERR_CUDA, "vh_transfer_solution: cannot allocate the table"));
+  if (n_rows > 0)
+    {
+      cudaMemcpyAsync(d_ptr, ptr, sizeof(int32_t) * ((size_t)n_rows + 1), cudaMemcpyHostToDevice, ctx->stream);
+      cudaMemcpyAsync(d_node, src_node, sizeof(int32_t) * (size_t)nent, cudaMemcpyHostToDevice, ctx->stream);
+      cudaMemcpyAsync(d_w, weight, sizeof(double) * (size_t)nent, cudaMemcpyHostToDevice, ctx->stream);
+      const int64_t n = (int64_t)n_rows * 18;
+      k_transfer<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n_rows, d_ptr, d_node, d_w, src->x_sol, ctx->x_sol);
+      ctx->n_launches++;
+      if (cudaGetLastError() != cudaSuccess)
+        return done(vh_fail(ctx, VH_ERR_CUDA, "vh_transfer_solution: kernel launch failed"));
+    }
+  // constraints_solution.distribute(distributed_solution_tmp); local_solution = distributed_solution_tmp (refine.cc:129-130,174-175)
+  if (rc == VH_OK)
+    rc = vhk_halo_exchange(ctx, ctx->x_sol);
+  if (rc == VH_OK)
+    rc = vhk_distribute(ctx, 1, ctx->x_sol);
+  if (rc == VH_OK)
+    rc = vhk_halo_exchange(ctx, ctx->x_sol);
+  if (rc == VH_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    rc = vh_fail(ctx, VH_ERR_CUDA, "vh_transfer_solution: device error");
+  ctx->have_matrix = ctx->have_update = ctx->have_trial = false;
+  return done(rc);
+}
+
 static int norm_of(vh_ctx *ctx, const double *v, double *out)
 {
   VH_TRY(vhk_dot(ctx, v, v, ctx->scal + VH_SCAL_NRM2));

@@ -56,12 +56,12 @@ int vhd_n_steps(void *h)
   Run *r = static_cast<Run *>(h);
   return r->femgl ? (int)r->femgl->history().size() : 0;
 }
-// out[11] = cycle, iteration, rhs_norm, linear_its, residual, alpha, trials, energy, t_assemble_ms, t_solve_ms, t_newton_ms
+// out[12] = cycle, iteration, rhs_norm, linear_its, residual, alpha, trials, energy, t_assemble_ms, t_solve_ms, t_newton_ms, t_setup_ms
 void vhd_step(void *h, int i, double *out)
 {
   const auto &s = static_cast<Run *>(h)->femgl->history()[i];
   out[0] = s.cycle, out[1] = s.iteration, out[2] = s.rhs_norm, out[3] = s.linear_its, out[4] = s.residual, out[5] = s.alpha,
-  out[6] = s.trials, out[7] = s.energy, out[8] = s.t_assemble_ms, out[9] = s.t_solve_ms, out[10] = s.t_newton_ms;
+  out[6] = s.trials, out[7] = s.energy, out[8] = s.t_assemble_ms, out[9] = s.t_solve_ms, out[10] = s.t_newton_ms, out[11] = s.t_setup_ms;
 }
 long long vhd_solution_size(void *h)
 {

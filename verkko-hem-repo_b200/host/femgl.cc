@@ -165,6 +165,7 @@ void FemGL<dim>::setup_system()
       vh_destroy(gpu);
       gpu = nullptr;
     }
+  const double t_create0 = now_ms();
   vh_mesh_desc d;
   std::memset(&d, 0, sizeof(d));
   RankTables &T    = *tables;
@@ -245,8 +246,9 @@ void FemGL<dim>::setup_system()
             s += T.c_weight[q] * host_solution[T.c_master[q]];
           host_solution[T.c_dof[l]] = s;
         }
-    }
-  check(vh_set_solution(gpu, host_solution.data()), "vh_set_solution");
+      check(vh_set_solution(gpu, host_solution.data()), "vh_set_solution");
+      last_setup_ms = now_ms() - t_create0;
+    } // later cycles: refine_grid() transfers the state on the device (vh_transfer_solution)
 }
 
 template <int dim>
@@ -330,57 +332,56 @@ template <int dim>
 void FemGL<dim>::refine_grid(std::string &refinement_strategy)
 {
   std::ostream &pcout = *out;
-  // keep the old mesh and solution for the transfer
-  check(vh_get_solution(gpu, host_solution.data()), "refine_grid");
-  std::unique_ptr<Mesh>       old_mesh(new Mesh(*triangulation));
-  std::unique_ptr<RankTables> old_tab(new RankTables(*tables));
-  const std::vector<double>   old_sol = host_solution;
+  const double  t_begin = now_ms();
+  // the old mesh and its GPU context stay alive until the solution has been transferred on the device
+  std::unique_ptr<Mesh> old_mesh(new Mesh(*triangulation));
+  vh_ctx               *old_gpu = gpu;
+  gpu                           = nullptr;
 
   std::vector<uint8_t> flags((size_t)triangulation->n_cells(), 0);
   if (refinement_strategy == "global")
     std::fill(flags.begin(), flags.end(), 1);
   else
-    { // The reference uses deal.II's KellyErrorEstimator + refine_and_coarsen_fixed_number (refine.cc:144-153), which is
-      // not available here.  Surrogate with the same interface semantics (a fixed FRACTION of cells): the indicator is
-      // the jump-free cell quantity h * |grad A|_cell estimated from the nodal values.
+    { // KellyErrorEstimator + refine_and_coarsen_fixed_number (refine.cc:144-153): the top `refine_ratio` fraction of the
+      // cells by the face-jump indicator (Mesh::kelly_indicator) is refined.  Coarsening is not available in the mini host.
       conf.enter_subsection("control parameters");
-      const double refine_ratio = conf.get_double("adaptive refinment ratio");
+      const double refine_ratio  = conf.get_double("adaptive refinment ratio");
+      const double coarsen_ratio = conf.get_double("adaptive coarsen ratio");
       conf.leave_subsection();
-      const int           n  = degree == 1 ? 8 : 27;
-      const int64_t       nc = triangulation->n_cells();
-      std::vector<double> ind(nc, 0.0);
-      for (int64_t e = 0; e < nc; ++e)
+      if (coarsen_ratio != 0.0)
         {
-          double s = 0.0;
-          for (int c = 0; c < 18; ++c)
-            {
-              double lo = 1e300, hi = -1e300;
-              for (int a = 0; a < n; ++a)
-                {
-                  const double v = old_sol[(size_t)18 * old_tab->cell_nodes[(size_t)e * n + a] + c];
-                  lo             = std::min(lo, v);
-                  hi             = std::max(hi, v);
-                }
-              s += (hi - lo) * (hi - lo);
-            }
-          ind[e] = s;
+          gpu = old_gpu;
+          throw std::runtime_error("FemGL::refine_grid: \"adaptive coarsen ratio\" != 0 is not supported by this host (no coarsening); "
+                                   "the reference's default is 0.0 (declare.cc:258)");
         }
-      std::vector<double> sorted(ind);
-      std::sort(sorted.begin(), sorted.end());
-      const int64_t n_ref = (int64_t)std::floor(refine_ratio * (double)nc);
-      const double  thr   = n_ref > 0 ? sorted[nc - n_ref] : 1e300;
+      check(vh_get_solution(old_gpu, host_solution.data()), "refine_grid"); // the estimator runs on the host mesh (refine.cc:144)
+      std::vector<double> eta;
+      triangulation->kelly_indicator(host_solution, eta);
+      const int64_t        nc = triangulation->n_cells();
+      std::vector<int64_t> order(nc);
       for (int64_t e = 0; e < nc; ++e)
-        flags[e] = ind[e] >= thr && ind[e] > 0.0;
+        order[e] = e;
+      std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return eta[x] > eta[y]; });
+      const int64_t n_ref = (int64_t)std::floor(refine_ratio * (double)nc); // exactly this many cells (fixed NUMBER)
+      for (int64_t k = 0; k < n_ref; ++k)
+        flags[order[k]] = 1;
     }
   triangulation->refine(flags);
-  // SolutionTransfer::interpolate (refine.cc:128-130,171-175): FE interpolation of the old field at the new nodes
-  triangulation->finalize(1);
-  std::vector<double> new_sol;
-  triangulation->interpolate_from(*old_mesh, old_sol, new_sol);
-  host_solution = new_sol;
-  setup_system(); // re-creates the GPU context for the new mesh and uploads host_solution (cycle > 0 keeps it)
+  const double t_mesh = now_ms();
+  setup_system(); // tables + GPU context of the new mesh (no state yet)
+  const double t_setup = now_ms();
   pcout << (refinement_strategy == "global" ? "setup_system() call is done ! this is global refinment" : "setup_system() call is done !")
         << std::endl;
+  // SolutionTransfer::interpolate + constraints_solution.distribute + ghosted copy (refine.cc:128-130, 171-175), on the device
+  std::vector<int32_t> tptr, tsrc;
+  std::vector<double>  tw;
+  triangulation->transfer_table(*old_mesh, tptr, tsrc, tw);
+  check(vh_transfer_solution(gpu, old_gpu, (int32_t)tptr.size() - 1, tptr.data(), tsrc.data(), tw.data()), "refine_grid");
+  vh_destroy(old_gpu);
+  host_solution.assign((size_t)18 * tables->n_owned_nodes, 0.0);
+  last_setup_ms = now_ms() - t_begin;
+  pcout << " refine_grid timings [ms]: estimate + refine " << t_mesh - t_begin << ", tables + GPU context " << t_setup - t_mesh
+        << ", solution transfer " << now_ms() - t_setup << std::endl;
   if (refinement_strategy != "global")
     pcout << "adaptive_refine_grid() call is done !" << std::endl;
 }
@@ -452,6 +453,8 @@ void FemGL<dim>::run()
           rec.t_newton_ms = now_ms() - t0;
           pcout << " newton iteration is done !" << std::endl;
           output_results("./refine-cycle_" + std::to_string(cycle) + "/");
+          rec.t_setup_ms = last_setup_ms; // context (re)build + state upload / transfer before the first step of a cycle
+          last_setup_ms  = 0.0;
           rec.rhs_norm   = system_rhs_l2;
           rec.linear_its = last_linear_its;
           rec.residual   = residual_l2;

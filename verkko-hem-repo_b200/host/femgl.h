@@ -42,6 +42,7 @@ public:
     int          trials;       // compute_residual() calls        (iteration.cc:187)
     double       energy;       // GL functional of the accepted state (not evaluated by the reference)
     double       t_assemble_ms, t_solve_ms, t_newton_ms;
+    double       t_setup_ms;   // tables + vh_create (+ vh_transfer_solution after refine_grid) charged to the cycle's first step
   };
   const std::vector<StepRecord> &history() const { return records; }
   const std::vector<double>     &solution() const { return host_solution; }
@@ -78,6 +79,7 @@ private:
   // quantities the reference keeps in vectors and queries with l2_norm()
   double system_rhs_l2 = 0, residual_l2 = 0, last_alpha = 0;
   int    last_linear_its = 0, last_trials = 0;
+  double last_setup_ms = 0;
 
   std::ostream           *out;
   std::vector<StepRecord> records;

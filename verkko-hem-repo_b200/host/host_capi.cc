@@ -240,6 +240,44 @@ int vhh_mesh_interpolate(void *new_mesh, void *old_mesh, const double *old_value
       return -1;
     }
 }
+// transfer table of Mesh::transfer_table (single rank: global == local node ids).  ptr[n_nodes+1]; src / weight must hold
+// n_nodes * (8 | 27) entries; returns the number of entries or -1.
+int64_t vhh_mesh_transfer_table(void *new_mesh, void *old_mesh, int32_t *ptr, int32_t *src, double *weight)
+{
+  try
+    {
+      Mesh                *N = static_cast<Mesh *>(new_mesh), *O = static_cast<Mesh *>(old_mesh);
+      std::vector<int32_t> p, s;
+      std::vector<double>  w;
+      N->transfer_table(*O, p, s, w);
+      std::memcpy(ptr, p.data(), p.size() * sizeof(int32_t));
+      std::memcpy(src, s.data(), s.size() * sizeof(int32_t));
+      std::memcpy(weight, w.data(), w.size() * sizeof(double));
+      return (int64_t)s.size();
+    }
+  catch (const std::exception &e)
+    {
+      g_err = e.what();
+      return -1;
+    }
+}
+// Kelly-type refinement indicator of Mesh::kelly_indicator; values in global node order, eta[n_cells]
+int vhh_mesh_kelly(void *mesh, const double *values, double *eta)
+{
+  try
+    {
+      Mesh               *M = static_cast<Mesh *>(mesh);
+      std::vector<double> v(values, values + 18 * M->n_nodes), e;
+      M->kelly_indicator(v, e);
+      std::memcpy(eta, e.data(), e.size() * sizeof(double));
+      return 0;
+    }
+  catch (const std::exception &e)
+    {
+      g_err = e.what();
+      return -1;
+    }
+}
 void *vhh_mesh_clone(void *m) { return new Mesh(*static_cast<Mesh *>(m)); }
 void  vhh_mesh_node_xyz(void *m, double *out)
 {

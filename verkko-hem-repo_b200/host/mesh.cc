@@ -601,25 +601,32 @@ void Mesh::finalize(int n_ranks_)
   }
 }
 
-void Mesh::interpolate_from(const Mesh &old_mesh, const std::vector<double> &old_values, std::vector<double> &new_values) const
+namespace
+{
+inline uint64_t leaf_key(int level, const int64_t g[3])
+{
+  return ((uint64_t)level << 58) | ((uint64_t)g[0] << 38) | ((uint64_t)g[1] << 19) | (uint64_t)g[2];
+}
+} // namespace
+
+void Mesh::transfer_table(const Mesh &old_mesh, std::vector<int32_t> &ptr, std::vector<int32_t> &src, std::vector<double> &weight) const
 {
   if (n_ranks < 1 || old_mesh.n_ranks < 1)
-    throw std::runtime_error("Mesh::interpolate_from: both meshes must be finalized");
-  if (old_mesh.degree != degree || (int64_t)old_values.size() != 18 * old_mesh.n_nodes)
-    throw std::invalid_argument("Mesh::interpolate_from: incompatible meshes / value array");
+    throw std::runtime_error("Mesh::transfer_table: both meshes must be finalized");
+  if (old_mesh.degree != degree)
+    throw std::invalid_argument("Mesh::transfer_table: incompatible meshes");
   const int n = degree == 1 ? 8 : 27;
   std::unordered_map<uint64_t, int64_t> where;
   where.reserve(old_mesh.leaves.size() * 2);
-  auto pack = [](int level, const int64_t g[3]) {
-    return ((uint64_t)level << 58) | ((uint64_t)g[0] << 38) | ((uint64_t)g[1] << 19) | (uint64_t)g[2];
-  };
   for (int64_t e = 0; e < old_mesh.n_cells(); ++e)
     {
       const Leaf   &l    = old_mesh.leaves[e];
       const int64_t g[3] = {l.g[0], l.g[1], l.g[2]};
-      where[pack(l.level, g)] = e;
+      where[leaf_key(l.level, g)] = e;
     }
-  new_values.assign((size_t)18 * n_nodes, 0.0);
+  ptr.assign(1, 0);
+  src.clear();
+  weight.clear();
   for (int64_t nd = 0; nd < n_nodes; ++nd)
     {
       const int64_t *X = &node_lattice[(size_t)3 * nd];
@@ -636,12 +643,12 @@ void Mesh::interpolate_from(const Mesh &old_mesh, const std::vector<double> &old
                 g[d] = ((int64_t)base[d] << lev) - 1;
               xi[d] = (double)(X[d] - g[d] * cs) / (double)cs;
             }
-          auto it = where.find(pack(lev, g));
+          auto it = where.find(leaf_key(lev, g));
           if (it != where.end())
             cell = it->second;
         }
       if (cell < 0)
-        throw std::runtime_error("Mesh::interpolate_from: node outside the old mesh");
+        throw std::runtime_error("Mesh::transfer_table: node outside the old mesh");
       for (int a = 0; a < n; ++a)
         {
           int t[3];
@@ -649,11 +656,103 @@ void Mesh::interpolate_from(const Mesh &old_mesh, const std::vector<double> &old
           const double w = lagrange(degree, t[0], xi[0]) * lagrange(degree, t[1], xi[1]) * lagrange(degree, t[2], xi[2]);
           if (w == 0.0)
             continue;
-          const double *src = &old_values[(size_t)18 * old_mesh.cell_nodes[(size_t)cell * n + a]];
-          double       *dst = &new_values[(size_t)18 * nd];
-          for (int c = 0; c < 18; ++c)
-            dst[c] += w * src[c];
+          src.push_back((int32_t)old_mesh.cell_nodes[(size_t)cell * n + a]);
+          weight.push_back(w);
         }
+      ptr.push_back((int32_t)src.size());
+    }
+}
+
+void Mesh::interpolate_from(const Mesh &old_mesh, const std::vector<double> &old_values, std::vector<double> &new_values) const
+{
+  if ((int64_t)old_values.size() != 18 * old_mesh.n_nodes)
+    throw std::invalid_argument("Mesh::interpolate_from: incompatible meshes / value array");
+  std::vector<int32_t> ptr, src;
+  std::vector<double>  w;
+  transfer_table(old_mesh, ptr, src, w);
+  new_values.assign((size_t)18 * n_nodes, 0.0);
+  for (int64_t nd = 0; nd < n_nodes; ++nd)
+    for (int k = ptr[nd]; k < ptr[nd + 1]; ++k)
+      for (int c = 0; c < 18; ++c)
+        new_values[(size_t)18 * nd + c] += w[k] * old_values[(size_t)18 * src[k] + c];
+}
+
+void Mesh::kelly_indicator(const std::vector<double> &values, std::vector<double> &eta) const
+{
+  if (n_ranks < 1 || (int64_t)values.size() != 18 * n_nodes)
+    throw std::invalid_argument("Mesh::kelly_indicator: mesh not finalized or value array of the wrong size");
+  const int     n  = degree == 1 ? 8 : 27;
+  const int64_t nc = n_cells();
+  std::unordered_map<uint64_t, int64_t> where;
+  where.reserve(leaves.size() * 2);
+  for (int64_t e = 0; e < nc; ++e)
+    {
+      const int64_t g[3] = {leaves[e].g[0], leaves[e].g[1], leaves[e].g[2]};
+      where[leaf_key(leaves[e].level, g)] = e;
+    }
+  // cell-mean gradient from the 8 vertex values (the first 8 local nodes are the vertices for Q1 and Q2)
+  std::vector<double> grad((size_t)nc * 54), hh((size_t)nc * 3);
+  for (int64_t e = 0; e < nc; ++e)
+    {
+      double o[3];
+      cell_box(e, o, &hh[3 * (size_t)e]);
+      for (int c = 0; c < 18; ++c)
+        for (int d = 0; d < 3; ++d)
+          {
+            double s = 0.0;
+            for (int v = 0; v < 8; ++v)
+              s += (((v >> d) & 1) ? 1.0 : -1.0) * values[(size_t)18 * cell_nodes[(size_t)e * n + v] + c];
+            grad[(size_t)e * 54 + 3 * c + d] = 0.25 * s / hh[3 * (size_t)e + d];
+          }
+    }
+  // integer coordinates in units of the finest half-cell: a level-l cell spans 2 << (Lmax - l) units per direction
+  eta.assign((size_t)nc, 0.0);
+  for (int64_t e = 0; e < nc; ++e)
+    {
+      const Leaf   &l  = leaves[e];
+      const int64_t cs = (int64_t)2 << (Lmax - l.level);
+      const double *h  = &hh[3 * (size_t)e];
+      const double  hK = std::sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]);
+      double        s  = 0.0;
+      for (int f = 0; f < 6; ++f)
+        {
+          const int    d = f / 2, side = f % 2, d0 = (d + 1) % 3, d1 = (d + 2) % 3;
+          const double area = h[d0] * h[d1];
+          for (int q = 0; q < 4; ++q)
+            { // a point just across the face, at the centre of quarter q of the face
+              int64_t X[3];
+              X[d]  = l.g[d] * cs + (side ? cs : -1);
+              X[d0] = l.g[d0] * cs + ((q & 1) ? (3 * cs) / 4 : cs / 4);
+              X[d1] = l.g[d1] * cs + ((q & 2) ? (3 * cs) / 4 : cs / 4);
+              const int64_t ext = ((int64_t)base[d] << Lmax) * 2;
+              if (X[d] < 0 || X[d] >= ext)
+                {
+                  const int b = bid[f];
+                  if (b < 5 || b > 10)
+                    break; // a physical boundary face: no contribution (no Neumann data, refine.cc:146)
+                  X[d] = X[d] < 0 ? ext - 1 : 0; // periodic pair: continue on the opposite face
+                }
+              int64_t nb = -1;
+              for (int lev = Lmax; lev >= 0 && nb < 0; --lev)
+                {
+                  const int64_t c2   = (int64_t)2 << (Lmax - lev);
+                  const int64_t g[3] = {X[0] / c2, X[1] / c2, X[2] / c2};
+                  auto          it   = where.find(leaf_key(lev, g));
+                  if (it != where.end())
+                    nb = it->second;
+                }
+              if (nb < 0)
+                continue;
+              double j2 = 0.0;
+              for (int c = 0; c < 18; ++c)
+                {
+                  const double j = grad[(size_t)nb * 54 + 3 * c + d] - grad[(size_t)e * 54 + 3 * c + d];
+                  j2 += j * j;
+                }
+              s += hK / 24.0 * 0.25 * area * j2;
+            }
+        }
+      eta[e] = std::sqrt(s);
     }
 }
 

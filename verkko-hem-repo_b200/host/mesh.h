@@ -72,6 +72,14 @@ public:
   // nodes of `old_mesh` (global node order, 18 values per node) at this mesh's nodes.  Both meshes must be finalized
   // and this mesh must be a refinement of old_mesh.
   void interpolate_from(const Mesh &old_mesh, const std::vector<double> &old_values, std::vector<double> &new_values) const;
+  // The same interpolation as a table, for the device-side transfer (vh_transfer_solution): row i = node i of this mesh,
+  // entries (node of old_mesh, weight) = the shape functions of the old cell that contains the node.  Global node ids.
+  void transfer_table(const Mesh &old_mesh, std::vector<int32_t> &ptr, std::vector<int32_t> &src, std::vector<double> &weight) const;
+  // Kelly-type refinement indicator (refine.cc:144-148, KellyErrorEstimator with no Neumann data): per cell
+  //   eta_K^2 = sum_{interior faces F of K} h_K/24 * |F| * sum_c [d_n u_c]^2,
+  // the jump of the normal derivative taken between the cell-mean gradients of the two leaves that share the face
+  // (quarter-face sampling, so finer and coarser neighbours across hanging-node faces are handled; periodic faces wrap).
+  void kelly_indicator(const std::vector<double> &values, std::vector<double> &eta) const;
 
   // ---- global data, valid after finalize() ----
   int                  degree;
