@@ -430,18 +430,42 @@ def kernel_numbers(ctx, T, info, degree, hbm_peak, peak_src, traffic_key):
     return roof, asm, kern
 
 
-def measure(vh, torch, dist, rank, world, local_rank, degree, refine, global_refine, steps, warmup, want_kernels, want_parity):
-    """Build the workload on `world` ranks and measure it.  Returns the dict of results (rank 0) or None."""
+def build_context(vh, dist, rank, world, local_rank, degree, refine, global_refine, precond, mg_coarsest):
+    """Context of the workload on this rank; with precond == "mg" also the coarser levels of the multigrid hierarchy (the same
+    box refined fewer times, same partition) attached to it.  Returns (mesh, tables, ctx, levels, create seconds)."""
     mesh = build_mesh(world, refine, degree, global_refine)
     T = mesh.tables(rank)
     t0 = time.perf_counter()
     ctx = vh.Context(T, device=local_rank)
-    create_s = time.perf_counter() - t0
-    if world > 1:
-        uid = [vh.Context.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(rank, world, uid[0])
-    ctx.set_coef_vector(coef_vector())
+
+    def init(c):
+        if world > 1:
+            uid = [vh.Context.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            c.comm_init(rank, world, uid[0])
+        c.set_coef_vector(coef_vector())
+
+    init(ctx)
+    levels = [ctx]
+    if precond == "mg":
+        top = global_refine if global_refine is not None else refine
+        mf, Tf, cf = mesh, T, ctx
+        for lv in range(top - 1, mg_coarsest - 1, -1):
+            mc = build_mesh(world, lv if global_refine is None else None, degree, lv if global_refine is not None else None)
+            Tc = mc.tables(rank)
+            cc = vh.Context(Tc, device=local_rank)
+            init(cc)
+            cf.mg_attach(cc, *vh.mg_prolongation(mf, Tf, mc, Tc))
+            levels.append(cc)
+            mf, Tf, cf = mc, Tc, cc
+        ctx.set_preconditioner("multigrid")
+    return mesh, T, ctx, levels, time.perf_counter() - t0
+
+
+def measure(vh, torch, dist, rank, world, local_rank, degree, refine, global_refine, steps, warmup, want_kernels, want_parity,
+            precond="bj", mg_coarsest=5):
+    """Build the workload on `world` ranks and measure it.  Returns the dict of results (rank 0) or None."""
+    mesh, T, ctx, levels, create_s = build_context(vh, dist, rank, world, local_rank, degree, refine, global_refine, precond, mg_coarsest)
     x0 = initial_state(T)[:18 * T.n_owned_nodes]
     n_dofs = 18 * mesh.n_nodes
     info = ctx.info()
@@ -513,12 +537,17 @@ def measure(vh, torch, dist, rank, world, local_rank, degree, refine, global_ref
         par = None
         if rank == 0:
             try:
-                m1 = build_mesh(1, refine, degree, global_refine) if global_refine is not None else \
-                    vh.Mesh(degree, [-20.0] * 3, [20.0, 20.0, -20.0 + 40.0 * world], base=(1, 1, world),
-                            face_bid=(1, 1, 1, 1, 4, 4), n_global_refine=refine).finalize(1)
-                T1 = m1.tables(0)
-                c1 = vh.Context(T1, device=local_rank)
-                c1.set_coef_vector(coef_vector())
+                if global_refine is not None:  # strong scaling: the same cube on one rank, same preconditioner
+                    _, T1, c1, lv1, _ = build_context(vh, None, 0, 1, local_rank, degree, None, global_refine, precond, mg_coarsest)
+                else:                          # weak scaling: the N stacked root cubes on one rank (block-Jacobi runs only)
+                    if precond == "mg":
+                        raise RuntimeError("parity run with the multigrid preconditioner needs a strong-scaling workload")
+                    m1 = vh.Mesh(degree, [-20.0] * 3, [20.0, 20.0, -20.0 + 40.0 * world], base=(1, 1, world),
+                                 face_bid=(1, 1, 1, 1, 4, 4), n_global_refine=refine).finalize(1)
+                    T1 = m1.tables(0)
+                    c1 = vh.Context(T1, device=local_rank)
+                    c1.set_coef_vector(coef_vector())
+                    lv1 = [c1]
                 x1 = initial_state(T1)[:18 * T1.n_owned_nodes]
                 n_par = min(3, len(runs[0]))
                 ms1, runs1 = run_steps(c1, x1, n_par)
@@ -531,12 +560,16 @@ def measure(vh, torch, dist, rank, world, local_rank, degree, refine, global_ref
                        "single_gpu_ms_per_step_first_steps": ms1 / n_par,
                        "n_gpu_ms_first_steps_note": "the 1-GPU time covers only the first %d steps of a run (fewer linear "
                                                     "iterations than the average step)" % n_par}
-                c1.close()
+                for c in lv1:
+                    c.close()
             except Exception as exc:
                 par = {"error": str(exc)}
         barrier()
         res["multi_gpu_parity"] = par
-    ctx.close()
+    res["preconditioner"] = ("multigrid V-cycle, %d levels (coarsest: refinement %d), Chebyshev(1)/block-Jacobi smoothing"
+                             % (len(levels), mg_coarsest)) if precond == "mg" else "nodal 18x18 block-Jacobi"
+    for c in levels:
+        c.close()
     return res
 
 
@@ -567,7 +600,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     main = measure(vh, torch, dist, rank, world, local_rank, args.degree, args.refine, args.global_refine, args.steps, args.warmup,
-                   want_kernels=True, want_parity=not args.no_parity)
+                   want_kernels=True, want_parity=not args.no_parity, precond=args.precond, mg_coarsest=args.mg_coarsest)
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "warm-up + timed + e2e Newton steps of the headline workload"
@@ -612,7 +645,7 @@ def run_ours(args):
                                 "between launches" % (main["roofline"]["moved_bytes_per_launch"] / 1e9),
                           "parallelism": "subdomain x%d (Morton partition, NCCL halo + peer-memory all-reduce)" % world,
                           "stop_rule": "run.cc:234-250: a run ends at residual <= 5e-6, the next timed step starts a new run from the IC"}}
-        for k in ("newton", "final_energy", "phase_ms_per_step", "gmres_its_per_step", "ms_per_gmres_it", "halo_ms_per_exchange",
+        for k in ("preconditioner", "newton", "final_energy", "phase_ms_per_step", "gmres_its_per_step", "ms_per_gmres_it", "halo_ms_per_exchange",
                   "allreduce_ms_per_dot", "roofline", "assembly", "kernels", "e2e", "gpu_launches", "multi_gpu_parity", "memory",
                   "context_create_s"):
             if k in main:
@@ -653,6 +686,10 @@ def main():
     ap.add_argument("--degree", type=int, default=None)
     ap.add_argument("--global-refine", type=int, default=None,
                     help="override: one cube with this many global refinements split over the GPUs (strong scaling)")
+    ap.add_argument("--precond", default="bj", choices=["bj", "mg"],
+                    help="GMRES preconditioner: bj = nodal block-Jacobi (north star), mg = geometric multigrid V-cycle over the "
+                         "coarser global refinements of the same box (Q1, strong-scaling workloads)")
+    ap.add_argument("--mg-coarsest", type=int, default=5, help="coarsest refinement level of the multigrid hierarchy")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c2", action="store_true", help="skip the configs[1] measurement next to the headline (N = 1)")
     ap.add_argument("--no-parity", action="store_true", help="skip the single-GPU parity run of rank 0 (N > 1)")

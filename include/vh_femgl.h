@@ -132,6 +132,28 @@ int vh_assemble(vh_ctx *ctx, double *rhs_l2);
  *      Iteration semantics follow deal.II SolverFGMRES.  VH_ERR_NOT_CONVERGED after max_it. ---- */
 int vh_solve(vh_ctx *ctx, double tol_rel, int max_it, int restart, int *iterations, double *final_residual);
 
+/* ---- preconditioner of vh_solve.  The reference builds a Trilinos-ML AMG hierarchy inside solve() (solve.cc:130-154);
+ *      the north star prescribes nodal block-Jacobi, which is the default here.  For meshes that come with a hierarchy
+ *      (global refinement: the host keeps the coarser meshes, deal.II: distribute_mg_dofs / MGTransfer) a geometric
+ *      multigrid V-cycle can replace it: every coarser level is an ordinary context created from that level's tables on
+ *      the same rank partition (vh_create, vh_comm_init, vh_set_coefficients), attached with its prolongation
+ *          x_fine[i] = sum_{k in [ptr[i], ptr[i+1])} weight[k] * x_coarse[coarse_node[k]]
+ *      (row i = LOCAL node i of the fine level, owned and ghost; coarse_node = LOCAL ids on the coarse level; rows of owned
+ *      nodes must be complete, rows of ghost nodes list the parents that are local).  Levels chain: attach level l+1 to l.
+ *      The coarse Jacobians are re-discretised at the injected Newton state in every vh_solve. ---- */
+typedef struct vh_mg_params
+{
+  int32_t pre, post;        /* Chebyshev degree of the pre- / post-smoother around block-Jacobi (default 1, 1) */
+  double  smoothing_range;  /* smoother interval [lambda_max/range, lambda_max] of M^-1 A          (default 4)    */
+  int32_t coarse_degree;    /* Chebyshev degree on the coarsest level                              (default 8)    */
+  double  coarse_range;     /*                                                                     (default 30)   */
+  int32_t n_power;          /* power iterations for lambda_max, once per level and context         (default 8)    */
+  double  safety;           /* lambda_max is multiplied by this                                    (default 1.1)  */
+} vh_mg_params;
+int vh_mg_attach(vh_ctx *fine, vh_ctx *coarse, int32_t n_rows, const int32_t *ptr, const int32_t *coarse_node, const double *weight);
+/* kind: 0 = block-Jacobi, 1 = multigrid V-cycle (needs vh_mg_attach); params may be NULL (defaults).  Collective. */
+int vh_set_preconditioner(vh_ctx *ctx, int kind, const vh_mg_params *params);
+
 /* ---- newton_iteration() pieces (iteration.cc:128-210) ---- */
 int vh_line_search_trial(vh_ctx *ctx, double alpha); /* trial = x + alpha*delta; constraints_solution.distribute; ghosts */
 int vh_residual(vh_ctx *ctx, double *l2);            /* compute_residual() on the trial vector ('l', residual.cc:164) */

@@ -392,3 +392,168 @@ def newton_step(T, x, coef, lin_tol, max_lin_it=10000, restart=30, damped=True, 
             break
     return dict(x=xt, delta=d, rhs=rhs, rhs_norm=bn, lin_its=its, lin_res=lres, res_norm=cur, alpha=alpha,
                 n_trials=n_trials, A=A, residual=r)
+
+
+# ------------------------------------------------------------------------------------------
+# geometric multigrid V-cycle as the GMRES preconditioner (csrc/vh_multigrid.cu restated; the GPU's optional replacement of
+# the reference's ML-AMG, solve.cc:130-154).  Levels: finest first, single rank.  Same arithmetic as the device code:
+# re-discretised coarse Jacobians at the injected state, Chebyshev around nodal block-Jacobi, lambda_max by power iteration
+# from a fixed start vector ONCE per level (kept in `lam`), zero initial guess, Dirichlet DoFs masked after the transfers.
+# ------------------------------------------------------------------------------------------
+MG_DEFAULTS = dict(pre=1, post=1, smoothing_range=4.0, coarse_degree=8, coarse_range=30.0, n_power=8, safety=1.1)
+
+
+def _dirichlet_mask(T):
+    m = np.zeros(18 * T.n_local_nodes, dtype=bool)
+    if T.c_dof.size:
+        m[T.c_dof[np.diff(T.c_ptr) == 0]] = True
+    return m
+
+
+def mg_setup(tables, prolongations, x_fine, coef, lam=None, **params):
+    """tables: per-level RankTables (finest first); prolongations[k] = (ptr, coarse_node, weight) between level k and k+1 (the
+    table vh_mg_attach receives).  Returns (levels, lam): lam is the list of eigenvalue bounds, to be passed back in for the
+    following Newton steps (the device estimates them once per context)."""
+    import scipy.sparse as sp
+    P = {**MG_DEFAULTS, **params}
+    levels = []
+    x = np.asarray(x_fine, dtype=np.float64)
+    for k, T in enumerate(tables):
+        assert T.n_ghost_nodes == 0
+        A, _ = assemble_global(T, x, coef, True)
+        A = sp.csr_matrix(A)
+        Dinv = block_jacobi_inverse(A, T.n_owned_nodes)
+        nb = T.n_owned_nodes
+        prec = (lambda D, n: (lambda v: np.einsum("ijk,ik->ij", D, v.reshape(n, 18)).ravel()))(Dinv, nb)
+        mask = _dirichlet_mask(T)
+        lev = dict(T=T, A=A, prec=prec, mask=mask)
+        if lam is not None:
+            lev["lam"] = lam[k]
+        else:
+            g = (18 * T.node_global[:nb, None] + np.arange(18)[None, :]).ravel()
+            v = np.where(g % 2 == 1, -1.0, 1.0) * (1.0 + (g % 7) / 7.0)
+            v[mask] = 0.0
+            for _ in range(P["n_power"]):
+                v = v / np.sqrt(v @ v)
+                v = prec(A @ v)
+            lev["lam"] = P["safety"] * float(np.sqrt(v @ v))
+        if k + 1 < len(tables):
+            ptr, cn, w = prolongations[k]
+            n_c = tables[k + 1].n_local_nodes
+            Pn = sp.csr_matrix((w, cn, ptr), shape=(T.n_local_nodes, n_c))
+            lev["P"] = sp.kron(Pn, sp.identity(18), format="csr")
+            # injection of the Newton state: the fine node that coincides with the coarse node (its weight-1 entry)
+            rows = np.repeat(np.arange(T.n_local_nodes), np.diff(ptr))
+            one = np.abs(w - 1.0) <= 1e-12
+            inj = np.zeros(n_c, dtype=np.int64)
+            inj[cn[one]] = rows[one]
+            x = x.reshape(-1, 18)[inj].ravel()
+        levels.append(lev)
+    return levels, [lev["lam"] for lev in levels]
+
+
+def _chebyshev(lev, b, x, degree, ratio):
+    A, prec = lev["A"], lev["prec"]
+    lmax, lmin = lev["lam"], lev["lam"] / ratio
+    theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
+    sigma = theta / delta
+    rho = 1.0 / sigma
+    r = b if x is None else b - A @ x
+    d = prec(r) * (1.0 / theta)
+    x = d.copy() if x is None else x + d
+    for _ in range(1, degree):
+        rho_new = 1.0 / (2.0 * sigma - rho)
+        r = b - A @ x
+        d = (rho_new * rho) * d + (2.0 * rho_new / delta) * prec(r)
+        x = x + d
+        rho = rho_new
+    return x
+
+
+def mg_vcycle(levels, k, b, **params):
+    """z = V(b) on level k with zero initial guess."""
+    P = {**MG_DEFAULTS, **params}
+    lev = levels[k]
+    if k == len(levels) - 1:
+        return _chebyshev(lev, b, None, P["coarse_degree"], P["coarse_range"])
+    x = _chebyshev(lev, b, None, P["pre"], P["smoothing_range"])
+    r = b - lev["A"] @ x
+    rc = lev["P"].T @ r
+    rc[levels[k + 1]["mask"]] = 0.0
+    xc = mg_vcycle(levels, k + 1, rc, **params)
+    x = x + np.where(lev["mask"], 0.0, lev["P"] @ xc)
+    x[lev["mask"]] = 0.0
+    return _chebyshev(lev, b, x, P["post"], P["smoothing_range"])
+
+
+def gmres_right(A, b, prec, tol_abs, max_it=10000, restart=30):
+    """gmres_block_jacobi with an arbitrary fixed right preconditioner (callable); same iteration semantics (A.5)."""
+    NO = b.size
+
+    def check(step, val):
+        if val <= tol_abs:
+            return "success"
+        if step >= max_it or np.isnan(val):
+            return "failure"
+        return "iterate"
+
+    x = np.zeros(NO)
+    acc, res, state, m = 0, 0.0, "iterate", restart
+    while state == "iterate":
+        aux = b - A @ x if np.any(x) else b.copy()
+        beta = float(np.sqrt(aux @ aux))
+        res = beta
+        state = check(acc, res)
+        if state == "success":
+            break
+        H = np.zeros((m + 1, m))
+        V = np.zeros((m, NO))
+        y = np.zeros(0)
+        a = beta
+        for j in range(m):
+            V[j] = aux / a if a != 0 else 0.0
+            aux = A @ prec(V[j])
+            H[0, j] = aux @ V[0]
+            for i in range(1, j + 1):
+                aux = aux - H[i - 1, j] * V[i - 1]
+                H[i, j] = aux @ V[i]
+            aux = aux - H[j, j] * V[j]
+            a = float(np.sqrt(aux @ aux))
+            H[j + 1, j] = a
+            if j > 0:
+                H1 = H[:j + 1, :j]
+                prhs = np.zeros(j + 1)
+                prhs[0] = beta
+                y, _, _, _ = np.linalg.lstsq(H1, prhs, rcond=None)
+                res = float(np.linalg.norm(prhs - H1 @ y))
+                acc += 1
+                state = check(acc, res)
+                if state != "iterate":
+                    break
+        if y.size:
+            x = x + prec(y @ V[:y.size])
+    return x, acc, res, state == "success"
+
+
+def newton_step_mg(tables, prolongations, x, coef, lin_tol, lam=None, damped=True, step=0.83, **params):
+    """newton_step with the multigrid V-cycle as the GMRES preconditioner.  Returns (dict as newton_step, lam)."""
+    T = tables[0]
+    levels, lam = mg_setup(tables, prolongations, x, coef, lam=lam, **params)
+    A = levels[0]["A"]
+    _, rhs = assemble_global(T, x, coef, False)
+    bn = float(np.linalg.norm(rhs))
+    d, its, lres, ok = gmres_right(A, rhs, lambda v: mg_vcycle(levels, 0, v, **params), lin_tol * bn)
+    if not ok:
+        raise RuntimeError("oracle GMRES (multigrid) did not converge")
+    d = distribute(T, d)
+    alpha, n_trials, cur, xt = 1.0, 0, bn, x
+    for i in range(100 if damped else 1):
+        alpha = step ** i if damped else 1.0
+        xt = distribute(T, x + alpha * d)
+        _, r = assemble_global(T, xt, coef, False)
+        cur = float(np.linalg.norm(r))
+        n_trials += 1
+        if damped and cur < bn:
+            break
+    return dict(x=xt, delta=d, rhs=rhs, rhs_norm=bn, lin_its=its, lin_res=lres, res_norm=cur, alpha=alpha, n_trials=n_trials,
+                A=A, levels=levels), lam

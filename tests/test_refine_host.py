@@ -72,3 +72,24 @@ def test_kelly_indicator_across_hanging_faces_and_periodic_pairs():
     g[:, 0] = np.abs(Xp[:, 2])                                       # z is a wall direction: only the kink at z = 0 counts
     eta = per.kelly_indicator(g.ravel())
     assert eta[np.abs(cp[:, 2]) < 0.5].min() > 0 and np.abs(eta[np.abs(cp[:, 2]) > 0.5]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("n_ranks", [1, 2, 4, 8])
+def test_multigrid_prolongation_tables_on_nested_partitions(n_ranks):
+    """The table vh_mg_attach receives: rows of owned fine nodes are complete interpolations whose parents are local on the
+    same rank's coarse level, and every coarse owned node coincides with a fine node owned by the same rank."""
+    mf = vh.Mesh(1, [-20.0] * 3, [20.0] * 3, n_global_refine=3).finalize(n_ranks)
+    mc = vh.Mesh(1, [-20.0] * 3, [20.0] * 3, n_global_refine=2).finalize(n_ranks)
+    for r in range(n_ranks):
+        Tf, Tc = mf.tables(r), mc.tables(r)
+        ptr, idx, w = vh.mg_prolongation(mf, Tf, mc, Tc)
+        assert ptr.size == Tf.n_local_nodes + 1 and idx.max() < Tc.n_local_nodes
+        rows = np.repeat(np.arange(Tf.n_local_nodes), np.diff(ptr))
+        rowsum = np.bincount(rows, weights=w, minlength=Tf.n_local_nodes)
+        assert np.abs(rowsum[:Tf.n_owned_nodes] - 1.0).max() <= 1e-14
+        one = (np.abs(w - 1.0) <= 1e-14) & (rows < Tf.n_owned_nodes)
+        assert np.isin(np.arange(Tc.n_owned_nodes), idx[one]).all()
+        # trilinear: a linear function of the coordinates is reproduced at the owned fine nodes
+        f = lambda X: 1.0 + 0.5 * X[:, 0] - 0.25 * X[:, 1] + 2.0 * X[:, 2]  # noqa: E731
+        got = np.bincount(rows, weights=w * f(Tc.node_xyz)[idx], minlength=Tf.n_local_nodes)
+        assert np.abs(got[:Tf.n_owned_nodes] - f(Tf.node_xyz)[:Tf.n_owned_nodes]).max() <= 1e-12

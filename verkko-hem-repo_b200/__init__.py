@@ -156,6 +156,7 @@ class Mesh:
         base = np.ascontiguousarray(base, dtype=np.int32)
         bid = np.ascontiguousarray(face_bid, dtype=np.int32)
         self.degree = degree
+        self.lo, self.hi, self.base, self.n_global_refine, self.locally_refined = lo.copy(), hi.copy(), base.copy(), n_global_refine, False
         self._h = L.vhh_mesh_create(degree, lo.ctypes.data_as(_dp), hi.ctypes.data_as(_dp), base.ctypes.data_as(_i32p),
                                     bid.ctypes.data_as(_i32p), n_global_refine)
         if not self._h:
@@ -175,6 +176,7 @@ class Mesh:
         flags = np.ascontiguousarray(flags, dtype=np.uint8)
         if host_lib().vhh_mesh_refine(self._h, flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), flags.size) != 0:
             raise RuntimeError(host_lib().vhh_last_error().decode())
+        self.locally_refined = True
 
     def finalize(self, n_ranks=1):
         if host_lib().vhh_mesh_finalize(self._h, n_ranks) != 0:
@@ -194,6 +196,7 @@ class Mesh:
     def clone(self):
         m = Mesh.__new__(Mesh)
         m.degree = self.degree
+        m.lo, m.hi, m.base, m.n_global_refine, m.locally_refined = self.lo, self.hi, self.base, self.n_global_refine, self.locally_refined
         m._h = host_lib().vhh_mesh_clone(self._h)
         m.n_ranks = 0
         return m
@@ -246,6 +249,49 @@ def matep(p, t, scc):
     host_lib().vhh_matep(float(p), float(t), int(bool(scc)), out.ctypes.data_as(_dp))
     keys = ["alpha", "beta1", "beta2", "beta3", "beta4", "beta5", "gapA", "gapB", "fA", "fB", "Tcp_mK", "tAB_RWS"]
     return dict(zip(keys, out.tolist()))
+
+
+def mg_prolongation(mesh_f, Tf, mesh_c, Tc):
+    """Prolongation table between two consecutive levels of a globally refined Q1 box mesh for ``vh_mg_attach``: row i =
+    LOCAL node i of the fine level (owned and ghost), entries = LOCAL nodes of the coarse level with the trilinear weights
+    (1, 1/2, 1/4, 1/8); parents that are not local on this rank's coarse level are dropped (they can only belong to ghost
+    rows).  Stand-in for what deal.II's MGTransfer holds.  Returns (ptr, coarse_node, weight)."""
+    if mesh_f.degree != 1 or mesh_c.degree != 1 or mesh_f.locally_refined or mesh_c.locally_refined:
+        raise ValueError("mg_prolongation: globally refined Q1 meshes only")
+    if mesh_f.n_global_refine != mesh_c.n_global_refine + 1 or Tf.c_master.size or Tc.c_master.size:
+        raise ValueError("mg_prolongation: consecutive refinement levels of one box without periodic / hanging constraints")
+    nf_side = mesh_f.base.astype(np.int64) << mesh_f.n_global_refine           # fine cells per direction
+    hf = (mesh_f.hi - mesh_f.lo) / nf_side
+    If = np.rint((Tf.node_xyz - mesh_f.lo[None, :]) / hf[None, :]).astype(np.int64)       # fine lattice coordinates
+    Ic = np.rint((Tc.node_xyz - mesh_f.lo[None, :]) / (2.0 * hf[None, :])).astype(np.int64)
+    nc1 = (nf_side // 2) + 1
+    key_c = (Ic[:, 2] * nc1[1] + Ic[:, 1]) * nc1[0] + Ic[:, 0]
+    order = np.argsort(key_c)
+    skeys = key_c[order]
+    n = Tf.n_local_nodes
+    rows, cols, vals = [], [], []
+    for corner in range(8):
+        w = np.ones(n)
+        J = np.zeros((n, 3), dtype=np.int64)
+        ok = np.ones(n, dtype=bool)
+        for d in range(3):
+            odd = (If[:, d] & 1) == 1
+            b = (corner >> d) & 1
+            J[:, d] = (If[:, d] >> 1) + np.where(odd, b, 0)
+            w *= np.where(odd, 0.5, 1.0)
+            ok &= odd | (b == 0)          # an even coordinate has one parent in this direction
+        key = (J[:, 2] * nc1[1] + J[:, 1]) * nc1[0] + J[:, 0]
+        pos = np.minimum(np.searchsorted(skeys, key), skeys.size - 1)
+        hit = ok & (skeys[pos] == key)
+        rows.append(np.nonzero(hit)[0])
+        cols.append(order[pos[hit]])
+        vals.append(w[hit])
+    rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+    o = np.lexsort((cols, rows))
+    rows, cols, vals = rows[o], cols[o], vals[o]
+    ptr = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(np.bincount(rows, minlength=n), out=ptr[1:])
+    return ptr, cols.astype(np.int32), vals
 
 
 def periodic_slab(degree, refine, half=(0.5, 0.5, 0.5), base=(1, 1, 1), n_ranks=1):

@@ -16,6 +16,15 @@ VH_OK = 0
 VH_ERR_NOT_CONVERGED = -4
 
 
+class _MGParams(ctypes.Structure):
+    _fields_ = [("pre", ctypes.c_int32), ("post", ctypes.c_int32), ("smoothing_range", ctypes.c_double),
+                ("coarse_degree", ctypes.c_int32), ("coarse_range", ctypes.c_double), ("n_power", ctypes.c_int32),
+                ("safety", ctypes.c_double)]
+
+
+MG_DEFAULTS = dict(pre=1, post=1, smoothing_range=4.0, coarse_degree=8, coarse_range=30.0, n_power=8, safety=1.1)
+
+
 class _Info(ctypes.Structure):
     _fields_ = [("n_owned_dofs", ctypes.c_int64), ("n_local_dofs", ctypes.c_int64), ("nnzb", ctypes.c_int64),
                 ("n_fast_rows", ctypes.c_int64), ("n_slow_cells", ctypes.c_int64), ("device_bytes", ctypes.c_int64),
@@ -47,6 +56,8 @@ def cuda_lib():
         for f in ("vh_set_solution", "vh_get_solution", "vh_get_newton_update", "vh_get_rhs", "vh_get_residual"):
             getattr(L, f).argtypes = [_vp, _dp]
         L.vh_transfer_solution.argtypes = [_vp, _vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _dp]
+        L.vh_mg_attach.argtypes = [_vp, _vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _dp]
+        L.vh_set_preconditioner.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_MGParams)]
         L.vh_assemble.argtypes = [_vp, _dp]
         L.vh_solve.argtypes = [_vp, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), _dp]
         L.vh_line_search_trial.argtypes = [_vp, ctypes.c_double]
@@ -159,6 +170,25 @@ class Context:
         i32 = ctypes.POINTER(ctypes.c_int32)
         self._chk(self.L.vh_transfer_solution(self._h, src_ctx._h, ptr.size - 1, ptr.ctypes.data_as(i32),
                                               src_node.ctypes.data_as(i32), weight.ctypes.data_as(_dp)))
+
+    # --- preconditioner ---
+    def mg_attach(self, coarse_ctx, ptr, coarse_node, weight):
+        """Attach the next coarser multigrid level with its prolongation table (vh_mg_attach)."""
+        ptr = np.ascontiguousarray(ptr, dtype=np.int32)
+        coarse_node = np.ascontiguousarray(coarse_node, dtype=np.int32)
+        weight = np.ascontiguousarray(weight, dtype=np.float64)
+        i32 = ctypes.POINTER(ctypes.c_int32)
+        self._chk(self.L.vh_mg_attach(self._h, coarse_ctx._h, ptr.size - 1, ptr.ctypes.data_as(i32), coarse_node.ctypes.data_as(i32),
+                                      weight.ctypes.data_as(_dp)))
+        self._mg_coarse = coarse_ctx  # keep the level alive as long as this context
+
+    def set_preconditioner(self, kind, **params):
+        """kind: "block-jacobi" | "multigrid" (or 0 | 1); params: fields of vh_mg_params (MG_DEFAULTS)."""
+        k = {"block-jacobi": 0, "bj": 0, "multigrid": 1, "mg": 1}.get(kind, kind)
+        p = None
+        if params:
+            p = _MGParams(**{**MG_DEFAULTS, **params})
+        self._chk(self.L.vh_set_preconditioner(self._h, int(k), ctypes.byref(p) if p is not None else None))
 
     # --- hot path ---
     def assemble(self):

@@ -314,6 +314,8 @@ int build(vh_ctx *ctx, const vh_mesh_desc *d)
         }
     }
   VH_TRY(vh_dev_upload(ctx, &ctx->dirmask, dmask.data(), dmask.size()));
+  if (d->node_global)
+    VH_TRY(vh_dev_upload(ctx, &ctx->node_global_dev, d->node_global, (size_t)n_owned));
 
   // ---- rows: which (cell, local node) pairs feed owned row I  (T(a) = {a} U masters(a)) ----
   std::vector<int32_t> inc_ptr(n_owned + 1, 0);
@@ -1044,10 +1046,11 @@ int vh_create(const vh_mesh_desc *d, int cuda_device, vh_ctx **out)
   ctx->NO      = 18 * (int64_t)ctx->n_owned;
   ctx->NL      = 18 * (int64_t)ctx->n_local;
   int rc       = VH_OK;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
       cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreate(&ctx->ev2) != cudaSuccess ||
       cudaEventCreate(&ctx->ev3) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_scal, cudaEventDisableTiming) != cudaSuccess)
     rc = vh_fail(ctx, VH_ERR_CUDA, "stream/event creation failed");
+  ctx->stream = ctx->own_stream;
   if (rc == VH_OK)
     rc = build(ctx, d);
   if (rc != VH_OK)
@@ -1067,12 +1070,13 @@ int vh_destroy(vh_ctx *ctx)
   cudaSetDevice(ctx->device);
   if (ctx->stream)
     cudaStreamSynchronize(ctx->stream);
+  vhk_mg_detach(ctx); // unlink multigrid levels (either direction); a coarse level gets its own stream back
   vh_comm_destroy(ctx);
   void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
                   ctx->diag_pos, ctx->minv, ctx->pvals, ctx->dpack, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_first, ctx->spmv_order, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->slow_rows, ctx->srow_ptr, ctx->srow_cell, ctx->srow_a, ctx->srow_posb, ctx->srow_wr, ctx->srow_bcons, ctx->srow_posI, ctx->srow_mnode, ctx->srow_mpos, ctx->srow_cons, ctx->push_ptr, ctx->push_dst, ctx->push_peer, ctx->push_ticket, ctx->row_slow,
                   ctx->Hq, ctx->Dblk, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
                   ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
-                  ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,
+                  ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->node_global_dev, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,
                   ctx->tab.Mf};
   for (void *p : ptrs)
     if (p)
@@ -1098,8 +1102,8 @@ int vh_destroy(vh_ctx *ctx)
     cudaEventDestroy(ctx->ev3);
   if (ctx->ev_scal)
     cudaEventDestroy(ctx->ev_scal);
-  if (ctx->stream)
-    cudaStreamDestroy(ctx->stream);
+  if (ctx->own_stream)
+    cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return VH_OK;
 }
@@ -1262,7 +1266,7 @@ static int norm_of(vh_ctx *ctx, const double *v, double *out)
   return VH_OK;
 }
 
-static int assemble_device(vh_ctx *ctx)
+extern "C++" int vhk_assemble_device(vh_ctx *ctx)
 {
   VH_TRY(vhk_pointwise(ctx, ctx->x_sol, true, false));
   if (ctx->rows_lazy && ctx->spmv_mf && ctx->packed)
@@ -1294,7 +1298,7 @@ int vh_assemble(vh_ctx *ctx, double *rhs_l2)
     return vh_fail(ctx, VH_ERR_STATE, "vh_assemble before vh_set_coefficients");
   VH_CUDA(cudaSetDevice(ctx->device));
   PhaseTimer tm(ctx, 0);
-  VH_TRY(assemble_device(ctx));
+  VH_TRY(vhk_assemble_device(ctx));
   tm.stop();
   ctx->have_matrix = true;
   ctx->have_update = false;
@@ -1316,6 +1320,8 @@ int vh_solve(vh_ctx *ctx, double tol_rel, int max_it, int restart, int *iteratio
   VH_TRY(ensure_basis(ctx, restart));
   PhaseTimer tm(ctx, 2);
   VH_TRY(vhk_block_jacobi_setup(ctx)); // "Solve: setup preconditioner" (solve.cc:133)
+  if (ctx->precond == 1)
+    VH_TRY(vhk_mg_setup(ctx)); // coarse levels of the multigrid hierarchy (the reference builds its AMG hierarchy here, solve.cc:152)
   double bnorm = 0;
   VH_TRY(norm_of(ctx, ctx->rhs, &bnorm));
   int    its = 0;
@@ -1471,6 +1477,13 @@ int vh_precondition(vh_ctx *ctx, const double *x_owned, double *y_owned)
     return vh_fail(ctx, VH_ERR_STATE, "vh_precondition before vh_assemble");
   VH_TRY(upload_owned(ctx, ctx->zbuf, x_owned));
   VH_TRY(vhk_block_jacobi_setup(ctx));
+  if (ctx->precond == 1)
+    { // the multigrid V-cycle (input must be zero at the Dirichlet DoFs, as every Krylov vector is)
+      VH_TRY(vhk_mg_setup(ctx));
+      VH_CUDA(cudaMemcpyAsync(ctx->tmpo, ctx->zbuf, sizeof(double) * ctx->NO, cudaMemcpyDeviceToDevice, ctx->stream));
+      VH_TRY(vhk_mg_apply(ctx, ctx->tmpo, ctx->zbuf));
+      return download_owned(ctx, ctx->zbuf, y_owned);
+    }
   VH_TRY(vhk_block_jacobi_apply(ctx, ctx->zbuf, ctx->tmpo));
   return download_owned(ctx, ctx->tmpo, y_owned);
 }
@@ -1501,7 +1514,7 @@ int vh_time_kernel(vh_ctx *ctx, int what, int reps, int do_flush, float *ms_avg)
           VH_TRY(vhk_spmv(ctx, ctx->x_sol, ctx->tmpo, true)); // timing only: masking is a separate, tiny kernel
           break;
         case 1:
-          VH_TRY(assemble_device(ctx));
+          VH_TRY(vhk_assemble_device(ctx));
           break;
         case 2:
           VH_TRY(residual_device(ctx, ctx->x_sol, ctx->resid));
@@ -1546,12 +1559,17 @@ int vh_get_timers(vh_ctx *ctx, double ms[5], int64_t *n_launches, int reset)
   for (int i = 0; i < 5; ++i)
     ms[i] = ctx->t_ms[i];
   if (n_launches)
-    *n_launches = ctx->n_launches;
+    { // kernels of the coarse multigrid levels count with the context that drives them
+      *n_launches = 0;
+      for (vh_ctx *L = ctx; L; L = L->mg_coarse)
+        *n_launches += L->n_launches;
+    }
   if (reset)
     {
       for (int i = 0; i < 5; ++i)
         ctx->t_ms[i] = 0;
-      ctx->n_launches = 0;
+      for (vh_ctx *L = ctx; L; L = L->mg_coarse)
+        L->n_launches = 0;
     }
   return VH_OK;
 }

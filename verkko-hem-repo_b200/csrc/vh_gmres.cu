@@ -121,6 +121,16 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
     tname.push_back(name);
   };
   static const bool   speculate = !(getenv("VH_GMRES_SPECULATE") && getenv("VH_GMRES_SPECULATE")[0] == '0');
+  // v_j = aux / a and z = M^-1 v_j (owned part of zbuf): block-Jacobi does both in one pass (and may push the interface values
+  // into the neighbours' ghost slots); the multigrid V-cycle takes the scaled vector as its right-hand side
+  const bool mg   = ctx->precond == 1;
+  const bool push = ctx->zpush && !mg;
+  auto       precondition_scaled = [&](const double *src, const double *a2, double *vj) -> int {
+    if (!mg)
+      return vhk_block_jacobi_apply_scaled(ctx, src, a2, vj, ctx->zbuf, push);
+    VH_TRY(vhk_scale_to(ctx, vj, src, a2));
+    return vhk_mg_apply(ctx, vj, ctx->zbuf);
+  };
   int                 accumulated = 0;
   double              res = 0.0;
   int                 state = ITERATE;
@@ -163,14 +173,14 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
               mark("step");
               // v_j = aux / a and z = M^-1 v_j (owned part of zbuf) in one pass; ghosts refreshed; aux = A z
               if (a != 0.0)
-                VH_TRY(vhk_block_jacobi_apply_scaled(ctx, aux, a2_d, vj, ctx->zbuf, ctx->zpush));
+                VH_TRY(precondition_scaled(aux, a2_d, vj));
               else
                 {
                   VH_CUDA(cudaMemsetAsync(vj, 0, sizeof(double) * NO, ctx->stream));
                   VH_CUDA(cudaMemsetAsync(ctx->zbuf, 0, sizeof(double) * NO, ctx->stream));
                 }
               mark("apply");
-              if (ctx->zpush && a != 0.0)
+              if (push && a != 0.0)
                 VH_TRY(vhk_halo_wait(ctx)); // the neighbours pushed their interface values into our ghost slots
               else
                 VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
@@ -202,9 +212,9 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
           if (speculate && j + 1 < m && accumulated + 2 <= max_it && !(j > 0 && res <= 4.0 * tol_abs))
             {
               mark("step");
-              VH_TRY(vhk_block_jacobi_apply_scaled(ctx, aux, a2_d, ctx->V + (size_t)(j + 1) * NO, ctx->zbuf, ctx->zpush));
+              VH_TRY(precondition_scaled(aux, a2_d, ctx->V + (size_t)(j + 1) * NO));
               mark("apply");
-              if (ctx->zpush)
+              if (push)
                 VH_TRY(vhk_halo_wait(ctx));
               else
                 VH_TRY(vhk_halo_exchange(ctx, ctx->zbuf));
@@ -265,7 +275,10 @@ int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iteratio
           VH_CUDA(cudaMemcpyAsync(ycoef, ctx->h_pinned, sizeof(double) * y.size(), cudaMemcpyHostToDevice, ctx->stream));
           VH_CUDA(cudaMemsetAsync(ctx->tmpo, 0, sizeof(double) * NO, ctx->stream));
           VH_TRY(vhk_axpy_dev(ctx, ctx->tmpo, ycoef, (int)y.size(), ctx->V, NO));
-          VH_TRY(vhk_block_jacobi_apply(ctx, ctx->tmpo, ctx->zbuf));
+          if (mg)
+            VH_TRY(vhk_mg_apply(ctx, ctx->tmpo, ctx->zbuf));
+          else
+            VH_TRY(vhk_block_jacobi_apply(ctx, ctx->tmpo, ctx->zbuf));
           VH_TRY(vhk_axpby(ctx, ctx->delta, 1.0, ctx->delta, 1.0, ctx->zbuf, NO));
           VH_CUDA(cudaStreamSynchronize(ctx->stream)); // h_pinned is reused by the next read
           x_is_zero = false;

@@ -82,10 +82,22 @@ struct VhConstraintsDev
   bool     has_masters = false;
 };
 
+// Multigrid V-cycle parameters (vh_mg_params of the public header; defaults = what tools/mg_experiment.py measured on C5)
+struct VhMGParams
+{
+  int    pre = 1, post = 1;  // Chebyshev degree of the pre- / post-smoother
+  double range = 4.0;        // smoother interval [lambda_max / range, lambda_max] of M^-1 A
+  int    coarse_degree = 8;  // Chebyshev degree on the coarsest level
+  double coarse_range  = 30.0;
+  int    n_power = 8;        // power iterations for lambda_max (once per level and context)
+  double safety  = 1.1;
+};
+
 struct vh_ctx
 {
   int          device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;     // the stream every kernel of this context is launched on (a coarse multigrid level: its parent's)
+  cudaStream_t own_stream = nullptr; // the stream this context created
   std::string  err;
 
   // sizes
@@ -212,6 +224,20 @@ struct vh_ctx
   double *Dblk      = nullptr; // [n_cells][nn][180] per-(cell, node) diagonal contributions (allocated on first use)
   double *dpack     = nullptr; // [n_fast][180] packed diagonal blocks of the lattice rows (what block-Jacobi reads while rows_stale)
 
+  // preconditioner of vh_solve: 0 = nodal block-Jacobi, 1 = multigrid V-cycle over the attached coarse levels (vh_multigrid.cu)
+  int        precond = 0;
+  vh_ctx    *mg_coarse = nullptr, *mg_parent = nullptr;
+  VhMGParams mg_params;
+  double     mg_lam = 0.0;                                  // safety * lambda_max(M^-1 A) of this level; 0 = not estimated yet
+  double    *mg_x = nullptr, *mg_r = nullptr;               // [NL] level solution / residual (ghosted)
+  double    *mg_b = nullptr, *mg_d = nullptr, *mg_t = nullptr; // [NO] level rhs, Chebyshev direction, A x
+  int32_t   *mg_p_ptr = nullptr, *mg_p_coarse = nullptr;    // P: rows = owned nodes of this level, entries = LOCAL nodes of the coarse level
+  double    *mg_p_w = nullptr;
+  int32_t   *mg_rt_ptr = nullptr, *mg_rt_fine = nullptr;    // P^T: rows = owned nodes of the coarse level, entries = LOCAL nodes of this level
+  double    *mg_rt_w = nullptr;
+  int32_t   *mg_inj = nullptr;                              // [coarse n_owned] coincident node of this level
+  int64_t   *node_global_dev = nullptr;                     // [n_owned] global node ids (start vector of the power iteration)
+
   // state flags
   bool have_matrix = false, have_update = false, have_trial = false;
 
@@ -305,6 +331,12 @@ int vhk_mgs_mode_local(vh_ctx *ctx);
 
 void vh_comm_destroy(vh_ctx *ctx);
 int  vh_p2p_alloc_local(vh_ctx *ctx, int n_ranks);
+
+// ---- multigrid preconditioner (vh_multigrid.cu) ----
+int  vhk_assemble_device(vh_ctx *ctx); // Jacobian phase of vh_assemble without timers / norms (vh_context.cu)
+int  vhk_mg_setup(vh_ctx *fine);       // per Newton step: coarse states, coarse Jacobians, block-Jacobi inverses, eigenvalue bounds
+int  vhk_mg_apply(vh_ctx *fine, const double *v_owned, double *z_local); // z = V-cycle(v), zero initial guess
+void vhk_mg_detach(vh_ctx *ctx);
 
 // ---- GMRES (vh_gmres.cu) ----
 int vh_gmres(vh_ctx *ctx, double tol_abs, int max_it, int restart, int *iterations, double *final_res);
