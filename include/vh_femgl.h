@@ -153,6 +153,8 @@ typedef struct vh_mg_params
 int vh_mg_attach(vh_ctx *fine, vh_ctx *coarse, int32_t n_rows, const int32_t *ptr, const int32_t *coarse_node, const double *weight);
 /* kind: 0 = block-Jacobi, 1 = multigrid V-cycle (needs vh_mg_attach); params may be NULL (defaults).  Collective. */
 int vh_set_preconditioner(vh_ctx *ctx, int kind, const vh_mg_params *params);
+/* diagnostics: safety * lambda_max(M^-1 A) the smoother of level `level` (0 = ctx) uses; 0 before the first vh_solve */
+int vh_mg_get_lambda(vh_ctx *ctx, int level, double *lambda_max);
 
 /* ---- newton_iteration() pieces (iteration.cc:128-210) ---- */
 int vh_line_search_trial(vh_ctx *ctx, double alpha); /* trial = x + alpha*delta; constraints_solution.distribute; ghosts */

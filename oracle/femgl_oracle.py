@@ -487,7 +487,8 @@ def mg_vcycle(levels, k, b, **params):
 
 
 def gmres_right(A, b, prec, tol_abs, max_it=10000, restart=30):
-    """gmres_block_jacobi with an arbitrary fixed right preconditioner (callable); same iteration semantics (A.5)."""
+    """SolverFGMRES iteration semantics (A.5) with an arbitrary right preconditioner (callable): z_j = M^-1 v_j is stored and the
+    update is x += sum_j y_j z_j, as in deal.II and in vh_gmres.cu with the multigrid preconditioner."""
     NO = b.size
 
     def check(step, val):
@@ -508,11 +509,13 @@ def gmres_right(A, b, prec, tol_abs, max_it=10000, restart=30):
             break
         H = np.zeros((m + 1, m))
         V = np.zeros((m, NO))
+        Z = np.zeros((m, NO))
         y = np.zeros(0)
         a = beta
         for j in range(m):
             V[j] = aux / a if a != 0 else 0.0
-            aux = A @ prec(V[j])
+            Z[j] = prec(V[j])
+            aux = A @ Z[j]
             H[0, j] = aux @ V[0]
             for i in range(1, j + 1):
                 aux = aux - H[i - 1, j] * V[i - 1]
@@ -531,7 +534,7 @@ def gmres_right(A, b, prec, tol_abs, max_it=10000, restart=30):
                 if state != "iterate":
                     break
         if y.size:
-            x = x + prec(y @ V[:y.size])
+            x = x + y @ Z[:y.size]
     return x, acc, res, state == "success"
 
 

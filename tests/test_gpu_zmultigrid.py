@@ -40,6 +40,8 @@ def test_vcycle_and_gmres_history_match_oracle(refine, n_levels, half, params):
     v = np.random.default_rng(2).uniform(-1, 1, A.shape[0])
     v[levels[0]["mask"]] = 0.0
     z = fine.precondition(v)
+    for k in range(n_levels):  # the eigenvalue bounds of the smoothers
+        assert abs(fine.mg_lambda(k) - lam[k]) <= 1e-10 * lam[k], (k, fine.mg_lambda(k), lam[k])
     z_ora = O.mg_vcycle(levels, 0, v, **params)
     assert np.abs(z - z_ora).max() <= 1e-11 * np.abs(z_ora).max()
     # GMRES with the V-cycle as right preconditioner: identical iteration count, same update

@@ -58,6 +58,7 @@ def cuda_lib():
         L.vh_transfer_solution.argtypes = [_vp, _vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _dp]
         L.vh_mg_attach.argtypes = [_vp, _vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _dp]
         L.vh_set_preconditioner.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_MGParams)]
+        L.vh_mg_get_lambda.argtypes = [_vp, ctypes.c_int, _dp]
         L.vh_assemble.argtypes = [_vp, _dp]
         L.vh_solve.argtypes = [_vp, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), _dp]
         L.vh_line_search_trial.argtypes = [_vp, ctypes.c_double]
@@ -189,6 +190,11 @@ class Context:
         if params:
             p = _MGParams(**{**MG_DEFAULTS, **params})
         self._chk(self.L.vh_set_preconditioner(self._h, int(k), ctypes.byref(p) if p is not None else None))
+
+    def mg_lambda(self, level=0):
+        v = ctypes.c_double()
+        self._chk(self.L.vh_mg_get_lambda(self._h, level, ctypes.byref(v)))
+        return v.value
 
     # --- hot path ---
     def assemble(self):

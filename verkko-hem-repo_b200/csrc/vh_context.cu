@@ -1075,7 +1075,7 @@ int vh_destroy(vh_ctx *ctx)
   void *ptrs[] = {ctx->cell_nodes, ctx->cell_h, ctx->cell_faces, ctx->cell_owned, ctx->dirmask, ctx->row_ptr, ctx->col, ctx->vals,
                   ctx->diag_pos, ctx->minv, ctx->pvals, ctx->dpack, ctx->cdiag, ctx->spmv_lane_tab, ctx->spmv_gather_tab, ctx->xmask, ctx->fast_posslot, ctx->fast_index, ctx->fast_rows, ctx->fast_cells, ctx->fast_a, ctx->fast_first, ctx->spmv_order, ctx->fast_slot, ctx->fast_class, ctx->class_tab, ctx->class_M, ctx->slow_rows, ctx->srow_ptr, ctx->srow_cell, ctx->srow_a, ctx->srow_posb, ctx->srow_wr, ctx->srow_bcons, ctx->srow_posI, ctx->srow_mnode, ctx->srow_mpos, ctx->srow_cons, ctx->push_ptr, ctx->push_dst, ctx->push_peer, ctx->push_ticket, ctx->row_slow,
                   ctx->Hq, ctx->Dblk, ctx->Rc, ctx->Dc, ctx->avgD, ctx->Ec, ctx->x_sol, ctx->x_trial, ctx->delta, ctx->zbuf,
-                  ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
+                  ctx->rhs, ctx->resid, ctx->w, ctx->tmpo, ctx->V, ctx->Zb, ctx->partials, ctx->scal, ctx->ticket, ctx->send_nodes,
                   ctx->recv_nodes, ctx->send_buf, ctx->recv_buf, ctx->flush_buf, ctx->node_global_dev, ctx->tab.N, ctx->tab.dN, ctx->tab.wq, ctx->tab.Gref,
                   ctx->tab.Mf};
   for (void *p : ptrs)

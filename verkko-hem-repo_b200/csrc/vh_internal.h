@@ -175,6 +175,8 @@ struct vh_ctx
   double *rhs = nullptr, *resid = nullptr, *w = nullptr, *tmpo = nullptr;          // [NO]
   double *V   = nullptr;                                                           // [(restart+1)][NO]
   int     V_cap = 0;
+  double *Zb    = nullptr; // [restart][NO] z_j = M^-1 v_j, kept only with the multigrid preconditioner (vh_gmres.cu)
+  int     Zb_cap = 0;
   // reductions
   double *partials = nullptr; // [VH_MAX_RED_BLOCKS]
   double *scal     = nullptr; // device scalars [VH_SCAL_COUNT]

@@ -8,8 +8,9 @@
 // Chebyshev iteration around the nodal 18x18 block-Jacobi of that level.  The host supplies the prolongation between two
 // consecutive levels as a CSR table over local nodes (deal.II: the entries of MGTransfer; mini host: trilinear weights).
 //   V(b):  x = cheb_pre(b);  r = b - A x;  b_c = mask(P^T r);  x_c = V_c(b_c);  x += mask(P x_c);  x = cheb_post(b, x)
-// with a zero initial guess, fixed degrees and fixed eigenvalue bounds: a FIXED LINEAR operator, so GMRES needs no flexible
-// variant and still stores only v_j (sum y_j z_j = M^-1 sum y_j v_j, vh_gmres.cu).
+// with a zero initial guess, fixed degrees and fixed eigenvalue bounds: a FIXED LINEAR operator.  GMRES keeps z_j = V(v_j)
+// with this preconditioner (deal.II's SolverFGMRES update x += sum y_j z_j; a cycle costs several operator applies and the
+// iteration counts are single-digit, vh_gmres.cu).
 // Exchange steps per level: ghost refresh of x before every operator apply, of r before the restriction and of x_c before the
 // prolongation (NCCL halo of that level's plan); no reductions inside the cycle.
 #include "vh_internal.h"
@@ -20,10 +21,11 @@
 
 namespace
 {
-// d = c1 d + c2 (M^-1 r);  x = (first ? d : x + d).  One warp per node, same streaming scheme as k_block_apply.
+// d = c1 d + c2 (M^-1 r);  x = x + d.  flags bit 0: d has no previous value (d = c2 M^-1 r), bit 1: x has none (x = d).
+// One warp per node, same streaming scheme as k_block_apply.
 __global__ void __launch_bounds__(256)
   k_cheb_update(int n_rows, const double *__restrict__ minv, const double *__restrict__ r, double *__restrict__ d, double *__restrict__ x,
-                double c1, double c2, int first)
+                double c1, double c2, int flags)
 {
   __shared__ double s_part[8][6 * 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -53,9 +55,9 @@ __global__ void __launch_bounds__(256)
       for (int k = 0; k < 9; ++k)
         s += s_part[wid][9 * lane + k];
       const size_t i  = (size_t)row * 18 + lane;
-      const double dn = first ? c2 * s : fma(c1, d[i], c2 * s);
+      const double dn = (flags & 1) ? c2 * s : fma(c1, d[i], c2 * s);
       d[i]            = dn;
-      x[i]            = first ? dn : x[i] + dn;
+      x[i]            = (flags & 2) ? dn : x[i] + dn;
     }
 }
 
@@ -160,7 +162,7 @@ int chebyshev(vh_ctx *L, const double *b, double *x, bool has_x, int degree, dou
       VH_TRY(residual(L, b, x, L->mg_r));
       r = L->mg_r;
     }
-  k_cheb_update<<<grid, 256, 0, L->stream>>>(L->n_owned, L->minv, r, L->mg_d, x, 0.0, 1.0 / theta, has_x ? 0 : 1);
+  k_cheb_update<<<grid, 256, 0, L->stream>>>(L->n_owned, L->minv, r, L->mg_d, x, 0.0, 1.0 / theta, has_x ? 1 : 3);
   VH_LAUNCH_CHECK();
   for (int i = 1; i < degree; ++i)
     {
@@ -177,7 +179,7 @@ int chebyshev(vh_ctx *L, const double *b, double *x, bool has_x, int degree, dou
 int estimate_lambda(vh_ctx *L, const VhMGParams &P)
 {
   vh_ctx *ctx = L;
-  double *nrm = L->scal + VH_SCAL_MISC + 6;
+  double *nrm = L->scal + VH_SCAL_MISC + 5; // slots MISC .. MISC+4 belong to vh_context.cu (VH_SCAL_COUNT = MISC + 6)
   if (L->n_owned > 0)
     {
       const int64_t n = (int64_t)L->n_owned * 18;
@@ -366,6 +368,19 @@ extern "C" int vh_mg_attach(vh_ctx *fine, vh_ctx *coarse, int32_t n_rows, const 
   coarse->mg_parent = fine;
   for (vh_ctx *k = coarse; k; k = k->mg_coarse)
     k->stream = fine->stream;
+  return VH_OK;
+}
+
+extern "C" int vh_mg_get_lambda(vh_ctx *ctx, int level, double *lambda_max)
+{
+  if (!ctx || !lambda_max)
+    return vh_fail(ctx, VH_ERR_ARG, "vh_mg_get_lambda: null argument");
+  vh_ctx *L = ctx;
+  for (int k = 0; k < level && L; ++k)
+    L = L->mg_coarse;
+  if (!L || level < 0)
+    return vh_fail(ctx, VH_ERR_ARG, "vh_mg_get_lambda: no such level");
+  *lambda_max = L->mg_lam;
   return VH_OK;
 }
 
