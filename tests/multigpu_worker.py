@@ -39,6 +39,7 @@ def main():
     periodic = len(sys.argv) > 1 and sys.argv[1] == "periodic"  # the reference's active grid: x/y-periodic slab
 
     hanging = len(sys.argv) > 1 and sys.argv[1] == "hanging"    # C4-shaped: locally refined slab, several levels
+    mg = len(sys.argv) > 1 and sys.argv[1] == "mg"              # multigrid V-cycle preconditioner, 3 levels (r4, r3, r2)
 
     def make(n_ranks):
         if periodic:
@@ -49,7 +50,26 @@ def main():
                 d = np.abs(m.cell_centers()[:, 2] - 0.4)
                 m.refine(d <= np.sort(d)[int(0.3 * m.n_cells)])
             return m.finalize(n_ranks)
-        return vh.unit_cube(1, 3, half=2.0, n_ranks=n_ranks)
+        return vh.unit_cube(1, 4 if mg else 3, half=2.0, n_ranks=n_ranks)
+
+    def hierarchy(n_ranks, r, fine_mesh, fine_tables, fine_ctx, collective):
+        """coarser levels of the multigrid hierarchy on the same partition, attached to fine_ctx"""
+        keep = []
+        mf, Tf, cf = fine_mesh, fine_tables, fine_ctx
+        for lv in (3, 2):
+            mc = vh.unit_cube(1, lv, half=2.0, n_ranks=n_ranks)
+            Tc = mc.tables(r)
+            cc = vh.Context(Tc, device=lr)
+            if collective:
+                u = [vh.Context.nccl_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(u, src=0)
+                cc.comm_init(rank, world, u[0])
+            cc.set_coef_vector(coef)
+            cf.mg_attach(cc, *vh.mg_prolongation(mf, Tf, mc, Tc))
+            keep.append(cc)
+            mf, Tf, cf = mc, Tc, cc
+        fine_ctx.set_preconditioner("multigrid")
+        return keep
 
     mesh = make(world)
     T = mesh.tables(rank)
@@ -58,6 +78,7 @@ def main():
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(rank, world, uid[0])
     ctx.set_coef_vector(coef)
+    levels = hierarchy(world, rank, mesh, T, ctx, True) if mg else []
     x = b_phase_state(T, seed=9)
     ctx.set_solution(x[:18 * T.n_owned_nodes])
     hist = newton(ctx, 2)
@@ -66,9 +87,11 @@ def main():
     dist.all_gather_object(gathered, (T.node_xyz[:T.n_owned_nodes].copy(), sol))
     ok = True
     if rank == 0:
-        T1 = make(1).tables(0)
+        m1 = make(1)
+        T1 = m1.tables(0)
         c1 = vh.Context(T1, device=lr)
         c1.set_coef_vector(coef)
+        lv1 = hierarchy(1, 0, m1, T1, c1, False) if mg else []
         c1.set_solution(b_phase_state(T1, seed=9))
         h1 = newton(c1, 2)
         s1 = c1.get_solution().reshape(-1, 18)

@@ -123,11 +123,14 @@ def test_c2_size_properties():
     ctx2.close()
 
 
-def test_two_gpu_run_equals_one_gpu_run():
+@pytest.mark.parametrize("mode", ["cube", "mg"])
+def test_two_gpu_run_equals_one_gpu_run(mode):
+    """mode mg: the same with the multigrid V-cycle preconditioner (three levels, every level partitioned over both ranks)."""
     if gpu_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tests", "multigpu_worker.py")]
+           "--master-port", "29533" if mode == "cube" else "29534", os.path.join(ROOT, "tests", "multigpu_worker.py")] + \
+          ([] if mode == "cube" else [mode])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTIGPU PARITY OK" in r.stdout

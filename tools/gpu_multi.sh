@@ -20,11 +20,12 @@ for mode in cube periodic hanging; do
   run_worker $mode VH_HALO_PUSH=1
 done
 run_worker cube VH_MGS_MODE=64
+run_worker mg VH_HALO_PUSH=0
 run_worker cube VH_MGS_MODE=1000 VH_P2P=0
-for push in 0 1; do
+for pc in bj mg; do
   port=$((port + 1))
-  tag="bench_n${N}_push${push}"
-  ( VH_HALO_PUSH=$push timeout 600 $TR --master-port $port bench.py --gpus $N --steps 3 --warmup 1 "$@" 2> gpurun_out/$tag.err | tail -1 ) > gpurun_out/$tag.json
+  tag="bench_n${N}_${pc}"
+  ( timeout 600 $TR --master-port $port bench.py --gpus $N --steps 5 --warmup 1 --precond $pc "$@" 2> gpurun_out/$tag.err | tail -1 ) > gpurun_out/$tag.json
   python - <<PY
 import json
 try:
