@@ -188,7 +188,8 @@ int vh_precondition(vh_ctx *ctx, const double *x_owned, double *y_owned);
  *         collective (every rank must call): 9 = 20 ghost refreshes, 10 = 20 inner products with their all-reduce */
 int vh_time_kernel(vh_ctx *ctx, int what, int reps, int flush_l2, float *ms_avg);
 /* Cumulative device time (ms) and launch counts since the last reset:
- *   [0] assemble [1] residual [2] solve [3] line search vector ops [4] halo; n_launches = kernels launched */
+ *   [0] assemble [1] residual [2] solve [3] line search vector ops [4] the preconditioner setup inside [2] (block inverses,
+ *   multigrid level re-discretisation; solve.cc:130-154); n_launches = kernels launched */
 int vh_get_timers(vh_ctx *ctx, double ms[5], int64_t *n_launches, int reset);
 /* CUDA-event stopwatch on the library's stream (the stream every kernel of this context is launched on). */
 int vh_timer_start(vh_ctx *ctx);

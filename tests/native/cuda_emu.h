@@ -208,4 +208,58 @@ inline T __ldg(const T *p)
 {
   return *p;
 }
+// warp votes / reductions over all 32 lanes (the emulated kernels use them with every lane of the warp alive)
+inline unsigned __reduce_max_sync(unsigned, unsigned v)
+{
+  emu::Block *b = emu::block();
+  const int   t = (int)emu::cur().tid.x, w = t / 32, l = t % 32;
+  std::memcpy(&b->shfl[w * 32 + l], &v, sizeof(v));
+  emu::yield_with(2);
+  unsigned m = 0;
+  for (int k = 0; k < 32; ++k)
+    {
+      unsigned o;
+      std::memcpy(&o, &b->shfl[w * 32 + k], sizeof(o));
+      m = o > m ? o : m;
+    }
+  emu::yield_with(2);
+  return m;
+}
+inline unsigned __ballot_sync(unsigned, bool pred)
+{
+  emu::Block    *b = emu::block();
+  const int      t = (int)emu::cur().tid.x, w = t / 32, l = t % 32;
+  const unsigned v = pred ? 1u : 0u;
+  std::memcpy(&b->shfl[w * 32 + l], &v, sizeof(v));
+  emu::yield_with(2);
+  unsigned m = 0;
+  for (int k = 0; k < 32; ++k)
+    {
+      unsigned o;
+      std::memcpy(&o, &b->shfl[w * 32 + k], sizeof(o));
+      m |= o << k;
+    }
+  emu::yield_with(2);
+  return m;
+}
+inline int      __ffs(unsigned v) { return __builtin_ffs((int)v); }
+inline unsigned __float_as_uint(float f)
+{
+  unsigned u;
+  std::memcpy(&u, &f, sizeof(u));
+  return u;
+}
+inline float __double2float_ru(double x)
+{
+  float f = (float)x;
+  if ((double)f < x)
+    f = std::nextafterf(f, INFINITY);
+  return f;
+}
+inline int atomicAdd(int *p, int v)
+{ // fibres of one OS thread: no race
+  const int old = *p;
+  *p += v;
+  return old;
+}
 #endif

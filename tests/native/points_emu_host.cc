@@ -16,6 +16,7 @@ using std::min;
 #include "../../verkko-hem-repo_b200/csrc/vh_diag_kernel.cuh"
 #include "../../verkko-hem-repo_b200/csrc/vh_apply_v2.cuh"
 #include "../../verkko-hem-repo_b200/csrc/vh_gather_kernels.cuh"
+#include "../../verkko-hem-repo_b200/csrc/vh_block_invert.cuh"
 
 // mode 0: assembly (WANT_H: writes Hq, Rc = -cell residual, Dc, avgD)      x = Newton state
 // mode 1: residual only (Rc)                                                x = trial state
@@ -162,6 +163,33 @@ extern "C" int vht_gather_emulated(int which, int n_fast, int dpc, const int32_t
   catch (const std::exception &e)
     {
       std::fprintf(stderr, "vht_gather_emulated: %s\n", e.what());
+      return -1;
+    }
+  return 0;
+}
+
+// block-Jacobi setup (vh_block_invert.cuh).  packed = 1: row i is lattice row i (fast_index = identity, one geometry class with
+// the 3x3 block M9 in slot 0), its diagonal block Sym(dpack[i]) + kron(I_6, M9) with the Dirichlet rule; packed = 0: full blocks.
+extern "C" int vht_block_invert_emulated(int n_rows, int packed, const double *blocks, const double *M9, const uint32_t *dirmask,
+                                         const double *cdiag, double *minv, int *n_singular)
+{
+  std::vector<int32_t> ident(n_rows), zeros(n_rows, 0);
+  for (int i = 0; i < n_rows; ++i)
+    ident[i] = i;
+  double classM[10] = {0};
+  for (int i = 0; i < 9; ++i)
+    classM[i] = M9[i];
+  *n_singular = 0;
+  try
+    {
+      emu::launch((unsigned)((n_rows + VH_INV_WARPS - 1) / VH_INV_WARPS), VH_INV_WARPS * 32, 0, [&] {
+        k_block_invert(n_rows, ident.data(), packed ? nullptr : blocks, minv, n_singular, nullptr, 10, 0, ident.data(), zeros.data(), classM,
+                       dirmask, cdiag, packed ? blocks : nullptr, packed);
+      });
+    }
+  catch (const std::exception &e)
+    {
+      std::fprintf(stderr, "vht_block_invert_emulated: %s\n", e.what());
       return -1;
     }
   return 0;

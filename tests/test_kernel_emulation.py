@@ -22,7 +22,7 @@ def _lib():
     src = os.path.join(ROOT, "tests", "native", "points_emu_host.cc")
     csrc = os.path.join(ROOT, "verkko-hem-repo_b200", "csrc")
     deps = [src, os.path.join(ROOT, "tests", "native", "cuda_emu.h")] + [os.path.join(csrc, f) for f in
-                                                                          ("vh_points_kernel.cuh", "vh_diag_kernel.cuh", "vh_apply_v2.cuh", "vh_gather_kernels.cuh", "vh_pointwise.cuh", "vh_internal.h")]
+                                                                          ("vh_points_kernel.cuh", "vh_diag_kernel.cuh", "vh_apply_v2.cuh", "vh_gather_kernels.cuh", "vh_block_invert.cuh", "vh_pointwise.cuh", "vh_internal.h")]
     out = os.path.join(ROOT, "tests", "native", "_build", "libvhpoints_emu.so")
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(p) for p in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -248,3 +248,56 @@ def test_emulated_lattice_row_pipeline_matches_oracle_global(kind, bt, apply_mod
     assert rc == 0
     y_ora = A @ z
     assert np.abs(y - y_ora).max() <= 1e-12 * np.abs(y_ora).max()
+
+
+def _sym_index(c, d):
+    """vh_sym_index of csrc/vh_pointwise.cuh: position of (c, d), c <= d, in the packed P180 layout"""
+    m = c >> 1
+    start = (36 * m - 2 * m * m + 18) if (c & 1) else (38 * m - 2 * m * m)
+    return start + d - 2 * m
+
+
+@pytest.mark.parametrize("packed", [0, 1])
+def test_emulated_block_invert(packed):
+    """k_block_invert (Gauss-Jordan with deferred scaling, pivoting by redux/ballot, staged through shared memory): A * minv = I
+    for full blocks and for packed lattice blocks Sym(P) + kron(I_6, M) with Dirichlet-masked rows; a singular block is counted."""
+    L = _lib()
+    rng = np.random.default_rng(11 + packed)
+    n = 13                                     # not a multiple of the 4 blocks per CTA
+    M9 = rng.uniform(-1, 1, (3, 3))
+    M9 = M9 + M9.T
+    dirmask = np.zeros(n, dtype=np.uint32)
+    cdiag = rng.uniform(1.0, 2.0, (n, 18))
+    A = np.zeros((n, 18, 18))
+    if packed:
+        blocks = np.zeros((n, 180))
+        dirmask[3] = (1 << 2) | (1 << 5) | (1 << 17)
+        dirmask[7] = 0x3FFFF
+        for i in range(n):
+            S = rng.uniform(-1, 1, (18, 18))
+            S = S + S.T + (0.0 if i % 3 else 6.0) * np.eye(18)   # indefinite and definite blocks
+            for c in range(18):
+                for d in range(c, 18):
+                    blocks[i, _sym_index(c, d)] = S[c, d]
+            A[i] = S + np.kron(np.eye(6), M9)
+            for c in range(18):
+                if (dirmask[i] >> c) & 1:
+                    A[i, c, :] = 0.0
+                    A[i, :, c] = 0.0
+                    A[i, c, c] = cdiag[i, c]
+    else:
+        blocks = rng.uniform(-1, 1, (n, 18, 18))
+        blocks[5] = np.eye(18)[rng.permutation(18)] * rng.uniform(0.5, 2.0, 18)   # needs pivoting in every step
+        blocks[9][:, 4] = 0.0                                                     # singular
+        A[:] = blocks
+    minv = np.full((n, 18, 18), np.nan)
+    nsing = ctypes.c_int(0)
+    rc = L.vht_block_invert_emulated(n, packed, _p(np.ascontiguousarray(blocks)), _p(np.ascontiguousarray(M9)), _p(dirmask, ctypes.c_uint32),
+                                     _p(cdiag), _p(minv), ctypes.byref(nsing))
+    assert rc == 0
+    assert nsing.value == (0 if packed else 1)
+    for i in range(n):
+        if not packed and i == 9:
+            assert np.array_equal(minv[i], np.eye(18))
+            continue
+        assert np.abs(A[i] @ minv[i] - np.eye(18)).max() <= 1e-11 * np.linalg.cond(A[i]), i

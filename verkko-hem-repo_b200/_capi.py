@@ -278,7 +278,7 @@ class Context:
         ms = (ctypes.c_double * 5)()
         n = ctypes.c_int64()
         self._chk(self.L.vh_get_timers(self._h, ms, ctypes.byref(n), 1 if reset else 0))
-        return dict(assemble=ms[0], residual=ms[1], solve=ms[2], vector=ms[3], halo=ms[4], launches=int(n.value))
+        return dict(assemble=ms[0], residual=ms[1], solve=ms[2], vector=ms[3], precond_setup=ms[4], launches=int(n.value))
 
 
 # ------------------------------------------------------------------------------------------

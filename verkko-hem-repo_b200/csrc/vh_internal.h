@@ -246,7 +246,7 @@ struct vh_ctx
   // accounting
   int64_t     n_launches = 0;
   double      t_ms[5]    = {0, 0, 0, 0, 0};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_scal = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev_scal = nullptr;
   int64_t     device_bytes = 0;
   void       *flush_buf   = nullptr;
   size_t      flush_bytes = 0;

@@ -245,114 +245,7 @@ __global__ void k_mask_dirichlet(int64_t n, const uint32_t *__restrict__ dirmask
 // ------------------------------------------------------------------------------------------------
 // block-Jacobi: invert the 18x18 diagonal blocks (Gauss-Jordan, partial pivoting), one warp per block
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-  k_block_invert(int n_rows, const int32_t *__restrict__ diag_pos, const double *__restrict__ vals, double *__restrict__ minv,
-                 int *__restrict__ n_singular, const double *__restrict__ pvals, int cm_stride, int diag_slot, const int32_t *__restrict__ fast_index,
-                 const int32_t *__restrict__ fast_class, const double *__restrict__ class_M, const uint32_t *__restrict__ dirmask,
-                 const double *__restrict__ cdiag, const double *__restrict__ dpack, int packed)
-{
-  // Register-resident Gauss-Jordan, one warp per block; the scaled pivot row is broadcast through shared memory
-  // (shuffles would be the bottleneck: ~650 per block).
-  __shared__ __align__(16) double s_row[4][18];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int row  = blockIdx.x * 4 + wid;
-  if (row >= n_rows)
-    return;
-  const int rr = lane < 18 ? lane : 17;
-  double    a[18];
-  const int fi = packed ? fast_index[row] : -1;
-  if (fi >= 0)
-    { // packed row: diagonal block = Sym(P) + kron(I_6, M_13), Dirichlet rows/columns -> sum_cells |a_ii| on the diagonal;
-      // P comes from dpack[fast row] while the lattice rows are not assembled (matrix-free default), else from the row itself
-      const double  *P  = dpack ? dpack + (size_t)fi * VH_SYMP : pvals + (size_t)diag_pos[row] * VH_SYMP;
-      const double  *M  = class_M + (size_t)fast_class[fi] * cm_stride + diag_slot * 10;
-      const uint32_t mI = dirmask[row];
-#pragma unroll
-      for (int c = 0; c < 18; ++c)
-        {
-          double v = __ldg(P + (rr <= c ? vh_sym_index(rr, c) : vh_sym_index(c, rr)));
-          if (rr / 3 == c / 3)
-            v += M[(rr % 3) * 3 + c % 3];
-          if (((mI >> rr) & 1u) || ((mI >> c) & 1u))
-            v = (rr == c) ? cdiag[(size_t)row * 18 + c] : 0.0;
-          a[c] = v;
-        }
-    }
-  else
-    {
-      const double *B = vals + (size_t)diag_pos[row] * VH_BLK;
-#pragma unroll
-      for (int c = 0; c < 18; ++c)
-        {
-          a[c] = __ldg(B + rr * 18 + c);
-        }
-    }
-  // In-place Gauss-Jordan: lane r keeps row r of the working matrix (18 doubles).  Step k picks the not yet used row with
-  // the largest |a[r][k]| (one redux.sync on the float-truncated magnitudes + a ballot; ties go to the lowest lane),
-  // scales it, and eliminates column k from every other row; the freed column k then stores the column of the inverse that
-  // became non-trivial in this step (the one of the pivot row pl_k).  Rows are never swapped: at the end the lane that
-  // pivoted on column k holds row k of A^-1 with its columns in the order pl_0 .. pl_17.
-  bool used     = lane >= 18;
-  int  mycol    = -1;
-  bool singular = false;
-  int  piv[18];
-#pragma unroll
-  for (int k = 0; k < 18; ++k)
-    {
-      const unsigned key  = used ? 0u : __float_as_uint(fabsf(__double2float_ru(fabs(a[k]))));
-      const unsigned best = __reduce_max_sync(0xffffffffu, key);
-      if (best == 0u)
-        {
-          singular = true;
-          break;
-        }
-      const int    pl  = __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;
-      const bool   me  = lane == pl;
-      const double f   = a[k];
-      const double inv = 1.0 / __shfl_sync(0xffffffffu, f, pl);
-      piv[k]           = pl;
-      if (me)
-        {
-          a[k] = 1.0;
-#pragma unroll
-          for (int c = 0; c < 18; ++c)
-            a[c] *= inv;
-#pragma unroll
-          for (int c = 0; c < 9; ++c)
-            *reinterpret_cast<double2 *>(&s_row[wid][2 * c]) = make_double2(a[2 * c], a[2 * c + 1]);
-          used  = true;
-          mycol = k;
-        }
-      __syncwarp();
-      if (!me)
-        {
-          a[k] = 0.0;
-#pragma unroll
-          for (int c = 0; c < 9; ++c)
-            {
-              const double2 p = *reinterpret_cast<const double2 *>(&s_row[wid][2 * c]);
-              a[2 * c]        = fma(-f, p.x, a[2 * c]);
-              a[2 * c + 1]    = fma(-f, p.y, a[2 * c + 1]);
-            }
-        }
-      __syncwarp();
-    }
-  if (singular)
-    {
-      if (lane == 0)
-        atomicAdd(n_singular, 1);
-      for (int i = lane; i < VH_BLK; i += 32)
-        minv[(size_t)row * VH_BLK + i] = (i / 18 == i % 18) ? 1.0 : 0.0;
-      return;
-    }
-  if (lane < 18)
-    {
-      double *out = minv + (size_t)row * VH_BLK + mycol * 18;
-#pragma unroll
-      for (int m = 0; m < 18; ++m)
-        out[piv[m]] = a[m];
-    }
-}
+#include "vh_block_invert.cuh"
 
 // y = blockdiag(minv) x : same streaming scheme as the SpMV with exactly one block per row
 __global__ void __launch_bounds__(256)
@@ -547,8 +440,39 @@ __global__ void __launch_bounds__(VH_MGS_THREADS, EPT == 8 ? 3 : (EPT == 0 ? 2 :
           const double *vp = step > 0 ? V + (size_t)(step - 1) * ld : nullptr; // subtract hprev * v_{step-1}
           const double *vu = step <= j ? V + (size_t)step * ld : nullptr;      // dot with v_step (or with w itself)
           double        s1 = 0.0;
-#pragma unroll 4
-          for (int64_t i = base; i < n; i += stride)
+          // main part: four 16-byte pieces of every stream requested before the first is used (12 loads in flight per thread:
+          // with only 2 co-resident blocks per SM the memory-level parallelism has to come from the thread itself)
+          int64_t i = base;
+          for (; i + 3 * stride + 1 < n; i += 4 * stride)
+            {
+              double2 wv[4], pv[4], uv[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                wv[u] = *reinterpret_cast<const double2 *>(w + i + u * stride);
+              if (vp)
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  pv[u] = __ldcs(reinterpret_cast<const double2 *>(vp + i + u * stride));
+              if (vu)
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  uv[u] = *reinterpret_cast<const double2 *>(vu + i + u * stride);
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                {
+                  if (vp)
+                    {
+                      wv[u].x = fma(-hprev, pv[u].x, wv[u].x);
+                      wv[u].y = fma(-hprev, pv[u].y, wv[u].y);
+                      *reinterpret_cast<double2 *>(w + i + u * stride) = wv[u];
+                    }
+                  if (!vu)
+                    uv[u] = wv[u];
+                  s  = fma(wv[u].x, uv[u].x, s);
+                  s1 = fma(wv[u].y, uv[u].y, s1);
+                }
+            }
+          for (; i < n; i += stride)
             {
               const bool two = i + 1 < n;
               double2    wv  = two ? *reinterpret_cast<const double2 *>(w + i) : make_double2(w[i], 0.0);
@@ -981,7 +905,7 @@ int vhk_block_jacobi_setup(vh_ctx *ctx)
     return VH_OK;
   int *d_sing = reinterpret_cast<int *>(ctx->scal + VH_SCAL_MISC);
   VH_CUDA(cudaMemsetAsync(d_sing, 0, sizeof(int), ctx->stream));
-  k_block_invert<<<(ctx->n_owned + 3) / 4, 128, 0, ctx->stream>>>(ctx->n_owned, ctx->diag_pos, ctx->vals, ctx->minv, d_sing,
+  k_block_invert<<<(ctx->n_owned + VH_INV_WARPS - 1) / VH_INV_WARPS, VH_INV_WARPS * 32, 0, ctx->stream>>>(ctx->n_owned, ctx->diag_pos, ctx->vals, ctx->minv, d_sing,
                                                                   ctx->packed ? ctx->pvals : nullptr, ctx->n_slots * 10, ctx->diag_slot, ctx->fast_index, ctx->fast_class,
                                                                   ctx->class_M, ctx->dirmask, ctx->cdiag,
                                                                   ctx->rows_stale ? ctx->dpack : nullptr, ctx->packed ? 1 : 0);

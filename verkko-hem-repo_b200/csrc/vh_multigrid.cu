@@ -17,7 +17,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace
 {
@@ -203,16 +206,62 @@ int estimate_lambda(vh_ctx *L, const VhMGParams &P)
   return VH_OK;
 }
 
-int vcycle(vh_ctx *L, const VhMGParams &P, const double *b, double *x)
+// VH_MG_TRACE=1: CUDA events around the parts of every cycle, printed to stderr after the cycle (diagnostic, like VH_GMRES_TRACE)
+struct MgTrace
+{
+  std::vector<cudaEvent_t>  ev;
+  std::vector<const char *> name;
+  std::vector<int>          level;
+  bool                      on = getenv("VH_MG_TRACE") && getenv("VH_MG_TRACE")[0] == '1';
+  void mark(vh_ctx *L, const char *what, int lv)
+  {
+    if (!on)
+      return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, L->stream);
+    ev.push_back(e);
+    name.push_back(what);
+    level.push_back(lv);
+  }
+  void flush(vh_ctx *L)
+  {
+    if (!on || ev.empty())
+      return;
+    cudaStreamSynchronize(L->stream);
+    fprintf(stderr, "[mg trace]");
+    for (size_t i = 1; i < ev.size(); ++i)
+      {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+        fprintf(stderr, " L%d.%s %.0f", level[i], name[i], ms * 1e3f);
+      }
+    fprintf(stderr, " (us)\n");
+    for (cudaEvent_t e : ev)
+      cudaEventDestroy(e);
+    ev.clear();
+    name.clear();
+    level.clear();
+  }
+};
+MgTrace g_trace;
+
+int vcycle(vh_ctx *L, const VhMGParams &P, const double *b, double *x, int lv = 0)
 {
   vh_ctx *ctx = L;
   vh_ctx *C   = L->mg_coarse;
   if (!C)
-    return chebyshev(L, b, x, false, P.coarse_degree, P.coarse_range);
+    {
+      VH_TRY(chebyshev(L, b, x, false, P.coarse_degree, P.coarse_range));
+      g_trace.mark(L, "coarse", lv);
+      return VH_OK;
+    }
   VH_TRY(chebyshev(L, b, x, false, P.pre, P.range));
+  g_trace.mark(L, "pre", lv);
   // r = b - A x, ghosts refreshed: the restriction of a coarse owned node reads fine nodes owned by the neighbours
   VH_TRY(residual(L, b, x, L->mg_r));
   VH_TRY(vhk_halo_exchange(L, L->mg_r));
+  g_trace.mark(L, "residual", lv);
   if (C->n_owned > 0)
     {
       const int64_t n = (int64_t)C->n_owned * 18;
@@ -220,7 +269,8 @@ int vcycle(vh_ctx *L, const VhMGParams &P, const double *b, double *x)
                                                                    C->mg_b);
       VH_LAUNCH_CHECK();
     }
-  VH_TRY(vcycle(C, P, C->mg_b, C->mg_x));
+  g_trace.mark(L, "restrict", lv);
+  VH_TRY(vcycle(C, P, C->mg_b, C->mg_x, lv + 1));
   VH_TRY(vhk_halo_exchange(C, C->mg_x));
   if (L->n_owned > 0)
     {
@@ -228,7 +278,10 @@ int vcycle(vh_ctx *L, const VhMGParams &P, const double *b, double *x)
       k_prolong_add<<<(unsigned)((n + 255) / 256), 256, 0, L->stream>>>(L->n_owned, L->mg_p_ptr, L->mg_p_coarse, L->mg_p_w, C->mg_x, L->dirmask, x);
       VH_LAUNCH_CHECK();
     }
-  return chebyshev(L, b, x, true, P.post, P.range);
+  g_trace.mark(L, "prolong", lv);
+  VH_TRY(chebyshev(L, b, x, true, P.post, P.range));
+  g_trace.mark(L, "post", lv);
+  return VH_OK;
 }
 } // namespace
 
@@ -266,7 +319,10 @@ int vhk_mg_setup(vh_ctx *fine)
 // z = V(v): one V-cycle with zero initial guess; v: owned vector, z: LOCAL vector (owned part written, ghosts stale)
 int vhk_mg_apply(vh_ctx *fine, const double *v_owned, double *z_local)
 {
-  return vcycle(fine, fine->mg_params, v_owned, z_local);
+  g_trace.mark(fine, "start", 0);
+  const int rc = vcycle(fine, fine->mg_params, v_owned, z_local);
+  g_trace.flush(fine);
+  return rc;
 }
 
 void vhk_mg_detach(vh_ctx *ctx)
