@@ -222,3 +222,23 @@ def test_device_side_solution_transfer_matches_host_interpolation():
     first = [h for h in out["history"] if h["iteration"] == 0]
     assert len(first) == 2 and all(h["t_setup_ms"] > 0 for h in first)
     assert "solution transfer" in out["log"]
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_c4_adaptive_cycles_multi_gpu_equal_single_gpu(world):
+    """BASELINE configs[3] through tools/c4_adaptive.py: slab with the A/B interface, adaptive cycles with hanging nodes under
+    the reference's cycle rule (run.cc:182-256).  world = 2: the partition moves with every cycle; rank 0 repeats the run on one
+    GPU and requires identical refinement flags and iteration counts and residual norms within 1e-10."""
+    if gpu_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    tool = os.path.join(ROOT, "tools", "c4_adaptive.py")
+    if world == 1:
+        cmd = [sys.executable, tool, "--cycles", "3"]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+               "--master-port", "29541", tool, "--cycles", "3", "--check-single"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "C4 ADAPTIVE DONE" in r.stdout
+    if world > 1:
+        assert "P-INDEPENDENCE OK" in r.stdout
