@@ -48,6 +48,10 @@ RESTART = 30         # SolverFGMRES default max_basis_size
 CONVERGE_ACC = 5e-6  # "converge accuracy" default, declare.cc:249 (run.cc:234-250)
 MAX_NEWTON = 41      # "Number of interations" default 40, inclusive upper bound (run.cc:207)
 
+# vh_mg_params of the multigrid runs (--mg-pre / --mg-post).  V(0,1): the right-hand side is restricted directly, so an inner
+# GMRES step costs two fine operator applies instead of the three of the library default V(1,1).  Measured at C5 on one B200
+# (profiles/r02g_mg_cycle_variants.txt): 107 ms per Newton step and 9 steps to converge against 126 ms and 8 steps.
+MG_PARAMS = {"pre": 0, "post": 1}
 WORKLOADS = {  # name -> (degree, refine per GPU (weak) or None, global refine (strong) or None)
     "c2": (1, 5, None),   # BASELINE configs[1]; for N > 1: N root cubes stacked along z (weak)
     "c3": (2, None, 5),   # BASELINE configs[2]
@@ -458,7 +462,7 @@ def build_context(vh, dist, rank, world, local_rank, degree, refine, global_refi
             cf.mg_attach(cc, *vh.mg_prolongation(mf, Tf, mc, Tc))
             levels.append(cc)
             mf, Tf, cf = mc, Tc, cc
-        ctx.set_preconditioner("multigrid")
+        ctx.set_preconditioner("multigrid", **MG_PARAMS)
     return mesh, T, ctx, levels, time.perf_counter() - t0
 
 
@@ -520,7 +524,7 @@ def measure(vh, torch, dist, rank, world, local_rank, degree, refine, global_ref
         bj = {"preconditioner": "nodal 18x18 block-Jacobi (north star)", "steps": n_bj, "ms_per_step": ms_bj / n_bj,
               "gmres_its_per_step": s_bj["gmres_its_total"] / n_bj, "first_run_gmres_its": s_bj["first_run_gmres_its"],
               "first_run_residuals": s_bj["first_run_residuals"]}
-        ctx.set_preconditioner("multigrid")
+        ctx.set_preconditioner("multigrid", **MG_PARAMS)
 
     summ = summarize_runs(runs)
     its_total = max(summ["gmres_its_total"], 1)
@@ -587,8 +591,9 @@ def measure(vh, torch, dist, rank, world, local_rank, degree, refine, global_ref
                 par = {"error": str(exc)}
         barrier()
         res["multi_gpu_parity"] = par
-    res["preconditioner"] = ("multigrid V-cycle, %d levels (coarsest: refinement %d), Chebyshev(1)/block-Jacobi smoothing"
-                             % (len(levels), mg_coarsest)) if precond == "mg" else "nodal 18x18 block-Jacobi"
+    res["preconditioner"] = ("multigrid V(%d,%d) cycle, %d levels (coarsest: refinement %d), Chebyshev/block-Jacobi smoothing"
+                             % (MG_PARAMS.get("pre", 1), MG_PARAMS.get("post", 1), len(levels), mg_coarsest)) if precond == "mg" \
+        else "nodal 18x18 block-Jacobi"
     for c in levels:
         c.close()
     return res
@@ -727,6 +732,8 @@ def main():
                          "block-Jacobi step time of the same context under block_jacobi); auto = mg where a hierarchy exists "
                          "(Q1 with --global-refine above --mg-coarsest, i.e. the c5 default), bj elsewhere")
     ap.add_argument("--mg-coarsest", type=int, default=5, help="coarsest refinement level of the multigrid hierarchy")
+    ap.add_argument("--mg-pre", type=int, default=None, help="Chebyshev degree of the pre-smoother (bench default 0; library default 1)")
+    ap.add_argument("--mg-post", type=int, default=None, help="Chebyshev degree of the post-smoother (default 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c2", action="store_true", help="skip the configs[1] measurement next to the headline (N = 1)")
     ap.add_argument("--no-parity", action="store_true", help="skip the single-GPU parity run of rank 0 (N > 1)")
@@ -740,6 +747,10 @@ def main():
         if d != WORKLOADS.get(args.workload, (d,))[0]:
             args.workload = "custom"
     args.degree, args.refine, args.global_refine = d, r, g
+    if args.mg_pre is not None:
+        MG_PARAMS["pre"] = args.mg_pre
+    if args.mg_post is not None:
+        MG_PARAMS["post"] = args.mg_post
     if args.precond == "auto":
         args.precond = "mg" if (d == 1 and g is not None and g > args.mg_coarsest) else "bj"
     if args.refine is None and args.global_refine is None:

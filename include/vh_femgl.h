@@ -112,6 +112,14 @@ int vh_set_solution(vh_ctx *ctx, const double *owned);     /* H2D + ghost refres
 int vh_get_solution(vh_ctx *ctx, double *owned);           /* D2H */
 int vh_get_newton_update(vh_ctx *ctx, double *owned);      /* locally_relevant_newton_solution (femgl.h:312) */
 int vh_get_rhs(vh_ctx *ctx, double *owned);                /* system_rhs (femgl.h:315)      */
+/* Output path (FemGL::output_results, io.cc:106-170, runs after every Newton step: run.cc:221-227).
+ * vh_snapshot_begin enqueues, behind everything already enqueued for this context, a copy of the LOCAL (owned, then ghost)
+ * parts of local_solution and of the Newton update (femgl.h:312-313: the two vectors DataOut reads) and their transfer to
+ * pinned host memory on a second stream; it returns at once and the next Newton step may start.  vh_snapshot_wait blocks
+ * until that snapshot has landed and hands out the two arrays (18 * n_local doubles each, library-owned, valid until the
+ * next vh_snapshot_begin or vh_destroy); the Newton update is all zero before the first vh_solve. */
+int vh_snapshot_begin(vh_ctx *ctx);
+int vh_snapshot_wait(vh_ctx *ctx, const double **solution_local, const double **update_local);
 int vh_get_residual(vh_ctx *ctx, double *owned);           /* residual_vector (femgl.h:316) */
 
 /* ---- refine_grid(): SolutionTransfer::interpolate + constraints_solution.distribute + ghosted copy on the device
@@ -143,7 +151,8 @@ int vh_solve(vh_ctx *ctx, double tol_rel, int max_it, int restart, int *iteratio
  *      The coarse Jacobians are re-discretised at the injected Newton state in every vh_solve. ---- */
 typedef struct vh_mg_params
 {
-  int32_t pre, post;        /* Chebyshev degree of the pre- / post-smoother around block-Jacobi (default 1, 1) */
+  int32_t pre, post;        /* Chebyshev degree of the pre- / post-smoother around block-Jacobi (default 1, 1); either may be 0
+                             * (V(0,k): the right-hand side is restricted directly, one operator apply fewer per cycle) */
   double  smoothing_range;  /* smoother interval [lambda_max/range, lambda_max] of M^-1 A          (default 4)    */
   int32_t coarse_degree;    /* Chebyshev degree on the coarsest level                              (default 8)    */
   double  coarse_range;     /*                                                                     (default 30)   */

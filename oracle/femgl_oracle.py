@@ -453,6 +453,8 @@ def mg_setup(tables, prolongations, x_fine, coef, lam=None, **params):
 
 
 def _chebyshev(lev, b, x, degree, ratio):
+    if degree == 0:  # V(0,k) / V(k,0): no smoothing on this side of the cycle
+        return np.zeros_like(b) if x is None else x
     A, prec = lev["A"], lev["prec"]
     lmax, lmin = lev["lam"], lev["lam"] / ratio
     theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
@@ -477,7 +479,7 @@ def mg_vcycle(levels, k, b, **params):
     if k == len(levels) - 1:
         return _chebyshev(lev, b, None, P["coarse_degree"], P["coarse_range"])
     x = _chebyshev(lev, b, None, P["pre"], P["smoothing_range"])
-    r = b - lev["A"] @ x
+    r = b - lev["A"] @ x if P["pre"] > 0 else b
     rc = lev["P"].T @ r
     rc[levels[k + 1]["mask"]] = 0.0
     xc = mg_vcycle(levels, k + 1, rc, **params)

@@ -233,12 +233,64 @@ def test_c4_adaptive_cycles_multi_gpu_equal_single_gpu(world):
         pytest.skip("needs %d GPUs" % world)
     tool = os.path.join(ROOT, "tools", "c4_adaptive.py")
     if world == 1:
-        cmd = [sys.executable, tool, "--cycles", "3"]
+        cmd = [sys.executable, tool, "--cycles", "2", "--initial-refine", "3", "--half", "3", "2", "4"]
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-               "--master-port", "29541", tool, "--cycles", "3", "--check-single"]
+               "--master-port", "29541", tool, "--cycles", "2", "--initial-refine", "3", "--half", "3", "2", "4", "--check-single"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "C4 ADAPTIVE DONE" in r.stdout
     if world > 1:
         assert "P-INDEPENDENCE OK" in r.stdout
+
+
+def test_snapshot_is_taken_in_stream_order_and_survives_the_next_step():
+    """vh_snapshot_begin / vh_snapshot_wait (output path, io.cc:106-170): the snapshot holds local_solution and the Newton
+    update as they were when it was requested, although the next Newton step runs before it is collected."""
+    T = vh.unit_cube(1, 3, half=2.0).tables(0)
+    ctx = vh.Context(T)
+    ctx.set_coef_vector(coef_vector(MATEP_SCC_ON, 2.0))
+    ctx.set_solution(b_phase_state(T, seed=4))
+    ctx.snapshot_begin()                       # before any solve: the update block is zero
+    s0, u0 = ctx.snapshot_wait()
+    assert np.array_equal(s0[:ctx.n_owned], ctx.get_solution()) and not u0.any()
+
+    def step():
+        bn = ctx.assemble()
+        ctx.solve(1e-1)
+        for i in range(100):
+            ctx.line_search_trial(0.83 ** i)
+            if ctx.residual() < bn:
+                break
+        ctx.accept_trial()
+
+    step()
+    sol1, upd1 = ctx.get_solution(), ctx.get_newton_update()
+    ctx.snapshot_begin()
+    step()                                     # the state moves on while the snapshot travels
+    s, u = ctx.snapshot_wait()
+    assert np.array_equal(s[:ctx.n_owned], sol1) and np.array_equal(u[:ctx.n_owned], upd1)
+    assert not np.array_equal(ctx.get_solution(), sol1)
+    ctx.close()
+
+
+def test_femgl_run_writes_vtu_after_every_newton_step(tmp_path, monkeypatch):
+    """FemGL::output_results of the mirror (additive key "write vtu output"): one .vtu + .pvtu per Newton step in the
+    reference's directories (run.cc:221-227), written by a thread next to the Newton loop; the last file holds the final state."""
+    from test_vtu_output import NAMES, read_vtu
+    monkeypatch.chdir(tmp_path)
+    prm = SLAB_PRM % (1, 1e3)
+    out = vh.run_prm(prm.replace("set geometry = retangle", "set geometry = retangle\n  set write vtu output = true"))
+    hist = out["history"]
+    assert os.path.exists(tmp_path / "setup_config" / "solution_00.0.vtu")
+    for h in hist:
+        d = tmp_path / ("refine-cycle_%d" % h["cycle"])
+        assert os.path.exists(d / ("solution_%02d.0.vtu" % h["iteration"])) and os.path.exists(d / ("solution_%02d.pvtu" % h["iteration"]))
+    last = hist[-1]
+    v = read_vtu(str(tmp_path / ("refine-cycle_%d" % last["cycle"]) / ("solution_%02d.0.vtu" % last["iteration"])))
+    sol = out["solution"].reshape(-1, 18)
+    assert v["n_points"] == sol.shape[0]
+    for c in range(18):
+        assert np.array_equal(v[NAMES[18 + c]], sol[:, c])
+    assert np.abs(np.stack([v[n] for n in NAMES[:18]])).max() > 0.0       # the Newton update of the last step
+    assert "output: the Newton loop waited" in out["log"]

@@ -24,7 +24,8 @@ def _hierarchy(refine, n_levels, half=20.0, bt=2.0):
 
 
 @pytest.mark.parametrize("refine,n_levels,half,params", [(3, 2, 2.0, {}), (4, 3, 2.0, {}), (4, 2, 20.0, {}),
-                                                         (3, 2, 2.0, dict(pre=2, post=3, smoothing_range=8.0, coarse_degree=5))])
+                                                         (3, 2, 2.0, dict(pre=2, post=3, smoothing_range=8.0, coarse_degree=5)),
+                                                         (4, 3, 2.0, dict(pre=0, post=1)), (4, 3, 2.0, dict(pre=1, post=0))])
 def test_vcycle_and_gmres_history_match_oracle(refine, n_levels, half, params):
     """half = 2: cells much smaller than the coherence length (gradient-dominated, the regime of the fine BASELINE meshes);
     half = 20, r4 -> r3: the coarsest spacing at which the re-discretised coarse operator still helps (tools/mg_experiment.py)."""

@@ -110,6 +110,9 @@ def run(args, rank, world, device, dist, flags_in=None):
                 ms_steps += ctx.timer_stop()
             n_steps += 1
             history.append(dict(cycle=cycle, iteration=it, rhs_norm=bn, linear_its=its, trials=trials, residual=res))
+            if rank == 0:
+                print("[%d rank(s)] cycle %d (%d DoFs) iteration %d: rhs %.6e, %d linear its, %d trials, residual %.6e"
+                      % (world, cycle, 18 * mesh.n_nodes, it, bn, its, trials, res), file=sys.stderr, flush=True)
             if abs(res - r_last) < args.threshold and res > CONVERGE_ACC and cycle < args.cycles:   # run.cc:235-240
                 break
             if res <= CONVERGE_ACC:
@@ -154,8 +157,12 @@ def run(args, rank, world, device, dist, flags_in=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cycles", type=int, default=4)
-    ap.add_argument("--initial-refine", type=int, default=3)
-    ap.add_argument("--half", type=float, nargs=3, default=[10.0, 10.0, 20.0])
+    # default geometry: h = 0.75 x 0.5 x 1.0 on the initial mesh, i.e. the coherence length (1 in these units) is resolved.
+    # On a slab of 20 x 20 x 40 refined 3 times (h = 2.5 .. 5) the discontinuous BnA state sits near a saddle of the
+    # under-resolved functional: the line search stalls (37 trials) and GMRES(30) + block-Jacobi stagnates in cycle 2, in the
+    # oracle as on the GPU.
+    ap.add_argument("--initial-refine", type=int, default=4)
+    ap.add_argument("--half", type=float, nargs=3, default=[6.0, 4.0, 8.0])
     ap.add_argument("--ratio", type=float, default=0.1, help="A-phase block range ratio")
     ap.add_argument("--refine-ratio", type=float, default=0.3)
     ap.add_argument("--threshold", type=float, default=1e3, help="Cycle x refinement threshold (all cycles)")

@@ -80,6 +80,7 @@ def host_lib():
         L.vhh_mesh_clone.restype = ctypes.c_void_p
         L.vhh_mesh_clone.argtypes = [ctypes.c_void_p]
         L.vhh_mesh_node_xyz.argtypes = [ctypes.c_void_p, _dp]
+        L.vhh_write_vtu.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, _dp, _dp]
         _host = L
     return _host
 
@@ -128,6 +129,22 @@ class RankTables:
 
     def desc_ptr(self):
         return ctypes.cast(self._desc, ctypes.c_void_p)
+
+    def write_vtu(self, directory, counter, solution_local=None, update_local=None, n_ranks=1):
+        """DataOut stand-in of the host mirror (host/vtu.cc; io.cc:106-170): <directory>/solution_<counter>.<rank>.vtu with the
+        owned cells of this rank, + the .pvtu record on rank 0.  The fields hold 18 values per LOCAL node (owned, then ghosts)."""
+        def arr(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            assert a.size == 18 * self.n_local_nodes
+            return a
+        s, u = arr(solution_local), arr(update_local)
+        d = directory if directory.endswith("/") else directory + "/"
+        if host_lib().vhh_write_vtu(self._h, self.rank, n_ranks, d.encode(), int(counter), s.ctypes.data_as(_dp) if s is not None else None,
+                                    u.ctypes.data_as(_dp) if u is not None else None) != 0:
+            raise RuntimeError(host_lib().vhh_last_error().decode())
+        return "%ssolution_%02d.%d.vtu" % (d, counter, self.rank)
 
     def face_csr(self):
         """Wall faces regrouped per cell: (face_ptr[n_cells+1], face_no[], face_bid[]) as int32."""

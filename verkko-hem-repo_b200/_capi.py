@@ -58,6 +58,8 @@ def cuda_lib():
         L.vh_transfer_solution.argtypes = [_vp, _vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _dp]
         L.vh_mg_attach.argtypes = [_vp, _vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _dp]
         L.vh_set_preconditioner.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_MGParams)]
+        L.vh_snapshot_begin.argtypes = [_vp]
+        L.vh_snapshot_wait.argtypes = [_vp, ctypes.POINTER(_dp), ctypes.POINTER(_dp)]
         L.vh_mg_get_lambda.argtypes = [_vp, ctypes.c_int, _dp]
         L.vh_assemble.argtypes = [_vp, _dp]
         L.vh_solve.argtypes = [_vp, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), _dp]
@@ -156,6 +158,17 @@ class Context:
 
     def get_newton_update(self):
         return self._get(self.L.vh_get_newton_update)
+
+    # --- output path (io.cc:106-170): asynchronous snapshot of the two LOCAL vectors DataOut reads ---
+    def snapshot_begin(self):
+        self._chk(self.L.vh_snapshot_begin(self._h))
+
+    def snapshot_wait(self):
+        """(local_solution, Newton update), 18 * n_local doubles each, copied out of the library's pinned buffer."""
+        s, u = _dp(), _dp()
+        self._chk(self.L.vh_snapshot_wait(self._h, ctypes.byref(s), ctypes.byref(u)))
+        n = 18 * self.tables.n_local_nodes
+        return np.ctypeslib.as_array(s, shape=(n,)).copy(), np.ctypeslib.as_array(u, shape=(n,)).copy()
 
     def get_rhs(self):
         return self._get(self.L.vh_get_rhs)

@@ -1088,6 +1088,19 @@ int vh_destroy(vh_ctx *ctx)
         if (p)
           cudaFree(p);
     }
+  if (ctx->snap_stream)
+    {
+      cudaStreamSynchronize(ctx->snap_stream);
+      cudaStreamDestroy(ctx->snap_stream);
+    }
+  if (ctx->snap_dev)
+    cudaFree(ctx->snap_dev);
+  if (ctx->snap_host)
+    cudaFreeHost(ctx->snap_host);
+  if (ctx->ev_snap_ready)
+    cudaEventDestroy(ctx->ev_snap_ready);
+  if (ctx->ev_snap_done)
+    cudaEventDestroy(ctx->ev_snap_done);
   if (ctx->h_pinned)
     cudaFreeHost(ctx->h_pinned);
   if (ctx->h_mgs)
@@ -1190,6 +1203,52 @@ int vh_get_residual(vh_ctx *ctx, double *owned)
 {
   VH_REQUIRE(ctx);
   return download_owned(ctx, ctx->resid, owned);
+}
+
+// ---- output path (io.cc:106-170 is called after EVERY Newton step, run.cc:221-227) ----
+// The snapshot is taken in stream order (a device-to-device copy of the two local vectors into a staging buffer, 0.2 ms at
+// C5) and leaves the device on a second stream, so the next Newton step runs while the 2 x 18 x n_local doubles travel to
+// pinned host memory and the host writes the file.
+int vh_snapshot_begin(vh_ctx *ctx)
+{
+  VH_REQUIRE(ctx);
+  VH_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)std::max<int64_t>(ctx->NL, 1);
+  if (!ctx->snap_stream)
+    {
+      VH_CUDA(cudaStreamCreateWithFlags(&ctx->snap_stream, cudaStreamNonBlocking));
+      VH_CUDA(cudaEventCreateWithFlags(&ctx->ev_snap_ready, cudaEventDisableTiming));
+      VH_CUDA(cudaEventCreateWithFlags(&ctx->ev_snap_done, cudaEventDisableTiming));
+      VH_TRY(vh_dev_alloc(ctx, &ctx->snap_dev, 2 * n));
+      VH_CUDA(cudaMallocHost((void **)&ctx->snap_host, 2 * n * sizeof(double)));
+    }
+  if (ctx->snap_pending) // the previous snapshot still owns the staging buffer
+    VH_CUDA(cudaEventSynchronize(ctx->ev_snap_done));
+  VH_CUDA(cudaMemcpyAsync(ctx->snap_dev, ctx->x_sol, sizeof(double) * (size_t)ctx->NL, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ctx->delta_holds_update)
+    VH_CUDA(cudaMemcpyAsync(ctx->snap_dev + n, ctx->delta, sizeof(double) * (size_t)ctx->NL, cudaMemcpyDeviceToDevice, ctx->stream));
+  else // no Newton update yet (output of the initial configuration, run.cc:196-200)
+    VH_CUDA(cudaMemsetAsync(ctx->snap_dev + n, 0, sizeof(double) * n, ctx->stream));
+  VH_CUDA(cudaEventRecord(ctx->ev_snap_ready, ctx->stream));
+  VH_CUDA(cudaStreamWaitEvent(ctx->snap_stream, ctx->ev_snap_ready, 0));
+  VH_CUDA(cudaMemcpyAsync(ctx->snap_host, ctx->snap_dev, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->snap_stream));
+  VH_CUDA(cudaEventRecord(ctx->ev_snap_done, ctx->snap_stream));
+  ctx->snap_pending = true;
+  return VH_OK;
+}
+
+int vh_snapshot_wait(vh_ctx *ctx, const double **solution_local, const double **update_local)
+{
+  VH_REQUIRE(ctx);
+  if (!ctx->snap_pending)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_snapshot_wait without vh_snapshot_begin");
+  VH_CUDA(cudaEventSynchronize(ctx->ev_snap_done));
+  const size_t n = (size_t)std::max<int64_t>(ctx->NL, 1);
+  if (solution_local)
+    *solution_local = ctx->snap_host;
+  if (update_local)
+    *update_local = ctx->snap_host + n;
+  return VH_OK;
 }
 
 // dst[i][c] = sum_k w_k src[node_k][c]: one thread per (row, component), rows of at most 27 entries
@@ -1351,6 +1410,7 @@ int vh_solve(vh_ctx *ctx, double tol_rel, int max_it, int restart, int *iteratio
       ctx->t_ms[4] += ms;
   }
   ctx->have_update = true;
+  ctx->delta_holds_update = true;
   return VH_OK;
 }
 

@@ -250,6 +250,12 @@ struct vh_ctx
   int64_t     device_bytes = 0;
   void       *flush_buf   = nullptr;
   size_t      flush_bytes = 0;
+  // output path (vh_snapshot_begin / vh_snapshot_wait): device staging + pinned host copy of [local_solution | Newton update]
+  double      *snap_dev = nullptr, *snap_host = nullptr;
+  cudaStream_t snap_stream = nullptr;
+  cudaEvent_t  ev_snap_ready = nullptr, ev_snap_done = nullptr;
+  bool         snap_pending = false;
+  bool         delta_holds_update = false; // delta still holds the last Newton update (also after vh_accept_trial)
 };
 
 #define VH_MAX_RED_BLOCKS 2048 /* ctx->partials holds 32x this many doubles (fused Gram-Schmidt: one set per step) */

@@ -155,6 +155,12 @@ int chebyshev(vh_ctx *L, const double *b, double *x, bool has_x, int degree, dou
         VH_TRY(vhk_halo_exchange(L, x));
       return VH_OK;
     }
+  if (degree == 0)
+    { // no smoothing on this side of the cycle: a zero initial guess stays zero
+      if (!has_x)
+        VH_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)L->NO, L->stream));
+      return VH_OK;
+    }
   const double lmax = L->mg_lam, lmin = L->mg_lam / ratio;
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
   double       rho = 1.0 / sigma;
@@ -259,7 +265,10 @@ int vcycle(vh_ctx *L, const VhMGParams &P, const double *b, double *x, int lv = 
   VH_TRY(chebyshev(L, b, x, false, P.pre, P.range));
   g_trace.mark(L, "pre", lv);
   // r = b - A x, ghosts refreshed: the restriction of a coarse owned node reads fine nodes owned by the neighbours
-  VH_TRY(residual(L, b, x, L->mg_r));
+  if (P.pre > 0)
+    VH_TRY(residual(L, b, x, L->mg_r));
+  else if (L->NO > 0) // x = 0: the residual is the right-hand side itself, no operator apply
+    VH_CUDA(cudaMemcpyAsync(L->mg_r, b, sizeof(double) * (size_t)L->NO, cudaMemcpyDeviceToDevice, L->stream));
   VH_TRY(vhk_halo_exchange(L, L->mg_r));
   g_trace.mark(L, "residual", lv);
   if (C->n_owned > 0)
@@ -450,9 +459,10 @@ extern "C" int vh_set_preconditioner(vh_ctx *ctx, int kind, const vh_mg_params *
     return vh_fail(ctx, VH_ERR_STATE, "vh_set_preconditioner: no coarse level attached (vh_mg_attach)");
   if (p)
     {
-      if (p->pre < 1 || p->post < 1 || p->coarse_degree < 1 || p->n_power < 1 || !(p->smoothing_range > 1.0) || !(p->coarse_range > 1.0) ||
-          !(p->safety >= 1.0))
-        return vh_fail(ctx, VH_ERR_ARG, "vh_set_preconditioner: degrees and n_power >= 1, ranges > 1, safety >= 1");
+      if (p->pre < 0 || p->post < 0 || p->pre + p->post < 1 || p->coarse_degree < 1 || p->n_power < 1 || !(p->smoothing_range > 1.0) ||
+          !(p->coarse_range > 1.0) || !(p->safety >= 1.0))
+        return vh_fail(ctx, VH_ERR_ARG, "vh_set_preconditioner: pre, post >= 0 with pre + post >= 1, coarse_degree and n_power >= 1, "
+                                        "ranges > 1, safety >= 1");
       ctx->mg_params.pre           = p->pre;
       ctx->mg_params.post          = p->post;
       ctx->mg_params.range         = p->smoothing_range;

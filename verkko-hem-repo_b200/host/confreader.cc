@@ -61,6 +61,8 @@ void confreader::declare_parameters()
     prm.declare_entry("polynomial degree", "1");          // main.cc:116 hard-codes FemGL<3>(1, prm)
     // the reference picks geometry / initial condition by (un)commenting sources in femgl/CMakeLists.txt:42-64
     prm.declare_entry("geometry", "cube");                // stem of a reference makegrid_<stem>.cc box variant (list: host/femgl.cc grid_variants); aliases cube, retangle, retangle-xy-periodic
+    // the reference writes a .vtu per rank + a .pvtu record after every Newton step (run.cc:221-227); the mirror does so on request
+    prm.declare_entry("write vtu output", "false");
     prm.declare_entry("initial condition", "B-phase");    // B-phase: setup_uniform_B-phase.cc | A-phase: setup_uniform_A-phase.cc | BnA: setup_uniform_BnA-flatwall-configuration.cc
   }
   prm.leave_subsection();

@@ -11,6 +11,7 @@
 //                        setup_uniform_BnA-flatwall-configuration.cc:201-245
 //   refine_grid()        /root/reference/femgl/src/refine.cc:109-181
 #include "femgl.h"
+#include "vtu.h"
 
 #include "../../include/vh_femgl.h"
 
@@ -79,6 +80,8 @@ FemGL<dim>::FemGL(unsigned int Q_degree, ParameterHandler &prmHandler, std::ostr
 template <int dim>
 FemGL<dim>::~FemGL()
 {
+  if (writer.joinable())
+    writer.join();
   if (gpu)
     vh_destroy(gpu);
 }
@@ -332,6 +335,7 @@ template <int dim>
 void FemGL<dim>::refine_grid(std::string &refinement_strategy)
 {
   std::ostream &pcout = *out;
+  finish_output(); // the writer thread reads the tables and the context of the mesh that is about to be replaced
   const double  t_begin = now_ms();
   // the old mesh and its GPU context stay alive until the solution has been transferred on the device
   std::unique_ptr<Mesh> old_mesh(new Mesh(*triangulation));
@@ -386,11 +390,48 @@ void FemGL<dim>::refine_grid(std::string &refinement_strategy)
     pcout << "adaptive_refine_grid() call is done !" << std::endl;
 }
 
+// io.cc:106-170 + run.cc:221-227: the reference writes both vectors after EVERY Newton step.  At GPU speeds a synchronous
+// download + file write would cost more than the step, so the snapshot is taken in stream order (vh_snapshot_begin returns at
+// once), leaves the device on a second stream, and a writer thread turns it into the .vtu / .pvtu pair (host/vtu.cc) while
+// the next Newton step runs.  Enabled by the additive key "write vtu output".
+template <int dim>
+void FemGL<dim>::finish_output() const
+{
+  if (writer.joinable())
+    writer.join();
+  if (!writer_error.empty())
+    {
+      const std::string e = writer_error;
+      writer_error.clear();
+      throw std::runtime_error("output_results: " + e);
+    }
+}
+
 template <int dim>
 void FemGL<dim>::output_results(const std::string &dirc) const
 {
-  // VTU/PVTU output (io.cc:106-170) is out of scope; the solution is available through solution().
-  (void)dirc;
+  if (!write_vtu || !gpu)
+    return;
+  const double t0 = now_ms();
+  finish_output(); // the previous file still reads the pinned snapshot buffer
+  check(vh_snapshot_begin(gpu), "output_results");
+  vh_ctx            *ctx = gpu;
+  const RankTables  *T = tables.get();
+  const int          counter = (int)iteration_loop;
+  writer = std::thread([this, ctx, T, dirc, counter] {
+    try
+      {
+        const double *sol = nullptr, *upd = nullptr;
+        if (vh_snapshot_wait(ctx, &sol, &upd) != VH_OK)
+          throw std::runtime_error(vh_last_error(ctx));
+        write_vtu_piece(*T, 0, 1, dirc, "solution", counter, sol, upd);
+      }
+    catch (const std::exception &e)
+      {
+        writer_error = e.what();
+      }
+  });
+  output_main_thread_ms += now_ms() - t0;
 }
 
 template <int dim>
@@ -409,6 +450,7 @@ void FemGL<dim>::run()
                                                  conf.get_double("Cycle 2 linear solver tol"), conf.get_double("Cycle 3 linear solver tol"),
                                                  conf.get_double("Cycle 4 linear solver tol")};
   const double        converge_acc            = conf.get_double("converge accuracy");
+  write_vtu                                   = conf.get_bool("write vtu output");
   conf.leave_subsection();
   if (n_cycles > 4)
     throw std::runtime_error("Number of refinements > 4: the reference declares tolerances for cycles 0..4 only");
@@ -477,6 +519,10 @@ void FemGL<dim>::run()
       if (residual_l2 <= converge_acc)
         break;
     }
+  finish_output();
+  if (write_vtu)
+    pcout << " output: the Newton loop waited " << output_main_thread_ms << " ms in total for output_results (snapshot + file asynchronous)"
+          << std::endl;
   if (gpu)
     check(vh_get_solution(gpu, host_solution.data()), "get_solution");
 }

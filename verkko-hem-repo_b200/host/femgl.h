@@ -11,6 +11,7 @@
 #include <memory>
 #include <ostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "matep.h"
@@ -83,6 +84,14 @@ private:
 
   std::ostream           *out;
   std::vector<StepRecord> records;
+
+  // output path: the snapshot leaves the device on a second stream and a writer thread produces the file while the next
+  // Newton step runs (at most one file in flight; joined before the mesh or the context changes)
+  bool                write_vtu = false;
+  mutable std::thread writer;
+  mutable std::string writer_error;
+  mutable double      output_main_thread_ms = 0.0; // time output_results() kept the Newton loop waiting, summed
+  void                finish_output() const;
 };
 } // namespace vhhost
 #endif

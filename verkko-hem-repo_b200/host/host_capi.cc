@@ -4,6 +4,7 @@
 #include "confreader.h"
 #include "matep.h"
 #include "mesh.h"
+#include "vtu.h"
 
 #include "../../include/vh_femgl.h"
 
@@ -283,6 +284,22 @@ void  vhh_mesh_node_xyz(void *m, double *out)
 {
   Mesh *M = static_cast<Mesh *>(m);
   std::memcpy(out, M->node_xyz.data(), M->node_xyz.size() * sizeof(double));
+}
+
+
+// DataOut stand-in (host/vtu.cc): piece of `rank` (of n_ranks) from tables `t`; returns 0 / -1 (vhh_last_error)
+int vhh_write_vtu(void *t, int rank, int n_ranks, const char *dir, int counter, const double *solution_local, const double *update_local)
+{
+  try
+    {
+      write_vtu_piece(*static_cast<RankTables *>(t), rank, n_ranks, dir, "solution", counter, solution_local, update_local);
+      return 0;
+    }
+  catch (const std::exception &e)
+    {
+      g_err = e.what();
+      return -1;
+    }
 }
 
 } // extern "C"
