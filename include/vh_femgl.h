@@ -160,7 +160,10 @@ typedef struct vh_mg_params
   double  safety;           /* lambda_max is multiplied by this                                    (default 1.1)  */
 } vh_mg_params;
 int vh_mg_attach(vh_ctx *fine, vh_ctx *coarse, int32_t n_rows, const int32_t *ptr, const int32_t *coarse_node, const double *weight);
-/* kind: 0 = block-Jacobi, 1 = multigrid V-cycle (needs vh_mg_attach); params may be NULL (defaults).  Collective. */
+/* kind: 0 = block-Jacobi, 1 = multigrid V-cycle over the levels attached with vh_mg_attach; params may be NULL (defaults).
+ * With NO level attached kind 1 is the cycle's coarsest-level solver alone: a Chebyshev polynomial of degree coarse_degree in
+ * the block-Jacobi-preconditioned operator on [lambda_max/coarse_range, lambda_max] - the polynomial preconditioner for
+ * meshes without a hierarchy (adaptive cycles).  Collective. */
 int vh_set_preconditioner(vh_ctx *ctx, int kind, const vh_mg_params *params);
 /* diagnostics: safety * lambda_max(M^-1 A) the smoother of level `level` (0 = ctx) uses; 0 before the first vh_solve */
 int vh_mg_get_lambda(vh_ctx *ctx, int level, double *lambda_max);

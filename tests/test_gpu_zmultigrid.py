@@ -25,7 +25,8 @@ def _hierarchy(refine, n_levels, half=20.0, bt=2.0):
 
 @pytest.mark.parametrize("refine,n_levels,half,params", [(3, 2, 2.0, {}), (4, 3, 2.0, {}), (4, 2, 20.0, {}),
                                                          (3, 2, 2.0, dict(pre=2, post=3, smoothing_range=8.0, coarse_degree=5)),
-                                                         (4, 3, 2.0, dict(pre=0, post=1)), (4, 3, 2.0, dict(pre=1, post=0))])
+                                                         (4, 3, 2.0, dict(pre=0, post=1)), (4, 3, 2.0, dict(pre=1, post=0)),
+                                                         (3, 1, 2.0, dict(coarse_degree=4, coarse_range=10.0))])  # no hierarchy: Chebyshev polynomial
 def test_vcycle_and_gmres_history_match_oracle(refine, n_levels, half, params):
     """half = 2: cells much smaller than the coherence length (gradient-dominated, the regime of the fine BASELINE meshes);
     half = 20, r4 -> r3: the coarsest spacing at which the re-discretised coarse operator still helps (tools/mg_experiment.py)."""
@@ -98,8 +99,10 @@ def test_multigrid_attach_errors():
     other = vh.Context(tabs[1])
     with pytest.raises(vh.VhError):
         ctxs[0].mg_attach(other, *prol[0])                 # already has a coarse level
+    other.set_preconditioner("multigrid")                  # nothing attached: the Chebyshev polynomial of block-Jacobi (allowed)
+    other.set_preconditioner("block-jacobi")
     with pytest.raises(vh.VhError):
-        other.set_preconditioner("multigrid")              # nothing attached
+        other.set_preconditioner("multigrid", pre=0, post=0)   # a cycle without any smoothing
     ptr, cn, w = prol[0]
     lone = vh.Context(tabs[0])
     with pytest.raises(vh.VhError):

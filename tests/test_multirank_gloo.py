@@ -105,7 +105,8 @@ def test_c4_adaptive_harness_partition_logic_two_ranks():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), os.path.join(root, "tools", "c4_adaptive.py"), "--dry", "--cycles", "3", "--check-single"]
+           "--master-port", str(_free_port()), os.path.join(root, "tools", "c4_adaptive.py"), "--dry", "--cycles", "3", "--initial-refine", "3",
+           "--check-single"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "P-INDEPENDENCE OK" in r.stdout and "C4 ADAPTIVE DONE" in r.stdout

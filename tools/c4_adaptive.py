@@ -14,7 +14,8 @@ after repartitioning: gather the owned values, interpolate on the host mesh, han
                                                       exercises the partition / gather / transfer logic under gloo on CPU)
 
 --check-single: rank 0 repeats the whole run on ONE GPU and the summary carries the P-independence verdict (identical
-refinement flags and iteration counts, residual norms within 1e-10)."""
+refinement flags, linear-iteration and line-search counts; residual norms within 1e-10 relative, or within 1e-12 of the run's
+first right-hand side for the nearly converged steps; final state within 1e-9)."""
 import argparse
 import json
 import os
@@ -87,6 +88,8 @@ def run(args, rank, world, device, dist, flags_in=None):
                 dist.broadcast_object_list(uid, src=0)
                 ctx.comm_init(rank, world, uid[0])
             ctx.set_coef_vector(coef)
+            if args.cheb_degree > 0:   # polynomial preconditioner: Chebyshev(degree) of block-Jacobi (no mesh hierarchy needed)
+                ctx.set_preconditioner("chebyshev", coarse_degree=args.cheb_degree, coarse_range=args.cheb_range)
             ctx.set_solution(x_local[: 18 * T.n_owned_nodes])
             t_create = time.perf_counter() - t0
         x_owned = x_local[: 18 * T.n_owned_nodes].copy()
@@ -98,7 +101,7 @@ def run(args, rank, world, device, dist, flags_in=None):
             else:
                 ctx.timer_start()
                 bn = ctx.assemble()
-                its, _ = ctx.solve(LIN_TOL)
+                its, _ = ctx.solve(args.lin_tol, args.max_lin_it, args.restart)
                 trials = 0
                 for i in range(100):
                     ctx.line_search_trial(LS_STEP ** i)
@@ -157,16 +160,23 @@ def run(args, rank, world, device, dist, flags_in=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cycles", type=int, default=4)
-    # default geometry: h = 0.75 x 0.5 x 1.0 on the initial mesh, i.e. the coherence length (1 in these units) is resolved.
-    # On a slab of 20 x 20 x 40 refined 3 times (h = 2.5 .. 5) the discontinuous BnA state sits near a saddle of the
-    # under-resolved functional: the line search stalls (37 trials) and GMRES(30) + block-Jacobi stagnates in cycle 2, in the
-    # oracle as on the GPU.
+    # Default configuration (measured, profiles/r02g_c4_probes.txt): slab 6 x 4 x 8 refined 4 times (h = 0.375 x 0.25 x 0.5: the
+    # coherence length, 1 in these units, is resolved), the reference's default cycle threshold 1.0 (declare.cc:203-240) and
+    # GMRES(100).  What does NOT work, in the oracle as on the GPU: a 20 x 20 x 40 slab refined 3 times (h = 2.5 .. 5) - the
+    # discontinuous BnA state sits near a saddle of the under-resolved functional and the line search stalls; and GMRES(30) +
+    # block-Jacobi on the final mesh (cells of 5 sizes, 7.5 M DoFs): the Jacobian is indefinite around the A/B interface and
+    # the restarted iteration stagnates (10 000 iterations without reaching 1e-1), while GMRES(100) needs 400-2 000 per step.
     ap.add_argument("--initial-refine", type=int, default=4)
-    ap.add_argument("--half", type=float, nargs=3, default=[6.0, 4.0, 8.0])
+    ap.add_argument("--half", type=float, nargs=3, default=[3.0, 2.0, 4.0])
     ap.add_argument("--ratio", type=float, default=0.1, help="A-phase block range ratio")
     ap.add_argument("--refine-ratio", type=float, default=0.3)
-    ap.add_argument("--threshold", type=float, default=1e3, help="Cycle x refinement threshold (all cycles)")
+    ap.add_argument("--threshold", type=float, default=1.0, help="Cycle x refinement threshold (all cycles; reference default 1.0)")
     ap.add_argument("--max-newton", type=int, default=10, help="Number of interations")
+    ap.add_argument("--restart", type=int, default=100, help="GMRES restart length (.prm key of the mirror: GMRES restart length)")
+    ap.add_argument("--lin-tol", type=float, default=LIN_TOL, help="Cycle x linear solver tol (all cycles)")
+    ap.add_argument("--max-lin-it", type=int, default=10000, help="maximum linear iteration number")
+    ap.add_argument("--cheb-degree", type=int, default=0, help="> 0: Chebyshev polynomial of this degree around block-Jacobi as the preconditioner")
+    ap.add_argument("--cheb-range", type=float, default=30.0)
     ap.add_argument("--dry", action="store_true")
     ap.add_argument("--check-single", action="store_true")
     ap.add_argument("--json", default=None)
@@ -190,10 +200,14 @@ def main():
             ha, hb = out["history"], one["history"]
             same_counts = len(ha) == len(hb) and all(a["linear_its"] == b["linear_its"] and a["trials"] == b["trials"] for a, b in zip(ha, hb))
             rel = max((abs(a["residual"] - b["residual"]) / abs(b["residual"]) for a, b in zip(ha, hb)), default=0.0) if len(ha) == len(hb) else None
+            # near convergence the residual norm is a difference of O(1) terms: its rounding noise scales with the first
+            # right-hand side of the run, not with the (1e-6 times smaller) residual itself
+            r0 = (hb[0]["rhs_norm"] if hb else 0.0) or 1.0
+            rel0 = max((abs(a["residual"] - b["residual"]) / r0 for a, b in zip(ha, hb)), default=0.0) if len(ha) == len(hb) else None
             sol = float(np.abs(xg - xg1).max() / np.abs(xg1).max()) if xg.shape == xg1.shape else None
-            ok = bool(same_flags and same_counts and rel is not None and rel <= 1e-10 and sol is not None and sol <= 1e-9)
+            ok = bool(same_flags and same_counts and rel is not None and (rel <= 1e-10 or rel0 <= 1e-12) and sol is not None and sol <= 1e-9)
             out["p_independence"] = dict(same_refinement_flags=bool(same_flags), same_iteration_counts=bool(same_counts),
-                                         max_rel_residual_diff=rel, max_rel_solution_diff=sol, ok=ok,
+                                         max_rel_residual_diff=rel, max_residual_diff_over_initial_rhs=rel0, max_rel_solution_diff=sol, ok=ok,
                                          single_gpu_ms_per_newton_step=[c["ms_per_newton_step"] for c in one["cycles"]])
         line = json.dumps(out)
         if args.json:

@@ -197,8 +197,9 @@ class Context:
         self._mg_coarse = coarse_ctx  # keep the level alive as long as this context
 
     def set_preconditioner(self, kind, **params):
-        """kind: "block-jacobi" | "multigrid" (or 0 | 1); params: fields of vh_mg_params (MG_DEFAULTS)."""
-        k = {"block-jacobi": 0, "bj": 0, "multigrid": 1, "mg": 1}.get(kind, kind)
+        """kind: "block-jacobi" | "multigrid" (or 0 | 1); params: fields of vh_mg_params (MG_DEFAULTS).  "chebyshev" = kind 1 on a
+        context without attached levels: the Chebyshev polynomial (degree coarse_degree) of block-Jacobi."""
+        k = {"block-jacobi": 0, "bj": 0, "multigrid": 1, "mg": 1, "chebyshev": 1}.get(kind, kind)
         p = None
         if params:
             p = _MGParams(**{**MG_DEFAULTS, **params})

@@ -455,8 +455,10 @@ extern "C" int vh_set_preconditioner(vh_ctx *ctx, int kind, const vh_mg_params *
     return vh_fail(nullptr, VH_ERR_ARG, "null context");
   if (kind != 0 && kind != 1)
     return vh_fail(ctx, VH_ERR_ARG, "vh_set_preconditioner: kind must be 0 (block-Jacobi) or 1 (multigrid)");
-  if (kind == 1 && !ctx->mg_coarse)
-    return vh_fail(ctx, VH_ERR_STATE, "vh_set_preconditioner: no coarse level attached (vh_mg_attach)");
+  // kind 1 without an attached coarse level: the cycle degenerates to its coarsest-level solver, i.e. a Chebyshev polynomial
+  // of degree coarse_degree in the block-Jacobi-preconditioned operator on [lambda / coarse_range, lambda] - a polynomial
+  // preconditioner for meshes without a hierarchy (adaptive cycles): GMRES(m) then spans m * coarse_degree operator powers
+  // per restart cycle, which is what restarted GMRES with plain block-Jacobi lacks on strongly graded meshes.
   if (p)
     {
       if (p->pre < 0 || p->post < 0 || p->pre + p->post < 1 || p->coarse_degree < 1 || p->n_power < 1 || !(p->smoothing_range > 1.0) ||
