@@ -103,6 +103,10 @@ const char *vh_last_error(const vh_ctx *ctx); /* ctx may be NULL: error of the l
 /* ---- multi-GPU: NCCL communicator over the ranks of one box (replaces MPI_COMM_WORLD, femgl.cc:111) ---- */
 int vh_nccl_unique_id(void *id_out /* VH_NCCL_UNIQUE_ID_BYTES */); /* call on rank 0, broadcast by the host */
 int vh_comm_init(vh_ctx *ctx, int rank, int n_ranks, const void *unique_id);
+/* Give ctx the communicator of another context of the same rank instead of creating one (the mesh of the next adaptive cycle,
+ * the levels of a multigrid hierarchy): setup_system() runs once per refinement cycle (refine.cc:126,169) and a new NCCL
+ * communicator costs seconds on 8 ranks.  Collective; the communicator is released with its last context. */
+int vh_comm_share(vh_ctx *ctx, vh_ctx *donor);
 
 /* ---- coefficients: K1..K3 (femgl.h:320-322), alpha/beta1..5 from Matep (femgl.cc:161-168), bt (femgl.h:338) ---- */
 int vh_set_coefficients(vh_ctx *ctx, double K1, double K2, double K3, double alpha, const double beta[5], double bt);

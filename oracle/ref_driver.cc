@@ -1,3 +1,6 @@
+// Derived from VerHem (verkko-Hem-repo), Copyright (C) 2023-present by Kuang. Zhang (author: Quang. Zhang, timohyva@github,
+// Helsinki Institute of Physics, University of Helsinki), GNU LGPL version 2.1 or later; original version:
+// https://github.com/VerHem/verkko-Hem-repo.  THIS FILE IS MODIFIED: the loop nests of femgl/src/assemble.cc and residual.cc as a test driver for the reference's own term files.  See NOTICE and LICENSE.
 // TEST INFRASTRUCTURE — not product code.  Never linked into the CUDA library.
 //
 // "O1": drives the reference's OWN pointwise term functions

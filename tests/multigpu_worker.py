@@ -60,10 +60,8 @@ def main():
             mc = vh.unit_cube(1, lv, half=2.0, n_ranks=n_ranks)
             Tc = mc.tables(r)
             cc = vh.Context(Tc, device=lr)
-            if collective:
-                u = [vh.Context.nccl_unique_id() if rank == 0 else None]
-                dist.broadcast_object_list(u, src=0)
-                cc.comm_init(rank, world, u[0])
+            if collective:   # the levels of a hierarchy share the fine level's communicator (vh_comm_share)
+                cc.comm_share(fine_ctx)
             cc.set_coef_vector(coef)
             cf.mg_attach(cc, *vh.mg_prolongation(mf, Tf, mc, Tc))
             keep.append(cc)

@@ -58,6 +58,7 @@ def cuda_lib():
         L.vh_transfer_solution.argtypes = [_vp, _vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _dp]
         L.vh_mg_attach.argtypes = [_vp, _vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _dp]
         L.vh_set_preconditioner.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_MGParams)]
+        L.vh_comm_share.argtypes = [_vp, _vp]
         L.vh_snapshot_begin.argtypes = [_vp]
         L.vh_snapshot_wait.argtypes = [_vp, ctypes.POINTER(_dp), ctypes.POINTER(_dp)]
         L.vh_mg_get_lambda.argtypes = [_vp, ctypes.c_int, _dp]
@@ -130,6 +131,10 @@ class Context:
     def comm_init(self, rank, n_ranks, unique_id):
         buf = ctypes.create_string_buffer(bytes(unique_id), 128)
         self._chk(self.L.vh_comm_init(self._h, rank, n_ranks, ctypes.cast(buf, _vp)))
+
+    def comm_share(self, donor):
+        """Use the NCCL communicator of another context of this rank (vh_comm_share): no new ncclCommInitRank."""
+        self._chk(self.L.vh_comm_share(self._h, donor._h))
 
     # --- coefficients / state ---
     def set_coefficients(self, K1, K2, K3, alpha, betas, bt):

@@ -251,19 +251,27 @@ static int setup_ghost_push(vh_ctx *ctx, nccl_comm comm)
   return VH_OK;
 }
 
-extern "C" int vh_comm_init(vh_ctx *ctx, int rank, int n_ranks, const void *unique_id)
+static int comm_setup(vh_ctx *ctx, int rank, int n_ranks, nccl_comm comm);
+
+static int comm_args_ok(vh_ctx *ctx, int rank, int n_ranks)
 {
   if (!ctx || n_ranks < 1 || rank < 0 || rank >= n_ranks)
     return vh_fail(ctx, VH_ERR_ARG, "vh_comm_init: bad rank / n_ranks");
+  for (int p : ctx->peer_rank)
+    if (p < 0 || p >= n_ranks || p == rank)
+      return vh_fail(ctx, VH_ERR_ARG, "vh_comm_init: halo plan names a peer outside the communicator");
+  return VH_OK;
+}
+
+extern "C" int vh_comm_init(vh_ctx *ctx, int rank, int n_ranks, const void *unique_id)
+{
+  VH_TRY(comm_args_ok(ctx, rank, n_ranks));
   ctx->rank    = rank;
   ctx->n_ranks = n_ranks;
   if (n_ranks == 1)
     return VH_OK;
   if (!unique_id)
     return vh_fail(ctx, VH_ERR_ARG, "vh_comm_init: unique_id is null");
-  for (int p : ctx->peer_rank)
-    if (p < 0 || p >= n_ranks || p == rank)
-      return vh_fail(ctx, VH_ERR_ARG, "vh_comm_init: halo plan names a peer outside the communicator");
   if (!load_nccl())
     return vh_fail(ctx, VH_ERR_NCCL, api().err);
   VH_CUDA(cudaSetDevice(ctx->device));
@@ -271,8 +279,40 @@ extern "C" int vh_comm_init(vh_ctx *ctx, int rank, int n_ranks, const void *uniq
   std::memcpy(&id, unique_id, sizeof(id));
   nccl_comm comm = nullptr;
   VH_NCCL(api().CommInitRank(&comm, n_ranks, id, rank));
-  ctx->nccl_comm = comm;
+  ctx->nccl_comm   = comm;
+  ctx->nccl_holder = std::shared_ptr<void>(comm, [](void *c) {
+    if (c && api().handle)
+      api().CommDestroy((nccl_comm)c);
+  });
+  return comm_setup(ctx, rank, n_ranks, comm);
+}
 
+// Same communicator for another context of the same rank (the next mesh of an adaptive cycle, the levels of a multigrid
+// hierarchy): ncclCommInitRank and the lazy peer connections of a new communicator cost seconds on 8 ranks, the mailboxes
+// and the ghost-push mapping of a context milliseconds.  Collective like vh_comm_init; the communicator lives until its
+// last context is destroyed.  The contexts sharing one are driven by one host thread in the same order on every rank.
+extern "C" int vh_comm_share(vh_ctx *ctx, vh_ctx *donor)
+{
+  if (!ctx || !donor || ctx == donor)
+    return vh_fail(ctx, VH_ERR_ARG, "vh_comm_share: null or identical contexts");
+  if (donor->device != ctx->device)
+    return vh_fail(ctx, VH_ERR_ARG, "vh_comm_share: the two contexts live on different devices");
+  VH_TRY(comm_args_ok(ctx, donor->rank, donor->n_ranks));
+  ctx->rank    = donor->rank;
+  ctx->n_ranks = donor->n_ranks;
+  if (donor->n_ranks == 1)
+    return VH_OK;
+  if (!donor->nccl_comm || !donor->nccl_holder)
+    return vh_fail(ctx, VH_ERR_STATE, "vh_comm_share: the donor context has no communicator (vh_comm_init)");
+  VH_CUDA(cudaSetDevice(ctx->device));
+  VH_CUDA(cudaStreamSynchronize(donor->stream)); // nothing of the donor is in flight on the communicator
+  ctx->nccl_comm   = donor->nccl_comm;
+  ctx->nccl_holder = donor->nccl_holder;
+  return comm_setup(ctx, ctx->rank, ctx->n_ranks, (nccl_comm)ctx->nccl_comm);
+}
+
+static int comm_setup(vh_ctx *ctx, int rank, int n_ranks, nccl_comm comm)
+{
   // ---- peer-memory mailboxes for the scalar all-reduces (VH_P2P=0 keeps ncclAllReduce) ----
   const char *e = getenv("VH_P2P");
   if (n_ranks <= VH_P2P_MAX_RANKS && !(e && e[0] == '0'))
@@ -401,8 +441,7 @@ void vh_comm_destroy(vh_ctx *ctx)
       ctx->mgs_tickets = nullptr;
       ctx->p2p         = false;
     }
-  if (ctx->nccl_comm && api().handle)
-    api().CommDestroy((nccl_comm)ctx->nccl_comm);
+  ctx->nccl_holder.reset(); // ncclCommDestroy when the last context sharing the communicator lets go
   ctx->nccl_comm = nullptr;
 }
 

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -188,6 +189,7 @@ struct vh_ctx
   // halo
   int                  rank = 0, n_ranks = 1;
   void                *nccl_comm = nullptr;
+  std::shared_ptr<void> nccl_holder; // owns the communicator; shared between the contexts of one rank (vh_comm_share)
   // peer-memory mailboxes (NVLink P2P through CUDA IPC) for latency-bound scalar all-reduces; see vh_halo.cu
   int                  mgs_mode = -1;      // fused Gram-Schmidt: elements per thread (8 / 32), 64 = streaming variant, 1000 = kernel chain, -1 = undecided
   bool                 p2p = false;

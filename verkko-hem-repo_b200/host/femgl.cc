@@ -1,3 +1,6 @@
+// Derived from VerHem (verkko-Hem-repo), Copyright (C) 2023-present by Kuang. Zhang (author: Quang. Zhang, timohyva@github,
+// Helsinki Institute of Physics, University of Helsinki), GNU LGPL version 2.1 or later; original version:
+// https://github.com/VerHem/verkko-Hem-repo.  THIS FILE IS MODIFIED: the control flow of femgl/src/{run,solve,iteration,refine}.cc around calls into the CUDA library.  See NOTICE and LICENSE.
 // See femgl.h.  Control flow and printed lines follow the reference:
 //   ctor                 /root/reference/femgl/src/femgl.cc:107-203
 //   run()                /root/reference/femgl/src/run.cc:108-260

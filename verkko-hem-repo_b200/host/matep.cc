@@ -1,3 +1,6 @@
+// Derived from VerHem (verkko-Hem-repo), Copyright (C) 2023-present by Kuang. Zhang (author: Quang. Zhang, timohyva@github,
+// Helsinki Institute of Physics, University of Helsinki), GNU LGPL version 2.1 or later; original version:
+// https://github.com/VerHem/verkko-Hem-repo.  THIS FILE IS MODIFIED: compact rewrite of matep/src/matep.cc with the same coefficient tables.  See NOTICE and LICENSE.
 #include "matep.h"
 
 #include <cmath>
