@@ -165,6 +165,15 @@ def workload_string(degree, refine, global_refine, n_dofs, n_cells):
                n_dofs, n_cells))
 
 
+def config_dict(degree, refine, global_refine, n_dofs, n_cells, n_gpus):
+    """The `config` object of the JSON line - identical in both arms (ours and --impl reference) for the same command line."""
+    return {"workload": workload_string(degree, refine, global_refine, n_dofs, n_cells),
+            "l2": "the working set of one operator apply (the H_q tables: 11.5 KB per Q1 cell, 38.9 KB per Q2 cell, on every rank) exceeds "
+                  "the 126 MB L2 in the Newton steps; the stand-alone kernel timings flush L2 between launches",
+            "parallelism": "subdomain x%d (Morton partition, NCCL halo + peer-memory all-reduce)" % n_gpus,
+            "stop_rule": "run.cc:234-250: a run ends at residual <= 5e-6, the next timed step starts a new run from the IC"}
+
+
 def initial_state(T):
     from helpers import b_phase_state, MATEP_SCC_ON
     return b_phase_state(T, MATEP_SCC_ON, noise=0.0)
@@ -309,11 +318,10 @@ def run_reference(args):
            "value": val, "unit": "DoF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak" if args.global_refine is None else "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_string(args.degree, args.refine, args.global_refine, n_dofs, n_cells),
-                      "reference_arm": "the reference's own CPU code for this path (oracle/_ref: its verbatim cell_mat_vec term files "
-                                       "driven by its literal (q,i,j) loops) on all host cores; %d-cell sample per step, extrapolated "
-                                       "linearly to the workload; its ML-AMG solve is left out (upper bound on its throughput)"
-                                       % last["cells"]},
+           "config": config_dict(args.degree, args.refine, args.global_refine, n_dofs, n_cells, args.gpus),
+           "reference_arm": "the reference's own CPU code for this path (oracle/_ref: its verbatim cell_mat_vec term files "
+                            "driven by its literal (q,i,j) loops) on all host cores; %d-cell sample per step, extrapolated "
+                            "linearly to the workload; its ML-AMG solve is left out (upper bound on its throughput)" % last["cells"],
            # NOT like-for-like with the GPU arm's Newton step (which includes the GMRES solve): compare phase by phase
            "comparable": False,
            "phases": {"assembly_dofs_per_s": float(np.mean(asm_cps)) / scale * dofs_per_cell,
@@ -677,11 +685,7 @@ def run_ours(args):
         out = {"metric": "femgl Newton-step throughput", "value": main["value"], "unit": "DoF/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": workload_string(args.degree, args.refine, args.global_refine, main["n_dofs"], main["n_cells"]),
-                          "l2": "working set per operator apply (%.2f GB on rank 0) exceeds the 126 MB L2; kernel timings flush L2 "
-                                "between launches" % (main["roofline"]["moved_bytes_per_launch"] / 1e9),
-                          "parallelism": "subdomain x%d (Morton partition, NCCL halo + peer-memory all-reduce)" % world,
-                          "stop_rule": "run.cc:234-250: a run ends at residual <= 5e-6, the next timed step starts a new run from the IC"}}
+               "config": config_dict(args.degree, args.refine, args.global_refine, main["n_dofs"], main["n_cells"], world)}
         for k in ("preconditioner", "newton", "final_energy", "phase_ms_per_step", "gmres_its_per_step", "ms_per_gmres_it", "ms_per_inner_step", "block_jacobi",
                   "halo_ms_per_exchange",
                   "allreduce_ms_per_dot", "roofline", "assembly", "kernels", "e2e", "gpu_launches", "multi_gpu_parity", "memory",
