@@ -467,7 +467,19 @@ def build_context(vh, dist, rank, world, local_rank, degree, refine, global_refi
             Tc = mc.tables(rank)
             cc = vh.Context(Tc, device=local_rank)
             init(cc)
-            cf.mg_attach(cc, *vh.mg_prolongation(mf, Tf, mc, Tc))
+            err = None
+            try:
+                cf.mg_attach(cc, *vh.mg_prolongation(mf, Tf, mc, Tc))
+            except (vh.VhError, RuntimeError) as exc:   # vh_mg_attach validates locally: agree before the next collective call
+                err = str(exc)
+            if world > 1:
+                import torch
+                flag = torch.tensor([0.0 if err is None else 1.0], device="cuda")
+                dist.all_reduce(flag)
+                if float(flag.item()) > 0 and err is None:
+                    err = "vh_mg_attach failed on another rank"
+            if err is not None:
+                raise vh.VhError(-2, "multigrid hierarchy rejected: " + err)
             levels.append(cc)
             mf, Tf, cf = mc, Tc, cc
         ctx.set_preconditioner("multigrid", **MG_PARAMS)

@@ -126,3 +126,25 @@ def test_random_refinement_rows_are_partition_independent():
         want = A1[dof_perm[:18 * T.n_owned_nodes]][:, dof_perm]
         assert abs(A - want).max() <= 1e-13 * abs(A1).max()
         assert np.abs(rhs - r1[dof_perm[:18 * T.n_owned_nodes]]).max() <= 1e-13 * np.abs(r1).max()
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_multigrid_levels_are_nested_on_every_partition(world):
+    """What vh_mg_attach requires of two consecutive levels (csrc/vh_multigrid.cu), checked on the host tables for the partitions
+    bench.py runs (1/2/4/8 ranks) and an odd one: the prolongation rows of the owned fine nodes are complete (weights sum to 1,
+    every parent is local on the coarse level) and every coarse owned node coincides with a fine node owned by the same rank."""
+    import verkko_hem_repo_b200 as vh
+    meshes = [vh.unit_cube(1, lv, half=20.0, n_ranks=world) for lv in (4, 3, 2)]
+    for rank in range(world):
+        tabs = [m.tables(rank) for m in meshes]
+        for k in range(2):
+            Tf, Tc = tabs[k], tabs[k + 1]
+            ptr, cn, w = vh.mg_prolongation(meshes[k], Tf, meshes[k + 1], Tc)
+            assert ptr.size - 1 == Tf.n_local_nodes and (cn.size == 0 or (cn.min() >= 0 and cn.max() < Tc.n_local_nodes))
+            rows = np.repeat(np.arange(Tf.n_local_nodes), np.diff(ptr))
+            total = np.bincount(rows, weights=w, minlength=Tf.n_local_nodes)[:Tf.n_owned_nodes]
+            assert total.size == 0 or np.abs(total - 1.0).max() <= 1e-12
+            one = (np.abs(w - 1.0) <= 1e-12) & (rows < Tf.n_owned_nodes) & (cn < Tc.n_owned_nodes)
+            has = np.zeros(Tc.n_owned_nodes, dtype=bool)
+            has[cn[one]] = True
+            assert has.all()
