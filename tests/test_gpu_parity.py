@@ -199,3 +199,37 @@ def test_errors_are_reported_not_swallowed():
     with pytest.raises(vh.VhError):
         ctx.solve(1e-1)  # no matrix yet
     ctx.close()
+
+
+def test_call_order_guards_of_the_newton_step():
+    """VH_ERR_STATE for calls out of the order run.cc:214-218 / iteration.cc:128-210 prescribe; in particular nothing of the
+    replaced state survives vh_accept_trial: a second line search, residual, acceptance, trial energy or solve must fail
+    instead of applying the stale Newton update once more."""
+    T = vh.unit_cube(1, 2, half=2.0).tables(0)
+    ctx = vh.Context(T)
+    with pytest.raises(vh.VhError):
+        ctx.assemble()                         # before vh_set_coefficients
+    ctx.set_coef_vector(coef_vector(MATEP_SCC_ON, 2.0))
+    ctx.set_solution(b_phase_state(T, seed=3))
+    for call in (lambda: ctx.solve(1e-1), lambda: ctx.line_search_trial(1.0), ctx.residual, ctx.accept_trial, lambda: ctx.energy(1)):
+        with pytest.raises(vh.VhError):
+            call()                             # nothing assembled / solved / tried yet
+    ctx.assemble()
+    with pytest.raises(vh.VhError):
+        ctx.line_search_trial(1.0)             # before vh_solve
+    ctx.solve(1e-1)
+    with pytest.raises(vh.VhError):
+        ctx.accept_trial()                     # before vh_line_search_trial
+    ctx.line_search_trial(1.0)
+    ctx.residual()
+    ctx.energy(1)
+    ctx.accept_trial()
+    x1 = ctx.get_solution()
+    for call in (lambda: ctx.line_search_trial(1.0), ctx.residual, ctx.accept_trial, lambda: ctx.energy(1), lambda: ctx.solve(1e-1)):
+        with pytest.raises(vh.VhError):
+            call()                             # the update, the trial vector and the matrix belonged to the replaced state
+    assert np.array_equal(ctx.get_solution(), x1)
+    ctx.energy(0)
+    ctx.assemble()                             # the next Newton step starts normally
+    ctx.solve(1e-1)
+    ctx.close()
